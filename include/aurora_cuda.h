@@ -1,0 +1,190 @@
+/*
+ * aurora_cuda.h — C ABI of libaurora_cuda.so, the B200-native batched LZ-family codec engine.
+ *
+ * This is the drop-in boundary for the hot path of Venomalia/AuroraLib.Compression (managed C#):
+ * every entry point below is what a P/Invoke (or ctypes / cgo / JNI) binding would call in place of
+ * the reference's managed loops.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree, src/AuroraLib.Compression/...):
+ *   ICompressionDecoder.Decompress(Stream, Stream)            Interfaces/ICompressionDecoder.cs:24
+ *   ICompressionEncoder.Compress(ReadOnlySpan<byte>, Stream, CompressionSettings)
+ *                                                             Interfaces/ICompressionEncoder.cs:19
+ *   IProvidesDecompressedSize.GetDecompressedSize(Stream)     Interfaces/IProvidesDecompressedSize.cs:20
+ *   IEndianDependentFormat.FormatByteOrder                    Interfaces/IEndianDependentFormat.cs:13
+ *   IFormatInfoProvider.IsMatch(Stream, ReadOnlySpan<char>)   e.g. Nintendo/Yaz0.cs:41-47, LZ10.cs:36-41
+ *   CompressionSettings(quality, maxWindowBits, strategy)     CompressionSettings.cs:38-50
+ *   LzProperties                                              LzProperties.cs:46-66
+ *   exceptions -> status codes                                Exceptions/DecompressedSizeException.cs:8-25
+ *
+ * The same symbols (prefix ora_ instead of aurora_, no context argument) are exported by the CPU
+ * oracle in oracle/ so that tests can A/B the two libraries.
+ */
+#ifndef AURORA_CUDA_H
+#define AURORA_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AURORA_ABI_VERSION 1
+
+/* ---- per-stream status: 1:1 with the reference's exception taxonomy ---- */
+typedef enum aurora_status {
+    AURORA_OK                 = 0,
+    AURORA_END_OF_STREAM      = 1, /* EndOfStreamException: truncated input                            */
+    AURORA_INVALID_IDENTIFIER = 2, /* InvalidIdentifierException: wrong magic / type byte              */
+    AURORA_SIZE_MISMATCH      = 3, /* DecompressedSizeException(expected, actual)                      */
+    AURORA_DST_TOO_SMALL      = 4, /* NotSupportedException from a non-expandable destination stream   */
+    AURORA_INVALID_DATA       = 5, /* InvalidDataException / ArgumentOutOfRangeException               */
+    AURORA_NOT_SUPPORTED      = 6, /* NotSupportedException (LZ4 dictID, ...)                          */
+    AURORA_INVALID_ARGUMENT   = 7, /* ArgumentException / ArgumentNullException                        */
+    AURORA_CUDA_ERROR         = 8  /* the device failed; see aurora_last_error_string                  */
+} aurora_status;
+
+/* ---- formats on the hot path ---- */
+typedef enum aurora_format {
+    AURORA_FMT_YAZ0         = 1,  /* Nintendo/Yaz0.cs                                        */
+    AURORA_FMT_YAZ1         = 2,  /* Nintendo/Yaz1.cs (magic "Yaz1")                         */
+    AURORA_FMT_YAY0         = 3,  /* Nintendo/Yay0.cs                                        */
+    AURORA_FMT_MIO0         = 4,  /* Nintendo/MIO0.cs                                        */
+    AURORA_FMT_LZ10         = 5,  /* Nintendo/LZ10.cs                                        */
+    AURORA_FMT_LZ11         = 6,  /* Nintendo/LZ11.cs                                        */
+    AURORA_FMT_LZSS         = 7,  /* Formats/Common/LZSS.cs (properties in opts.lzss)        */
+    AURORA_FMT_LZ4          = 8,  /* LZ4.Decompress: legacy / v1 frame / skippable by magic  */
+    AURORA_FMT_LZ4_BLOCK    = 9,  /* LZ4.DecompressBlockHeaderless / CompressBlockHeaderless */
+    AURORA_FMT_LZ4_LEGACY   = 10, /* LZ4Legacy.cs (encode: legacy frame; decode == LZ4)      */
+    AURORA_FMT_LZO          = 11, /* Formats/Common/LZO.cs (headerless LZO1X)                */
+    AURORA_FMT_SNAPPY       = 12, /* Snappy.cs framing format                                */
+    AURORA_FMT_SNAPPY_BLOCK = 13, /* Snappy.DecompressHeaderless / CompressHeaderless        */
+    AURORA_FMT_PRS          = 14  /* Sega/PRS.cs                                             */
+} aurora_format;
+
+typedef enum aurora_endian {
+    AURORA_ENDIAN_LITTLE = 0,
+    AURORA_ENDIAN_BIG    = 1,
+    AURORA_ENDIAN_DEFAULT = 2 /* the class default: Big for Yaz0/Yay0/MIO0/PRS */
+} aurora_endian;
+
+/* LzProperties (LzProperties.cs:9-44).  Fill with aurora_lz_props_window / aurora_lz_props_bits. */
+typedef struct aurora_lz_props {
+    int32_t windows_bits;
+    int32_t length_bits;
+    int32_t min_length;
+    int32_t max_length;
+    int32_t max_distance;
+    int32_t min_distance;
+    int32_t windows_start;
+    int32_t reserved;
+} aurora_lz_props;
+
+/* Blittable option block shared by decode and encode.  Zero-initialise, set struct_size. */
+typedef struct aurora_codec_opts {
+    uint32_t struct_size;      /* sizeof(aurora_codec_opts)                                            */
+    int32_t  byte_order;       /* aurora_endian: FormatByteOrder (Yaz0/Yay0/MIO0/PRS)                  */
+    /* CompressionSettings (encode only).  quality < 0 means default(CompressionSettings) == 8.        */
+    int32_t  quality;          /* 0..15                                                                */
+    int32_t  max_window_bits;  /* 0 or 7..28                                                           */
+    int32_t  strategy;         /* bit0 = CompresionStrategy.CompatibilityMode                          */
+    int32_t  vram_mode;        /* LZ10/LZ11 GbaVramCompatibilityMode: -1 class default, 0 off, 1 on    */
+    /* LZSS */
+    aurora_lz_props lzss;      /* windows_bits == 0 -> LZSS.DefaultProperties ((byte)12, 4, 2)         */
+    int32_t  lzss_initial_fill;/* LZSS.DecompressHeaderless initialFill                                */
+    /* LZ4 (encode) */
+    uint32_t lz4_block_size;   /* LZ4.BlockSize: 0 -> Block4MB                                         */
+    int32_t  lz4_verify;       /* decode: 1 = verify XXH32 checksums (LZ4.HashAlgorithm set),
+                                  0 = skip (HashAlgorithm == null, the library default)                */
+    /* Yaz0 */
+    uint32_t yaz0_alignment;   /* Yaz0.MemoryAlignment written by the encoder                          */
+    uint32_t reserved[6];
+} aurora_codec_opts;
+
+typedef struct aurora_ctx aurora_ctx;
+
+/* ---- lifetime ---- */
+/* device_mask: bit i selects CUDA device i; 0 = all visible devices. */
+aurora_ctx* aurora_init(uint32_t device_mask);
+void        aurora_shutdown(aurora_ctx* ctx);
+int         aurora_device_count(void);
+int         aurora_ctx_device_count(const aurora_ctx* ctx);
+int         aurora_abi_version(void);
+const char* aurora_last_error_string(const aurora_ctx* ctx);
+const char* aurora_status_string(int status);
+
+/* pinned host memory for the blittable batch buffers (cudaHostAlloc) */
+void* aurora_pinned_alloc(size_t bytes);
+void  aurora_pinned_free(void* p);
+
+/* LzProperties constructors (LzProperties.cs:46-55 and :57-66) */
+void aurora_lz_props_window(aurora_lz_props* out, int32_t windows_size, int32_t max_length,
+                            int32_t min_length, int32_t windows_start, int32_t min_distance);
+void aurora_lz_props_bits(aurora_lz_props* out, int32_t distance_bits, int32_t length_bits,
+                          int32_t threshold);
+void aurora_codec_opts_init(aurora_codec_opts* opts);
+
+/*
+ * ---- batch entry points over HOST buffers (the call the C# shim makes) ----
+ * Stream i occupies src_base[src_off[i] .. src_off[i]+src_len[i]).  Decoded bytes go to
+ * dst_base[dst_off[i] .. dst_off[i]+dst_cap[i]).  All per-stream arrays have n entries.
+ * Streams are sharded over the context's devices by size; no stream aborts the batch: errors
+ * are reported in status[i].  Returns AURORA_OK, AURORA_INVALID_ARGUMENT or AURORA_CUDA_ERROR.
+ */
+
+/* IProvidesDecompressedSize.GetDecompressedSize for n streams.  Formats without a size header
+ * (LZ4*, LZO, PRS) report AURORA_NOT_SUPPORTED unless size_scan != 0, in which case the stream
+ * is parsed on the device without copying (a size-only pre-pass, SURVEY.md §7 "hard parts"). */
+int aurora_decoded_size_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n,
+                              const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
+                              int size_scan, uint64_t* out_size, int32_t* status);
+
+/* IsMatch(Stream) for n streams (magic checks and the LZ10/LZ11/PRS token-walk heuristics). */
+int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n,
+                          const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
+                          uint8_t* match);
+
+/* Decompress(Stream source, Stream destination) for n streams.
+ * out_len[i]  = bytes the reference would have written (may exceed dst_cap[i] on overshoot),
+ * consumed[i] = source.Position after the call, relative to the start of stream i. */
+int aurora_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n,
+                        const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
+                        uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* dst_cap,
+                        uint64_t* out_len, uint64_t* consumed, int32_t* status);
+
+/* Upper bound of the compressed size of a raw_len-byte input in `format` (all qualities). */
+uint64_t aurora_encode_bound(int format, uint64_t raw_len);
+
+/* Compress(ReadOnlySpan<byte> source, Stream destination, CompressionSettings) for n buffers. */
+int aurora_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n,
+                        const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
+                        uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* dst_cap,
+                        uint64_t* out_len, int32_t* status);
+
+/*
+ * ---- device-resident variants (single device, inputs already in HBM; used by bench `value`) ----
+ * All pointers are device pointers on `device` (an index into the context's device list);
+ * descriptor arrays are device arrays too.  src_off/dst_off must be multiples of 16.
+ * `stream` is a cudaStream_t passed as void* (NULL = the context's own stream for that device);
+ * the call is asynchronous with respect to the host: synchronise the stream before reading results.
+ */
+int aurora_decode_batch_device(aurora_ctx* ctx, int device, int format, const aurora_codec_opts* opts,
+                               size_t n, const uint8_t* d_src_base, uint64_t src_total,
+                               const uint64_t* d_src_off, const uint64_t* d_src_len,
+                               uint8_t* d_dst_base, const uint64_t* d_dst_off, const uint64_t* d_dst_cap,
+                               uint64_t* d_out_len, uint64_t* d_consumed, int32_t* d_status,
+                               void* stream);
+
+int aurora_encode_batch_device(aurora_ctx* ctx, int device, int format, const aurora_codec_opts* opts,
+                               size_t n, const uint8_t* d_src_base, uint64_t src_total,
+                               const uint64_t* d_src_off, const uint64_t* d_src_len,
+                               uint8_t* d_dst_base, const uint64_t* d_dst_off, const uint64_t* d_dst_cap,
+                               uint64_t* d_out_len, int32_t* d_status, void* stream);
+
+/* Number of kernels this library has launched since aurora_init (all devices). */
+uint64_t aurora_kernel_launch_count(const aurora_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AURORA_CUDA_H */
