@@ -1,0 +1,625 @@
+// api.cu — host side of libaurora_cuda.so: context, per-device queues and buffers, stream sharding and the
+// C ABI declared in include/aurora_cuda.h.  No CPU codec lives here: every Decompress/Compress goes to
+// the sm_100a kernels (decode_flaglz.cu, decode_bytelz.cu, encode_lz.cu) and fails with AURORA_CUDA_ERROR
+// when no device is usable.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace aurora;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct DeviceCtx {
+    int dev = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf src, dst, desc, ticket, scratch;
+    HostBuf hdesc;
+    std::mutex mu;   // one batch at a time per device
+};
+
+}  // namespace
+
+struct aurora_ctx {
+    std::vector<DeviceCtx*> devs;
+    std::string last_error;
+    std::atomic<uint64_t> launches{0};
+    std::mutex err_mu;
+    void set_error(const std::string& s) {
+        std::lock_guard<std::mutex> g(err_mu);
+        last_error = s;
+    }
+};
+
+namespace {
+
+thread_local std::string g_init_error;
+
+#define CU_TRY(ctx, expr)                                                                           \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+            return AURORA_CUDA_ERROR;                                                               \
+        }                                                                                           \
+    } while (0)
+
+bool is_flaglz(int f) {
+    return f == AURORA_FMT_YAZ0 || f == AURORA_FMT_YAZ1 || f == AURORA_FMT_YAY0 || f == AURORA_FMT_MIO0 ||
+           f == AURORA_FMT_LZ10 || f == AURORA_FMT_LZ11 || f == AURORA_FMT_LZSS;
+}
+bool is_bytelz(int f) {
+    return f == AURORA_FMT_LZ4 || f == AURORA_FMT_LZ4_BLOCK || f == AURORA_FMT_LZ4_LEGACY || f == AURORA_FMT_LZO ||
+           f == AURORA_FMT_SNAPPY || f == AURORA_FMT_SNAPPY_BLOCK || f == AURORA_FMT_PRS;
+}
+
+int ceil_log2(long long x) {
+    int b = 0;
+    while ((1LL << b) < x) b++;
+    return b;
+}
+
+// resolve the option block into kernel parameters; returns a per-batch status override (OK = run)
+int fill_decode_params(DecodeParams& p, int format, const aurora_codec_opts* o) {
+    p.format = format;
+    p.byte_order = o ? o->byte_order : AURORA_ENDIAN_DEFAULT;
+    if (p.byte_order != AURORA_ENDIAN_LITTLE && p.byte_order != AURORA_ENDIAN_BIG) p.byte_order = AURORA_ENDIAN_DEFAULT;
+    p.size_only = 0;
+    p.lz4_verify = o ? o->lz4_verify : 0;
+    aurora_lz_props lz;
+    if (o && o->lzss.windows_bits != 0) lz = o->lzss;
+    else aurora_lz_props_bits(&lz, 12, 4, 2);   // LZSS.DefaultProperties (LZSS.cs:33)
+    p.lzss = LzssParams{lz.windows_bits, lz.length_bits, lz.min_length, lz.max_distance, lz.windows_start,
+                        o ? o->lzss_initial_fill : 0};
+    if (format == AURORA_FMT_LZSS) {
+        if (lz.windows_bits < 1 || lz.windows_bits > 12 || lz.length_bits < 1 || lz.length_bits > 8 || lz.max_distance < 2 ||
+            lz.max_distance > 4096 || lz.min_length < 1 || lz.min_length > 255)
+            return AURORA_NOT_SUPPORTED;
+    }
+    return AURORA_OK;
+}
+
+cudaError_t launch_decode(const DecodeParams& p, int sm_count, cudaStream_t st) {
+    if (is_flaglz(p.format)) return launch_decode_flaglz(p, sm_count, st);
+    return launch_decode_bytelz(p, sm_count, st);
+}
+
+struct Range {
+    size_t begin, end;
+};
+
+// contiguous ranges of streams with balanced byte counts (streams are independent: SURVEY.md §8e)
+std::vector<Range> shard(size_t n, int g, const uint64_t* a, const uint64_t* b) {
+    std::vector<Range> r;
+    if (g <= 1 || n < size_t(g) * 2) {
+        r.push_back(Range{0, n});
+        return r;
+    }
+    long double total = 0;
+    for (size_t i = 0; i < n; i++) total += (long double)(a[i] + (b ? b[i] : 0) + 64);
+    size_t i = 0;
+    long double acc = 0;
+    for (int k = 0; k < g; k++) {
+        size_t start = i;
+        long double target = total * (k + 1) / g;
+        while (i < n && (acc < target || k == g - 1)) {
+            acc += (long double)(a[i] + (b ? b[i] : 0) + 64);
+            i++;
+        }
+        r.push_back(Range{start, i});
+    }
+    r.back().end = n;
+    return r;
+}
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) & ~(a - 1); }
+
+// Layout of one shard's source or destination bytes on the device: either the host span copied as one
+// piece (offsets keep their value relative to the 16-byte aligned span start) or a packed re-layout.
+struct Layout {
+    bool span = true;
+    uint64_t lo = 0;        // host offset of device byte 0 (span mode)
+    uint64_t bytes = 0;     // device bytes
+    std::vector<uint64_t> dev_off;
+};
+
+Layout plan_layout(const uint64_t* off, const uint64_t* len, size_t b, size_t e) {
+    Layout L;
+    uint64_t lo = ~0ull, hi = 0, sum = 0;
+    for (size_t i = b; i < e; i++) {
+        lo = std::min(lo, off[i]);
+        hi = std::max(hi, off[i] + len[i]);
+        sum += len[i];
+    }
+    if (b == e) { lo = hi = 0; }
+    lo &= ~15ull;
+    L.dev_off.resize(e - b);
+    if (hi - lo <= sum + sum / 4 + (1u << 20) + 64 * (e - b)) {
+        L.span = true;
+        L.lo = lo;
+        L.bytes = align_up(hi - lo, 16);
+        for (size_t i = b; i < e; i++) L.dev_off[i - b] = off[i] - lo;
+    } else {
+        L.span = false;
+        uint64_t pos = 0;
+        for (size_t i = b; i < e; i++) {
+            L.dev_off[i - b] = pos;
+            pos += align_up(len[i], 16);
+        }
+        L.bytes = pos;
+    }
+    return L;
+}
+
+int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_opts* opts, size_t b, size_t e,
+                 const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
+                 const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t* out_len, uint64_t* consumed, int32_t* status,
+                 int size_only) {
+    const size_t n = e - b;
+    if (n == 0) return AURORA_OK;
+    std::lock_guard<std::mutex> guard(d->mu);
+    CU_TRY(ctx, cudaSetDevice(d->dev));
+    DecodeParams P{};
+    const int override_status = fill_decode_params(P, format, opts);
+    if (override_status != AURORA_OK) {
+        for (size_t i = b; i < e; i++) {
+            status[i] = override_status;
+            if (out_len) out_len[i] = 0;
+            if (consumed) consumed[i] = 0;
+        }
+        return AURORA_OK;
+    }
+    P.size_only = size_only;
+    const Layout S = plan_layout(src_off, src_len, b, e);
+    Layout D;
+    if (!size_only) D = plan_layout(dst_off, dst_cap, b, e);
+    else D.dev_off.assign(n, 0);
+
+    CU_TRY(ctx, d->src.reserve(S.bytes + 16));
+    CU_TRY(ctx, d->dst.reserve(D.bytes + 16));
+    // descriptors: src_off, src_len, dst_off, dst_cap | out_len, consumed | status
+    const size_t desc_bytes = n * (6 * sizeof(uint64_t) + sizeof(int32_t)) + 64;
+    CU_TRY(ctx, d->desc.reserve(desc_bytes));
+    CU_TRY(ctx, d->hdesc.reserve(desc_bytes));
+    CU_TRY(ctx, d->ticket.reserve(256));
+    uint64_t* h = static_cast<uint64_t*>(d->hdesc.p);
+    uint64_t* dv = static_cast<uint64_t*>(d->desc.p);
+    for (size_t i = 0; i < n; i++) {
+        h[i] = S.dev_off[i];
+        h[n + i] = src_len[b + i];
+        h[2 * n + i] = D.dev_off[i];
+        h[3 * n + i] = size_only ? 0 : dst_cap[b + i];
+    }
+    cudaStream_t st = d->stream;
+    CU_TRY(ctx, cudaMemcpyAsync(dv, h, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    uint8_t* dsrc = static_cast<uint8_t*>(d->src.p);
+    uint8_t* ddst = static_cast<uint8_t*>(d->dst.p);
+    if (S.span) {
+        uint64_t hi = 0;
+        for (size_t i = b; i < e; i++) hi = std::max(hi, src_off[i] + src_len[i]);
+        if (hi > S.lo) CU_TRY(ctx, cudaMemcpyAsync(dsrc, src_base + S.lo, hi - S.lo, cudaMemcpyHostToDevice, st));
+    } else {
+        for (size_t i = b; i < e; i++)
+            if (src_len[i]) CU_TRY(ctx, cudaMemcpyAsync(dsrc + S.dev_off[i - b], src_base + src_off[i], src_len[i], cudaMemcpyHostToDevice, st));
+    }
+    CU_TRY(ctx, cudaMemsetAsync(d->ticket.p, 0, 64, st));
+
+    P.src_base = dsrc;
+    P.src_limit = align_up(S.bytes, 16);
+    P.src_off = dv;
+    P.src_len = dv + n;
+    P.dst_base = ddst;
+    P.dst_off = dv + 2 * n;
+    P.dst_cap = dv + 3 * n;
+    P.out_len = dv + 4 * n;
+    P.consumed = dv + 5 * n;
+    P.status = reinterpret_cast<int32_t*>(dv + 6 * n);
+    P.order = nullptr;
+    P.ticket = static_cast<unsigned int*>(d->ticket.p);
+    P.n = uint32_t(n);
+    CU_TRY(ctx, launch_decode(P, d->sm_count, st));
+    ctx->launches++;
+
+    // results
+    CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, 2 * n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (!size_only) {
+        if (D.span) {
+            uint64_t hi = 0;
+            for (size_t i = b; i < e; i++) hi = std::max(hi, dst_off[i] + dst_cap[i]);
+            if (hi > D.lo) CU_TRY(ctx, cudaMemcpyAsync(dst_base + D.lo, ddst, hi - D.lo, cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+        } else {
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            for (size_t i = b; i < e; i++) {
+                const uint64_t nbytes = std::min<uint64_t>(h[4 * n + (i - b)], dst_cap[i]);
+                if (nbytes) CU_TRY(ctx, cudaMemcpyAsync(dst_base + dst_off[i], ddst + D.dev_off[i - b], nbytes, cudaMemcpyDeviceToHost, st));
+            }
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+        }
+    } else {
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    const int32_t* hs = reinterpret_cast<const int32_t*>(h + 6 * n);
+    for (size_t i = 0; i < n; i++) {
+        if (out_len) out_len[b + i] = h[4 * n + i];
+        if (consumed) consumed[b + i] = h[5 * n + i];
+        if (status) status[b + i] = hs[i];
+    }
+    return AURORA_OK;
+}
+
+template <typename F>
+int for_each_shard(aurora_ctx* ctx, const std::vector<Range>& ranges, F&& f) {
+    if (ranges.size() == 1) return f(ctx->devs[0], ranges[0]);
+    std::vector<int> rc(ranges.size(), AURORA_OK);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < ranges.size(); k++) th.emplace_back([&, k] { rc[k] = f(ctx->devs[k], ranges[k]); });
+    for (auto& t : th) t.join();
+    for (int r : rc)
+        if (r != AURORA_OK) return r;
+    return AURORA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aurora_abi_version(void) { return AURORA_ABI_VERSION; }
+
+int aurora_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+aurora_ctx* aurora_init(uint32_t device_mask) {
+    int n = aurora_device_count();
+    if (n <= 0) {
+        g_init_error = "no CUDA device visible";
+        return nullptr;
+    }
+    aurora_ctx* ctx = new aurora_ctx();
+    for (int i = 0; i < n && i < 32; i++) {
+        if (device_mask != 0 && !(device_mask & (1u << i))) continue;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) != cudaSuccess) continue;
+        if (prop.major < 10) continue;   // sm_100a code only
+        DeviceCtx* d = new DeviceCtx();
+        d->dev = i;
+        d->sm_count = prop.multiProcessorCount;
+        if (cudaSetDevice(i) != cudaSuccess || cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete d;
+            continue;
+        }
+        ctx->devs.push_back(d);
+    }
+    if (ctx->devs.empty()) {
+        g_init_error = "no sm_100 device among the visible CUDA devices";
+        delete ctx;
+        return nullptr;
+    }
+    return ctx;
+}
+
+void aurora_shutdown(aurora_ctx* ctx) {
+    if (!ctx) return;
+    for (DeviceCtx* d : ctx->devs) {
+        cudaSetDevice(d->dev);
+        cudaStreamSynchronize(d->stream);
+        d->src.release();
+        d->dst.release();
+        d->desc.release();
+        d->ticket.release();
+        d->scratch.release();
+        d->hdesc.release();
+        cudaStreamDestroy(d->stream);
+        delete d;
+    }
+    delete ctx;
+}
+
+int aurora_ctx_device_count(const aurora_ctx* ctx) { return ctx ? int(ctx->devs.size()) : 0; }
+
+const char* aurora_last_error_string(const aurora_ctx* ctx) {
+    if (!ctx) return g_init_error.c_str();
+    return ctx->last_error.c_str();
+}
+
+const char* aurora_status_string(int s) {
+    static const char* names[] = {"OK", "END_OF_STREAM", "INVALID_IDENTIFIER", "SIZE_MISMATCH", "DST_TOO_SMALL",
+                                  "INVALID_DATA", "NOT_SUPPORTED", "INVALID_ARGUMENT", "CUDA_ERROR"};
+    return (s >= 0 && s <= 8) ? names[s] : "UNKNOWN";
+}
+
+void* aurora_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+void aurora_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+void aurora_lz_props_window(aurora_lz_props* out, int32_t windows_size, int32_t max_length, int32_t min_length,
+                            int32_t windows_start, int32_t min_distance) {
+    out->windows_bits = ceil_log2(windows_size);
+    out->length_bits = ceil_log2((long long)max_length - min_length) & 0xFF;
+    out->min_length = min_length;
+    out->max_length = max_length;
+    out->max_distance = windows_size;
+    out->min_distance = min_distance;
+    out->windows_start = windows_start;
+    out->reserved = 0;
+}
+
+void aurora_lz_props_bits(aurora_lz_props* out, int32_t distance_bits, int32_t length_bits, int32_t threshold) {
+    out->windows_bits = distance_bits;
+    out->length_bits = length_bits;
+    out->min_length = threshold + 1;
+    out->max_distance = 1 << distance_bits;
+    out->max_length = (1 << length_bits) + threshold;
+    out->windows_start = out->max_distance - (1 << length_bits) - threshold;
+    out->min_distance = 1;
+    out->reserved = 0;
+}
+
+void aurora_codec_opts_init(aurora_codec_opts* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->struct_size = sizeof(*o);
+    o->byte_order = AURORA_ENDIAN_DEFAULT;
+    o->quality = -1;
+    o->vram_mode = -1;
+}
+
+uint64_t aurora_kernel_launch_count(const aurora_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int aurora_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
+                        const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
+                        const uint64_t* dst_cap, uint64_t* out_len, uint64_t* consumed, int32_t* status) {
+    if (!ctx) return AURORA_INVALID_ARGUMENT;
+    if (n == 0) return AURORA_OK;
+    if (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_cap || !status || !(is_flaglz(format) || is_bytelz(format))) {
+        ctx->set_error("aurora_decode_batch: null argument or unknown format");
+        return AURORA_INVALID_ARGUMENT;
+    }
+    if (n > 0xFFFFFFF0ull) return AURORA_INVALID_ARGUMENT;
+    const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, dst_cap);
+    return for_each_shard(ctx, ranges, [&](DeviceCtx* d, Range r) {
+        return decode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
+                            out_len, consumed, status, 0);
+    });
+}
+
+int aurora_decoded_size_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
+                              const uint64_t* src_off, const uint64_t* src_len, int size_scan, uint64_t* out_size,
+                              int32_t* status) {
+    if (!ctx) return AURORA_INVALID_ARGUMENT;
+    if (n == 0) return AURORA_OK;
+    if (!src_base || !src_off || !src_len || !out_size || !status) return AURORA_INVALID_ARGUMENT;
+    const int bo = opts ? opts->byte_order : AURORA_ENDIAN_DEFAULT;
+    auto be32 = [](const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; };
+    auto le32 = [](const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); };
+    if (is_flaglz(format)) {
+        // GetDecompressedSize is a header peek (e.g. Yaz0.cs:50-55, LZ10.cs:47-57): a few bytes of host memory
+        for (size_t i = 0; i < n; i++) {
+            const uint8_t* p = src_base + src_off[i];
+            const uint64_t len = src_len[i];
+            int st = AURORA_OK;
+            uint64_t sz = 0;
+            if (format == AURORA_FMT_LZ10 || format == AURORA_FMT_LZ11) {
+                const uint8_t id = format == AURORA_FMT_LZ10 ? 0x10 : 0x11;
+                if (len < 1) st = AURORA_END_OF_STREAM;
+                else if (p[0] != id) st = AURORA_INVALID_IDENTIFIER;
+                else if (len < 4) st = AURORA_END_OF_STREAM;
+                else {
+                    sz = uint32_t(p[1]) | (uint32_t(p[2]) << 8) | (uint32_t(p[3]) << 16);
+                    if (sz == 0) {
+                        if (len < 8) st = AURORA_END_OF_STREAM;
+                        else sz = le32(p + 4);
+                    }
+                }
+            } else {
+                const char* magic = format == AURORA_FMT_YAZ0 ? "Yaz0" : format == AURORA_FMT_YAZ1 ? "Yaz1" : format == AURORA_FMT_YAY0 ? "Yay0"
+                                    : format == AURORA_FMT_MIO0 ? "MIO0" : "LZSS";
+                if (len < 4) st = AURORA_END_OF_STREAM;
+                else if (std::memcmp(p, magic, 4) != 0) st = AURORA_INVALID_IDENTIFIER;
+                else if (len < 8) st = AURORA_END_OF_STREAM;
+                else if (format == AURORA_FMT_LZSS || format == AURORA_FMT_YAY0) sz = be32(p + 4);   // Yay0.cs:45-46 reads BE regardless
+                else if (format == AURORA_FMT_YAZ0 || format == AURORA_FMT_YAZ1) sz = bo == AURORA_ENDIAN_LITTLE ? le32(p + 4) : be32(p + 4);
+                else {   // MIO0.cs:42-48: detected order
+                    bool big = true;
+                    if (bo == AURORA_ENDIAN_LITTLE) big = false;
+                    else if (bo != AURORA_ENDIAN_BIG && len >= 16) {
+                        const uint32_t cb = be32(p + 8), lb = be32(p + 12), cl = le32(p + 8), ll = le32(p + 12);
+                        const bool pb = cb >= 0x10 && cb <= lb && lb <= len, pl = cl >= 0x10 && cl <= ll && ll <= len;
+                        big = pb || !pl;
+                    }
+                    sz = big ? be32(p + 4) : le32(p + 4);
+                }
+            }
+            out_size[i] = sz;
+            status[i] = st;
+        }
+        return AURORA_OK;
+    }
+    if (!is_bytelz(format)) return AURORA_INVALID_ARGUMENT;
+    if (!size_scan) {
+        for (size_t i = 0; i < n; i++) {
+            out_size[i] = 0;
+            status[i] = AURORA_NOT_SUPPORTED;   // LZ4/LZO/Snappy/PRS do not implement IProvidesDecompressedSize
+        }
+        return AURORA_OK;
+    }
+    // size-only pre-pass on the device: same parser, all stores dropped
+    std::vector<uint64_t> zero(n, 0), cons(n);
+    uint8_t dummy[16];
+    const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, nullptr);
+    int rc = for_each_shard(ctx, ranges, [&](DeviceCtx* d, Range r) {
+        return decode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dummy, zero.data(), zero.data(),
+                            out_size, cons.data(), status, 1);
+    });
+    if (rc != AURORA_OK) return rc;
+    for (size_t i = 0; i < n; i++)
+        if (status[i] == AURORA_DST_TOO_SMALL) status[i] = AURORA_OK;
+    return AURORA_OK;
+}
+
+int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
+                          const uint64_t* src_off, const uint64_t* src_len, uint8_t* match) {
+    (void)opts;
+    if (!ctx) return AURORA_INVALID_ARGUMENT;
+    if (n == 0) return AURORA_OK;
+    if (!src_base || !src_off || !src_len || !match) return AURORA_INVALID_ARGUMENT;
+    auto magic16 = [&](size_t i, const void* m, size_t k) {
+        return 0x10 < src_len[i] && src_len[i] >= k && std::memcmp(src_base + src_off[i], m, k) == 0;
+    };
+    static const uint8_t snappy_id[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t* p = src_base + src_off[i];
+        bool m = false;
+        switch (format) {
+            case AURORA_FMT_YAZ0: m = magic16(i, "Yaz0", 4); break;
+            case AURORA_FMT_YAZ1: m = magic16(i, "Yaz1", 4); break;
+            case AURORA_FMT_YAY0: m = magic16(i, "Yay0", 4); break;
+            case AURORA_FMT_MIO0: m = magic16(i, "MIO0", 4); break;
+            case AURORA_FMT_LZSS: m = magic16(i, "LZSS", 4); break;
+            case AURORA_FMT_LZ4_LEGACY: m = magic16(i, "\x02\x21\x4C\x18", 4); break;
+            case AURORA_FMT_SNAPPY: m = magic16(i, snappy_id, 10); break;
+            case AURORA_FMT_LZ4:
+                if (0x10 < src_len[i]) {
+                    const uint32_t v = uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
+                    m = v == 0x184C2102u || v == 0x184D2204u || (v >= 0x184D2A50u && v <= 0x184D2A5Fu);
+                }
+                break;
+            case AURORA_FMT_LZO:   // LZO.cs:31-39 without a file name
+                m = src_len[i] > 0 && (p[0] < 0x20);
+                break;
+            default:
+                ctx->set_error("aurora_is_match_batch: the token-walk heuristics (LZ10/LZ11/PRS) are not built yet");
+                return AURORA_NOT_SUPPORTED;
+        }
+        match[i] = m ? 1 : 0;
+    }
+    return AURORA_OK;
+}
+
+int aurora_decode_batch_device(aurora_ctx* ctx, int device, int format, const aurora_codec_opts* opts, size_t n,
+                               const uint8_t* d_src_base, uint64_t src_total, const uint64_t* d_src_off,
+                               const uint64_t* d_src_len, uint8_t* d_dst_base, const uint64_t* d_dst_off,
+                               const uint64_t* d_dst_cap, uint64_t* d_out_len, uint64_t* d_consumed, int32_t* d_status,
+                               void* stream) {
+    if (!ctx || device < 0 || device >= int(ctx->devs.size())) return AURORA_INVALID_ARGUMENT;
+    if (n == 0) return AURORA_OK;
+    if (!(is_flaglz(format) || is_bytelz(format)) || n > 0xFFFFFFF0ull) return AURORA_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(d_src_base) & 15) != 0) {
+        ctx->set_error("aurora_decode_batch_device: d_src_base must be 16-byte aligned");
+        return AURORA_INVALID_ARGUMENT;
+    }
+    DeviceCtx* d = ctx->devs[device];
+    std::lock_guard<std::mutex> guard(d->mu);
+    CU_TRY(ctx, cudaSetDevice(d->dev));
+    DecodeParams P{};
+    if (fill_decode_params(P, format, opts) != AURORA_OK) {
+        ctx->set_error("aurora_decode_batch_device: unsupported LZSS properties");
+        return AURORA_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
+    CU_TRY(ctx, d->ticket.reserve(256));
+    CU_TRY(ctx, cudaMemsetAsync(d->ticket.p, 0, 64, st));
+    P.src_base = d_src_base;
+    P.src_limit = align_up(src_total, 16);   // the allocation must be readable up to the next multiple of 16
+    P.src_off = d_src_off;
+    P.src_len = d_src_len;
+    P.dst_base = d_dst_base;
+    P.dst_off = d_dst_off;
+    P.dst_cap = d_dst_cap;
+    P.out_len = d_out_len;
+    P.consumed = d_consumed;
+    P.status = d_status;
+    P.order = nullptr;
+    P.ticket = static_cast<unsigned int*>(d->ticket.p);
+    P.n = uint32_t(n);
+    CU_TRY(ctx, launch_decode(P, d->sm_count, st));
+    ctx->launches++;
+    return AURORA_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+uint64_t aurora_encode_bound(int format, uint64_t raw_len) {
+    // worst case of every token writer on the hot path: all literals + flag bits + headers / chunk framing
+    switch (format) {
+        case AURORA_FMT_LZ4:
+        case AURORA_FMT_LZ4_LEGACY:
+        case AURORA_FMT_LZ4_BLOCK: return raw_len + raw_len / 255 + 64 + 8 * (raw_len / 0x400000 + 1);
+        case AURORA_FMT_SNAPPY:
+        case AURORA_FMT_SNAPPY_BLOCK: return raw_len + raw_len / 60 + 32 + 16 * (raw_len / 0x10000 + 1);
+        case AURORA_FMT_LZO: return raw_len + raw_len / 255 + 32;
+        default: return raw_len + raw_len / 8 + 64;
+    }
+}
+
+int aurora_encode_batch(aurora_ctx* ctx, int, const aurora_codec_opts*, size_t, const uint8_t*, const uint64_t*,
+                        const uint64_t*, uint8_t*, const uint64_t*, const uint64_t*, uint64_t*, int32_t*) {
+    if (ctx) ctx->set_error("aurora_encode_batch: encoder kernels not built yet");
+    return AURORA_NOT_SUPPORTED;
+}
+
+int aurora_encode_batch_device(aurora_ctx* ctx, int, int, const aurora_codec_opts*, size_t, const uint8_t*, uint64_t,
+                               const uint64_t*, const uint64_t*, uint8_t*, const uint64_t*, const uint64_t*, uint64_t*,
+                               int32_t*, void*) {
+    if (ctx) ctx->set_error("aurora_encode_batch_device: encoder kernels not built yet");
+    return AURORA_NOT_SUPPORTED;
+}
+
+}  // extern "C"

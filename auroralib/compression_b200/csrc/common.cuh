@@ -1,0 +1,110 @@
+// common.cuh — shared device/host definitions for libaurora_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../../include/aurora_cuda.h"
+
+namespace aurora {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// LZSS parameters resolved on the host from aurora_lz_props (LzProperties.cs)
+struct LzssParams {
+    int windows_bits, length_bits, min_length, max_distance, windows_start, initial_fill;
+};
+
+// One batch on one device.  All pointers are device pointers.
+struct DecodeParams {
+    const uint8_t* src_base;
+    uint64_t src_limit;          // readable bytes from src_base, a multiple of 16 (TMA bulk granularity)
+    const uint64_t* src_off;
+    const uint64_t* src_len;
+    uint8_t* dst_base;
+    const uint64_t* dst_off;
+    const uint64_t* dst_cap;
+    uint64_t* out_len;
+    uint64_t* consumed;
+    int32_t* status;
+    const uint32_t* order;       // optional: stream indices, largest first (nullptr = identity)
+    unsigned int* ticket;        // global work counter (zeroed by the launcher)
+    uint32_t n;
+    int format;
+    int byte_order;              // aurora_endian
+    int size_only;               // parse without copying (decoded_size_batch size_scan)
+    int lz4_verify;              // LZ4.HashAlgorithm set: verify XXH32 checksums
+    LzssParams lzss;
+};
+
+struct EncodeParams {
+    const uint8_t* src_base;
+    uint64_t src_limit;
+    const uint64_t* src_off;
+    const uint64_t* src_len;
+    uint8_t* dst_base;
+    const uint64_t* dst_off;
+    const uint64_t* dst_cap;
+    uint64_t* out_len;
+    int32_t* status;
+    unsigned int* ticket;
+    uint32_t n;
+    int format;
+    int byte_order;
+    // CompressionSettings -> LzChainMatchFinder parameters (LzChainMatchFinder.cs:108-119)
+    int max_chain, lazy_threshold, min_length, max_length, min_distance, max_distance, no_self_overlap, use_min_table;
+    uint32_t yaz0_alignment;
+    LzssParams lzss;
+    uint8_t* scratch;            // per-resident-warp match-finder tables
+    uint64_t scratch_per_warp;
+};
+
+// kernel launchers (one translation unit per kernel family); all return cudaGetLastError()
+cudaError_t launch_decode_flaglz(const DecodeParams& p, int sm_count, cudaStream_t st);
+cudaError_t launch_decode_bytelz(const DecodeParams& p, int sm_count, cudaStream_t st);
+cudaError_t launch_encode_lz(const EncodeParams& p, int sm_count, cudaStream_t st);
+size_t encode_scratch_per_warp(int format);
+int encode_resident_warps(int sm_count);
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// mbarrier + 1-D TMA bulk copy (global -> shared), the sm_90+/sm_100a async staging path.
+// SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK (see /opt/skills/guides/B200_PROFILING.md).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// bytes and both addresses must be multiples of 16
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#endif
+
+}  // namespace aurora

@@ -1,0 +1,618 @@
+// decode_bytelz.cu — batched decoder for the byte-tagged LZ family with 64 KiB (8 KiB for PRS) windows:
+// LZ4 (raw block, legacy frame, v1 frame, skippable frames), Snappy (raw block and framing format), LZO1X
+// and SEGA PRS.  One compressed stream per warp.
+//
+// Reference semantics restated on the device (paths under /root/reference/src):
+//   LZ4 block      AuroraLib.Compression/Formats/Common/LZ4.cs:176-200, ReadExtension :241-252
+//   LZ4 containers LZ4.cs:50-111, LZ4.Frame.cs:107-174, LZ4.FrameDescriptor.cs:18-26
+//   Snappy         Formats/Common/Snappy.cs:39-68 (framing), :109-122 (varint), :205-250 (block)
+//   LZO            Formats/Common/LZO.cs:49-139, ReadExtendedInt :252-262
+//   PRS            AuroraLib.Compression.Sega/Sega/PRS.cs:42-102, :161-218
+//   window         AuroraLib.Compression/IO/LzWindows.cs:72-100 (BackCopy), :124-135 (CopyFrom)
+//
+// Design: the token walk of these formats is inherently sequential (every token's position depends on
+// the previous token's extension bytes), so the warp walks tokens uniformly — every lane evaluates the
+// same tag from the TMA-staged shared-memory copy of the input — and spends its 32 lanes on the two
+// things that are parallel: literal runs (input ring -> HBM) and match copies (HBM -> HBM through L1/L2,
+// out[dst+i] = out[dst-d + (i mod d)]).  The window is up to 64 KiB, so unlike the flag-LZ family the
+// output is written straight to global memory and back-references are served by L1/L2.
+#include "common.cuh"
+#include "stage.cuh"
+
+namespace aurora {
+
+namespace {
+
+enum Kind { B_LZ4 = 0, B_LZ4_BLOCK = 1, B_SNAPPY = 2, B_SNAPPY_BLOCK = 3, B_LZO = 4, B_PRS = 5 };
+
+constexpr int kWarpsPerBlock = 16;
+constexpr int kSmemPerWarp = kInRing + 64;
+
+// Output cursor on global memory.  `win_base` is the output position where the current LzWindows
+// instance was created: references before it read the (zero) pre-history of a fresh ring.
+struct GOut {
+    uint8_t* dst;
+    uint64_t cap;
+    uint32_t written;
+    uint32_t win_base;
+    uint32_t ring_len;
+    bool size_only;
+
+    // LzWindows.Write / CopyFrom: `len` bytes from the staged input at relative position ipos
+    __device__ __forceinline__ void lit_copy(InStream& in, uint32_t ipos, uint32_t len) {
+        const uint32_t lane = lane_id();
+        uint32_t done = 0;
+        while (done < len) {
+            const uint32_t piece = min(len - done, 512u);
+            in.ensure(ipos + done, piece);
+            for (uint32_t i = lane; i < piece; i += 32) {
+                const uint64_t o = uint64_t(written) + done + i;
+                const uint32_t v = in.at(ipos + done + i);
+                if (o < cap) dst[o] = uint8_t(v);
+            }
+            done += piece;
+        }
+        written += len;
+        __syncwarp();
+    }
+    // LzWindows.BackCopy(distance, length) on the flat output
+    __device__ __forceinline__ void match_copy(uint32_t d, uint32_t len) {
+        const uint32_t lane = lane_id();
+        if (d == 0) d = ring_len;   // BackCopy(0, n) re-reads the ring slot it writes: one window back
+        const int64_t srcp = int64_t(written) - int64_t(d);
+        const bool wrap = d < len;
+        for (uint32_t i = lane; i < len; i += 32) {
+            const int64_t s = srcp + (wrap ? i % d : i);
+            uint8_t v = 0;
+            if (s >= int64_t(win_base) && uint64_t(s) < cap) v = dst[s];
+            const uint64_t o = uint64_t(written) + i;
+            if (o < cap) dst[o] = v;
+        }
+        written += len;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void new_window() { win_base = written; }
+    // LzWindows.CopyFrom (IO/LzWindows.cs:124-135) reads ring-sized pieces with ReadExactly: on a truncated
+    // input only the pieces that could be read completely are committed.  Returns false on truncation.
+    __device__ __forceinline__ bool copy_from(InStream& in, uint32_t ipos, uint32_t len, uint32_t avail) {
+        if (len <= avail) {
+            lit_copy(in, ipos, len);
+            return true;
+        }
+        uint32_t done = 0;
+        for (;;) {
+            const uint32_t rp = (written - win_base) & (ring_len - 1);
+            const uint32_t piece = min(len - done, ring_len - rp);
+            if (piece > avail - done) break;
+            lit_copy(in, ipos + done, piece);
+            done += piece;
+        }
+        return false;
+    }
+};
+
+struct Res {
+    int status;
+    uint32_t consumed;
+};
+
+// ------------------------------------------------------------------------------------------------ LZ4
+// LZ4.cs:241-252 on the staged input; returns false when the block is exhausted (IndexOutOfRange)
+__device__ __forceinline__ bool lz4_ext(InStream& in, uint32_t& sp, uint32_t end, uint32_t& length) {
+    if (length == 15) {
+        uint32_t b;
+        do {
+            if (sp >= end) return false;
+            in.ensure(sp, 8);
+            b = in.at(sp++);
+            length += b;
+        } while (b == 255);
+    }
+    return true;
+}
+
+// LZ4.cs:176-200.  The block occupies relative input bytes [sp, end).
+__device__ int lz4_block(InStream& in, GOut& out, uint32_t sp, uint32_t end) {
+    while (sp < end) {
+        in.ensure(sp, 16);
+        const uint32_t token = in.at(sp++);
+        uint32_t plain = token >> 4;
+        if (!lz4_ext(in, sp, end, plain)) return AURORA_END_OF_STREAM;
+        if (uint64_t(sp) + plain > end) return AURORA_END_OF_STREAM;
+        out.lit_copy(in, sp, plain);
+        sp += plain;
+        if (sp >= end) break;
+        if (sp + 2 > end) return AURORA_END_OF_STREAM;
+        in.ensure(sp, 16);
+        const uint32_t d = in.at(sp) | (in.at(sp + 1) << 8);
+        sp += 2;
+        uint32_t ml = token & 15;
+        if (!lz4_ext(in, sp, end, ml)) return AURORA_END_OF_STREAM;
+        out.match_copy(d, ml + 4);
+    }
+    return AURORA_OK;
+}
+
+__device__ __forceinline__ uint32_t rd32(InStream& in, uint32_t p) {
+    in.ensure(p, 8);
+    return in.at(p) | (in.at(p + 1) << 8) | (in.at(p + 2) << 16) | (in.at(p + 3) << 24);
+}
+__device__ __forceinline__ bool lz4_magic(uint32_t v) {
+    return v == 0x184C2102u || v == 0x184D2204u || (v >= 0x184D2A50u && v <= 0x184D2A5Fu);
+}
+
+// LZ4.cs:50-111 + LZ4.Frame.cs:107-174
+__device__ Res lz4_container(InStream& in, GOut& out, uint32_t slen, int verify) {
+    uint32_t sp = 0;
+    while (sp < slen) {
+        if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+        uint32_t magic = rd32(in, sp);
+        sp += 4;
+        for (;;) {   // SwitchStart
+            if (magic == 0x184C2102u) {   // legacy: ReadLZ4L
+                if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                uint32_t bs = rd32(in, sp);
+                sp += 4;
+                uint32_t next_magic = 0;
+                for (;;) {
+                    if (uint64_t(sp) + bs > slen) return Res{AURORA_END_OF_STREAM, slen};
+                    out.new_window();   // a fresh LzWindows per legacy block (LZ4.cs:164)
+                    const int st = lz4_block(in, out, sp, sp + bs);
+                    if (st != AURORA_OK) return Res{st, sp + bs};
+                    sp += bs;
+                    if (sp >= slen) return Res{AURORA_OK, sp};               // ReadByte() == -1
+                    in.ensure(sp, 8);
+                    if (in.at(sp) == 0xFF) return Res{AURORA_OK, sp + 1};   // (sbyte)0xFF == -1: the encoder's end flag
+                    if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                    bs = rd32(in, sp);
+                    sp += 4;
+                    if (lz4_magic(bs)) { next_magic = bs; break; }
+                }
+                magic = next_magic;
+                continue;
+            } else if (magic == 0x184D2204u) {   // v1 frame
+                const uint32_t dest_start = out.written;
+                if (sp + 2 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                in.ensure(sp, 32);
+                const uint32_t FLG = in.at(sp), BD = in.at(sp + 1);
+                sp += 2;
+                uint32_t bmax;
+                switch ((BD & 0x70) >> 4) {
+                    case 4: bmax = 0x10000; break;
+                    case 5: bmax = 0x40000; break;
+                    case 6: bmax = 0x100000; break;
+                    case 7: bmax = 0x400000; break;
+                    default: return Res{AURORA_INVALID_DATA, sp};
+                }
+                uint64_t content = 0;
+                if (FLG & 8) {
+                    if (sp + 8 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                    content = uint64_t(rd32(in, sp)) | (uint64_t(rd32(in, sp + 4)) << 32);
+                    sp += 8;
+                }
+                if (FLG & 1) {
+                    if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                    sp += 4;
+                }
+                if (sp + 1 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                sp += 1;   // header checksum byte: read, never verified (LZ4.FrameDescriptor.cs:25)
+                if (FLG & 1) return Res{AURORA_NOT_SUPPORTED, sp};
+                out.new_window();   // one window for all blocks of the frame (linked blocks)
+                for (;;) {
+                    if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                    const uint32_t bsz = rd32(in, sp);
+                    sp += 4;
+                    if (bsz == 0) break;
+                    const bool stored = (bsz & 0x80000000u) != 0;
+                    const uint32_t sz = bsz & 0x7FFFFFFFu;
+                    if (sz > bmax) return Res{AURORA_INVALID_DATA, sp};
+                    if (uint64_t(sp) + sz > slen) return Res{AURORA_END_OF_STREAM, slen};
+                    const uint32_t blk = sp;
+                    sp += sz;
+                    if (FLG & 16) {
+                        if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                        sp += 4;
+                        if (verify) return Res{AURORA_NOT_SUPPORTED, sp};
+                    }
+                    if (stored) {
+                        out.lit_copy(in, blk, sz);
+                    } else {
+                        const int st = lz4_block(in, out, blk, blk + sz);
+                        if (st != AURORA_OK) return Res{st, sp};
+                    }
+                }
+                if ((FLG & 8) && uint64_t(out.written) != uint64_t(dest_start) + content) return Res{AURORA_SIZE_MISMATCH, sp};
+                if (FLG & 4) {
+                    if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                    sp += 4;
+                    if (verify) return Res{AURORA_NOT_SUPPORTED, sp};
+                }
+                break;
+            } else if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) {   // skippable
+                if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                const uint32_t bs = rd32(in, sp);
+                sp += 4;
+                const uint64_t np = uint64_t(sp) + bs;
+                sp = np > slen ? slen : uint32_t(np);   // Position may run past the end; the loop then stops
+                break;
+            } else {
+                return Res{AURORA_OK, sp - 4};
+            }
+        }
+    }
+    return Res{AURORA_OK, sp};
+}
+
+// ------------------------------------------------------------------------------------------------ Snappy
+// Snappy.cs:205-250 on relative input starting at sp; returns the position after the block's last token
+__device__ Res snappy_block(InStream& in, GOut& out, uint32_t sp, uint32_t slen) {
+    // ReadDecompressedSize (:109-122)
+    uint32_t size = 0, shift = 0, b;
+    do {
+        if (sp >= slen) return Res{AURORA_END_OF_STREAM, slen};
+        in.ensure(sp, 8);
+        b = in.at(sp++);
+        if (shift < 32) size |= (b & 0x7F) << shift;
+        shift += 7;
+    } while (b & 0x80);
+    const uint64_t end_position = uint64_t(out.written) + size;
+    if (!out.size_only && end_position > out.cap) return Res{AURORA_DST_TOO_SMALL, sp};   // SetLength on a fixed destination
+    out.new_window();
+    while (out.written < end_position) {
+        if (sp >= slen) return Res{AURORA_END_OF_STREAM, slen};
+        in.ensure(sp, 16);
+        const uint32_t tag = in.at(sp++);
+        const uint32_t type = tag & 3;
+        uint32_t length = tag >> 2;
+        uint32_t distance;
+        if (type == 0) {
+            if (length >= 60) {
+                const uint32_t nb = length - 59;
+                if (sp + nb > slen) return Res{AURORA_END_OF_STREAM, slen};
+                length = 0;
+                for (uint32_t i = 0; i < nb; i++) length |= in.at(sp + i) << (8 * i);
+                sp += nb;
+            }
+            const int32_t l1 = int32_t(length) + 1;
+            if (l1 < 0) return Res{AURORA_INVALID_DATA, sp};
+            if (!out.copy_from(in, sp, uint32_t(l1), slen - sp)) return Res{AURORA_END_OF_STREAM, slen};
+            sp += uint32_t(l1);
+            continue;
+        } else if (type == 1) {
+            if (sp + 1 > slen) return Res{AURORA_END_OF_STREAM, slen};
+            length = (length & 7) + 3;
+            distance = ((tag >> 5) << 8) | in.at(sp);
+            sp += 1;
+        } else if (type == 2) {
+            if (sp + 2 > slen) return Res{AURORA_END_OF_STREAM, slen};
+            distance = in.at(sp) | (in.at(sp + 1) << 8);
+            sp += 2;
+        } else {
+            if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+            distance = in.at(sp) | (in.at(sp + 1) << 8) | (in.at(sp + 2) << 16) | (in.at(sp + 3) << 24);
+            sp += 4;
+            if (distance > 0x10000u) return Res{AURORA_INVALID_DATA, sp};   // aliases in the reference's 64 KiB ring
+        }
+        out.match_copy(distance, length + 1);
+    }
+    return Res{AURORA_OK, sp};
+}
+
+// Snappy.cs:39-68
+__device__ Res snappy_framed(InStream& in, GOut& out, uint32_t slen) {
+    if (slen < 10) return Res{AURORA_END_OF_STREAM, slen};
+    in.ensure(0, 16);
+    const uint32_t id[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 10; i++) ok = ok && in.at(i) == id[i];
+    if (!ok) return Res{AURORA_INVALID_IDENTIFIER, 10};
+    uint32_t sp = 10;
+    while (sp < slen) {
+        in.ensure(sp, 16);
+        const uint32_t type = in.at(sp);
+        if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+        const uint32_t clen = in.at(sp + 1) | (in.at(sp + 2) << 8) | (in.at(sp + 3) << 16);
+        sp += 4;
+        if (type == 0) {
+            if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+            sp += 4;   // CRC skipped (:50)
+            const Res r = snappy_block(in, out, sp, slen);
+            if (r.status != AURORA_OK) return r;
+            sp = r.consumed;
+        } else if (type == 1) {
+            if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+            sp += 4;
+            if (clen < 4) return Res{AURORA_INVALID_DATA, sp};
+            const uint32_t n = min(clen - 4, slen - sp);   // SubStream.CopyTo copies what is there
+            out.lit_copy(in, sp, n);
+            sp += n;
+        } else {
+            if (type >= 0x02 && type <= 0x7F) return Res{AURORA_INVALID_DATA, sp};
+            const uint64_t np = uint64_t(sp) + clen;
+            sp = np > slen ? slen : uint32_t(np);
+        }
+    }
+    return Res{AURORA_OK, sp};
+}
+
+// ------------------------------------------------------------------------------------------------ LZO
+// LZO.cs:252-262
+__device__ __forceinline__ bool lzo_ext(InStream& in, uint32_t& sp, uint32_t slen, uint32_t& length) {
+    uint32_t b;
+    for (;;) {
+        if (sp >= slen) return false;
+        in.ensure(sp, 8);
+        b = in.at(sp++);
+        if (b != 0) break;
+        length += 255;
+    }
+    length += b;
+    return true;
+}
+
+// LZO.cs:49-139
+__device__ Res lzo_decode(InStream& in, GOut& out, uint32_t slen) {
+    uint32_t sp = 0, plain = 0, length, distance;
+    const Res eos{AURORA_END_OF_STREAM, slen};
+    if (sp >= slen) return eos;
+    in.ensure(sp, 16);
+    uint32_t flag = in.at(sp++);
+    if (flag > 17) {
+        length = flag - 17;
+        if (!out.copy_from(in, sp, length, slen - sp)) return eos;
+        sp += length;
+        if (sp >= slen) return eos;
+        in.ensure(sp, 16);
+        flag = in.at(sp++);
+    }
+    for (;;) {
+        in.ensure(sp, 16);
+        const uint32_t code = flag >> 4;
+        bool literal_run = false;
+        if (code == 0) {
+            if (plain == 0) {
+                length = 3 + flag;
+                if (length == 3) {
+                    length = 18;
+                    if (!lzo_ext(in, sp, slen, length)) return eos;
+                }
+                plain = 4;
+                if (!out.copy_from(in, sp, length, slen - sp)) return eos;
+                sp += length;
+                literal_run = true;
+            } else if (plain <= 3) {
+                if (sp >= slen) return eos;
+                distance = (in.at(sp++) << 2) + (flag >> 2) + 1;
+                length = 2;
+            } else {
+                if (sp >= slen) return eos;
+                distance = (in.at(sp++) << 2) + (flag >> 2) + (2048 + 1);
+                length = 3;
+            }
+        } else if (code == 1) {
+            length = 2 + (flag & 7);
+            if (length == 2) {
+                length = 9;
+                if (!lzo_ext(in, sp, slen, length)) return eos;
+            }
+            distance = 16384 + ((flag & 8) << 11);
+            if (sp + 2 > slen) return eos;
+            in.ensure(sp, 8);
+            flag = in.at(sp++);
+            distance |= (in.at(sp++) << 6) | (flag >> 2);
+            if (distance == 16384) return Res{AURORA_OK, sp};
+        } else if (code <= 3) {
+            length = 2 + (flag & 0x1f);
+            if (length == 2) {
+                length = 33;
+                if (!lzo_ext(in, sp, slen, length)) return eos;
+            }
+            if (sp + 2 > slen) return eos;
+            in.ensure(sp, 8);
+            flag = in.at(sp++);
+            distance = ((in.at(sp++) << 6) | (flag >> 2)) + 1;
+        } else if (code <= 7) {
+            length = 3 + ((flag >> 5) & 1);
+            if (sp >= slen) return eos;
+            distance = (in.at(sp++) << 3) + ((flag >> 2) & 7) + 1;
+        } else {
+            length = 5 + ((flag >> 5) & 3);
+            if (sp >= slen) return eos;
+            distance = (in.at(sp++) << 3) + ((flag & 0x1c) >> 2) + 1;
+        }
+        if (!literal_run) {
+            plain = flag & 3;
+            out.match_copy(distance, length);
+            if (!out.copy_from(in, sp, plain, slen - sp)) return eos;
+            sp += plain;
+        }
+        if (sp >= slen) return eos;   // while ((flag = ReadByte()) != -1) ... throw EndOfStream
+        in.ensure(sp, 16);
+        flag = in.at(sp++);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ PRS
+struct PrsBits {
+    uint32_t cur, left;
+    bool msb;
+    // FlagReader.Readbit (IO/FlagReader.cs:53-65): the flag byte is fetched lazily from the same stream
+    __device__ __forceinline__ int bit(InStream& in, uint32_t& sp, uint32_t slen) {
+        if (left == 0) {
+            if (sp >= slen) return -1;
+            in.ensure(sp, 8);
+            cur = in.at(sp++);
+            left = 8;
+        }
+        const uint32_t sh = msb ? left - 1 : 8 - left;
+        left--;
+        return (cur >> sh) & 1;
+    }
+};
+
+// PRS.cs:59-102 (copy == true) and ValidateByteOrder :172-218 (copy == false; status kPrsValid / kPrsInvalid)
+constexpr int kPrsValid = 100, kPrsInvalid = 101;
+template <bool kCopy>
+__device__ Res prs_walk(InStream& in, GOut& out, uint32_t slen, bool big) {
+    PrsBits fr{0, 0, big};
+    uint32_t sp = 0;
+    uint32_t produced = 0;
+    int budget = 3;
+    const Res eos{AURORA_END_OF_STREAM, slen};
+    while (sp < slen) {
+        int b = fr.bit(in, sp, slen);
+        if (b < 0) return eos;
+        if (b) {
+            if (sp >= slen) return kCopy ? eos : Res{kPrsInvalid, sp};   // validate: Position++ runs past the end, loop ends, false
+            if (kCopy) out.lit_copy(in, sp, 1);
+            sp++;
+            produced++;
+        } else {
+            uint32_t distance, length;
+            b = fr.bit(in, sp, slen);
+            if (b < 0) return eos;
+            if (b) {
+                if (sp + 2 > slen) return eos;
+                in.ensure(sp, 8);
+                const uint32_t v = big ? (in.at(sp) << 8) | in.at(sp + 1) : in.at(sp) | (in.at(sp + 1) << 8);
+                sp += 2;
+                if (v == 0) return kCopy ? Res{AURORA_OK, sp} : Res{kPrsValid, sp};
+                length = v & 7;
+                distance = 0x2000 - (v >> 3);
+                if (length == 0) {
+                    if (sp >= slen) return eos;
+                    length = in.at(sp++) + 1;
+                } else {
+                    length += 2;
+                }
+            } else {
+                const int b1 = fr.bit(in, sp, slen);
+                if (b1 < 0) return eos;
+                const int b0 = fr.bit(in, sp, slen);
+                if (b0 < 0) return eos;
+                length = uint32_t(b1 * 2 + b0) + 2;
+                if (sp >= slen) return eos;
+                in.ensure(sp, 8);
+                distance = 0x100 - in.at(sp++);
+            }
+            if (kCopy) {
+                out.match_copy(distance, length);
+            } else {
+                if (distance > produced) return Res{kPrsInvalid, sp};
+                if (budget == 0) return Res{kPrsValid, sp};
+                budget--;
+                produced += length;
+            }
+        }
+    }
+    return kCopy ? eos : Res{kPrsInvalid, sp};
+}
+
+// PRS.cs:42-57 + GetByteOrder :161-170
+__device__ Res prs_decode(InStream& in, GOut& out, uint32_t slen, const uint8_t* src, const DecodeParams& P) {
+    if (slen == 0) return Res{AURORA_END_OF_STREAM, 0};
+    in.ensure(0, 8);
+    const uint32_t flag = in.at(0);
+    int detected = -1;   // 0 little, 1 big
+    if (flag > 12 && (flag & 1)) {
+        const Res v = prs_walk<false>(in, out, slen, false);
+        if (v.status == AURORA_END_OF_STREAM) return Res{AURORA_END_OF_STREAM, 0};   // the exception leaves GetByteOrder; `finally` restored Position
+        if (v.status == kPrsValid) detected = 0;
+        in.begin(P.src_base, P.src_limit, src);
+    }
+    if (detected < 0 && (flag & 128)) {
+        const Res v = prs_walk<false>(in, out, slen, true);
+        if (v.status == AURORA_END_OF_STREAM) return Res{AURORA_END_OF_STREAM, 0};
+        if (v.status == kPrsValid) detected = 1;
+        in.begin(P.src_base, P.src_limit, src);
+    }
+    const bool first_big = detected == 1;
+    out.new_window();
+    Res r = prs_walk<true>(in, out, slen, first_big);
+    if (r.status != AURORA_OK) {
+        in.begin(P.src_base, P.src_limit, src);
+        out.written = 0;
+        out.new_window();
+        r = prs_walk<true>(in, out, slen, !first_big);
+    }
+    return r;
+}
+
+template <int K>
+__device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream& in) {
+    const uint8_t* src = P.src_base + P.src_off[idx];
+    const uint64_t slen64 = P.src_len[idx];
+    const uint32_t slen = slen64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : uint32_t(slen64);
+    GOut out;
+    out.dst = P.dst_base + P.dst_off[idx];
+    out.cap = P.size_only ? 0 : P.dst_cap[idx];
+    out.written = 0;
+    out.win_base = 0;
+    out.ring_len = (K == B_PRS) ? 0x2000u : 0x10000u;
+    out.size_only = P.size_only != 0;
+    in.begin(P.src_base, P.src_limit, src);
+    Res r;
+    if (K == B_LZ4) r = lz4_container(in, out, slen, P.lz4_verify);
+    else if (K == B_LZ4_BLOCK) {
+        const int st = lz4_block(in, out, 0, slen);
+        r = Res{st, slen};
+    } else if (K == B_SNAPPY) r = snappy_framed(in, out, slen);
+    else if (K == B_SNAPPY_BLOCK) r = snappy_block(in, out, 0, slen);
+    else if (K == B_LZO) r = lzo_decode(in, out, slen);
+    else r = prs_decode(in, out, slen, src, P);
+    if (r.status == AURORA_OK && uint64_t(out.written) > out.cap) r.status = AURORA_DST_TOO_SMALL;
+    if (lane_id() == 0) {
+        P.out_len[idx] = out.written;
+        P.consumed[idx] = r.consumed;
+        P.status[idx] = r.status;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) decode_bytelz_kernel(const DecodeParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    uint8_t* wbase = smem + size_t(warp) * kSmemPerWarp;
+    InStream in;
+    in.init(wbase, reinterpret_cast<uint64_t*>(wbase + kInRing));
+    __syncwarp();
+    fence_proxy_async();
+    for (;;) {
+        uint32_t t = 0;
+        if (lane_id() == 0) t = atomicAdd(P.ticket, 1u);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= P.n) break;
+        const uint32_t idx = P.order ? P.order[t] : t;
+        decode_stream<K>(P, idx, in);
+    }
+    in.drain_inflight();
+}
+
+template <int K>
+cudaError_t launch(const DecodeParams& p, int sm_count, cudaStream_t st) {
+    const int threads = kWarpsPerBlock * 32;
+    const size_t smem = size_t(kWarpsPerBlock) * kSmemPerWarp;
+    int blocks = sm_count * 2;
+    const int needed = int((p.n + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    if (needed < blocks) blocks = needed > 0 ? needed : 1;
+    decode_bytelz_kernel<K><<<blocks, threads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_decode_bytelz(const DecodeParams& p, int sm_count, cudaStream_t st) {
+    switch (p.format) {
+        case AURORA_FMT_LZ4:
+        case AURORA_FMT_LZ4_LEGACY: return launch<B_LZ4>(p, sm_count, st);
+        case AURORA_FMT_LZ4_BLOCK: return launch<B_LZ4_BLOCK>(p, sm_count, st);
+        case AURORA_FMT_SNAPPY: return launch<B_SNAPPY>(p, sm_count, st);
+        case AURORA_FMT_SNAPPY_BLOCK: return launch<B_SNAPPY_BLOCK>(p, sm_count, st);
+        case AURORA_FMT_LZO: return launch<B_LZO>(p, sm_count, st);
+        case AURORA_FMT_PRS: return launch<B_PRS>(p, sm_count, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace aurora

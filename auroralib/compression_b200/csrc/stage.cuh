@@ -1,0 +1,105 @@
+// stage.cuh — TMA-staged input sub-streams and small warp primitives shared by the decode kernels.
+#pragma once
+#include "common.cuh"
+
+namespace aurora {
+
+constexpr int kInChunk = 1024;       // TMA bulk chunk
+constexpr int kInRing = 2 * kInChunk;
+constexpr int kInMask = kInRing - 1;
+constexpr int kLookahead = 192;      // input bytes one parse step may touch past its cursor
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged input sub-stream: a 2 x 1 KiB shared-memory ring filled by cp.async.bulk (1-D TMA) with one
+// mbarrier per slot.  All members are warp-uniform registers.  Loads are numbered by a counter that runs
+// over the lifetime of the warp (slot = k & 1, mbarrier parity = (k >> 1) & 1), so phases stay
+// consistent across streams; stream chunk c maps to load kbase + (c - cbase).  Access is sequential
+// with occasional forward jumps (skipped frames), which re-base the mapping.
+// Positions passed to ensure()/at() are relative to the pointer given to begin().
+// ---------------------------------------------------------------------------------------------
+struct InStream {
+    uint8_t* ring;
+    uint64_t* bar;
+    const uint8_t* gbase;   // 16-byte aligned global address of stream chunk 0
+    uint32_t glimit;        // loadable bytes from gbase (multiple of 16)
+    uint32_t nchunks;       // ceil(glimit / kInChunk)
+    uint32_t skew;          // relative byte 0 sits at gbase + skew
+    uint32_t kbase, cbase;  // load number / stream chunk of the current mapping
+    uint32_t issued, ready; // running load counters
+    uint32_t rbias;         // ring index of relative byte 0 under the current mapping
+
+    __device__ __forceinline__ void init(uint8_t* r, uint64_t* b) {
+        ring = r;
+        bar = b;
+        issued = ready = 0;
+        if (lane_id() == 0) {
+            mbar_init(&bar[0], 1);
+            mbar_init(&bar[1], 1);
+        }
+    }
+    __device__ __forceinline__ void drain_inflight() {
+        while (ready < issued) {
+            mbar_wait(&bar[ready & 1], (ready >> 1) & 1);
+            ready++;
+        }
+    }
+    __device__ __forceinline__ void rebase(uint32_t chunk) {
+        drain_inflight();
+        kbase = issued;
+        cbase = chunk;
+        rbias = skew + ((kbase - cbase) & 1u) * kInChunk;
+    }
+    __device__ __forceinline__ void begin(const uint8_t* src_base, uint64_t src_limit, const uint8_t* p) {
+        skew = uint32_t(reinterpret_cast<uintptr_t>(p) & 15);
+        gbase = p - skew;
+        const uint64_t lim = uint64_t((src_base + src_limit) - gbase);
+        glimit = lim > 0xFFFFFFF0ull ? 0xFFFFFFF0u : uint32_t(lim);
+        nchunks = (glimit + kInChunk - 1) / kInChunk;
+        rebase(0);
+    }
+    // make relative bytes [pos, pos + span) readable (span <= kInChunk); pos never moves backwards
+    __device__ __forceinline__ void ensure(uint32_t pos, uint32_t span = kLookahead) {
+        const uint32_t lo = (pos + skew) / kInChunk;
+        const uint32_t hi = (pos + skew + span) / kInChunk;
+        uint32_t cend = cbase + (issued - kbase);   // next stream chunk to issue
+        if (lo > cend) {
+            rebase(lo);
+            cend = lo;
+        }
+        const uint32_t want = min(lo + 2, nchunks);
+        if (cend < want) {
+            __syncwarp();
+            if (lane_id() == 0) {
+                fence_proxy_async();
+                for (uint32_t c = cend; c < want; c++) {
+                    const uint32_t k = kbase + (c - cbase);
+                    const uint32_t bytes = min(uint32_t(kInChunk), glimit - c * kInChunk);
+                    mbar_expect_tx(&bar[k & 1], bytes);
+                    tma_bulk_g2s(ring + (k & 1) * kInChunk, gbase + size_t(c) * kInChunk, bytes, &bar[k & 1]);
+                }
+            }
+            issued += want - cend;
+        }
+        const uint32_t want_c = min(hi + 1, nchunks);
+        if (want_c > cbase) {
+            const uint32_t want_k = kbase + (want_c - cbase);
+            while (int32_t(want_k - ready) > 0) {
+                mbar_wait(&bar[ready & 1], (ready >> 1) & 1);
+                ready++;
+            }
+        }
+    }
+    __device__ __forceinline__ uint32_t at(uint32_t pos) const { return ring[(pos + rbias) & kInMask]; }
+};
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const int lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+}  // namespace aurora

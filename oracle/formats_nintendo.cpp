@@ -314,6 +314,10 @@ void mio0_decode(Src& source, Sink& destination, const CodecOpts& o) {
     int64_t bufferLength = source.len - source.pos;
     const uint8_t* src = source.p + source.pos;
     source.pos = source.len;
+    // The reference indexes the span lazily (IndexOutOfRangeException at the first bad access); the oracle
+    // and the GPU path reject sub-stream pointers outside the blob up front, like Yay0's Span.Slice does.
+    if (compressedDataPointer < 0 || compressedDataPointer > bufferLength || uncompressedDataPointer < 0 || uncompressedDataPointer > bufferLength)
+        fail(INVALID_DATA);
     auto at = [&](int i) -> uint8_t {
         if (i < 0 || i >= bufferLength) fail(END_OF_STREAM);   // IndexOutOfRangeException on the span: input exhausted
         return src[i];

@@ -97,7 +97,7 @@ struct Src {
         return ok;
     }
     void MatchThrow(const void* magic, int n) {
-        if (pos + n > len) fail(END_OF_STREAM);
+        if (pos + n > len) { pos = len; fail(END_OF_STREAM); }
         if (!Match(magic, n)) fail(INVALID_IDENTIFIER);
     }
 };

@@ -1,0 +1,217 @@
+"""GPU parity tests proper: libaurora_cuda.so (through the C ABI) against the CPU oracle, byte for byte.
+
+Bar: bit-exact output, out_len, consumed and status on every input — valid, truncated and corrupt."""
+import numpy as np
+import pytest
+
+from auroralib.compression_b200 import _abi as A
+from tests.util import ALL_FORMATS, SIZED_FORMATS, corrupt, fmt_id, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(codec, oracle, fmt, comps, caps, opts=None, what=""):
+    outs, out_len, consumed, status = codec.decode_batch(fmt, comps, caps, opts)
+    ref, rlen, rcons, rst = oracle.decode_batch(fmt, comps, caps, opts)
+    bad = [i for i in range(len(comps)) if status[i] != rst[i] or out_len[i] != rlen[i] or consumed[i] != rcons[i] or outs[i] != ref[i]]
+    if bad:
+        i = bad[0]
+        first_diff = next((k for k in range(min(len(outs[i]), len(ref[i]))) if outs[i][k] != ref[i][k]), None)
+        pytest.fail(f"{fmt_id(fmt)} {what}: {len(bad)}/{len(comps)} streams differ; first #{i}: status gpu={status[i]} ref={rst[i]}, "
+                    f"out_len {out_len[i]}/{rlen[i]}, consumed {consumed[i]}/{rcons[i]}, srclen {len(comps[i])}, cap {caps[i]}, first diff at {first_diff}")
+    return outs, status
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS, ids=fmt_id)
+def test_bmp_prefixes_roundtrip(codec, oracle, bmp, fmt):
+    """The reference's EncodingAndDecodingMatchTest sizes/qualities (CompressionAlgorithmTest.cs:81-130)."""
+    cases = [(10, 4), (10240, 8), (10240, 15), (1048576, 0), (1024000, 0), (len(bmp), 8)]
+    raws, comps = [], []
+    for n, q in cases:
+        c, st = oracle.encode(fmt, bmp[:n], A.make_opts(quality=q))
+        assert st == 0
+        raws.append(bmp[:n])
+        comps.append(c)
+    outs, status = _compare(codec, oracle, fmt, comps, [len(r) for r in raws], what="bmp prefixes")
+    assert (status == 0).all()
+    assert all(o == r for o, r in zip(outs, raws))
+
+
+def test_lzss_golden_vector(codec, oracle, bmp, test_lz):
+    """LzssStaticDecodingTest (CompressionAlgorithmTest.cs:30-48): Test.lz with LzProperties((byte)10, 6, 2)."""
+    opts = A.make_opts(lzss=A.lz_props_bits(10, 6, 2))
+    size, st = codec.decoded_size_batch(A.FMT_LZSS, [test_lz], opts)
+    assert st[0] == 0 and size[0] == len(bmp)
+    outs, out_len, consumed, status = codec.decode_batch(A.FMT_LZSS, [test_lz], [len(bmp)], opts)
+    assert status[0] == 0 and outs[0] == bmp and consumed[0] == len(test_lz)
+    assert oracle.xxh64(outs[0]) == 11520079745250749767
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS, ids=fmt_id)
+def test_synthetic_batch(codec, oracle, fmt):
+    """Ragged batch: sizes 0..40 KiB (plus a few larger), five content classes, qualities 0/4/8/12."""
+    rng = np.random.default_rng(1000 + fmt)
+    raws = []
+    for i in range(160):
+        n = int(rng.choice([0, 1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 100, 255, 256, 257, 511, 512, 513, 1000,
+                            4095, 4096, 4097, 8191, 8192, 8193, 20000, 40000, 70000, 140000]))
+        raws.append(synth(rng, n, i % 5))
+    comps = []
+    keep = []
+    for q in (0, 4, 8, 12):
+        part = raws[q // 4::4]
+        c, st = oracle.encode_batch(fmt, part, A.make_opts(quality=q))
+        for r, cc, s in zip(part, c, st):
+            if s == 0:   # LZ4 encoders reject inputs shorter than 5 bytes like the reference
+                keep.append(r)
+                comps.append(cc)
+    outs, status = _compare(codec, oracle, fmt, comps, [len(r) for r in keep], what="synthetic")
+    # Round trip wherever the reference's own encoder/decoder pair round-trips.  Known reference quirks that do
+    # not (and that the GPU path reproduces bit for bit): empty inputs for LZ10/LZ11/LZ4Legacy/LZO,
+    # LZO's dropped-first-match double literal run, PRS's byte-order heuristic on high-entropy data.
+    ok = status == 0
+    n_rt = sum(1 for i in range(len(keep)) if ok[i] and outs[i] == keep[i])
+    assert n_rt >= len(keep) - (12 if fmt == A.FMT_PRS else 6), (n_rt, len(keep))
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS, ids=fmt_id)
+def test_corrupt_and_truncated(codec, oracle, fmt):
+    """Fuzz: truncated / bit-flipped / padded / empty inputs must give the oracle's status, length and bytes."""
+    rng = np.random.default_rng(2000 + fmt)
+    comps, caps = [], []
+    for i in range(240):
+        raw = synth(rng, int(rng.integers(5, 9000)), i % 5)
+        c, st = oracle.encode(fmt, raw, A.make_opts(quality=int(rng.choice([0, 8]))))
+        assert st == 0
+        comps.append(corrupt(rng, c, i % 5))
+        caps.append(len(raw) + int(rng.choice([0, 0, 0, 64, 5000])))
+    _compare(codec, oracle, fmt, comps, caps, what="fuzz")
+
+
+@pytest.mark.parametrize("fmt", ALL_FORMATS, ids=fmt_id)
+def test_capacity_edges(codec, oracle, fmt):
+    """Destination capacities below / at / above the decoded size (non-expandable MemoryStream behaviour)."""
+    rng = np.random.default_rng(3000 + fmt)
+    comps, caps = [], []
+    for i in range(60):
+        raw = synth(rng, int(rng.integers(6, 5000)), i % 5)
+        c, st = oracle.encode(fmt, raw, A.make_opts(quality=8))
+        assert st == 0
+        comps.append(c)
+        caps.append(max(0, len(raw) + int(rng.choice([-len(raw), -17, -1, 0, 1, 100]))))
+    _compare(codec, oracle, fmt, comps, caps, what="capacity")
+
+
+@pytest.mark.parametrize("fmt", [A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_YAY0, A.FMT_MIO0], ids=fmt_id)
+@pytest.mark.parametrize("enc_order", [A.ENDIAN_BIG, A.ENDIAN_LITTLE])
+@pytest.mark.parametrize("dec_order", [A.ENDIAN_DEFAULT, A.ENDIAN_BIG, A.ENDIAN_LITTLE])
+def test_byte_orders(codec, oracle, fmt, enc_order, dec_order):
+    """FormatByteOrder Big/Little headers; Yaz0's swapped-size retry (Yaz0.cs:67-78); Yay0/MIO0 auto-detect."""
+    rng = np.random.default_rng(4000 + fmt)
+    raws = [synth(rng, int(n), i % 5) for i, n in enumerate(rng.integers(1, 30000, size=24))]
+    comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=8, byte_order=enc_order))
+    assert (st == 0).all()
+    # capacity large enough for the wrong-endian size too, so that both attempts can run
+    caps = [max(len(r), 1 << 16) for r in raws]
+    outs, status = _compare(codec, oracle, fmt, comps, caps, A.make_opts(byte_order=dec_order), what=f"enc{enc_order}/dec{dec_order}")
+    if dec_order == enc_order or (dec_order == A.ENDIAN_DEFAULT and (enc_order == A.ENDIAN_BIG or fmt in (A.FMT_YAY0, A.FMT_MIO0))):
+        assert (status == 0).all() and all(o == r for o, r in zip(outs, raws))
+
+
+@pytest.mark.parametrize("props", [(12, 4, 2), (10, 6, 2), (11, 5, 1), (8, 8, 2), ("w", 0x1000, 18, 3, 0xFEE)], ids=str)
+def test_lzss_properties(codec, oracle, props):
+    """LZSS with other LzProperties (Level5LZSS / LZ0x style windows, Lzss0Properties, initialFill)."""
+    lz = A.lz_props_window(*props[1:]) if props[0] == "w" else A.lz_props_bits(*props)
+    rng = np.random.default_rng(5000)
+    raws = [synth(rng, int(n), i % 5) for i, n in enumerate(rng.integers(1, 20000, size=40))]
+    for fill in (0, 0x20):
+        opts = A.make_opts(lzss=lz, quality=8, lzss_initial_fill=fill)
+        comps, st = oracle.encode_batch(A.FMT_LZSS, raws, opts)
+        assert (st == 0).all()
+        outs, status = _compare(codec, oracle, A.FMT_LZSS, comps, [len(r) for r in raws], opts, what=f"lzss{props} fill{fill}")
+        assert (status == 0).all() and all(o == r for o, r in zip(outs, raws))
+
+
+def test_prehistory_references(codec, oracle):
+    """Back-references before the start of the output read the window's pre-history (zeros / initialFill):
+    hand-made LZ10, Yaz0 and LZSS streams whose first token is a match."""
+    lz10 = bytes([0x10, 40, 0, 0, 0b10100000, 0xF0, 0x05, 0x41, 0xF0, 0x00, 0x42, 0x43, 0x44, 0x45, 0x46])
+    yaz0 = b"Yaz0" + (40).to_bytes(4, "big") + bytes(8) + bytes([0b01011111, 0xF0, 0x05, 0x41, 0x00, 0x20, 3, 0x42, 0x43, 0x44, 0x45, 0x46])
+    for fmt, blob in ((A.FMT_LZ10, lz10), (A.FMT_YAZ0, yaz0)):
+        _compare(codec, oracle, fmt, [blob], [64], what="prehistory")
+    lzss = b"LZSS" + (37).to_bytes(4, "big") + bytes(8) + bytes([0b00000010, 0xEE, 0xFF, 0x41, 0x00, 0x0F, 0x05, 0x03])
+    for fill in (0, 0x20):
+        _compare(codec, oracle, A.FMT_LZSS, [lzss], [64], A.make_opts(lzss_initial_fill=fill), what="prehistory lzss")
+
+
+def test_lz4_containers(codec, oracle, bmp):
+    """LZ4.Decompress dispatch (LZ4.cs:50-94): v1 frames (block sizes, stored blocks), legacy frames,
+    skippable frames, concatenations, trailing garbage, frames with content-size / checksum flags."""
+    rng = np.random.default_rng(6000)
+    raw = bmp[:300000]
+    noise = rng.integers(0, 256, size=70000, dtype=np.uint8).tobytes()
+    f64, _ = oracle.encode(A.FMT_LZ4, raw, A.make_opts(quality=4, lz4_block_size=0x10000))
+    f256, _ = oracle.encode(A.FMT_LZ4, raw, A.make_opts(quality=0, lz4_block_size=0x40000))
+    fnoise, _ = oracle.encode(A.FMT_LZ4, noise, A.make_opts(quality=0, lz4_block_size=0x10000))   # stored blocks
+    leg, _ = oracle.encode(A.FMT_LZ4_LEGACY, raw, A.make_opts(quality=4))
+    skip = (0x184D2A53).to_bytes(4, "little") + (11).to_bytes(4, "little") + b"hello world"
+    blk, _ = oracle.encode(A.FMT_LZ4_BLOCK, raw[:50000], A.make_opts(quality=8))
+    # hand-built v1 frame with content size + block checksums + content checksum (the decoder skips them: HashAlgorithm null)
+    flg = 0x40 | 8 | 16 | 4
+    hand = (0x184D2204).to_bytes(4, "little") + bytes([flg, 0x40]) + (50000).to_bytes(8, "little") + b"\x00" + \
+        len(blk).to_bytes(4, "little") + blk + b"\xAA\xBB\xCC\xDD" + (0).to_bytes(4, "little") + b"\x11\x22\x33\x44"
+    wrong_size = (0x184D2204).to_bytes(4, "little") + bytes([0x40 | 8, 0x40]) + (49999).to_bytes(8, "little") + b"\x00" + \
+        len(blk).to_bytes(4, "little") + blk + (0).to_bytes(4, "little")
+    dict_id = (0x184D2204).to_bytes(4, "little") + bytes([0x41, 0x40]) + b"\x01\x02\x03\x04\x00"
+    bad_bd = (0x184D2204).to_bytes(4, "little") + bytes([0x40, 0x30, 0x00])
+    blobs = [f64, f256, fnoise, leg, skip + f64, f64 + skip + f256, f64 + b"garbage!", leg[:-1] + f64, hand, wrong_size,
+             dict_id, bad_bd, skip, f64[:1000], leg[:777]]
+    caps = [700000] * len(blobs)
+    for fmt in (A.FMT_LZ4, A.FMT_LZ4_LEGACY):
+        _compare(codec, oracle, fmt, blobs, caps, what="containers")
+
+
+def test_snappy_framing(codec, oracle, bmp):
+    rng = np.random.default_rng(7000)
+    raw = bmp[:200000]
+    noise = rng.integers(0, 256, size=70000, dtype=np.uint8).tobytes()
+    a, _ = oracle.encode(A.FMT_SNAPPY, raw, A.make_opts(quality=8))
+    b, _ = oracle.encode(A.FMT_SNAPPY, noise, A.make_opts(quality=0))   # stored chunks
+    skippable = bytes([0x80, 3, 0, 0, 1, 2, 3])
+    reserved = bytes([0x05, 1, 0, 0, 9])
+    blobs = [a, b, a + skippable + b[10:], a + reserved, a[:5000], a + a, b[:20000]]
+    _compare(codec, oracle, A.FMT_SNAPPY, blobs, [600000] * len(blobs), what="framing")
+
+
+def test_size_scan(codec, oracle, bmp):
+    """decoded_size_batch: header peek for the sized formats, device size-only pre-pass for the others."""
+    raws = [bmp[:n] for n in (100, 5000, 70000, 300000)]
+    for fmt in ALL_FORMATS:
+        comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=4))
+        assert (st == 0).all()
+        size, status = codec.decoded_size_batch(fmt, comps, size_scan=True)
+        assert (status == 0).all(), fmt_id(fmt)
+        assert [int(s) for s in size] == [len(r) for r in raws], fmt_id(fmt)
+        if fmt not in SIZED_FORMATS:
+            _, status = codec.decoded_size_batch(fmt, comps, size_scan=False)
+            assert (status == A.NOT_SUPPORTED).all()
+
+
+def test_large_batch_many_warps(codec, oracle, bmp):
+    """More streams than resident warps (persistent-grid ticketing) with unaligned source offsets."""
+    rng = np.random.default_rng(8000)
+    raws = [bmp[int(o):int(o) + int(n)] for o, n in zip(rng.integers(0, 900000, size=6000), rng.integers(1, 6000, size=6000))]
+    for fmt in (A.FMT_LZ10, A.FMT_YAZ0, A.FMT_LZ4_BLOCK, A.FMT_MIO0):
+        comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=0))
+        ok = [i for i in range(len(raws)) if st[i] == 0]
+        comps = [comps[i] for i in ok]
+        rr = [raws[i] for i in ok]
+        # pack with 1-byte alignment so that stream starts are not 16-byte aligned (TMA skew path)
+        from auroralib.compression_b200.batch import layout, pack
+        base, off, ln = pack(comps, align=1)
+        caps, doff, total = layout([len(r) for r in rr], align=1)
+        dst = np.zeros(total + 16, dtype=np.uint8)
+        out_len, consumed, status = codec.decode_packed(fmt, base, off, ln, dst, doff, caps)
+        assert (status == 0).all(), fmt_id(fmt)
+        got = [dst[int(doff[i]):int(doff[i]) + int(caps[i])].tobytes() for i in range(len(rr))]
+        assert got == rr, fmt_id(fmt)
