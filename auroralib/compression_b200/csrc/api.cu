@@ -308,6 +308,141 @@ int for_each_shard(aurora_ctx* ctx, const std::vector<Range>& ranges, F&& f) {
     return AURORA_OK;
 }
 
+// CompressionSettings + LzProperties -> LzChainMatchFinder parameters (LzChainMatchFinder.cs:42-119)
+int isqrt2q(int q) {
+    int r = 0;
+    while ((r + 1) * (r + 1) <= 2 * q) r++;
+    return r;
+}
+
+int fill_encode_params(EncodeParams& p, int format, const aurora_codec_opts* o) {
+    int q = (o && o->quality >= 0) ? o->quality : 8;   // default(CompressionSettings) == Balanced
+    if (q > 15) return AURORA_INVALID_ARGUMENT;
+    const int mwb = o ? o->max_window_bits : 0;
+    if (mwb != 0 && (mwb < 7 || mwb > 28)) return AURORA_INVALID_ARGUMENT;
+    aurora_lz_props lz;
+    switch (format) {
+        case AURORA_FMT_LZ10: {
+            const bool vram = !o || o->vram_mode != 0;   // LZ10.cs:33 default true (-1 = default)
+            aurora_lz_props_window(&lz, 0x1000, 18, 3, 0, vram ? 2 : 1);
+            break;
+        }
+        case AURORA_FMT_LZ11: {
+            const bool vram = o && o->vram_mode > 0;     // LZ11.cs:29 default false
+            aurora_lz_props_window(&lz, 0x1000, 0x4000, 3, 0, vram ? 2 : 1);
+            break;
+        }
+        case AURORA_FMT_YAZ0:
+        case AURORA_FMT_YAZ1:
+        case AURORA_FMT_YAY0: aurora_lz_props_window(&lz, 0x1000, 0xff + 0x12, 3, 0, 1); break;
+        case AURORA_FMT_MIO0: aurora_lz_props_window(&lz, 0x1000, 18, 3, 0, 1); break;
+        case AURORA_FMT_LZSS:
+            if (o && o->lzss.windows_bits != 0) lz = o->lzss;
+            else aurora_lz_props_bits(&lz, 12, 4, 2);
+            if (lz.windows_bits < 1 || lz.windows_bits > 24 || lz.length_bits < 1 || lz.length_bits > 8) return AURORA_INVALID_ARGUMENT;
+            break;
+        default: return AURORA_NOT_SUPPORTED;
+    }
+    p.format = format;
+    p.byte_order = o ? o->byte_order : AURORA_ENDIAN_DEFAULT;
+    p.max_chain = q < 6 ? q + 1 : q >= 11 ? 1 << (q - 5) : ((1 << (q >> 1)) | ((1 << (q >> 1)) >> (q & 1)));
+    p.lazy_threshold = 3 + q / 3;
+    p.hash_bits = 15 + isqrt2q(q);
+    int windows_bits = std::max(1, lz.windows_bits);
+    p.max_distance = lz.max_distance;
+    if (mwb != 0) {
+        windows_bits = std::max(windows_bits, mwb);
+        p.max_distance = std::max(p.max_distance, 1 << mwb);
+    }
+    p.chain_bits = std::min(17 + isqrt2q(q), windows_bits);
+    p.min_length = lz.min_length;
+    p.max_length = lz.max_length;
+    p.min_distance = lz.min_distance;
+    p.no_self_overlap = o ? (o->strategy & 1) : 0;
+    p.use_min_table = q >= 10;
+    p.yaz0_alignment = o ? o->yaz0_alignment : 0;
+    p.lzss = LzssParams{lz.windows_bits, lz.length_bits, lz.min_length, lz.max_distance, lz.windows_start, 0};
+    return AURORA_OK;
+}
+
+int encode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_opts* opts, size_t b, size_t e,
+                 const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
+                 const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t* out_len, int32_t* status) {
+    const size_t n = e - b;
+    if (n == 0) return AURORA_OK;
+    std::lock_guard<std::mutex> guard(d->mu);
+    CU_TRY(ctx, cudaSetDevice(d->dev));
+    EncodeParams P{};
+    if (fill_encode_params(P, format, opts) != AURORA_OK) return AURORA_INVALID_ARGUMENT;
+    const Layout S = plan_layout(src_off, src_len, b, e);
+    const Layout D = plan_layout(dst_off, dst_cap, b, e);
+    uint64_t max_len = 0;
+    for (size_t i = b; i < e; i++) max_len = std::max(max_len, src_len[i]);
+    const int warps = encode_resident_warps(d->sm_count);
+    P.scratch_per_warp = encode_scratch_per_warp(format, P.hash_bits, P.chain_bits, max_len);
+    CU_TRY(ctx, d->scratch.reserve(size_t(warps) * P.scratch_per_warp));
+    CU_TRY(ctx, d->src.reserve(S.bytes + 16));
+    CU_TRY(ctx, d->dst.reserve(D.bytes + 16));
+    const size_t desc_bytes = n * (5 * sizeof(uint64_t) + sizeof(int32_t)) + 64;
+    CU_TRY(ctx, d->desc.reserve(desc_bytes));
+    CU_TRY(ctx, d->hdesc.reserve(desc_bytes));
+    CU_TRY(ctx, d->ticket.reserve(256));
+    uint64_t* h = static_cast<uint64_t*>(d->hdesc.p);
+    uint64_t* dv = static_cast<uint64_t*>(d->desc.p);
+    for (size_t i = 0; i < n; i++) {
+        h[i] = S.dev_off[i];
+        h[n + i] = src_len[b + i];
+        h[2 * n + i] = D.dev_off[i];
+        h[3 * n + i] = dst_cap[b + i];
+    }
+    cudaStream_t st = d->stream;
+    CU_TRY(ctx, cudaMemcpyAsync(dv, h, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    uint8_t* dsrc = static_cast<uint8_t*>(d->src.p);
+    uint8_t* ddst = static_cast<uint8_t*>(d->dst.p);
+    if (S.span) {
+        uint64_t hi = 0;
+        for (size_t i = b; i < e; i++) hi = std::max(hi, src_off[i] + src_len[i]);
+        if (hi > S.lo) CU_TRY(ctx, cudaMemcpyAsync(dsrc, src_base + S.lo, hi - S.lo, cudaMemcpyHostToDevice, st));
+    } else {
+        for (size_t i = b; i < e; i++)
+            if (src_len[i]) CU_TRY(ctx, cudaMemcpyAsync(dsrc + S.dev_off[i - b], src_base + src_off[i], src_len[i], cudaMemcpyHostToDevice, st));
+    }
+    CU_TRY(ctx, cudaMemsetAsync(d->ticket.p, 0, 64, st));
+    P.scratch = static_cast<uint8_t*>(d->scratch.p);
+    P.src_base = dsrc;
+    P.src_limit = S.bytes;
+    P.src_off = dv;
+    P.src_len = dv + n;
+    P.dst_base = ddst;
+    P.dst_off = dv + 2 * n;
+    P.dst_cap = dv + 3 * n;
+    P.out_len = dv + 4 * n;
+    P.status = reinterpret_cast<int32_t*>(dv + 5 * n);
+    P.ticket = static_cast<unsigned int*>(d->ticket.p);
+    P.n = uint32_t(n);
+    CU_TRY(ctx, launch_encode_lz(P, warps, st));
+    ctx->launches++;
+    CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    const int32_t* hs = reinterpret_cast<const int32_t*>(h + 5 * n);
+    if (D.span) {
+        uint64_t hi = 0;
+        for (size_t i = b; i < e; i++) hi = std::max(hi, dst_off[i] + std::min<uint64_t>(h[4 * n + (i - b)], dst_cap[i]));
+        if (hi > D.lo) CU_TRY(ctx, cudaMemcpyAsync(dst_base + D.lo, ddst, hi - D.lo, cudaMemcpyDeviceToHost, st));
+    } else {
+        for (size_t i = b; i < e; i++) {
+            const uint64_t nbytes = std::min<uint64_t>(h[4 * n + (i - b)], dst_cap[i]);
+            if (nbytes) CU_TRY(ctx, cudaMemcpyAsync(dst_base + dst_off[i], ddst + D.dev_off[i - b], nbytes, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; i++) {
+        out_len[b + i] = h[4 * n + i];
+        status[b + i] = hs[i];
+    }
+    return AURORA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -609,17 +744,73 @@ uint64_t aurora_encode_bound(int format, uint64_t raw_len) {
     }
 }
 
-int aurora_encode_batch(aurora_ctx* ctx, int, const aurora_codec_opts*, size_t, const uint8_t*, const uint64_t*,
-                        const uint64_t*, uint8_t*, const uint64_t*, const uint64_t*, uint64_t*, int32_t*) {
-    if (ctx) ctx->set_error("aurora_encode_batch: encoder kernels not built yet");
-    return AURORA_NOT_SUPPORTED;
+int aurora_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
+                        const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
+                        const uint64_t* dst_cap, uint64_t* out_len, int32_t* status) {
+    if (!ctx) return AURORA_INVALID_ARGUMENT;
+    if (n == 0) return AURORA_OK;
+    if (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_cap || !out_len || !status || n > 0xFFFFFFF0ull) {
+        ctx->set_error("aurora_encode_batch: null argument");
+        return AURORA_INVALID_ARGUMENT;
+    }
+    EncodeParams probe{};
+    const int rc = fill_encode_params(probe, format, opts);
+    if (rc != AURORA_OK) {
+        ctx->set_error("aurora_encode_batch: this format has no GPU encoder yet (LZ10, LZ11, Yaz0, Yaz1, LZSS, MIO0, Yay0 do)");
+        return rc;
+    }
+    const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, nullptr);
+    return for_each_shard(ctx, ranges, [&](DeviceCtx* d, Range r) {
+        return encode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status);
+    });
 }
 
-int aurora_encode_batch_device(aurora_ctx* ctx, int, int, const aurora_codec_opts*, size_t, const uint8_t*, uint64_t,
-                               const uint64_t*, const uint64_t*, uint8_t*, const uint64_t*, const uint64_t*, uint64_t*,
-                               int32_t*, void*) {
-    if (ctx) ctx->set_error("aurora_encode_batch_device: encoder kernels not built yet");
-    return AURORA_NOT_SUPPORTED;
+int aurora_encode_batch_device(aurora_ctx* ctx, int device, int format, const aurora_codec_opts* opts, size_t n,
+                               const uint8_t* d_src_base, uint64_t src_total, const uint64_t* d_src_off,
+                               const uint64_t* d_src_len, uint8_t* d_dst_base, const uint64_t* d_dst_off,
+                               const uint64_t* d_dst_cap, uint64_t* d_out_len, int32_t* d_status, void* stream) {
+    if (!ctx || device < 0 || device >= int(ctx->devs.size())) return AURORA_INVALID_ARGUMENT;
+    if (n == 0) return AURORA_OK;
+    if (n > 0xFFFFFFF0ull) return AURORA_INVALID_ARGUMENT;
+    DeviceCtx* d = ctx->devs[device];
+    std::lock_guard<std::mutex> guard(d->mu);
+    CU_TRY(ctx, cudaSetDevice(d->dev));
+    EncodeParams P{};
+    const int rc = fill_encode_params(P, format, opts);
+    if (rc != AURORA_OK) {
+        ctx->set_error("aurora_encode_batch_device: this format has no GPU encoder yet");
+        return rc;
+    }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
+    // MIO0/Yay0 stage their code and literal sections per warp, sized by the largest stream of the batch
+    uint64_t max_len = 0;
+    if (format == AURORA_FMT_MIO0 || format == AURORA_FMT_YAY0) {
+        CU_TRY(ctx, d->hdesc.reserve(n * sizeof(uint64_t)));
+        CU_TRY(ctx, cudaMemcpyAsync(d->hdesc.p, d_src_len, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        const uint64_t* hl = static_cast<const uint64_t*>(d->hdesc.p);
+        for (size_t i = 0; i < n; i++) max_len = std::max(max_len, hl[i]);
+    }
+    const int warps = encode_resident_warps(d->sm_count);
+    P.scratch_per_warp = encode_scratch_per_warp(format, P.hash_bits, P.chain_bits, max_len);
+    CU_TRY(ctx, d->scratch.reserve(size_t(warps) * P.scratch_per_warp));
+    CU_TRY(ctx, d->ticket.reserve(256));
+    CU_TRY(ctx, cudaMemsetAsync(d->ticket.p, 0, 64, st));
+    P.scratch = static_cast<uint8_t*>(d->scratch.p);
+    P.src_base = d_src_base;
+    P.src_limit = src_total;
+    P.src_off = d_src_off;
+    P.src_len = d_src_len;
+    P.dst_base = d_dst_base;
+    P.dst_off = d_dst_off;
+    P.dst_cap = d_dst_cap;
+    P.out_len = d_out_len;
+    P.status = d_status;
+    P.ticket = static_cast<unsigned int*>(d->ticket.p);
+    P.n = uint32_t(n);
+    CU_TRY(ctx, launch_encode_lz(P, warps, st));
+    ctx->launches++;
+    return AURORA_OK;
 }
 
 }  // extern "C"

@@ -52,7 +52,8 @@ struct EncodeParams {
     int format;
     int byte_order;
     // CompressionSettings -> LzChainMatchFinder parameters (LzChainMatchFinder.cs:108-119)
-    int max_chain, lazy_threshold, min_length, max_length, min_distance, max_distance, no_self_overlap, use_min_table;
+    int max_chain, lazy_threshold, hash_bits, chain_bits, min_length, max_length, min_distance, max_distance, no_self_overlap,
+        use_min_table;
     uint32_t yaz0_alignment;
     LzssParams lzss;
     uint8_t* scratch;            // per-resident-warp match-finder tables
@@ -62,8 +63,8 @@ struct EncodeParams {
 // kernel launchers (one translation unit per kernel family); all return cudaGetLastError()
 cudaError_t launch_decode_flaglz(const DecodeParams& p, int sm_count, cudaStream_t st);
 cudaError_t launch_decode_bytelz(const DecodeParams& p, int sm_count, cudaStream_t st);
-cudaError_t launch_encode_lz(const EncodeParams& p, int sm_count, cudaStream_t st);
-size_t encode_scratch_per_warp(int format);
+cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st);
+size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64_t max_src_len);
 int encode_resident_warps(int sm_count);
 
 #ifdef __CUDACC__

@@ -1,8 +1,466 @@
-// encode_lz.cu — encoder kernels (placeholder until the match-search kernels land in this round).
+// encode_lz.cu — batched encoder for the flag-byte LZ77 family (LZ10, LZ11, Yaz0/Yaz1, LZSS, MIO0, Yay0).
+// One raw buffer per warp.
+//
+// Reference semantics restated on the device (paths under /root/reference/src):
+//   match finder  AuroraLib.Compression/MatchFinder/LzChainMatchFinder.cs: parameters :108-119, Reset :121-128,
+//                 Insert :130-140, FindNextBestMatch :157-212, MatchSearch :214-246, ChainMatches :248-282,
+//                 ComputeHash :288-299, GetMatchLength :338-357
+//   token writers Nintendo/LZ10.cs:67-80,:113-137; LZ11.cs:65-81,:135-171; Yaz0.cs:82-98 + Yay0.cs:152-184;
+//                 Yay0.cs:63-78; MIO0.cs:64-81,:159-184; Formats/Common/LZSS.cs:72-89,:132-160
+//   flag packing  AuroraLib.Compression/IO/FlagWriter.cs:70-80 (WriteBit), :111-127 (Flush)
+//
+// Round-1 design: exact emulation.  The reference's parse is sequential state (head/chain/min tables updated
+// as the cursor moves, greedy with one-step lazy lookahead), so each warp replays it for its stream with the
+// same hash function and the same table sizes (tables live in a per-warp slice of a global scratch buffer,
+// the 4-byte-hash head table is 2 MiB at the default quality 8), which makes the output byte-identical to
+// the reference encoder.  The 32 lanes are spent on the parts that are data parallel: the common-prefix
+// comparison of every chain candidate (32 bytes per step, ballot for the first mismatch) and the table reset.
+// The one-thread-per-window-position search with a shared-memory hash table is the planned replacement
+// ("what comes next").
 #include "common.cuh"
 
 namespace aurora {
-cudaError_t launch_encode_lz(const EncodeParams&, int, cudaStream_t) { return cudaErrorNotSupported; }
-size_t encode_scratch_per_warp(int) { return 0; }
-int encode_resident_warps(int sm_count) { return sm_count * 8; }
+
+namespace {
+
+constexpr int kEncWarpsPerBlock = 4;
+
+struct Finder {
+    int* head;
+    int* chain;
+    int* mint;
+    int hash_bits, hash_mask, chain_mask, max_chain, lazy, min_len, max_len, min_dist, max_dist;
+    uint32_t min_mask;
+    bool no_self_overlap, has_min;
+    int position;
+};
+
+__device__ __forceinline__ uint32_t load_u32le(const uint8_t* p) {
+    return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
+}
+
+// LzChainMatchFinder.cs:288-299
+__device__ __forceinline__ void compute_hash(const Finder& f, const uint8_t* d, int& h4, int& hm) {
+    const uint32_t prim = 2654435761u;
+    uint32_t v = load_u32le(d);
+    uint32_t mn = v & f.min_mask;
+    v *= prim;
+    mn *= prim;
+    h4 = int(v >> (32 - f.hash_bits)) & f.hash_mask;
+    hm = int((mn >> 16) & 0xFFFF);
+}
+
+// :130-140 (lane 0 owns the tables; the values it reads back are broadcast by the callers)
+__device__ __forceinline__ void finder_insert(Finder& f, int pos, int h4, int hm) {
+    if (lane_id() == 0) {
+        if (f.chain_mask != 0) f.chain[pos & f.chain_mask] = f.head[h4];
+        f.head[h4] = pos;
+        if (f.has_min) f.mint[hm] = pos;
+    }
+    __syncwarp();
+}
+
+// :338-357 — common prefix of data[a..] and data[b..], capped at max; 32 bytes per step
+__device__ __forceinline__ int match_length(const uint8_t* data, int a, int b, int max) {
+    const int lane = lane_id();
+    for (int base = 0; base < max; base += 32) {
+        const int i = base + lane;
+        const bool eq = i < max && data[a + i] == data[b + i];
+        const uint32_t ne = __ballot_sync(kFull, !eq);
+        if (ne) return base + __ffs(ne) - 1;
+    }
+    return max;
+}
+
+// :214-282
+__device__ void match_search(Finder& f, const uint8_t* data, int data_len, int pos, int& best_dist, int& best_len) {
+    int h4, hm;
+    compute_hash(f, data + pos, h4, hm);
+    int cur = __shfl_sync(kFull, lane_id() == 0 ? f.head[h4] : 0, 0);
+    const int best_possible = min(data_len - pos, f.max_len);
+    best_dist = best_len = 0;
+    int best_score = -1;
+    int attempts = f.max_chain;
+    while (cur != -1 && attempts-- > 0) {
+        const int distance = pos - cur;
+        if (distance > f.max_dist) break;
+        int next = -1;
+        if (f.chain_mask != 0) next = __shfl_sync(kFull, lane_id() == 0 ? f.chain[cur & f.chain_mask] : 0, 0);
+        if (distance < f.min_dist) {
+            cur = next;
+            continue;
+        }
+        int len = match_length(data, pos, cur, best_possible);
+        if (f.no_self_overlap && len > distance) len = distance;
+        const int score = len - f.min_len;
+        if (score > best_score) {
+            best_score = score;
+            best_len = len;
+            best_dist = distance;
+            if (best_len == best_possible) break;
+        }
+        cur = next;
+    }
+    if (best_len == 0 && f.has_min) {
+        cur = __shfl_sync(kFull, lane_id() == 0 ? f.mint[hm] : 0, 0);
+        if (cur != -1) {
+            int distance = pos - cur;
+            if (distance < f.min_dist) distance = f.min_dist;
+            if (distance <= f.max_dist) {
+                best_len = match_length(data, pos, pos - distance, best_possible);
+                if (f.no_self_overlap && best_len > distance) best_len = distance;
+                best_dist = distance;
+            }
+        }
+    }
+    finder_insert(f, pos, h4, hm);
+}
+
+struct Match {
+    int offset, distance, length;
+};
+
+// :157-212
+__device__ Match find_next_best_match(Finder& f, const uint8_t* data, int length) {
+    const int limit = length - 4;
+    while (f.position <= limit) {
+        int best_dist, best_len;
+        match_search(f, data, length, f.position, best_dist, best_len);
+        if (best_len < f.min_len) {
+            f.position++;
+            continue;
+        }
+        int skip = 0;
+        if (best_len <= f.lazy && f.position + 1 <= limit) {
+            const int next_pos = f.position + 1;
+            int nd, nl;
+            match_search(f, data, length, next_pos, nd, nl);
+            if (nl > best_len) {
+                best_len = nl;
+                best_dist = nd;
+                f.position = next_pos;
+            } else {
+                skip++;
+            }
+        }
+        const Match m{f.position, best_dist, best_len};
+        const int end = f.position + best_len;
+        f.position++;
+        f.position += skip;
+        while (f.position < end && f.position <= limit) {
+            int h4, hm;
+            compute_hash(f, data + f.position, h4, hm);
+            finder_insert(f, f.position, h4, hm);
+            f.position++;
+        }
+        return m;
+    }
+    f.position = length;
+    return Match{length, 0, 0};
+}
+
+// FlagWriter (IO/FlagWriter.cs) over a bounded output: the flag byte of a group is reserved when the group's
+// first byte or bit arrives and patched when the 8th bit (or Dispose) comes — the same byte layout as the
+// reference's "flag word, then the buffered token bytes".
+struct Writer {
+    uint8_t* out;
+    uint64_t cap;
+    uint64_t pos;
+    int64_t flag_pos;
+    uint32_t flag_val, bits;
+    bool msb_first, overflow;
+    __device__ __forceinline__ void put(uint64_t at, uint32_t b) {
+        if (at < cap) {
+            if (lane_id() == 0) out[at] = uint8_t(b);
+        } else {
+            overflow = true;
+        }
+    }
+    __device__ __forceinline__ void raw_byte(uint32_t b) { put(pos++, b); }
+    __device__ __forceinline__ void group() {
+        if (flag_pos < 0) {
+            flag_pos = int64_t(pos++);
+            flag_val = 0;
+            bits = 0;
+        }
+    }
+    __device__ __forceinline__ void byte(uint32_t b) {
+        group();
+        put(pos++, b);
+    }
+    __device__ __forceinline__ void bit(bool v) {
+        group();
+        if (v) flag_val |= msb_first ? (0x80u >> bits) : (1u << bits);
+        if (++bits == 8) {
+            put(uint64_t(flag_pos), flag_val);
+            flag_pos = -1;
+        }
+    }
+    __device__ __forceinline__ void dispose() {
+        if (flag_pos >= 0) put(uint64_t(flag_pos), flag_val);
+        flag_pos = -1;
+    }
+};
+
+enum EncKind { E_LZ10 = 0, E_LZ11 = 1, E_YAZ0 = 2, E_LZSS = 3, E_MIO0 = 4, E_YAY0 = 5 };
+
+__device__ __forceinline__ void put_u32(Writer& w, uint32_t v, bool big) {
+    for (int i = 0; i < 4; i++) w.raw_byte(big ? (v >> (24 - 8 * i)) & 0xFF : (v >> (8 * i)) & 0xFF);
+}
+
+template <int K>
+__device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
+    const uint8_t* src = P.src_base + P.src_off[idx];
+    const uint64_t n64 = P.src_len[idx];
+    const int lane = lane_id();
+    int status = AURORA_OK;
+    uint64_t out_len = 0;
+    if (n64 > 0x7FFFFFF0ull) {
+        status = AURORA_INVALID_ARGUMENT;
+    } else {
+        const int n = int(n64);
+        // Reset (:121-128)
+        {
+            int4 m1 = make_int4(-1, -1, -1, -1);
+            int4* h = reinterpret_cast<int4*>(f.head);
+            for (int i = lane; i < (f.hash_mask + 1) / 4; i += 32) h[i] = m1;
+            if (f.max_chain != 1) {
+                int4* c = reinterpret_cast<int4*>(f.chain);
+                for (int i = lane; i < (f.chain_mask + 1) / 4; i += 32) c[i] = m1;
+            }
+            if (f.has_min) {
+                int4* t = reinterpret_cast<int4*>(f.mint);
+                for (int i = lane; i < 65536 / 4; i += 32) t[i] = m1;
+            }
+            f.position = 0;
+            __syncwarp();
+            __threadfence_block();
+        }
+        Writer w;
+        w.out = P.dst_base + P.dst_off[idx];
+        w.cap = P.dst_cap[idx];
+        w.pos = 0;
+        w.flag_pos = -1;
+        w.flag_val = w.bits = 0;
+        w.msb_first = K != E_LZSS;
+        w.overflow = false;
+        const bool big = P.byte_order != AURORA_ENDIAN_LITTLE;   // class default Big
+
+        // split-stream formats assemble three sections; codes and literals are staged behind the flag section
+        uint8_t* codes = nullptr;
+        uint8_t* lits = nullptr;
+        uint32_t ncodes = 0, nlits = 0;
+        if (K == E_MIO0 || K == E_YAY0) {
+            // worst case: n literal bytes, n/3*2 code bytes (+ n/18 extended lengths counted in lits)
+            codes = reinterpret_cast<uint8_t*>(f.head) + P.scratch_per_warp - 2 * (size_t(n) + 64);
+            lits = codes + size_t(n) + 32;
+        }
+
+        // ---- headers
+        if (K == E_LZ10 || K == E_LZ11) {
+            const uint32_t id = K == E_LZ10 ? 0x10 : 0x11;
+            if (n <= 0xFFFFFF) {
+                put_u32(w, id | (uint32_t(n) << 8), false);
+            } else {
+                put_u32(w, id, false);
+                put_u32(w, uint32_t(n), false);
+            }
+        } else if (K == E_YAZ0) {
+            const char* magic = P.format == AURORA_FMT_YAZ1 ? "Yaz1" : "Yaz0";
+            for (int i = 0; i < 4; i++) w.raw_byte(uint8_t(magic[i]));
+            put_u32(w, uint32_t(n), big);
+            put_u32(w, P.yaz0_alignment, big);
+            put_u32(w, 0, false);
+        } else if (K == E_LZSS) {
+            w.raw_byte('L'); w.raw_byte('Z'); w.raw_byte('S'); w.raw_byte('S');
+            put_u32(w, uint32_t(n), true);
+            put_u32(w, 0, false);   // compressed size, patched below
+            put_u32(w, 0, false);
+        } else {
+            const char* magic = K == E_MIO0 ? "MIO0" : "Yay0";
+            for (int i = 0; i < 4; i++) w.raw_byte(uint8_t(magic[i]));
+            put_u32(w, uint32_t(n), big);
+            put_u32(w, 0, big);   // offsets patched below
+            put_u32(w, 0, big);
+        }
+        const uint64_t body_start = w.pos;
+
+        // ---- token loop (the common shape of all CompressHeaderless bodies)
+        const int lz_n = P.lzss.max_distance - 1, lz_f = (1 << P.lzss.length_bits) - 1;
+        int sp = 0;
+        for (;;) {
+            const Match m = find_next_best_match(f, src, n);
+            int plain = m.offset - sp;
+            while (plain != 0) {
+                plain--;
+                const uint32_t b = src[sp++];
+                if (K == E_MIO0 || K == E_YAY0) {
+                    if (lane == 0) lits[nlits] = uint8_t(b);
+                    nlits++;
+                    w.bit(true);
+                } else {
+                    w.byte(b);
+                    w.bit(K == E_YAZ0 || K == E_LZSS);   // Yaz0/LZSS: 1 = literal; LZ10/LZ11: 0 = literal
+                }
+            }
+            if (m.length == 0) break;
+            const uint32_t d1 = uint32_t(m.distance - 1) & 0xFFF;
+            if (K == E_LZ10) {
+                const uint32_t v = uint32_t(m.length - 3) << 12 | d1;
+                w.byte((v >> 8) & 0xFF);
+                w.byte(v & 0xFF);
+                w.bit(true);
+            } else if (K == E_LZ11) {
+                if (m.length <= 16) {
+                    const uint32_t v = (uint32_t(m.length - 1) << 12 | d1) & 0xFFFF;
+                    w.byte(v >> 8);
+                    w.byte(v & 0xFF);
+                } else if (m.length <= 272) {
+                    w.byte((uint32_t(m.length - 17) & 0xFF) >> 4);
+                    const uint32_t v = (uint32_t(m.length - 17) << 12 | d1) & 0xFFFF;
+                    w.byte(v >> 8);
+                    w.byte(v & 0xFF);
+                } else {
+                    const uint32_t v = 0x10000000u | (uint32_t(m.length - 273) & 0xFFFF) << 12 | d1;
+                    w.byte(v >> 24);
+                    w.byte((v >> 16) & 0xFF);
+                    w.byte((v >> 8) & 0xFF);
+                    w.byte(v & 0xFF);
+                }
+                w.bit(true);
+            } else if (K == E_YAZ0) {
+                if (m.length < 18) {
+                    const uint32_t v = (uint32_t(m.distance - 1) | uint32_t(m.length - 2) << 12) & 0xFFFF;
+                    w.byte(v >> 8);
+                    w.byte(v & 0xFF);
+                } else {
+                    w.byte(d1 >> 8);
+                    w.byte(d1 & 0xFF);
+                    w.byte(uint32_t(m.length - 0x12) & 0xFF);
+                }
+                w.bit(false);
+            } else if (K == E_LZSS) {
+                const int offset = (P.lzss.windows_start + sp - m.distance) & lz_n;
+                const uint32_t v = (uint32_t(offset & 0xFF) | uint32_t(offset & 0xFF00) << P.lzss.length_bits |
+                                    uint32_t((m.length - P.lzss.min_length) & lz_f) << 8) & 0xFFFF;
+                w.byte(v & 0xFF);
+                w.byte(v >> 8);
+                w.bit(false);
+            } else {   // MIO0 / Yay0 codes go to their own section
+                uint32_t v;
+                if (K == E_MIO0) v = (uint32_t(m.distance - 1) | uint32_t(m.length - 3) << 12) & 0xFFFF;
+                else if (m.length < 18) v = (uint32_t(m.distance - 1) | uint32_t(m.length - 2) << 12) & 0xFFFF;
+                else v = d1;
+                if (lane == 0) {
+                    codes[ncodes] = uint8_t(v >> 8);
+                    codes[ncodes + 1] = uint8_t(v & 0xFF);
+                }
+                ncodes += 2;
+                if (K == E_YAY0 && m.length >= 18) {
+                    if (lane == 0) lits[nlits] = uint8_t(m.length - 0x12);
+                    nlits++;
+                }
+                w.bit(false);
+            }
+            sp += m.length;
+        }
+        if (K == E_MIO0 || K == E_YAY0) {
+            // the flag section holds only flag bytes: the Writer reserved one byte per group and wrote nothing else
+            w.dispose();
+            __syncwarp();
+            const uint64_t comp_off = w.pos, lit_off = w.pos + ncodes;
+            for (uint32_t i = lane; i < ncodes; i += 32)
+                if (comp_off + i < w.cap) w.out[comp_off + i] = codes[i];
+            for (uint32_t i = lane; i < nlits; i += 32)
+                if (lit_off + i < w.cap) w.out[lit_off + i] = lits[i];
+            w.pos = lit_off + nlits;
+            if (w.pos > w.cap) w.overflow = true;
+            const uint64_t save = w.pos;
+            w.pos = 8;
+            put_u32(w, uint32_t(comp_off), big);
+            put_u32(w, uint32_t(lit_off), big);
+            w.pos = save;
+        } else {
+            w.dispose();
+            if (K == E_LZSS) {
+                const uint64_t save = w.pos;
+                w.pos = 8;
+                put_u32(w, uint32_t(save - body_start), true);
+                w.pos = save;
+            }
+        }
+        out_len = w.pos;
+        if (w.overflow) status = AURORA_DST_TOO_SMALL;
+    }
+    if (lane == 0) {
+        P.out_len[idx] = out_len;
+        P.status[idx] = status;
+    }
+    __syncwarp();
+}
+
+template <int K>
+__global__ void __launch_bounds__(kEncWarpsPerBlock * 32) encode_lz_kernel(const EncodeParams P) {
+    const int warp_global = blockIdx.x * kEncWarpsPerBlock + (threadIdx.x >> 5);
+    uint8_t* scratch = P.scratch + size_t(warp_global) * P.scratch_per_warp;
+    Finder f;
+    // LzChainMatchFinder.cs:42-106 with the derived parameters of :108-119 (resolved on the host)
+    f.hash_bits = P.hash_bits;
+    f.hash_mask = (1 << P.hash_bits) - 1;
+    f.max_chain = P.max_chain;
+    f.chain_mask = P.max_chain == 1 ? 0 : (1 << P.chain_bits) - 1;
+    f.lazy = P.lazy_threshold;
+    f.min_len = P.min_length;
+    f.max_len = P.max_length;
+    f.min_dist = P.min_distance;
+    f.max_dist = P.max_distance;
+    f.no_self_overlap = P.no_self_overlap != 0;
+    f.has_min = P.use_min_table != 0 && P.min_length < 4;
+    f.min_mask = f.has_min ? 0xFFFFFFFFu >> ((4 - P.min_length) * 8) : 0u;
+    f.head = reinterpret_cast<int*>(scratch);
+    f.chain = f.head + (size_t(1) << P.hash_bits);
+    f.mint = f.chain + (size_t(1) << P.chain_bits);
+    f.position = 0;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane_id() == 0) t = atomicAdd(P.ticket, 1u);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= P.n) break;
+        encode_stream<K>(P, t, f);
+    }
+}
+
+template <int K>
+cudaError_t launch(const EncodeParams& p, int warps, cudaStream_t st) {
+    int blocks = (warps + kEncWarpsPerBlock - 1) / kEncWarpsPerBlock;
+    const int needed = int((p.n + kEncWarpsPerBlock - 1) / kEncWarpsPerBlock);
+    if (needed < blocks) blocks = needed > 0 ? needed : 1;
+    encode_lz_kernel<K><<<blocks, kEncWarpsPerBlock * 32, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int encode_resident_warps(int sm_count) { return sm_count * 16; }
+
+// head + chain + min tables, plus (MIO0/Yay0) staging for the code and literal sections
+size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64_t max_src_len) {
+    size_t bytes = (size_t(1) << hash_bits) * 4 + (size_t(1) << chain_bits) * 4 + 65536 * 4;
+    if (format == AURORA_FMT_MIO0 || format == AURORA_FMT_YAY0) bytes += 2 * (size_t(max_src_len) + 64);
+    return (bytes + 255) & ~size_t(255);
+}
+
+cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st) {
+    switch (p.format) {
+        case AURORA_FMT_LZ10: return launch<E_LZ10>(p, warps, st);
+        case AURORA_FMT_LZ11: return launch<E_LZ11>(p, warps, st);
+        case AURORA_FMT_YAZ0:
+        case AURORA_FMT_YAZ1: return launch<E_YAZ0>(p, warps, st);
+        case AURORA_FMT_LZSS: return launch<E_LZSS>(p, warps, st);
+        case AURORA_FMT_MIO0: return launch<E_MIO0>(p, warps, st);
+        case AURORA_FMT_YAY0: return launch<E_YAY0>(p, warps, st);
+        default: return cudaErrorNotSupported;
+    }
+}
+
 }  // namespace aurora

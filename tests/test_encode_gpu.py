@@ -1,0 +1,80 @@
+"""GPU encoder parity: the device replays the reference's match finder exactly, so the compressed bytes must equal
+the oracle encoder's output (which reproduces the reference's published Q0 ratios), and must round-trip through
+the oracle decoder.  Contract: round trip byte-exact, ratio within 0.5 % of the reference."""
+import numpy as np
+import pytest
+
+from auroralib.compression_b200 import _abi as A
+from tests.util import fmt_id, synth
+
+pytestmark = pytest.mark.gpu
+
+ENC_FORMATS = [A.FMT_LZ10, A.FMT_LZ11, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS, A.FMT_MIO0, A.FMT_YAY0]
+
+
+def _check(codec, oracle, fmt, raws, opts):
+    got, st = codec.encode_batch(fmt, raws, opts)
+    ref, rst = oracle.encode_batch(fmt, raws, opts)
+    assert (st == rst).all() and (st == 0).all(), (fmt_id(fmt), st, rst)
+    bad = [i for i in range(len(raws)) if got[i] != ref[i]]
+    assert not bad, f"{fmt_id(fmt)}: {len(bad)}/{len(raws)} streams differ from the oracle encoder; first #{bad[0]} len {len(raws[bad[0]])}: {len(got[bad[0]])} vs {len(ref[bad[0]])} bytes"
+    outs, out_len, consumed, dst = oracle.decode_batch(fmt, got, [max(len(r), 1) for r in raws], opts)
+    for i, r in enumerate(raws):
+        if len(r) == 0 and fmt in (A.FMT_LZ10, A.FMT_LZ11):
+            continue   # the reference cannot decode its own empty LZ10/LZ11 stream (size 0 -> reads a u32)
+        assert dst[i] == 0 and outs[i] == r and consumed[i] == len(got[i]), (fmt_id(fmt), i, dst[i])
+    return got
+
+
+@pytest.mark.parametrize("fmt", ENC_FORMATS, ids=fmt_id)
+@pytest.mark.parametrize("quality", [0, 4, 8, 12, 15])
+def test_bmp_prefixes(codec, oracle, bmp, fmt, quality):
+    raws = [bmp[:n] for n in (10, 256, 10240, 65536, 300000)]
+    _check(codec, oracle, fmt, raws, A.make_opts(quality=quality))
+
+
+@pytest.mark.parametrize("fmt", ENC_FORMATS, ids=fmt_id)
+def test_published_q0_sizes(codec, oracle, bmp, fmt):
+    """Benchmarks.md Q0 ratios on the first 1 024 000 bytes of Test.bmp."""
+    expected = {A.FMT_YAZ0: 183160, A.FMT_YAZ1: 183160, A.FMT_YAY0: 183160, A.FMT_LZ10: 261953, A.FMT_MIO0: 261898,
+                A.FMT_LZSS: 261898, A.FMT_LZ11: 179455}[fmt]
+    got, st = codec.encode_batch(fmt, [bmp[:1024000]], A.make_opts(quality=0))
+    assert st[0] == 0 and len(got[0]) == expected
+
+
+@pytest.mark.parametrize("fmt", ENC_FORMATS, ids=fmt_id)
+def test_synthetic_ragged(codec, oracle, fmt):
+    rng = np.random.default_rng(9000 + fmt)
+    raws = [synth(rng, int(n), i % 5) for i, n in enumerate(
+        rng.choice([0, 1, 2, 3, 4, 5, 7, 8, 9, 16, 17, 33, 100, 255, 256, 257, 1000, 4095, 4096, 4097, 8192, 20000, 70000], size=120))]
+    _check(codec, oracle, fmt, raws, A.make_opts(quality=8))
+    _check(codec, oracle, fmt, raws[:40], A.make_opts(quality=15, strategy=1))   # CompatibilityMode: noSelfOverlap
+
+
+def test_options(codec, oracle, bmp):
+    raws = [bmp[1000:40000], bytes(5000), bmp[:7]]
+    for vram in (0, 1):
+        _check(codec, oracle, A.FMT_LZ10, raws, A.make_opts(quality=8, vram_mode=vram))
+        _check(codec, oracle, A.FMT_LZ11, raws, A.make_opts(quality=8, vram_mode=vram))
+    for order in (A.ENDIAN_BIG, A.ENDIAN_LITTLE):
+        for fmt in (A.FMT_YAZ0, A.FMT_YAY0, A.FMT_MIO0):
+            _check(codec, oracle, fmt, raws, A.make_opts(quality=4, byte_order=order))
+    _check(codec, oracle, A.FMT_YAZ0, raws, A.make_opts(quality=4, yaz0_alignment=0x20))
+    for props in (A.lz_props_bits(10, 6, 2), A.lz_props_bits(12, 4, 2), A.lz_props_window(0x1000, 18, 3, 0xFEE)):
+        _check(codec, oracle, A.FMT_LZSS, raws, A.make_opts(quality=8, lzss=props))
+
+
+def test_capacity_too_small(codec, bmp):
+    from auroralib.compression_b200.batch import layout, pack
+    base, off, ln = pack([bmp[:20000]])
+    caps, doff, total = layout([100])
+    dst = np.zeros(256, dtype=np.uint8)
+    out_len, status = codec.encode_packed(A.FMT_LZ10, base, off, ln, dst, doff, caps)
+    assert status[0] == A.DST_TOO_SMALL and out_len[0] > 100
+    assert dst[100:].sum() == 0   # nothing written past the capacity
+
+
+def test_unsupported_formats_say_so(codec, bmp):
+    from auroralib.compression_b200 import AuroraError
+    with pytest.raises(AuroraError):
+        codec.encode_batch(A.FMT_LZ4, [bmp[:1000]])
