@@ -41,10 +41,11 @@ static CodecOpts to_opts(const aurora_codec_opts* c) {
     return o;
 }
 
-DecodeResult decode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap) {
+DecodeResult decode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap, bool size_only) {
     DecodeResult r;
     Src s(src, n);
     Sink d(dst, cap);
+    d.size_only = size_only;
     try {
         switch (fmt) {
             case FMT_YAZ0: yaz0_decode(s, d, o, "Yaz0"); break;
@@ -223,7 +224,7 @@ int ora_decoded_size_batch(int format, const aurora_codec_opts* opts, size_t n, 
         } catch (const Error& e) {
             st = e.status;
             if (st == NOT_SUPPORTED && size_scan) {   // size-only pre-pass: decode into a zero-capacity sink
-                DecodeResult r = decode_one(format, o, src_base + src_off[i], int64_t(src_len[i]), nullptr, 0);
+                DecodeResult r = decode_one(format, o, src_base + src_off[i], int64_t(src_len[i]), nullptr, 0, true);
                 st = (r.status == DST_TOO_SMALL) ? OK : r.status;
                 sz = uint64_t(r.out_len);
             }

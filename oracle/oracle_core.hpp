@@ -112,9 +112,10 @@ struct Sink {
     int64_t cap;
     int64_t pos = 0;
     int64_t length = 0;
+    bool size_only = false;   // size-scan pre-pass: count, never store, never refuse a length
     Sink(uint8_t* p_, int64_t c) : p(p_), cap(c) {}
     void SetLength(int64_t n) {
-        if (n > cap) fail(DST_TOO_SMALL);
+        if (n > cap && !size_only) fail(DST_TOO_SMALL);
         length = n;
     }
     void Write(const uint8_t* s, int64_t n) {
@@ -462,7 +463,7 @@ void prs_encode(const uint8_t* src, int n, OutBuf& out, const CodecOpts& o);
 uint32_t decoded_size(int fmt, Src& s, const CodecOpts& o);   // throws NOT_SUPPORTED where absent
 bool is_match(int fmt, Src& s, const CodecOpts& o);
 
-DecodeResult decode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap);
+DecodeResult decode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap, bool size_only = false);
 int encode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t n, std::vector<uint8_t>& out);
 
 }  // namespace ora
