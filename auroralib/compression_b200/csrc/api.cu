@@ -61,6 +61,8 @@ struct DeviceCtx {
     int dev = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy engines of the pipelined host path
+    std::vector<cudaEvent_t> ev_in, ev_k;
     DevBuf src, dst, desc, ticket, scratch;
     HostBuf hdesc;
     std::mutex mu;   // one batch at a time per device
@@ -242,50 +244,115 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     CU_TRY(ctx, cudaMemcpyAsync(dv, h, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     uint8_t* dsrc = static_cast<uint8_t*>(d->src.p);
     uint8_t* ddst = static_cast<uint8_t*>(d->dst.p);
-    if (S.span) {
-        uint64_t hi = 0;
-        for (size_t i = b; i < e; i++) hi = std::max(hi, src_off[i] + src_len[i]);
-        if (hi > S.lo) CU_TRY(ctx, cudaMemcpyAsync(dsrc, src_base + S.lo, hi - S.lo, cudaMemcpyHostToDevice, st));
-    } else {
-        for (size_t i = b; i < e; i++)
-            if (src_len[i]) CU_TRY(ctx, cudaMemcpyAsync(dsrc + S.dev_off[i - b], src_base + src_off[i], src_len[i], cudaMemcpyHostToDevice, st));
-    }
-    CU_TRY(ctx, cudaMemsetAsync(d->ticket.p, 0, 64, st));
-
     P.src_base = dsrc;
     P.src_limit = align_up(S.bytes, 16);
-    P.src_off = dv;
-    P.src_len = dv + n;
     P.dst_base = ddst;
-    P.dst_off = dv + 2 * n;
-    P.dst_cap = dv + 3 * n;
-    P.out_len = dv + 4 * n;
-    P.consumed = dv + 5 * n;
-    P.status = reinterpret_cast<int32_t*>(dv + 6 * n);
     P.order = nullptr;
     P.ticket = static_cast<unsigned int*>(d->ticket.p);
-    P.n = uint32_t(n);
-    CU_TRY(ctx, launch_decode(P, d->sm_count, st));
-    ctx->launches++;
 
-    // results
-    CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, 2 * n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (!size_only) {
-        if (D.span) {
+    // Pipelined host path: the shard is cut into byte-balanced pieces; piece k+1 is uploaded (H2D engine) while piece
+    // k decodes and piece k-1 is downloaded (D2H engine), so end-to-end time tends to max(H2D, D2H) instead of their sum.
+    uint64_t total_bytes = S.bytes + D.bytes;
+    size_t pieces = 1;
+    if (S.span && (size_only || D.span) && total_bytes > (64ull << 20) && n >= 64) pieces = std::min<size_t>(16, std::max<size_t>(2, total_bytes >> 28));
+    if (pieces > 1) {
+        while (d->ev_in.size() < pieces) {
+            cudaEvent_t e1, e2;
+            CU_TRY(ctx, cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            d->ev_in.push_back(e1);
+            d->ev_k.push_back(e2);
+        }
+        CU_TRY(ctx, cudaMemsetAsync(d->ticket.p, 0, 256, st));
+        CU_TRY(ctx, cudaEventRecord(d->ev_k[0], st));   // descriptors + tickets are in place
+        CU_TRY(ctx, cudaStreamWaitEvent(d->s_in, d->ev_k[0], 0));
+        // piece boundaries by cumulative bytes
+        std::vector<size_t> cut(pieces + 1, n);
+        cut[0] = 0;
+        {
+            uint64_t acc = 0;
+            size_t k = 1;
+            for (size_t i = 0; i < n && k < pieces; i++) {
+                acc += src_len[b + i] + (size_only ? 0 : dst_cap[b + i]);
+                if (acc >= total_bytes * k / pieces) cut[k++] = i + 1;
+            }
+        }
+        for (size_t k = 0; k < pieces; k++) {
+            const size_t i0 = cut[k], i1 = cut[k + 1];
+            if (i1 <= i0) continue;
+            uint64_t lo = ~0ull, hi = 0;
+            for (size_t i = i0; i < i1; i++) {
+                lo = std::min(lo, src_off[b + i]);
+                hi = std::max(hi, src_off[b + i] + src_len[b + i]);
+            }
+            lo &= ~15ull;
+            if (hi > lo) CU_TRY(ctx, cudaMemcpyAsync(dsrc + (lo - S.lo), src_base + lo, hi - lo, cudaMemcpyHostToDevice, d->s_in));
+            CU_TRY(ctx, cudaEventRecord(d->ev_in[k], d->s_in));
+            CU_TRY(ctx, cudaStreamWaitEvent(st, d->ev_in[k], 0));
+            DecodeParams Q = P;
+            Q.src_off = dv + i0;
+            Q.src_len = dv + n + i0;
+            Q.dst_off = dv + 2 * n + i0;
+            Q.dst_cap = dv + 3 * n + i0;
+            Q.out_len = dv + 4 * n + i0;
+            Q.consumed = dv + 5 * n + i0;
+            Q.status = reinterpret_cast<int32_t*>(dv + 6 * n) + i0;
+            Q.ticket = static_cast<unsigned int*>(d->ticket.p) + k;
+            Q.n = uint32_t(i1 - i0);
+            CU_TRY(ctx, launch_decode(Q, d->sm_count, st));
+            ctx->launches++;
+            if (!size_only) {
+                CU_TRY(ctx, cudaEventRecord(d->ev_k[k], st));
+                CU_TRY(ctx, cudaStreamWaitEvent(d->s_out, d->ev_k[k], 0));
+                uint64_t dlo = ~0ull, dhi = 0;
+                for (size_t i = i0; i < i1; i++) {
+                    dlo = std::min(dlo, dst_off[b + i]);
+                    dhi = std::max(dhi, dst_off[b + i] + dst_cap[b + i]);
+                }
+                if (dhi > dlo) CU_TRY(ctx, cudaMemcpyAsync(dst_base + dlo, ddst + (dlo - D.lo), dhi - dlo, cudaMemcpyDeviceToHost, d->s_out));
+            }
+        }
+        CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, 2 * n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        CU_TRY(ctx, cudaStreamSynchronize(d->s_out));
+    } else {
+        if (S.span) {
             uint64_t hi = 0;
-            for (size_t i = b; i < e; i++) hi = std::max(hi, dst_off[i] + dst_cap[i]);
-            if (hi > D.lo) CU_TRY(ctx, cudaMemcpyAsync(dst_base + D.lo, ddst, hi - D.lo, cudaMemcpyDeviceToHost, st));
-            CU_TRY(ctx, cudaStreamSynchronize(st));
+            for (size_t i = b; i < e; i++) hi = std::max(hi, src_off[i] + src_len[i]);
+            if (hi > S.lo) CU_TRY(ctx, cudaMemcpyAsync(dsrc, src_base + S.lo, hi - S.lo, cudaMemcpyHostToDevice, st));
+        } else {
+            for (size_t i = b; i < e; i++)
+                if (src_len[i]) CU_TRY(ctx, cudaMemcpyAsync(dsrc + S.dev_off[i - b], src_base + src_off[i], src_len[i], cudaMemcpyHostToDevice, st));
+        }
+        CU_TRY(ctx, cudaMemsetAsync(d->ticket.p, 0, 64, st));
+        P.src_off = dv;
+        P.src_len = dv + n;
+        P.dst_off = dv + 2 * n;
+        P.dst_cap = dv + 3 * n;
+        P.out_len = dv + 4 * n;
+        P.consumed = dv + 5 * n;
+        P.status = reinterpret_cast<int32_t*>(dv + 6 * n);
+        P.n = uint32_t(n);
+        CU_TRY(ctx, launch_decode(P, d->sm_count, st));
+        ctx->launches++;
+        CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, 2 * n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (!size_only) {
+            if (D.span) {
+                uint64_t hi = 0;
+                for (size_t i = b; i < e; i++) hi = std::max(hi, dst_off[i] + dst_cap[i]);
+                if (hi > D.lo) CU_TRY(ctx, cudaMemcpyAsync(dst_base + D.lo, ddst, hi - D.lo, cudaMemcpyDeviceToHost, st));
+                CU_TRY(ctx, cudaStreamSynchronize(st));
+            } else {
+                CU_TRY(ctx, cudaStreamSynchronize(st));
+                for (size_t i = b; i < e; i++) {
+                    const uint64_t nbytes = std::min<uint64_t>(h[4 * n + (i - b)], dst_cap[i]);
+                    if (nbytes) CU_TRY(ctx, cudaMemcpyAsync(dst_base + dst_off[i], ddst + D.dev_off[i - b], nbytes, cudaMemcpyDeviceToHost, st));
+                }
+                CU_TRY(ctx, cudaStreamSynchronize(st));
+            }
         } else {
             CU_TRY(ctx, cudaStreamSynchronize(st));
-            for (size_t i = b; i < e; i++) {
-                const uint64_t nbytes = std::min<uint64_t>(h[4 * n + (i - b)], dst_cap[i]);
-                if (nbytes) CU_TRY(ctx, cudaMemcpyAsync(dst_base + dst_off[i], ddst + D.dev_off[i - b], nbytes, cudaMemcpyDeviceToHost, st));
-            }
-            CU_TRY(ctx, cudaStreamSynchronize(st));
         }
-    } else {
-        CU_TRY(ctx, cudaStreamSynchronize(st));
     }
     const int32_t* hs = reinterpret_cast<const int32_t*>(h + 6 * n);
     for (size_t i = 0; i < n; i++) {
@@ -470,7 +537,9 @@ aurora_ctx* aurora_init(uint32_t device_mask) {
         DeviceCtx* d = new DeviceCtx();
         d->dev = i;
         d->sm_count = prop.multiProcessorCount;
-        if (cudaSetDevice(i) != cudaSuccess || cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        if (cudaSetDevice(i) != cudaSuccess || cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d->s_out, cudaStreamNonBlocking) != cudaSuccess) {
             delete d;
             continue;
         }
@@ -495,6 +564,10 @@ void aurora_shutdown(aurora_ctx* ctx) {
         d->ticket.release();
         d->scratch.release();
         d->hdesc.release();
+        for (cudaEvent_t e : d->ev_in) cudaEventDestroy(e);
+        for (cudaEvent_t e : d->ev_k) cudaEventDestroy(e);
+        cudaStreamDestroy(d->s_in);
+        cudaStreamDestroy(d->s_out);
         cudaStreamDestroy(d->stream);
         delete d;
     }

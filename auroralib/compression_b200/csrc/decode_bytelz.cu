@@ -26,7 +26,7 @@ namespace {
 enum Kind { B_LZ4 = 0, B_LZ4_BLOCK = 1, B_SNAPPY = 2, B_SNAPPY_BLOCK = 3, B_LZO = 4, B_PRS = 5 };
 
 constexpr int kWarpsPerBlock = 16;
-constexpr int kSmemPerWarp = kInRing + 64;
+constexpr int kSmemPerWarp = kInStage + 64;
 
 // Output cursor on global memory.  `win_base` is the output position where the current LzWindows
 // instance was created: references before it read the (zero) pre-history of a fresh ring.
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) decode_bytelz_kernel(c
     const int warp = threadIdx.x >> 5;
     uint8_t* wbase = smem + size_t(warp) * kSmemPerWarp;
     InStream in;
-    in.init(wbase, reinterpret_cast<uint64_t*>(wbase + kInRing));
+    in.init(wbase, reinterpret_cast<uint64_t*>(wbase + kInStage));
     __syncwarp();
     fence_proxy_async();
     for (;;) {

@@ -34,6 +34,17 @@ constexpr int kRingMask = kRing - 1;
 constexpr int kWindow = 4096;        // largest back-reference distance of the family
 constexpr int kSubMax = 2048;        // output bytes resolved per sub-batch (ring keeps window + sub-batch + drain slack)
 constexpr int kFlush = 512;          // bytes per ring->HBM drain step (16 B per lane)
+constexpr int kQueue = 256;          // match descriptors per G32 iteration (32 groups x 8 tokens)
+constexpr int kSubMaxG = 2304;       // G32: output bytes per iteration (>= the largest single group)
+
+// ceil(2^20 / d): i mod d for the self-overlapping copy without an integer division (exact for i, d < 512)
+struct RcpTable {
+    uint32_t v[512];
+    constexpr RcpTable() : v() {
+        for (uint32_t d = 1; d < 512; ++d) v[d] = ((1u << 20) + d - 1) / d;
+    }
+};
+__constant__ RcpTable c_rcp = RcpTable();
 
 enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5 };
 
@@ -42,8 +53,10 @@ struct Traits {
     static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : 1;
     static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0) ? 273 : (K == K_LZSS) ? 258 : 65808;
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
-    static constexpr int kWarps = kStreams == 1 ? 11 : 8;   // x2 blocks per SM
-    static constexpr int kSmemPerWarp = kRing + kStreams * kInRing + 64;
+    static constexpr bool kG32 = (K == K_LZ10 || K == K_LZSS);   // one flag group per lane (256 tokens per iteration)
+    static constexpr int kQueueBytes = kG32 ? kQueue * 8 + 128 : 0;       // match queue + group offsets
+    static constexpr int kSmemPerWarp = kRing + kStreams * kInStage + kQueueBytes + 64;
+    static constexpr int kWarps = (113 * 1024 - kRing) / kSmemPerWarp;    // x2 blocks per SM (8 KiB ring-alignment slack per block)
 };
 
 // out[dst+i] = out[dst-d + (i mod d)], i < len : LzWindows.BackCopy (IO/LzWindows.cs:72-100) on the flat ring.
@@ -53,6 +66,12 @@ __device__ __forceinline__ void ring_copy_match(uint8_t* ring, uint32_t dstp, ui
     const uint32_t srcp = dstp - d;
     if (d >= len) {
         for (uint32_t i = lane; i < len; i += 32) ring[(dstp + i) & kRingMask] = ring[(srcp + i) & kRingMask];
+    } else if (len < 512) {
+        const uint32_t r = c_rcp.v[d];   // d < len < 512: uniform constant-bank load
+        for (uint32_t i = lane; i < len; i += 32) {
+            const uint32_t off = i - ((i * r) >> 20) * d;
+            ring[(dstp + i) & kRingMask] = ring[(srcp + off) & kRingMask];
+        }
     } else {
         for (uint32_t i = lane; i < len; i += 32) ring[(dstp + i) & kRingMask] = ring[(srcp + i % d) & kRingMask];
     }
@@ -60,6 +79,7 @@ __device__ __forceinline__ void ring_copy_match(uint8_t* ring, uint32_t dstp, ui
 
 struct OutState {
     uint8_t* ring;
+    uint32_t rbase;    // shared address of the ring (8 KiB aligned)
     uint8_t* dst;
     uint32_t limit;    // bytes of the destination that may be written
     uint32_t flushed;  // output position drained to HBM so far (multiple of kFlush)
@@ -323,6 +343,245 @@ __device__ BodyResult decode_body(InStream* in, OutState& out, const uint32_t sl
     return BodyResult{status, written, consumed};
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// G32 token core for the fixed-token-size interleaved formats (LZ10, LZSS): one flag GROUP per lane, i.e. up to
+// 256 tokens per warp iteration.  The only serial part is the chain of 32 flag bytes (p += 9 + popc(matches));
+// every lane then sizes its own 8 tokens, one packed warp scan gives output bases and match-queue slots, literals
+// are scattered lane-locally and the matches of all groups are replayed in stream order from a shared-memory queue.
+// All shared-memory traffic uses 32-bit shared addresses; the output ring is 8 KiB aligned, so the wrapped
+// address (pos & mask) | base is a single LOP3.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
+// one queued match: out[pos + i] = out[pos - d + (i mod d)], i < len, on the 8 KiB aligned ring at shared address rb
+template <bool kShort>   // kShort: len <= 32 guaranteed (LZ10: 18)
+__device__ __forceinline__ void ring_copy_queued(uint32_t rb, uint32_t pos, uint32_t d, uint32_t len) {
+    const uint32_t lane = lane_id();
+    const uint32_t srcp = pos - d;
+    if (d >= len) {
+        if (kShort) {
+            if (lane < len) sts_u8(((pos + lane) & kRingMask) | rb, lds_u8(((srcp + lane) & kRingMask) | rb));
+        } else {
+            for (uint32_t i = lane; i < len; i += 32) sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + i) & kRingMask) | rb));
+        }
+    } else {
+        const uint32_t r = c_rcp.v[d & 511];   // d < len <= 273: uniform constant-bank load
+        if (kShort) {
+            if (lane < len) {
+                const uint32_t off = lane - ((lane * r) >> 20) * d;
+                sts_u8(((pos + lane) & kRingMask) | rb, lds_u8(((srcp + off) & kRingMask) | rb));
+            }
+        } else {
+            for (uint32_t i = lane; i < len; i += 32) {
+                const uint32_t off = i - ((i * r) >> 20) * d;
+                sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + off) & kRingMask) | rb));
+            }
+        }
+    }
+}
+
+template <int K>
+__device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_t qaddr, const uint32_t gaddr, const uint32_t slen,
+                                      const uint32_t size, const uint32_t body_off, const LzssParams& lz) {
+    const uint32_t lane = lane_id();
+    const uint32_t rb = out.rbase;
+    uint32_t written = 0, cur = body_off, consumed = body_off;
+    int status = AURORA_OK;
+    const uint32_t lmask = (1u << lz.length_bits) - 1u;
+    constexpr bool kShort = (K == K_LZ10);
+
+    while (written < size) {
+        in[0].ensure(cur, kInMirror - 16);
+        const uint32_t wa = smem_u32(in[0].window(cur));
+        // ---- chain of 32 group starts; bounded by 32 * 17 = 544 < kInMirror for any data
+        uint32_t ca = wa;
+#pragma unroll
+        for (int g = 0; g < 32; g++) {
+            sts_u32(gaddr + 4 * g, ca);
+            const uint32_t f = lds_u8(ca);
+            ca = ca + 9 + __popc((K == K_LZ10) ? f : (f ^ 0xFFu));
+        }
+        const uint32_t chain_end = ca - wa;
+        __syncwarp();
+        const uint32_t mya = lds_u32(gaddr + 4 * lane);
+        const uint32_t myrel = mya - wa;
+        const uint32_t f = lds_u8(mya);
+        const uint32_t m = (K == K_LZ10) ? f : (f ^ 0xFFu);   // match bits in wire bit order
+
+        // ---- pass 1: sizes of my 8 tokens
+        uint32_t b1v[8], orel[8];
+        uint32_t gsize = 0;
+        {
+            uint32_t a = mya + 1;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
+                const uint32_t b1 = lds_u8(a);
+                b1v[j] = b1;
+                orel[j] = gsize;
+                uint32_t len;
+                if (K == K_LZ10) len = ism ? (b1 >> 4) + 3 : 1;
+                else len = ism ? (lds_u8(a + 1) & lmask) + uint32_t(lz.min_length) : 1;
+                gsize += len;
+                a += ism ? 2 : 1;
+            }
+        }
+        const uint32_t nm = __popc(m);
+        const uint32_t incl = warp_incl_scan(gsize | (nm << 20));
+        const uint32_t gincl = incl & 0xFFFFFu, gexcl = gincl - gsize;
+        const uint32_t qexcl = (incl >> 20) - nm;
+        const uint32_t remaining = size - written;
+        const uint32_t all = __shfl_sync(kFull, incl, 31);
+        const uint32_t total_all = all & 0xFFFFFu;
+        const uint32_t gbase = written + gexcl;
+        uint32_t total, nq, nlan;
+
+        if (total_all <= min(remaining, uint32_t(kSubMaxG)) && cur + chain_end <= slen) {
+            // ---- fast path: all 256 tokens execute
+            uint32_t a = mya + 1, qa = qaddr + 8 * qexcl;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
+                const uint32_t pos = gbase + orel[j];
+                if (!ism) {
+                    sts_u8((pos & kRingMask) | rb, b1v[j]);
+                } else {
+                    const uint32_t b1 = b1v[j], b2 = lds_u8(a + 1);
+                    uint32_t len, dist;
+                    if (K == K_LZ10) {
+                        len = (b1 >> 4) + 3;
+                        dist = (((b1 & 0xF) << 8) | b2) + 1;
+                    } else {
+                        len = (b2 & lmask) + uint32_t(lz.min_length);
+                        const uint32_t raw = ((b2 >> lz.length_bits) << 8) | b1;
+                        const uint32_t ring_len = 1u << lz.windows_bits;
+                        const uint32_t offset = (uint32_t(lz.max_distance) + raw - uint32_t(lz.windows_start)) & uint32_t(lz.max_distance - 1);
+                        const uint32_t rp = pos & (ring_len - 1);
+                        dist = rp >= offset ? rp - offset : rp - offset + ring_len;
+                        if (dist == 0) dist = ring_len;
+                    }
+                    sts_u64(qa, pos, len | (dist << 16));
+                    qa += 8;
+                }
+                a += ism ? 2 : 1;
+            }
+            total = total_all;
+            nq = all >> 20;
+            nlan = 32;
+            consumed = cur + chain_end;
+        } else {
+            // ---- slow path (end of the output, end of the input, or an oversized iteration): cut token by token
+            const bool taken = gexcl < remaining && gincl <= uint32_t(kSubMaxG);
+            const uint32_t lim = remaining - gexcl;   // only meaningful when taken
+            uint32_t jexec = 0;
+            bool eos_here = false;
+            {
+                const uint32_t gabs = cur + myrel;   // blob offset of my flag byte
+                uint32_t a = gabs + 1;
+                bool stop = false;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
+                    const uint32_t tend = a + (ism ? 2 : 1);
+                    const bool want = orel[j] < lim;
+                    const bool bad = gabs >= slen || tend > slen;
+                    if (!stop && want && bad) eos_here = true;
+                    stop = stop || !want || bad;
+                    if (!stop) jexec = j + 1;
+                    a = tend;
+                }
+            }
+            if (!taken) {
+                jexec = 0;
+                eos_here = false;
+            }
+            const uint32_t eosmask = __ballot_sync(kFull, eos_here);
+            if (eosmask) {
+                const uint32_t gb = __ffs(eosmask) - 1;
+                if (lane > gb) jexec = 0;
+                status = AURORA_END_OF_STREAM;
+            }
+            nlan = __popc(__ballot_sync(kFull, jexec > 0));   // a prefix of the lanes
+            if (nlan == 0) break;
+            const uint32_t last = nlan - 1;
+            uint32_t oend = 0, qi = qexcl, aend = 0;
+            {
+                uint32_t a = mya + 1;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
+                    const bool e = uint32_t(j) < jexec;
+                    const uint32_t pos = gbase + orel[j];
+                    const uint32_t next_o = (j == 7) ? gsize : orel[(j + 1) & 7];
+                    if (e && !ism) sts_u8((pos & kRingMask) | rb, b1v[j]);
+                    if (e && ism) {
+                        const uint32_t b1 = b1v[j], b2 = lds_u8(a + 1);
+                        uint32_t len, dist;
+                        if (K == K_LZ10) {
+                            len = (b1 >> 4) + 3;
+                            dist = (((b1 & 0xF) << 8) | b2) + 1;
+                        } else {
+                            len = (b2 & lmask) + uint32_t(lz.min_length);
+                            const uint32_t raw = ((b2 >> lz.length_bits) << 8) | b1;
+                            const uint32_t ring_len = 1u << lz.windows_bits;
+                            const uint32_t offset = (uint32_t(lz.max_distance) + raw - uint32_t(lz.windows_start)) & uint32_t(lz.max_distance - 1);
+                            const uint32_t rp = pos & (ring_len - 1);
+                            dist = rp >= offset ? rp - offset : rp - offset + ring_len;
+                            if (dist == 0) dist = ring_len;
+                        }
+                        sts_u64(qaddr + 8 * qi, pos, len | (dist << 16));
+                        qi++;
+                    }
+                    a += ism ? 2 : 1;
+                    if (e) {
+                        oend = next_o;
+                        aend = a - wa;
+                    }
+                }
+            }
+            total = __shfl_sync(kFull, gexcl + oend, last);
+            nq = __shfl_sync(kFull, qi, last);
+            consumed = cur + __shfl_sync(kFull, aend, last);
+        }
+        __syncwarp();
+        // ---- matches, in stream order
+        for (uint32_t q = 0; q < nq; q++) {
+            const uint2 e = lds_u64(qaddr + 8 * q);
+            ring_copy_queued<kShort>(rb, e.x, e.y >> 16, e.y & 0xFFFFu);
+            __syncwarp();
+        }
+        out.drain(written + total);
+        written += total;
+        if (status != AURORA_OK) break;
+        cur += (nlan == 32) ? chain_end : __shfl_sync(kFull, myrel, nlan & 31);
+    }
+    out.finish(written);
+    if (status == AURORA_OK) {
+        if (K == K_LZSS ? written != size : written > size) status = AURORA_SIZE_MISMATCH;
+    }
+    return BodyResult{status, written, consumed};
+}
+
 // pre-history of the window: zeros (LzWindows.cs:53 rents an uncleared array) or LZSS initialFill
 __device__ __forceinline__ void ring_prefill(uint8_t* ring, uint32_t fill) {
     const uint32_t w = fill * 0x01010101u;
@@ -333,7 +592,7 @@ __device__ __forceinline__ void ring_prefill(uint8_t* ring, uint32_t fill) {
 }
 
 template <int K>
-__device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in, uint8_t* ring) {
+__device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in, uint8_t* ring, uint32_t qaddr, uint32_t gaddr) {
     const uint32_t lane = lane_id();
     const uint8_t* src = P.src_base + P.src_off[idx];
     const uint64_t slen64 = P.src_len[idx];
@@ -415,6 +674,7 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                 ring_prefill(ring, K == K_LZSS ? uint32_t(P.lzss.initial_fill) & 0xFFu : 0u);
                 OutState out;
                 out.ring = ring;
+                out.rbase = smem_u32(ring);
                 out.dst = dst;
                 out.limit = uint32_t(min(uint64_t(0xFFFFFFFFu), cap));
                 out.flushed = 0;
@@ -426,7 +686,15 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                 } else {
                     in[0].begin(P.src_base, P.src_limit, src);
                 }
-                const BodyResult r = decode_body<K>(in, out, slen, size, body_off, comp_off, lit_off, P.lzss);
+                BodyResult r;
+                bool g32 = Traits<K>::kG32;
+                if (K == K_LZSS) g32 = 8u * (((1u << P.lzss.length_bits) - 1u) + uint32_t(P.lzss.min_length)) <= uint32_t(kSubMaxG);
+                if constexpr (Traits<K>::kG32) {
+                    if (g32) r = decode_body_g32<K>(in, out, qaddr, gaddr, slen, size, body_off, P.lzss);
+                    else r = decode_body<K>(in, out, slen, size, body_off, comp_off, lit_off, P.lzss);
+                } else {
+                    r = decode_body<K>(in, out, slen, size, body_off, comp_off, lit_off, P.lzss);
+                }
                 status = r.status;
                 written = r.written;
                 consumed = r.consumed;
@@ -450,12 +718,17 @@ template <int K>
 __global__ void __launch_bounds__(Traits<K>::kWarps * 32, 2) decode_flaglz_kernel(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
-    uint8_t* wbase = smem + size_t(warp) * Traits<K>::kSmemPerWarp;
-    uint8_t* ring = wbase;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + kRing + Traits<K>::kStreams * kInRing);
+    // rings first, 8 KiB aligned in the shared window (wrapped ring addresses become one LOP3); the launcher adds 8 KiB of slack
+    const uint32_t s0 = smem_u32(smem);
+    uint8_t* aligned = smem + (((s0 + kRing - 1) & ~uint32_t(kRing - 1)) - s0);
+    uint8_t* ring = aligned + size_t(warp) * kRing;
+    uint8_t* wbase = aligned + size_t(Traits<K>::kWarps) * kRing + size_t(warp) * (Traits<K>::kSmemPerWarp - kRing);
+    uint8_t* qbase = wbase + Traits<K>::kStreams * kInStage;
+    const uint32_t qaddr = smem_u32(qbase), gaddr = qaddr + kQueue * 8;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qbase + Traits<K>::kQueueBytes);
     InStream in[Traits<K>::kStreams];
 #pragma unroll
-    for (int s = 0; s < Traits<K>::kStreams; s++) in[s].init(wbase + kRing + s * kInRing, bars + 2 * s);
+    for (int s = 0; s < Traits<K>::kStreams; s++) in[s].init(wbase + s * kInStage, bars + 2 * s);
     __syncwarp();
     fence_proxy_async();
 
@@ -465,7 +738,7 @@ __global__ void __launch_bounds__(Traits<K>::kWarps * 32, 2) decode_flaglz_kerne
         t = __shfl_sync(kFull, t, 0);
         if (t >= P.n) break;
         const uint32_t idx = P.order ? P.order[t] : t;
-        decode_stream<K>(P, idx, in, ring);
+        decode_stream<K>(P, idx, in, ring, qaddr, gaddr);
     }
 #pragma unroll
     for (int s = 0; s < Traits<K>::kStreams; s++) in[s].drain_inflight();
@@ -474,7 +747,7 @@ __global__ void __launch_bounds__(Traits<K>::kWarps * 32, 2) decode_flaglz_kerne
 template <int K>
 cudaError_t launch(const DecodeParams& p, int sm_count, cudaStream_t st) {
     const int threads = Traits<K>::kWarps * 32;
-    const size_t smem = size_t(Traits<K>::kWarps) * Traits<K>::kSmemPerWarp;
+    const size_t smem = size_t(Traits<K>::kWarps) * Traits<K>::kSmemPerWarp + kRing;   // + alignment slack for the rings
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -8,6 +8,8 @@ constexpr int kInChunk = 1024;       // TMA bulk chunk
 constexpr int kInRing = 2 * kInChunk;
 constexpr int kInMask = kInRing - 1;
 constexpr int kLookahead = 192;      // input bytes one parse step may touch past its cursor
+constexpr int kInMirror = 640;       // copy of slot 0's head behind the ring: any window of <= 640 bytes is contiguous
+constexpr int kInStage = kInRing + kInMirror;   // shared-memory bytes of one staged sub-stream
 
 // ---------------------------------------------------------------------------------------------
 // TMA-staged input sub-stream: a 2 x 1 KiB shared-memory ring filled by cp.async.bulk (1-D TMA) with one
@@ -74,8 +76,10 @@ struct InStream {
                 for (uint32_t c = cend; c < want; c++) {
                     const uint32_t k = kbase + (c - cbase);
                     const uint32_t bytes = min(uint32_t(kInChunk), glimit - c * kInChunk);
-                    mbar_expect_tx(&bar[k & 1], bytes);
+                    const uint32_t mir = (k & 1) ? 0u : min(bytes, uint32_t(kInMirror));
+                    mbar_expect_tx(&bar[k & 1], bytes + mir);
                     tma_bulk_g2s(ring + (k & 1) * kInChunk, gbase + size_t(c) * kInChunk, bytes, &bar[k & 1]);
+                    if (mir) tma_bulk_g2s(ring + kInRing, gbase + size_t(c) * kInChunk, mir, &bar[k & 1]);
                 }
             }
             issued += want - cend;
@@ -90,6 +94,8 @@ struct InStream {
         }
     }
     __device__ __forceinline__ uint32_t at(uint32_t pos) const { return ring[(pos + rbias) & kInMask]; }
+    // pointer to relative byte `pos`, contiguous for kInMirror bytes (after ensure(pos, <= kInMirror))
+    __device__ __forceinline__ const uint8_t* window(uint32_t pos) const { return ring + ((pos + rbias) & kInMask); }
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
