@@ -54,7 +54,7 @@ struct Traits {
     static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0) ? 273 : (K == K_LZSS) ? 258 : 65808;
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
     static constexpr bool kG32 = (K == K_LZ10 || K == K_LZSS);   // one flag group per lane (256 tokens per iteration)
-    static constexpr int kQueueBytes = kG32 ? kQueue * 8 + 128 : 0;       // match queue + group offsets
+    static constexpr int kQueueBytes = kG32 ? kQueue * 8 + 256 : 0;       // match queue + group offsets / group descriptors
     static constexpr int kSmemPerWarp = kRing + kStreams * kInStage + kQueueBytes + 64;
     static constexpr int kWarps = (113 * 1024 - kRing) / kSmemPerWarp;    // x2 blocks per SM (8 KiB ring-alignment slack per block)
 };
@@ -400,6 +400,66 @@ __device__ __forceinline__ void ring_copy_queued(uint32_t rb, uint32_t pos, uint
     }
 }
 
+
+// Replays the queued matches of one iteration in stream order.  Entries are {pos, len | d << 16}.
+// Run merging: encoders split a long run (or a 32-byte tile) into maximum-length matches with the same distance that
+// follow each other without a gap; such a chain is exactly one longer periodic copy out[o] = out[o - d].  A parallel
+// post-pass (one entry per lane, chains cut at 32-entry blocks) compacts every chain into one entry in place, then the
+// replay is a plain loop with the next entry prefetched.
+// (A variant that ran hazard-free groups of four independent matches as one warp step was measured slower.)
+__device__ __forceinline__ void ring_copy_any(uint32_t rb, uint32_t pos, uint32_t d, uint32_t len) {
+    const uint32_t lane = lane_id();
+    const uint32_t srcp = pos - d;
+    if (len <= 32) {
+        if (lane < len) {
+            uint32_t off = lane;
+            if (d < len) off = lane - ((lane * c_rcp.v[d]) >> 20) * d;
+            sts_u8(((pos + lane) & kRingMask) | rb, lds_u8(((srcp + off) & kRingMask) | rb));
+        }
+    } else if (d >= len) {
+        for (uint32_t i = lane; i < len; i += 32) sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + i) & kRingMask) | rb));
+    } else if (len < 512) {
+        const uint32_t r = c_rcp.v[d];
+        for (uint32_t i = lane; i < len; i += 32) {
+            const uint32_t off = i - ((i * r) >> 20) * d;
+            sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + off) & kRingMask) | rb));
+        }
+    } else {
+        for (uint32_t i = lane; i < len; i += 32) sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + i % d) & kRingMask) | rb));
+    }
+}
+
+__device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint32_t nq) {
+    const uint32_t lane = lane_id();
+    if (nq == 0) return;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t nout = 0;
+    for (uint32_t base = 0; base < nq; base += 32) {
+        const uint32_t q = base + lane;
+        const bool have = q < nq;
+        const uint2 e = lds_u64(qaddr + 8 * q);
+        const uint32_t px = __shfl_up_sync(kFull, e.x, 1), py = __shfl_up_sync(kFull, e.y, 1);
+        const bool cont = have && lane > 0 && e.x == px + (py & 0xFFFFu) && (e.y >> 16) == (py >> 16);
+        const uint32_t heads = __ballot_sync(kFull, have && !cont);
+        const uint32_t valid = __ballot_sync(kFull, have);
+        // last entry of my chain: the lane before the next head (or the last valid lane of the block)
+        const uint32_t after = heads & ~lt & ~(1u << lane);
+        const uint32_t last = after ? uint32_t(__ffs(after) - 2) : uint32_t(31 - __clz(valid));
+        const uint32_t tx = __shfl_sync(kFull, e.x, last & 31), ty = __shfl_sync(kFull, e.y, last & 31);
+        __syncwarp();
+        if (have && !cont) sts_u64(qaddr + 8 * (nout + __popc(heads & lt)), e.x, (tx + (ty & 0xFFFFu) - e.x) | (e.y & 0xFFFF0000u));
+        nout += __popc(heads);
+    }
+    __syncwarp();
+    uint2 e = lds_u64(qaddr);
+    for (uint32_t q = 0; q < nout; q++) {
+        const uint2 nx = lds_u64(qaddr + 8 * (q + 1));   // one slot past the end is readable (slack behind the queue)
+        ring_copy_any(rb, e.x, e.y >> 16, e.y & 0xFFFFu);
+        __syncwarp();
+        e = nx;
+    }
+}
+
 template <int K>
 __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_t qaddr, const uint32_t gaddr, const uint32_t slen,
                                       const uint32_t size, const uint32_t body_off, const LzssParams& lz) {
@@ -564,12 +624,7 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
             consumed = cur + __shfl_sync(kFull, aend, last);
         }
         __syncwarp();
-        // ---- matches, in stream order
-        for (uint32_t q = 0; q < nq; q++) {
-            const uint2 e = lds_u64(qaddr + 8 * q);
-            ring_copy_queued<kShort>(rb, e.x, e.y >> 16, e.y & 0xFFFFu);
-            __syncwarp();
-        }
+        replay_matches(rb, qaddr, nq);
         out.drain(written + total);
         written += total;
         if (status != AURORA_OK) break;
