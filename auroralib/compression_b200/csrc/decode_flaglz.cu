@@ -53,7 +53,7 @@ struct Traits {
     static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : 1;
     static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0) ? 273 : (K == K_LZSS) ? 258 : 65808;
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
-    static constexpr bool kG32 = (K == K_LZ10 || K == K_LZSS);   // one flag group per lane (256 tokens per iteration)
+    static constexpr bool kG32 = (K == K_LZ10 || K == K_LZSS || K == K_YAZ0);   // one flag group per lane (256 tokens per iteration)
     static constexpr int kQueueBytes = kG32 ? kQueue * 8 + 256 : 0;       // match queue + group offsets / group descriptors
     static constexpr int kSmemPerWarp = kRing + kStreams * kInStage + kQueueBytes + 64;
     static constexpr int kWarps = (113 * 1024 - kRing) / kSmemPerWarp;    // x2 blocks per SM (8 KiB ring-alignment slack per block)
@@ -637,6 +637,157 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
     return BodyResult{status, written, consumed};
 }
 
+// ---------------------------------------------------------------------------------------------
+// G32 core for Yaz0/Yaz1 (Yay0.cs:110-144 through Yaz0.cs:91-92).  A match token is 2 bytes, or 3 when the high nibble
+// of its first byte is 0, so a group's size depends on its own data and the chain of group starts cannot be a pure
+// popcount chain.  The chain is still the only serial part: per group the warp loads the flag byte, builds a ballot mask
+// E of "high nibble == 0" over the group's next 32 bytes, and walks only the MATCH tokens of the group (highest flag bit
+// first) accumulating the number of 3-byte tokens: token i starts at 1 + i + matches_before + ext_before, and its
+// ext bit is E[that offset - 1].  About 14 + 11 * matches instructions per group; everything else is lane-parallel.
+// (A fixed-point iteration over guessed group starts was tried first; on data with many long matches it needs one
+// round per group and was slower.)
+// ---------------------------------------------------------------------------------------------
+__device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const uint32_t qaddr, const uint32_t gaddr, const uint32_t slen,
+                                           const uint32_t size, const uint32_t body_off) {
+    const uint32_t lane = lane_id();
+    const uint32_t rb = out.rbase;
+    uint32_t written = 0, cur = body_off, consumed = body_off;
+    int status = AURORA_OK;
+
+    while (written < size) {
+        in[0].ensure(cur, kInMirror - 16);
+        const uint32_t wa = smem_u32(in[0].window(cur));
+        const uint32_t wlimit = kInMirror - 40;   // a group may start in the first 600 bytes of the window (it is <= 25 bytes)
+        // ---- exact chain of group starts
+        uint32_t ca = wa, nvalid = 0;
+#pragma unroll 1
+        for (int g = 0; g < 32; g++) {
+            if (ca - wa > wlimit) break;
+            sts_u32(gaddr + 4 * g, ca);
+            const uint32_t fb = lds_u8(ca);
+            const uint32_t E = __ballot_sync(kFull, (lds_u8(ca + 1 + lane) >> 4) == 0);
+            uint32_t mm = fb ^ 0xFFu, x = 0, cnt = 0;
+            while (mm) {
+                const uint32_t hb = 31 - __clz(mm);
+                x += (E >> (7 - hb + cnt + x)) & 1u;
+                cnt++;
+                mm ^= 1u << hb;
+            }
+            ca += 9 + cnt + x;
+            nvalid = g + 1;
+        }
+        __syncwarp();
+        const bool valid = lane < nvalid;
+        const uint32_t mya = valid ? lds_u32(gaddr + 4 * lane) : wa;
+        const uint32_t myrel = mya - wa;
+
+        // ---- pass 1: my 8 tokens
+        uint32_t b1v[8], lenv[8], orel[8];
+        uint32_t gsize = 0, gin;
+        const uint32_t f = lds_u8(mya);
+        {
+            uint32_t a = mya + 1;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool lit = (f >> (7 - j)) & 1;
+                const uint32_t b1 = lds_u8(a);
+                const uint32_t n = b1 >> 4;
+                const bool ext = !lit && n == 0;
+                const uint32_t b3 = lds_u8(a + 2);
+                b1v[j] = b1;
+                orel[j] = gsize;
+                lenv[j] = lit ? 1u : (ext ? b3 + 0x12u : n + 2u);
+                gsize += lenv[j];
+                a += lit ? 1u : (ext ? 3u : 2u);
+            }
+            gin = a - mya;
+        }
+        const uint32_t nm = __popc(f ^ 0xFFu);
+        const uint32_t incl = warp_incl_scan(valid ? (gsize | (nm << 20)) : 0u);
+        const uint32_t gincl = incl & 0xFFFFFu, gexcl = gincl - (valid ? gsize : 0u);
+        const uint32_t qexcl = (incl >> 20) - (valid ? nm : 0u);
+        const uint32_t remaining = size - written;
+        const uint32_t gbase = written + gexcl;
+        // ---- which of my tokens execute (end of output, end of input, iteration byte budget)
+        const bool taken = valid && gexcl < remaining && gincl <= uint32_t(kSubMaxG);
+        const uint32_t lim = remaining - gexcl;
+        uint32_t jexec = 0;
+        bool eos_here = false;
+        {
+            const uint32_t gabs = cur + myrel;
+            uint32_t a = gabs + 1;
+            bool stop = false;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool lit = (f >> (7 - j)) & 1;
+                const bool ext = !lit && (b1v[j] >> 4) == 0;
+                const uint32_t need = a + (lit ? 1u : 2u);   // the extended-length byte is optional (ReadByte)
+                const bool want = orel[j] < lim;
+                const bool bad = gabs >= slen || need > slen;
+                if (!stop && want && bad) eos_here = true;
+                stop = stop || !want || bad;
+                if (!stop) jexec = j + 1;
+                a = need + (ext ? 1u : 0u);
+            }
+        }
+        if (!taken) {
+            jexec = 0;
+            eos_here = false;
+        }
+        const uint32_t eosmask = __ballot_sync(kFull, eos_here);
+        if (eosmask) {
+            const uint32_t gb = __ffs(eosmask) - 1;
+            if (lane > gb) jexec = 0;
+            status = AURORA_END_OF_STREAM;
+        }
+        const uint32_t nlan = __popc(__ballot_sync(kFull, jexec > 0));
+        if (nlan == 0) break;
+        const uint32_t last = nlan - 1;
+        uint32_t oend = 0, qi = qexcl, aend = 0;
+        {
+            uint32_t a = mya + 1;
+            const uint32_t gabs1 = cur + myrel + 1;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool lit = (f >> (7 - j)) & 1;
+                const bool e = uint32_t(j) < jexec;
+                const uint32_t b1 = b1v[j];
+                const bool ext = !lit && (b1 >> 4) == 0;
+                const uint32_t pos = gbase + orel[j];
+                uint32_t len = lenv[j];
+                const uint32_t tabs = gabs1 + (a - (mya + 1));   // blob offset of this token
+                const bool have_ext = tabs + 2 < slen;
+                if (ext && !have_ext) len = 0x11;   // Stream.ReadByte() == -1 at EOF (Yay0.cs:131)
+                if (e && lit) sts_u8((pos & kRingMask) | rb, b1);
+                if (e && !lit) {
+                    const uint32_t b2 = lds_u8(a + 1);
+                    sts_u64(qaddr + 8 * qi, pos, len | (((((b1 & 0xF) << 8) | b2) + 1) << 16));
+                    qi++;
+                }
+                a += lit ? 1u : ((ext && have_ext) ? 3u : 2u);
+                if (e) {
+                    oend = orel[j] + len;
+                    aend = a - wa;
+                }
+            }
+        }
+        const uint32_t total = __shfl_sync(kFull, gexcl + oend, last);
+        const uint32_t nq = __shfl_sync(kFull, qi, last);
+        consumed = cur + __shfl_sync(kFull, aend, last);
+        __syncwarp();
+        replay_matches(rb, qaddr, nq);
+        out.drain(written + total);
+        written += total;
+        if (status != AURORA_OK) break;
+        // resume at the first group that was not executed (its start is exact: it follows exact groups)
+        const uint32_t next_rel = __shfl_sync(kFull, myrel + gin, last);
+        cur += next_rel;
+    }
+    out.finish(written);
+    if (status == AURORA_OK && written > size) status = AURORA_SIZE_MISMATCH;
+    return BodyResult{status, written, consumed};
+}
+
 // pre-history of the window: zeros (LzWindows.cs:53 rents an uncleared array) or LZSS initialFill
 __device__ __forceinline__ void ring_prefill(uint8_t* ring, uint32_t fill) {
     const uint32_t w = fill * 0x01010101u;
@@ -744,7 +895,9 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                 BodyResult r;
                 bool g32 = Traits<K>::kG32;
                 if (K == K_LZSS) g32 = 8u * (((1u << P.lzss.length_bits) - 1u) + uint32_t(P.lzss.min_length)) <= uint32_t(kSubMaxG);
-                if constexpr (Traits<K>::kG32) {
+                if constexpr (K == K_YAZ0) {
+                    r = decode_body_g32_yaz0(in, out, qaddr, gaddr, slen, size, body_off);
+                } else if constexpr (Traits<K>::kG32) {
                     if (g32) r = decode_body_g32<K>(in, out, qaddr, gaddr, slen, size, body_off, P.lzss);
                     else r = decode_body<K>(in, out, slen, size, body_off, comp_off, lit_off, P.lzss);
                 } else {
