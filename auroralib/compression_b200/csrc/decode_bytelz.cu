@@ -25,51 +25,131 @@ namespace {
 
 enum Kind { B_LZ4 = 0, B_LZ4_BLOCK = 1, B_SNAPPY = 2, B_SNAPPY_BLOCK = 3, B_LZO = 4, B_PRS = 5 };
 
-constexpr int kWarpsPerBlock = 16;
-constexpr int kSmemPerWarp = kInStage + 64;
+constexpr int kORing = 2048;            // per-warp output ring: the most recent decoded bytes stay in shared memory
+//           // per-warp output ring: the most recent decoded bytes stay in shared memory
+constexpr int kORingMask = kORing - 1;
+constexpr int kOKeep = 1024;            // back-references reaching at most this far are served from the ring
+constexpr int kOPiece = 512;            // bytes per copy step / drain step
+constexpr int kSmemPerWarp = kORing + kInStage + 64;
+constexpr int kWarpsPerBlock = 23;      // x2 blocks per SM = 46 warps (latency bound: occupancy beats registers; measured)
+                                        // leaves ~70 KiB of L1 for the far back-references (measured best: profiles/)
 
-// Output cursor on global memory.  `win_base` is the output position where the current LzWindows
-// instance was created: references before it read the (zero) pre-history of a fresh ring.
+// Output cursor.  Decoded bytes are produced into an 8 KiB shared-memory ring (8 KiB aligned, so the wrapped address
+// is one LOP3) and drained to HBM in 512-byte steps with 16-byte vector stores; a back-reference is served from the
+// ring when it reaches at most kOKeep bytes back and from global memory (already drained) otherwise, so the common
+// short-distance copies never wait for an HBM/L2 round trip.  `win_base` is the output position where the current
+// LzWindows instance was created: references before it read the (zero) pre-history of a fresh ring.
 struct GOut {
     uint8_t* dst;
     uint64_t cap;
+    uint32_t rb;         // shared address of the ring
     uint32_t written;
+    uint32_t flushed;    // multiple of kOPiece
     uint32_t win_base;
-    uint32_t ring_len;
+    uint32_t ring_len;   // the reference's window size (BackCopy(0, n) semantics)
     bool size_only;
+    bool aligned;
 
+    __device__ __forceinline__ void drain() {
+        const uint32_t lane = lane_id();
+        while (written - flushed >= uint32_t(kOPiece)) {
+            const uint64_t end = uint64_t(flushed) + kOPiece;
+            if (end <= cap && aligned) {
+                uint4 v;
+                const uint32_t a = ((flushed + lane * 16) & kORingMask) | rb;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+                *reinterpret_cast<uint4*>(dst + flushed + lane * 16) = v;
+            } else {
+                for (uint32_t i = lane; i < uint32_t(kOPiece); i += 32)
+                    if (uint64_t(flushed) + i < cap) dst[flushed + i] = uint8_t(lds_u8(((flushed + i) & kORingMask) | rb));
+            }
+            flushed += kOPiece;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        const uint32_t lane = lane_id();
+        drain();
+        for (uint32_t p = flushed + lane; p < written; p += 32)
+            if (uint64_t(p) < cap) dst[p] = uint8_t(lds_u8((p & kORingMask) | rb));
+        flushed = written;
+    }
     // LzWindows.Write / CopyFrom: `len` bytes from the staged input at relative position ipos
     __device__ __forceinline__ void lit_copy(InStream& in, uint32_t ipos, uint32_t len) {
         const uint32_t lane = lane_id();
         uint32_t done = 0;
         while (done < len) {
-            const uint32_t piece = min(len - done, 512u);
+            const uint32_t piece = min(len - done, uint32_t(kOPiece));
             in.ensure(ipos + done, piece);
-            for (uint32_t i = lane; i < piece; i += 32) {
-                const uint64_t o = uint64_t(written) + done + i;
-                const uint32_t v = in.at(ipos + done + i);
-                if (o < cap) dst[o] = uint8_t(v);
-            }
+            const uint32_t wa = smem_u32(in.window(ipos + done));
+            for (uint32_t i = lane; i < piece; i += 32) sts_u8(((written + i) & kORingMask) | rb, lds_u8(wa + i));
+            written += piece;
             done += piece;
+            __syncwarp();
+            drain();
         }
-        written += len;
-        __syncwarp();
     }
-    // LzWindows.BackCopy(distance, length) on the flat output
+    // LzWindows.BackCopy(distance, length): out[o] = out[o - d], realised as out[dst+i] = out[dst-d + (i mod d)] per piece
     __device__ __forceinline__ void match_copy(uint32_t d, uint32_t len) {
         const uint32_t lane = lane_id();
         if (d == 0) d = ring_len;   // BackCopy(0, n) re-reads the ring slot it writes: one window back
-        const int64_t srcp = int64_t(written) - int64_t(d);
-        const bool wrap = d < len;
-        for (uint32_t i = lane; i < len; i += 32) {
-            const int64_t s = srcp + (wrap ? i % d : i);
-            uint8_t v = 0;
-            if (s >= int64_t(win_base) && uint64_t(s) < cap) v = dst[s];
-            const uint64_t o = uint64_t(written) + i;
-            if (o < cap) dst[o] = v;
+        uint32_t done = 0;
+        while (done < len) {
+            const uint32_t piece = min(len - done, uint32_t(kOPiece));
+            const uint32_t base = written;
+            const int32_t srcp = int32_t(base) - int32_t(d);
+            const bool wrap = d < piece;                      // then d < 512: reciprocal table applies
+            const uint32_t r = wrap ? c_rcp.v[d & 511] : 0u;
+            const bool near = d <= uint32_t(kOKeep);
+            for (uint32_t i = lane; i < piece; i += 32) {
+                const uint32_t off = i - ((i * r) >> 20) * d;   // i mod d when wrapping, i otherwise (r == 0)
+                const int32_t s = srcp + int32_t(off);
+                uint32_t v = 0;
+                if (s >= int32_t(win_base)) {
+                    if (near) v = lds_u8((uint32_t(s) & kORingMask) | rb);
+                    else if (uint64_t(s) < cap) v = dst[s];
+                }
+                sts_u8(((base + i) & kORingMask) | rb, v);
+            }
+            written += piece;
+            done += piece;
+            __syncwarp();
+            drain();
         }
-        written += len;
+    }
+    // One short LZ4 sequence (lit + mlen <= 32) as a single warp step: lanes [0, lit) copy the literals from the staged
+    // input, lanes [lit, lit + mlen) copy the match, when the match source lies entirely before this sequence's
+    // literals (otherwise literals first, then the match).  The caller has made the literal bytes readable.
+    __device__ __forceinline__ void seq_copy_small(InStream& in, uint32_t ipos, uint32_t lit, uint32_t d, uint32_t mlen) {
+        const uint32_t lane = lane_id();
+        if (d == 0) d = ring_len;
+        const uint32_t base = written, mbase = base + lit;
+        const int32_t srcp = int32_t(mbase) - int32_t(d);
+        const uint32_t wa = smem_u32(in.window(ipos));
+        const bool near = d <= uint32_t(kOKeep);
+        const uint32_t r = d < mlen ? c_rcp.v[d & 511] : 0u;
+        const bool indep = srcp + int32_t(min(mlen, d)) <= int32_t(base);
+        if (!indep) {
+            if (lane < lit) sts_u8(((base + lane) & kORingMask) | rb, lds_u8(wa + lane));
+            __syncwarp();
+        }
+        const uint32_t first = indep ? 0u : lit;
+        if (lane >= first && lane < lit + mlen) {
+            uint32_t v = 0;
+            if (lane < lit) {
+                v = lds_u8(wa + lane);
+            } else {
+                const uint32_t i = lane - lit;
+                const int32_t s = srcp + int32_t(i - ((i * r) >> 20) * d);
+                if (s >= int32_t(win_base)) {
+                    if (near) v = lds_u8((uint32_t(s) & kORingMask) | rb);
+                    else if (uint64_t(s) < cap) v = dst[s];
+                }
+            }
+            sts_u8(((base + lane) & kORingMask) | rb, v);
+        }
+        written += lit + mlen;
         __syncwarp();
+        drain();
     }
     __device__ __forceinline__ void new_window() { win_base = written; }
     // LzWindows.CopyFrom (IO/LzWindows.cs:124-135) reads ring-sized pieces with ReadExactly: on a truncated
@@ -114,8 +194,17 @@ __device__ __forceinline__ bool lz4_ext(InStream& in, uint32_t& sp, uint32_t end
 // LZ4.cs:176-200.  The block occupies relative input bytes [sp, end).
 __device__ int lz4_block(InStream& in, GOut& out, uint32_t sp, uint32_t end) {
     while (sp < end) {
-        in.ensure(sp, 16);
-        const uint32_t token = in.at(sp++);
+        in.ensure(sp, 64);
+        const uint32_t token = in.at(sp);
+        if ((token >> 4) != 15 && (token & 15) != 15 && sp + 3 + (token >> 4) <= end && (token >> 4) + (token & 15) + 4 <= 32) {
+            // fast path: no extension bytes, literals + match fit one warp step (the vast majority of sequences)
+            const uint32_t lit = token >> 4, off = sp + 1 + lit;
+            const uint32_t d = in.at(off) | (in.at(off + 1) << 8);
+            out.seq_copy_small(in, sp + 1, lit, d, (token & 15) + 4);
+            sp = off + 2;
+            continue;
+        }
+        sp++;
         uint32_t plain = token >> 4;
         if (!lz4_ext(in, sp, end, plain)) return AURORA_END_OF_STREAM;
         if (uint64_t(sp) + plain > end) return AURORA_END_OF_STREAM;
@@ -533,6 +622,7 @@ __device__ Res prs_decode(InStream& in, GOut& out, uint32_t slen, const uint8_t*
     if (r.status != AURORA_OK) {
         in.begin(P.src_base, P.src_limit, src);
         out.written = 0;
+        out.flushed = 0;
         out.new_window();
         r = prs_walk<true>(in, out, slen, !first_big);
     }
@@ -540,15 +630,18 @@ __device__ Res prs_decode(InStream& in, GOut& out, uint32_t slen, const uint8_t*
 }
 
 template <int K>
-__device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream& in) {
+__device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream& in, uint32_t rb) {
     const uint8_t* src = P.src_base + P.src_off[idx];
     const uint64_t slen64 = P.src_len[idx];
     const uint32_t slen = slen64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : uint32_t(slen64);
     GOut out;
     out.dst = P.dst_base + P.dst_off[idx];
     out.cap = P.size_only ? 0 : P.dst_cap[idx];
+    out.rb = rb;
     out.written = 0;
+    out.flushed = 0;
     out.win_base = 0;
+    out.aligned = (reinterpret_cast<uintptr_t>(out.dst) & 15) == 0;
     out.ring_len = (K == B_PRS) ? 0x2000u : 0x10000u;
     out.size_only = P.size_only != 0;
     in.begin(P.src_base, P.src_limit, src);
@@ -561,6 +654,7 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream& in)
     else if (K == B_SNAPPY_BLOCK) r = snappy_block(in, out, 0, slen);
     else if (K == B_LZO) r = lzo_decode(in, out, slen);
     else r = prs_decode(in, out, slen, src, P);
+    out.finish();
     if (r.status == AURORA_OK && uint64_t(out.written) > out.cap) r.status = AURORA_DST_TOO_SMALL;
     if (lane_id() == 0) {
         P.out_len[idx] = out.written;
@@ -573,7 +667,10 @@ template <int K>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) decode_bytelz_kernel(const DecodeParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
-    uint8_t* wbase = smem + size_t(warp) * kSmemPerWarp;
+    const uint32_t s0 = smem_u32(smem);
+    uint8_t* aligned = smem + (((s0 + kORing - 1) & ~uint32_t(kORing - 1)) - s0);
+    const uint32_t rb = smem_u32(aligned + size_t(warp) * kORing);
+    uint8_t* wbase = aligned + size_t(kWarpsPerBlock) * kORing + size_t(warp) * (kSmemPerWarp - kORing);
     InStream in;
     in.init(wbase, reinterpret_cast<uint64_t*>(wbase + kInStage));
     __syncwarp();
@@ -584,7 +681,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) decode_bytelz_kernel(c
         t = __shfl_sync(kFull, t, 0);
         if (t >= P.n) break;
         const uint32_t idx = P.order ? P.order[t] : t;
-        decode_stream<K>(P, idx, in);
+        decode_stream<K>(P, idx, in, rb);
     }
     in.drain_inflight();
 }
@@ -592,7 +689,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) decode_bytelz_kernel(c
 template <int K>
 cudaError_t launch(const DecodeParams& p, int sm_count, cudaStream_t st) {
     const int threads = kWarpsPerBlock * 32;
-    const size_t smem = size_t(kWarpsPerBlock) * kSmemPerWarp;
+    const size_t smem = size_t(kWarpsPerBlock) * kSmemPerWarp + kORing;   // + alignment slack for the rings
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(decode_bytelz_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = true;
+    }
     int blocks = sm_count * 2;
     const int needed = int((p.n + kWarpsPerBlock - 1) / kWarpsPerBlock);
     if (needed < blocks) blocks = needed > 0 ? needed : 1;

@@ -37,14 +37,6 @@ constexpr int kFlush = 512;          // bytes per ring->HBM drain step (16 B per
 constexpr int kQueue = 256;          // match descriptors per G32 iteration (32 groups x 8 tokens)
 constexpr int kSubMaxG = 2304;       // G32: output bytes per iteration (>= the largest single group)
 
-// ceil(2^20 / d): i mod d for the self-overlapping copy without an integer division (exact for i, d < 512)
-struct RcpTable {
-    uint32_t v[512];
-    constexpr RcpTable() : v() {
-        for (uint32_t d = 1; d < 512; ++d) v[d] = ((1u << 20) + d - 1) / d;
-    }
-};
-__constant__ RcpTable c_rcp = RcpTable();
 
 enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5 };
 
@@ -352,27 +344,6 @@ __device__ BodyResult decode_body(InStream* in, OutState& out, const uint32_t sl
 // All shared-memory traffic uses 32-bit shared addresses; the output ring is 8 KiB aligned, so the wrapped
 // address (pos & mask) | base is a single LOP3.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
-}
-
 // one queued match: out[pos + i] = out[pos - d + (i mod d)], i < len, on the 8 KiB aligned ring at shared address rb
 template <bool kShort>   // kShort: len <= 32 guaranteed (LZ10: 18)
 __device__ __forceinline__ void ring_copy_queued(uint32_t rb, uint32_t pos, uint32_t d, uint32_t len) {

@@ -98,6 +98,38 @@ struct InStream {
     __device__ __forceinline__ const uint8_t* window(uint32_t pos) const { return ring + ((pos + rbias) & kInMask); }
 };
 
+// ---- shared-memory accessors on 32-bit shared addresses (explicit program order for the ring traffic)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
+
+// ceil(2^20 / d): i mod d for the self-overlapping copy without an integer division (exact for i, d < 512)
+struct RcpTable {
+    uint32_t v[512];
+    constexpr RcpTable() : v() {
+        for (uint32_t d = 1; d < 512; ++d) v[d] = ((1u << 20) + d - 1) / d;
+    }
+};
+static __constant__ RcpTable c_rcp = RcpTable();
+
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     const int lane = lane_id();
 #pragma unroll
