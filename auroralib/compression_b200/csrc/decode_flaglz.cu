@@ -45,7 +45,7 @@ struct Traits {
     static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : 1;
     static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0) ? 273 : (K == K_LZSS) ? 258 : 65808;
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
-    static constexpr bool kG32 = (K == K_LZ10 || K == K_LZSS || K == K_YAZ0);   // one flag group per lane (256 tokens per iteration)
+    static constexpr bool kG32 = (K != K_LZ11);   // one flag group per lane (256 tokens per iteration)
     static constexpr int kQueueBytes = kG32 ? kQueue * 8 + 256 : 0;       // match queue + group offsets / group descriptors
     static constexpr int kSmemPerWarp = kRing + kStreams * kInStage + kQueueBytes + 64;
     static constexpr int kWarps = (113 * 1024 - kRing) / kSmemPerWarp;    // x2 blocks per SM (8 KiB ring-alignment slack per block)
@@ -759,6 +759,151 @@ __device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const ui
     return BodyResult{status, written, consumed};
 }
 
+// ---------------------------------------------------------------------------------------------
+// G32 core for the split-stream formats MIO0 (MIO0.cs:105-149) and Yay0 (Yay0.cs:110-144): flags, 2-byte codes and
+// literals (+ Yay0's extended-length bytes) are three sub-streams, so there is no serial chain at all: lane g takes
+// flag byte g, a scan of the match counts gives its code cursor, (Yay0) a scan of its 3-byte-token count gives its
+// literal cursor, and a third scan of the group output sizes gives its output base.
+//   in[0] flags (relative to blob offset 0x10), in[1] codes (relative to comp_off), in[2] literals (relative to lit_off)
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ BodyResult decode_body_g32_split(InStream* in, OutState& out, const uint32_t qaddr, const uint32_t slen, const uint32_t size,
+                                            const uint32_t comp_off, const uint32_t lit_off) {
+    const uint32_t lane = lane_id();
+    const uint32_t rb = out.rbase;
+    uint32_t written = 0, cur = 0, ccur = 0, lcur = 0;
+    int status = AURORA_OK;
+
+    while (written < size) {
+        in[0].ensure(cur, 64);
+        in[1].ensure(ccur, kInMirror - 16);
+        in[2].ensure(lcur, kInMirror - 16);
+        const uint32_t fa = smem_u32(in[0].window(cur)), ca = smem_u32(in[1].window(ccur)), la = smem_u32(in[2].window(lcur));
+        const uint32_t f = lds_u8(fa + lane);
+        const uint32_t m = f ^ 0xFFu;   // match bits, MSB first
+        const uint32_t nm = __popc(m);
+        const uint32_t mincl = warp_incl_scan(nm);
+        const uint32_t mb = mincl - nm;   // matches before my group
+        // my codes' first bytes (and, Yay0, how many of them are 3-byte tokens)
+        uint32_t c1v[8];
+        uint32_t next = 0;
+        {
+            uint32_t k = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ism = (m >> (7 - j)) & 1;
+                c1v[j] = lds_u8(ca + 2 * (mb + k));
+                if (K == K_YAY0 && ism && (c1v[j] >> 4) == 0) next++;
+                k += ism ? 1 : 0;
+            }
+        }
+        uint32_t eb = 0;   // extended-length bytes before my group (they live in the literal stream)
+        if (K == K_YAY0) eb = warp_incl_scan(next) - next;
+        const uint32_t lb = 8 * lane - mb + eb;   // literal-stream bytes before my group
+        // ---- pass 1: sizes
+        uint32_t lenv[8], orel[8], litv[8];
+        uint32_t gsize = 0;
+        {
+            uint32_t li = lb;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ism = (m >> (7 - j)) & 1;
+                const uint32_t n = c1v[j] >> 4;
+                const bool ext = K == K_YAY0 && ism && n == 0;
+                const bool extc = ext && lit_off + lcur + li < slen;   // ReadByte() == -1 at EOF: length 0x11, nothing consumed
+                const uint32_t v = lds_u8(la + li);   // literal value or extended length
+                litv[j] = v;
+                orel[j] = gsize;
+                if (K == K_MIO0) lenv[j] = ism ? n + 3 : 1;
+                else lenv[j] = !ism ? 1u : (ext ? (extc ? v + 0x12u : 0x11u) : n + 2u);
+                gsize += lenv[j];
+                li += (!ism || ext) ? 1 : 0;   // raw count: once the literal stream is exhausted every later byte is too
+            }
+        }
+        const uint32_t gincl = warp_incl_scan(gsize), gexcl = gincl - gsize;
+        const uint32_t remaining = size - written;
+        const uint32_t gbase = written + gexcl;
+        const bool taken = gexcl < remaining && gincl <= uint32_t(kSubMaxG);
+        const uint32_t lim = remaining - gexcl;
+        // ---- which of my tokens execute
+        uint32_t jexec = 0;
+        bool eos_here = false;
+        {
+            const bool fbad = 0x10 + cur + lane >= slen;
+            uint32_t k = 0, li = lb;
+            bool stop = false;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ism = (m >> (7 - j)) & 1;
+                const bool ext = K == K_YAY0 && ism && (c1v[j] >> 4) == 0;
+                const bool want = orel[j] < lim;
+                const bool bad = fbad || (ism ? comp_off + ccur + 2 * (mb + k) + 2 > slen : lit_off + lcur + li + 1 > slen);
+                if (!stop && want && bad) eos_here = true;
+                stop = stop || !want || bad;
+                if (!stop) jexec = j + 1;
+                k += ism ? 1 : 0;
+                li += (!ism || ext) ? 1 : 0;
+            }
+        }
+        if (!taken) {
+            jexec = 0;
+            eos_here = false;
+        }
+        const uint32_t eosmask = __ballot_sync(kFull, eos_here);
+        if (eosmask) {
+            const uint32_t gb = __ffs(eosmask) - 1;
+            if (lane > gb) jexec = 0;
+            status = AURORA_END_OF_STREAM;
+        }
+        const uint32_t nlan = __popc(__ballot_sync(kFull, jexec > 0));
+        if (nlan == 0) break;
+        const uint32_t last = nlan - 1;
+        // ---- pass 2
+        uint32_t oend = 0, qi = mb, kend = 0, lend = 0;
+        {
+            uint32_t k = 0, li = lb;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ism = (m >> (7 - j)) & 1;
+                const bool e = uint32_t(j) < jexec;
+                const bool ext = K == K_YAY0 && ism && (c1v[j] >> 4) == 0;
+                const uint32_t pos = gbase + orel[j];
+                const uint32_t len = lenv[j];
+                if (e && !ism) sts_u8((pos & kRingMask) | rb, litv[j]);
+                if (e && ism) {
+                    const uint32_t b2 = lds_u8(ca + 2 * (mb + k) + 1);
+                    sts_u64(qaddr + 8 * qi, pos, len | (((((c1v[j] & 0xF) << 8) | b2) + 1) << 16));
+                    qi++;
+                }
+                k += ism ? 1 : 0;
+                li += (!ism || ext) ? 1 : 0;
+                if (e) {
+                    oend = orel[j] + len;
+                    kend = mb + k;
+                    lend = li;
+                }
+            }
+        }
+        const uint32_t total = __shfl_sync(kFull, gexcl + oend, last);
+        const uint32_t nq = __shfl_sync(kFull, kend, last);
+        const uint32_t nl = __shfl_sync(kFull, lend, last);
+        __syncwarp();
+        replay_matches(rb, qaddr, nq);
+        out.drain(written + total);
+        written += total;
+        ccur += 2 * nq;
+        {
+            const uint32_t lavail = slen > lit_off + lcur ? slen - (lit_off + lcur) : 0u;
+            lcur += min(nl, lavail);   // extended-length reads at EOF consumed nothing
+        }
+        cur += nlan;
+        if (status != AURORA_OK) break;
+    }
+    out.finish(written);
+    if (status == AURORA_OK && written > size) status = AURORA_SIZE_MISMATCH;
+    return BodyResult{status, written, max(comp_off + ccur, lit_off + lcur)};
+}
+
 // pre-history of the window: zeros (LzWindows.cs:53 rents an uncleared array) or LZSS initialFill
 __device__ __forceinline__ void ring_prefill(uint8_t* ring, uint32_t fill) {
     const uint32_t w = fill * 0x01010101u;
@@ -866,7 +1011,9 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                 BodyResult r;
                 bool g32 = Traits<K>::kG32;
                 if (K == K_LZSS) g32 = 8u * (((1u << P.lzss.length_bits) - 1u) + uint32_t(P.lzss.min_length)) <= uint32_t(kSubMaxG);
-                if constexpr (K == K_YAZ0) {
+                if constexpr (K == K_MIO0 || K == K_YAY0) {
+                    r = decode_body_g32_split<K>(in, out, qaddr, slen, size, comp_off, lit_off);
+                } else if constexpr (K == K_YAZ0) {
                     r = decode_body_g32_yaz0(in, out, qaddr, gaddr, slen, size, body_off);
                 } else if constexpr (Traits<K>::kG32) {
                     if (g32) r = decode_body_g32<K>(in, out, qaddr, gaddr, slen, size, body_off, P.lzss);

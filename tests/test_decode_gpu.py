@@ -215,3 +215,25 @@ def test_large_batch_many_warps(codec, oracle, bmp):
         assert (status == 0).all(), fmt_id(fmt)
         got = [dst[int(doff[i]):int(doff[i]) + int(caps[i])].tobytes() for i in range(len(rr))]
         assert got == rr, fmt_id(fmt)
+
+
+def test_multi_device_sharding(oracle, bmp):
+    """aurora_init(0) opens every visible B200; a host batch is cut into byte-balanced contiguous shards, one worker
+    thread and one stream set per device, no collective.  Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+    from auroralib.compression_b200 import BatchCodec
+    c = BatchCodec(0)
+    try:
+        if c.device_count < 2:
+            pytest.skip("one GPU visible")
+        rng = np.random.default_rng(11)
+        raws = [bmp[int(o):int(o) + int(n)] for o, n in zip(rng.integers(0, 900000, size=3000), rng.integers(1, 60000, size=3000))]
+        for fmt in (A.FMT_LZ10, A.FMT_YAZ0, A.FMT_LZ4_BLOCK):
+            comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=0))
+            keep = [i for i in range(len(raws)) if st[i] == 0]
+            outs, out_len, consumed, status = c.decode_batch(fmt, [comps[i] for i in keep], [len(raws[i]) for i in keep])
+            assert (status == 0).all() and outs == [raws[i] for i in keep], fmt_id(fmt)
+        enc, st = c.encode_batch(A.FMT_LZ10, raws[:500], A.make_opts(quality=8))
+        ref, rst = oracle.encode_batch(A.FMT_LZ10, raws[:500], A.make_opts(quality=8))
+        assert (st == 0).all() and enc == ref
+    finally:
+        c.close()
