@@ -730,6 +730,40 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
         return 0x10 < src_len[i] && src_len[i] >= k && std::memcmp(src_base + src_off[i], m, k) == 0;
     };
     static const uint8_t snappy_id[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};
+    if (format == AURORA_FMT_LZ10 || format == AURORA_FMT_LZ11 || format == AURORA_FMT_PRS) {
+        // token-walk heuristics run on the device, one thread per candidate stream (csrc/ismatch.cu)
+        if (n > 0xFFFFFFF0ull) return AURORA_INVALID_ARGUMENT;
+        DeviceCtx* d = ctx->devs[0];
+        std::lock_guard<std::mutex> guard(d->mu);
+        CU_TRY(ctx, cudaSetDevice(d->dev));
+        const Layout S = plan_layout(src_off, src_len, 0, n);
+        CU_TRY(ctx, d->src.reserve(S.bytes + 16));
+        CU_TRY(ctx, d->desc.reserve(n * 17 + 64));
+        CU_TRY(ctx, d->hdesc.reserve(n * 17 + 64));
+        uint64_t* h = static_cast<uint64_t*>(d->hdesc.p);
+        uint64_t* dv = static_cast<uint64_t*>(d->desc.p);
+        for (size_t i = 0; i < n; i++) {
+            h[i] = S.dev_off[i];
+            h[n + i] = src_len[i];
+        }
+        cudaStream_t st = d->stream;
+        uint8_t* dsrc = static_cast<uint8_t*>(d->src.p);
+        CU_TRY(ctx, cudaMemcpyAsync(dv, h, 2 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        if (S.span) {
+            uint64_t hi = 0;
+            for (size_t i = 0; i < n; i++) hi = std::max(hi, src_off[i] + src_len[i]);
+            if (hi > S.lo) CU_TRY(ctx, cudaMemcpyAsync(dsrc, src_base + S.lo, hi - S.lo, cudaMemcpyHostToDevice, st));
+        } else {
+            for (size_t i = 0; i < n; i++)
+                if (src_len[i]) CU_TRY(ctx, cudaMemcpyAsync(dsrc + S.dev_off[i], src_base + src_off[i], src_len[i], cudaMemcpyHostToDevice, st));
+        }
+        uint8_t* dm = reinterpret_cast<uint8_t*>(dv + 2 * n);
+        CU_TRY(ctx, launch_is_match(dsrc, dv, dv + n, dm, uint32_t(n), format, st));
+        ctx->launches++;
+        CU_TRY(ctx, cudaMemcpyAsync(match, dm, n, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        return AURORA_OK;
+    }
     for (size_t i = 0; i < n; i++) {
         const uint8_t* p = src_base + src_off[i];
         bool m = false;
@@ -751,8 +785,8 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
                 m = src_len[i] > 0 && (p[0] < 0x20);
                 break;
             default:
-                ctx->set_error("aurora_is_match_batch: the token-walk heuristics (LZ10/LZ11/PRS) are not built yet");
-                return AURORA_NOT_SUPPORTED;
+                ctx->set_error("aurora_is_match_batch: unknown format");
+                return AURORA_INVALID_ARGUMENT;
         }
         match[i] = m ? 1 : 0;
     }

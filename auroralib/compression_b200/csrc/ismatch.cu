@@ -1,0 +1,150 @@
+// ismatch.cu — batched IsMatch heuristics that walk tokens: LZ10.Validate (Nintendo/LZ10.cs:139-175),
+// LZ11.Validate (LZ11.cs:173-223) and PRS.GetByteOrder / ValidateByteOrder (Sega/PRS.cs:161-218).
+// The walks stop at the 4th plausible match, so they are short and independent: one THREAD per candidate
+// stream, reading the blob straight from global memory (this is the data-parallel form of the CLI's
+// byte-by-byte `-scan` loop, Commands/ScanDecompressCommand.cs:23-39).  An exception inside the reference's
+// walk (a read past the end) makes IsMatch false here, like the oracle.
+#include "common.cuh"
+
+namespace aurora {
+
+namespace {
+
+struct BitReader {   // FlagReader with a 1-byte flag word (IO/FlagReader.cs:53-65)
+    const uint8_t* p;
+    uint64_t len, pos;
+    uint32_t cur, left;
+    bool msb, fail;
+    __device__ int bit() {
+        if (left == 0) {
+            if (pos >= len) { fail = true; return 0; }
+            cur = p[pos++];
+            left = 8;
+        }
+        const uint32_t sh = msb ? left - 1 : 8 - left;
+        left--;
+        return (cur >> sh) & 1;
+    }
+    __device__ uint32_t byte() {
+        if (pos >= len) { fail = true; return 0; }
+        return p[pos++];
+    }
+};
+
+__device__ bool lz1x_validate(const uint8_t* p, uint64_t len, bool lz11) {
+    if (!(8 < len)) return false;   // stream.Position + 0x8 < stream.Length
+    if (p[0] != (lz11 ? 0x11 : 0x10)) return false;
+    uint64_t pos = 4;
+    uint32_t size = uint32_t(p[1]) | (uint32_t(p[2]) << 8) | (uint32_t(p[3]) << 16);
+    if (size == 0) {
+        size = uint32_t(p[4]) | (uint32_t(p[5]) << 8) | (uint32_t(p[6]) << 16) | (uint32_t(p[7]) << 24);
+        pos = 8;
+    }
+    if (size == 0) return false;
+    int budget = 3;
+    uint64_t produced = 0;
+    BitReader r{p, len, pos, 0, 0, true, false};
+    while (r.pos < len) {
+        const int b = r.bit();
+        if (r.fail) return false;
+        if (b) {
+            uint32_t distance, length;
+            const uint32_t b1 = r.byte(), b2 = r.byte();
+            if (lz11 && (b1 >> 4) == 0) {
+                const uint32_t b3 = r.byte();
+                distance = (((b2 & 0xf) << 8) | b3) + 1;
+                length = (((b1 & 0xf) << 4) | (b2 >> 4)) + 17;
+            } else if (lz11 && (b1 >> 4) == 1) {
+                const uint32_t b3 = r.byte(), b4 = r.byte();
+                distance = (((b3 & 0xf) << 8) | b4) + 1;
+                length = (((b1 & 0xf) << 12) | (b2 << 4) | (b3 >> 4)) + 273;
+            } else {
+                distance = (((b1 & 0xf) << 8) | b2) + 1;
+                length = (b1 >> 4) + (lz11 ? 1 : 3);
+            }
+            if (r.fail) return false;
+            if (distance > produced) return false;
+            if (budget == 0) return true;
+            budget--;
+            produced += length;
+        } else {
+            r.pos++;   // source.Position++ (no bounds check in the reference)
+            produced++;
+        }
+    }
+    return produced == size;
+}
+
+// 1 valid, 0 invalid, -1 exception
+__device__ int prs_validate(const uint8_t* p, uint64_t len, bool big) {
+    int budget = 3;
+    uint64_t produced = 0;
+    BitReader r{p, len, 0, 0, 0, big, false};
+    while (r.pos < len) {
+        int b = r.bit();
+        if (r.fail) return -1;
+        if (b) {
+            r.pos++;
+            produced++;
+        } else {
+            uint32_t distance, length;
+            b = r.bit();
+            if (r.fail) return -1;
+            if (b) {
+                if (r.pos + 2 > len) return -1;
+                const uint32_t v = big ? (uint32_t(p[r.pos]) << 8) | p[r.pos + 1] : uint32_t(p[r.pos]) | (uint32_t(p[r.pos + 1]) << 8);
+                r.pos += 2;
+                if (v == 0) return 1;
+                length = v & 7;
+                distance = 0x2000 - (v >> 3);
+                if (length == 0) {
+                    length = r.byte() + 1;
+                    if (r.fail) return -1;
+                } else {
+                    length += 2;
+                }
+            } else {
+                const int b1 = r.bit(), b0 = r.bit();
+                if (r.fail) return -1;
+                length = uint32_t(b1 * 2 + b0) + 2;
+                distance = 0x100 - r.byte();
+                if (r.fail) return -1;
+            }
+            if (distance > produced) return 0;
+            if (budget == 0) return 1;
+            budget--;
+            produced += length;
+        }
+    }
+    return 0;
+}
+
+__global__ void is_match_kernel(const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* match, uint32_t n, int format) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = src_base + src_off[i];
+    const uint64_t len = src_len[i];
+    bool m = false;
+    if (format == AURORA_FMT_LZ10) m = lz1x_validate(p, len, false);
+    else if (format == AURORA_FMT_LZ11) m = lz1x_validate(p, len, true);
+    else if (format == AURORA_FMT_PRS) {
+        if (4 < len) {   // stream.Position + 0x4 < stream.Length
+            const uint32_t flag = p[0];
+            int v = 0;
+            if (flag > 12 && (flag & 1)) v = prs_validate(p, len, false);
+            if (v == 0 && (flag & 128)) v = prs_validate(p, len, true);
+            m = v == 1;
+        }
+    }
+    match[i] = m ? 1 : 0;
+}
+
+}  // namespace
+
+cudaError_t launch_is_match(const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* match, uint32_t n,
+                            int format, cudaStream_t st) {
+    is_match_kernel<<<(n + 127) / 128, 128, 0, st>>>(src_base, src_off, src_len, match, n, format);
+    return cudaGetLastError();
+}
+
+}  // namespace aurora
