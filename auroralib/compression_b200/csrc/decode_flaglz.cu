@@ -76,23 +76,26 @@ struct OutState {
     uint32_t limit;    // bytes of the destination that may be written
     uint32_t flushed;  // output position drained to HBM so far (multiple of kFlush)
     bool aligned;
+    // Chunks are retired as soon as they are produced, also past `limit` (overshooting tokens, destination smaller
+    // than the output): bytes beyond the limit are dropped, but the bytes below it must leave the ring before a
+    // long match wraps over them.
     __device__ __forceinline__ void drain(uint32_t produced) {
         const uint32_t lane = lane_id();
-        const uint32_t upto = min(produced, limit);
-        while (flushed + kFlush <= upto) {
-            if (aligned) {
+        while (flushed + kFlush <= produced) {
+            if (aligned && flushed + kFlush <= limit) {
                 const uint4 v = *reinterpret_cast<const uint4*>(ring + ((flushed + lane * 16) & kRingMask));
                 *reinterpret_cast<uint4*>(dst + flushed + lane * 16) = v;
-            } else {
-                for (uint32_t i = lane; i < kFlush; i += 32) dst[flushed + i] = ring[(flushed + i) & kRingMask];
+            } else if (flushed < limit) {
+                for (uint32_t i = lane; i < kFlush; i += 32)
+                    if (flushed + i < limit) dst[flushed + i] = ring[(flushed + i) & kRingMask];
             }
             flushed += kFlush;
         }
     }
     __device__ __forceinline__ void finish(uint32_t produced) {
         const uint32_t lane = lane_id();
-        const uint32_t upto = min(produced, limit);
         drain(produced);
+        const uint32_t upto = min(produced, limit);
         for (uint32_t p = flushed + lane; p < upto; p += 32) dst[p] = ring[p & kRingMask];
     }
 };

@@ -76,10 +76,11 @@ def test_synthetic_batch(codec, oracle, fmt):
 
 @pytest.mark.parametrize("fmt", ALL_FORMATS, ids=fmt_id)
 def test_corrupt_and_truncated(codec, oracle, fmt):
-    """Fuzz: truncated / bit-flipped / padded / empty inputs must give the oracle's status, length and bytes."""
+    """Fuzz: truncated / bit-flipped / padded / empty inputs must give the oracle's status, length and bytes.
+    (600 streams per format; run-heavy classes exercise Yaz0/Yay0 extended lengths at EOF and the merged-run replay.)"""
     rng = np.random.default_rng(2000 + fmt)
     comps, caps = [], []
-    for i in range(240):
+    for i in range(600):
         raw = synth(rng, int(rng.integers(5, 9000)), i % 5)
         c, st = oracle.encode(fmt, raw, A.make_opts(quality=int(rng.choice([0, 8]))))
         assert st == 0
