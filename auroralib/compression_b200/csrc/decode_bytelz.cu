@@ -554,7 +554,19 @@ __device__ Res prs_walk(InStream& in, GOut& out, uint32_t slen, bool big) {
         if (b < 0) return eos;
         if (b) {
             if (sp >= slen) return kCopy ? eos : Res{kPrsInvalid, sp};   // validate: Position++ runs past the end, loop ends, false
-            if (kCopy) out.lit_copy(in, sp, 1);
+            if (kCopy) {
+                // the literal bits that follow in the SAME flag byte govern the next input bytes: copy the run at once
+                uint32_t n = 1;
+                while (fr.left > 0 && ((fr.cur >> (fr.msb ? fr.left - 1 : 8 - fr.left)) & 1u)) {
+                    n++;
+                    fr.left--;
+                }
+                const uint32_t avail = slen - sp;
+                out.lit_copy(in, sp, min(n, avail));
+                if (n > avail) return eos;   // ReadUInt8 at the end of the input
+                sp += n;
+                continue;
+            }
             sp++;
             produced++;
         } else {
