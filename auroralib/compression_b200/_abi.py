@@ -30,11 +30,12 @@ class CodecOpts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("byte_order", C.c_int32), ("quality", C.c_int32),
                 ("max_window_bits", C.c_int32), ("strategy", C.c_int32), ("vram_mode", C.c_int32),
                 ("lzss", LzProps), ("lzss_initial_fill", C.c_int32), ("lz4_block_size", C.c_uint32),
-                ("lz4_verify", C.c_int32), ("yaz0_alignment", C.c_uint32), ("reserved", C.c_uint32 * 6)]
+                ("lz4_verify", C.c_int32), ("yaz0_alignment", C.c_uint32), ("balance", C.c_uint32),
+                ("reserved", C.c_uint32 * 5)]
 
 
 def make_opts(byte_order=ENDIAN_DEFAULT, quality=-1, max_window_bits=0, strategy=0, vram_mode=-1,
-              lzss=None, lzss_initial_fill=0, lz4_block_size=0, lz4_verify=0, yaz0_alignment=0):
+              lzss=None, lzss_initial_fill=0, lz4_block_size=0, lz4_verify=0, yaz0_alignment=0, balance=0):
     o = CodecOpts()
     o.struct_size = C.sizeof(CodecOpts)
     o.byte_order = byte_order
@@ -48,6 +49,7 @@ def make_opts(byte_order=ENDIAN_DEFAULT, quality=-1, max_window_bits=0, strategy
     o.lz4_block_size = lz4_block_size
     o.lz4_verify = lz4_verify
     o.yaz0_alignment = yaz0_alignment
+    o.balance = balance
     return o
 
 

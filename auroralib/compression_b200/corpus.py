@@ -101,8 +101,9 @@ def generate(cls, n_streams, size, seed=0xA0120000, device="cpu"):
     g = torch.Generator(device=dev)
     g.manual_seed(seed + "TMXB".index(cls))
     parts = []
-    for s in range(0, n_streams, _CHUNK):
-        parts.append(_GEN[cls](min(_CHUNK, n_streams - s), size, g, dev))
+    chunk = max(1, min(_CHUNK, (1 << 26) // max(size, 1)))   # bound the int64 index temporaries (~8 x chunk x size bytes)
+    for s in range(0, n_streams, chunk):
+        parts.append(_GEN[cls](min(chunk, n_streams - s), size, g, dev))
     if not parts:
         return torch.zeros((0, size), dtype=torch.uint8, device=dev)
     return torch.cat(parts, 0)

@@ -63,7 +63,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy engines of the pipelined host path
     std::vector<cudaEvent_t> ev_in, ev_k;
-    DevBuf src, dst, desc, ticket, scratch;
+    DevBuf src, dst, desc, ticket, scratch, order;
     HostBuf hdesc;
     std::mutex mu;   // one batch at a time per device
 };
@@ -249,6 +249,17 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     P.dst_base = ddst;
     P.order = nullptr;
     P.ticket = static_cast<unsigned int*>(d->ticket.p);
+    // wide size spread (max > 2 x mean): hand streams to warps largest first to cut the tail
+    bool balance = false;
+    if (!size_only && n >= 64 && !(opts && opts->balance == 2)) {
+        uint64_t mx = 0, sum = 0;
+        for (size_t i = b; i < e; i++) {
+            mx = std::max(mx, dst_cap[i]);
+            sum += dst_cap[i];
+        }
+        balance = mx > 2 * (sum / n + 1);
+    }
+    if (balance) CU_TRY(ctx, d->order.reserve(n * sizeof(uint32_t) + 256));
 
     // Pipelined host path: the shard is cut into byte-balanced pieces; piece k+1 is uploaded (H2D engine) while piece
     // k decodes and piece k-1 is downloaded (D2H engine), so end-to-end time tends to max(H2D, D2H) instead of their sum.
@@ -299,6 +310,13 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
             Q.status = reinterpret_cast<int32_t*>(dv + 6 * n) + i0;
             Q.ticket = static_cast<unsigned int*>(d->ticket.p) + k;
             Q.n = uint32_t(i1 - i0);
+            if (balance) {
+                uint32_t* hist = static_cast<uint32_t*>(d->order.p);
+                uint32_t* ord = hist + 64 + i0;
+                CU_TRY(ctx, launch_size_order(Q.dst_cap, Q.n, hist, ord, st));
+                ctx->launches += 3;
+                Q.order = ord;
+            }
             CU_TRY(ctx, launch_decode(Q, d->sm_count, st));
             ctx->launches++;
             if (!size_only) {
@@ -333,6 +351,12 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
         P.consumed = dv + 5 * n;
         P.status = reinterpret_cast<int32_t*>(dv + 6 * n);
         P.n = uint32_t(n);
+        if (balance) {
+            uint32_t* hist = static_cast<uint32_t*>(d->order.p);
+            CU_TRY(ctx, launch_size_order(P.dst_cap, P.n, hist, hist + 64, st));
+            ctx->launches += 3;
+            P.order = hist + 64;
+        }
         CU_TRY(ctx, launch_decode(P, d->sm_count, st));
         ctx->launches++;
         CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, 2 * n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -563,6 +587,7 @@ void aurora_shutdown(aurora_ctx* ctx) {
         d->desc.release();
         d->ticket.release();
         d->scratch.release();
+        d->order.release();
         d->hdesc.release();
         for (cudaEvent_t e : d->ev_in) cudaEventDestroy(e);
         for (cudaEvent_t e : d->ev_k) cudaEventDestroy(e);
@@ -827,6 +852,15 @@ int aurora_decode_batch_device(aurora_ctx* ctx, int device, int format, const au
     P.consumed = d_consumed;
     P.status = d_status;
     P.order = nullptr;
+    if (opts && opts->balance == 1 && n > 1) {
+        // largest-first hand-out (streams with a wide size spread, config C3): three tiny kernels, no host sync
+        CU_TRY(ctx, d->order.reserve(n * sizeof(uint32_t) + 256));
+        uint32_t* hist = static_cast<uint32_t*>(d->order.p);
+        uint32_t* ord = hist + 64;
+        CU_TRY(ctx, launch_size_order(d_dst_cap, uint32_t(n), hist, ord, st));
+        ctx->launches += 3;
+        P.order = ord;
+    }
     P.ticket = static_cast<unsigned int*>(d->ticket.p);
     P.n = uint32_t(n);
     CU_TRY(ctx, launch_decode(P, d->sm_count, st));

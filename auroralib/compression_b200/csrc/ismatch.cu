@@ -139,7 +139,34 @@ __global__ void is_match_kernel(const uint8_t* src_base, const uint64_t* src_off
     match[i] = m ? 1 : 0;
 }
 
+// ---- largest-first stream order for batches with a wide size spread: counting sort by floor(log2(size)) ----
+__global__ void order_hist_kernel(const uint64_t* size, uint32_t n, uint32_t* hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&hist[63 - __clzll((long long)(size[i] | 1))], 1u);
+}
+__global__ void order_scan_kernel(uint32_t* hist) {   // one thread: descending exclusive offsets over 64 buckets
+    uint32_t acc = 0;
+    for (int b = 63; b >= 0; b--) {
+        const uint32_t c = hist[b];
+        hist[b] = acc;
+        acc += c;
+    }
+}
+__global__ void order_scatter_kernel(const uint64_t* size, uint32_t n, uint32_t* hist, uint32_t* order) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[atomicAdd(&hist[63 - __clzll((long long)(size[i] | 1))], 1u)] = i;
+}
+
 }  // namespace
+
+cudaError_t launch_size_order(const uint64_t* d_size, uint32_t n, uint32_t* d_hist64, uint32_t* d_order, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(d_hist64, 0, 64 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    order_hist_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_size, n, d_hist64);
+    order_scan_kernel<<<1, 1, 0, st>>>(d_hist64);
+    order_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_size, n, d_hist64, d_order);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_is_match(const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* match, uint32_t n,
                             int format, cudaStream_t st) {

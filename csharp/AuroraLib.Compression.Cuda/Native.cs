@@ -37,7 +37,8 @@ namespace AuroraLib.Compression.Cuda
         public uint Lz4BlockSize;
         public int Lz4Verify;
         public uint Yaz0Alignment;
-        public fixed uint Reserved[6];
+        public uint Balance;           // 0 auto, 1 largest-first on, 2 off
+        public fixed uint Reserved[5];
     }
 
     internal static unsafe class Native

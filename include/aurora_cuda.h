@@ -98,7 +98,9 @@ typedef struct aurora_codec_opts {
                                   0 = skip (HashAlgorithm == null, the library default)                */
     /* Yaz0 */
     uint32_t yaz0_alignment;   /* Yaz0.MemoryAlignment written by the encoder                          */
-    uint32_t reserved[6];
+    uint32_t balance;          /* decode: hand streams to warps largest first (device counting sort by size class):
+                                  0 = auto (host path: when max size > 2 x mean; device path: off), 1 = on, 2 = off */
+    uint32_t reserved[5];
 } aurora_codec_opts;
 
 typedef struct aurora_ctx aurora_ctx;
