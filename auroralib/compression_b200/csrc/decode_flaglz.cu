@@ -425,12 +425,37 @@ __device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint
         nout += __popc(heads);
     }
     __syncwarp();
-    uint2 e = lds_u64(qaddr);
-    for (uint32_t q = 0; q < nout; q++) {
-        const uint2 nx = lds_u64(qaddr + 8 * (q + 1));   // one slot past the end is readable (slack behind the queue)
-        ring_copy_any(rb, e.x, e.y >> 16, e.y & 0xFFFFu);
+    // Two entries per step: when the second match's source ends at or before the first match's destination the two
+    // copies are independent, so both loads are issued before both stores (one barrier, twice the ILP); the slots
+    // past the end of the queue are readable (slack behind the queue).
+    uint2 e0 = lds_u64(qaddr), e1 = lds_u64(qaddr + 8);
+    uint32_t q = 0;
+    while (q + 1 < nout) {
+        const uint2 n0 = lds_u64(qaddr + 8 * (q + 2)), n1 = lds_u64(qaddr + 8 * (q + 3));
+        const uint32_t len0 = e0.y & 0xFFFFu, d0 = e0.y >> 16, len1 = e1.y & 0xFFFFu, d1 = e1.y >> 16;
+        if (max(len0, len1) <= 32 && e1.x - d1 + min(len1, d1) <= e0.x) {
+            uint32_t off0 = lane, off1 = lane;
+            if (d0 < len0) off0 = lane - ((lane * c_rcp.v[d0]) >> 20) * d0;
+            if (d1 < len1) off1 = lane - ((lane * c_rcp.v[d1]) >> 20) * d1;
+            uint32_t v0 = 0, v1 = 0;
+            if (lane < len0) v0 = lds_u8(((e0.x - d0 + off0) & kRingMask) | rb);
+            if (lane < len1) v1 = lds_u8(((e1.x - d1 + off1) & kRingMask) | rb);
+            if (lane < len0) sts_u8(((e0.x + lane) & kRingMask) | rb, v0);
+            if (lane < len1) sts_u8(((e1.x + lane) & kRingMask) | rb, v1);
+            __syncwarp();
+        } else {
+            ring_copy_any(rb, e0.x, d0, len0);
+            __syncwarp();
+            ring_copy_any(rb, e1.x, d1, len1);
+            __syncwarp();
+        }
+        e0 = n0;
+        e1 = n1;
+        q += 2;
+    }
+    if (q < nout) {
+        ring_copy_any(rb, e0.x, e0.y >> 16, e0.y & 0xFFFFu);
         __syncwarp();
-        e = nx;
     }
 }
 
