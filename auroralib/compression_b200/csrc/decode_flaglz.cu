@@ -433,15 +433,17 @@ __device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint
     while (q + 1 < nout) {
         const uint2 n0 = lds_u64(qaddr + 8 * (q + 2)), n1 = lds_u64(qaddr + 8 * (q + 3));
         const uint32_t len0 = e0.y & 0xFFFFu, d0 = e0.y >> 16, len1 = e1.y & 0xFFFFu, d1 = e1.y >> 16;
-        if (max(len0, len1) <= 32 && e1.x - d1 + min(len1, d1) <= e0.x) {
-            uint32_t off0 = lane, off1 = lane;
-            if (d0 < len0) off0 = lane - ((lane * c_rcp.v[d0]) >> 20) * d0;
-            if (d1 < len1) off1 = lane - ((lane * c_rcp.v[d1]) >> 20) * d1;
-            uint32_t v0 = 0, v1 = 0;
-            if (lane < len0) v0 = lds_u8(((e0.x - d0 + off0) & kRingMask) | rb);
-            if (lane < len1) v1 = lds_u8(((e1.x - d1 + off1) & kRingMask) | rb);
-            if (lane < len0) sts_u8(((e0.x + lane) & kRingMask) | rb, v0);
-            if (lane < len1) sts_u8(((e1.x + lane) & kRingMask) | rb, v1);
+        if (max(len0, len1) < 512 && e1.x - d1 + min(len1, d1) <= e0.x) {
+            const uint32_t r0 = d0 < len0 ? c_rcp.v[d0] : 0u, r1 = d1 < len1 ? c_rcp.v[d1] : 0u;   // 0: no wrap, off = i
+            const uint32_t s0 = e0.x - d0, s1 = e1.x - d1, lmax = max(len0, len1);
+            for (uint32_t i = lane; i < lmax; i += 32) {
+                const uint32_t off0 = i - ((i * r0) >> 20) * d0, off1 = i - ((i * r1) >> 20) * d1;
+                uint32_t v0 = 0, v1 = 0;
+                if (i < len0) v0 = lds_u8(((s0 + off0) & kRingMask) | rb);
+                if (i < len1) v1 = lds_u8(((s1 + off1) & kRingMask) | rb);
+                if (i < len0) sts_u8(((e0.x + i) & kRingMask) | rb, v0);
+                if (i < len1) sts_u8(((e1.x + i) & kRingMask) | rb, v1);
+            }
             __syncwarp();
         } else {
             ring_copy_any(rb, e0.x, d0, len0);
