@@ -712,9 +712,12 @@ __device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const ui
         // ---- which of my tokens execute (end of output, end of input, iteration byte budget)
         const bool taken = valid && gexcl < remaining && gincl <= uint32_t(kSubMaxG);
         const uint32_t lim = remaining - gexcl;
-        uint32_t jexec = 0;
+        uint32_t jexec = 8;
         bool eos_here = false;
-        {
+        // fast path: every token of every valid group executes (not the end of the output, all input bytes present)
+        const uint32_t all_out = __shfl_sync(kFull, gincl, 31);
+        if (!(all_out <= min(remaining, uint32_t(kSubMaxG)) && cur + (ca - wa) <= slen)) {
+            jexec = 0;
             const uint32_t gabs = cur + myrel;
             uint32_t a = gabs + 1;
             bool stop = false;
@@ -856,9 +859,14 @@ __device__ BodyResult decode_body_g32_split(InStream* in, OutState& out, const u
         const bool taken = gexcl < remaining && gincl <= uint32_t(kSubMaxG);
         const uint32_t lim = remaining - gexcl;
         // ---- which of my tokens execute
-        uint32_t jexec = 0;
+        uint32_t jexec = 8;
         bool eos_here = false;
-        {
+        // fast path: all 256 tokens execute (not the end of the output, all three sub-streams have their bytes)
+        const uint32_t all_out = __shfl_sync(kFull, gincl, 31), all_m = __shfl_sync(kFull, mincl, 31);
+        const uint32_t all_l = 256 - all_m + ((K == K_YAY0) ? __shfl_sync(kFull, eb + next, 31) : 0u);
+        if (!(all_out <= min(remaining, uint32_t(kSubMaxG)) && 0x10 + cur + 32 <= slen && comp_off + ccur + 2 * all_m <= slen &&
+              lit_off + lcur + all_l <= slen)) {
+            jexec = 0;
             const bool fbad = 0x10 + cur + lane >= slen;
             uint32_t k = 0, li = lb;
             bool stop = false;
