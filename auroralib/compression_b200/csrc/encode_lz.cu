@@ -23,7 +23,7 @@ namespace aurora {
 
 namespace {
 
-constexpr int kEncWarpsPerBlock = 4;
+constexpr int kEncWarpsPerBlock = 8;
 
 struct Finder {
     int* head;
@@ -441,7 +441,7 @@ cudaError_t launch(const EncodeParams& p, int warps, cudaStream_t st) {
 
 }  // namespace
 
-int encode_resident_warps(int sm_count) { return sm_count * 16; }
+int encode_resident_warps(int sm_count) { return sm_count * 48; }
 
 // head + chain + min tables, plus (MIO0/Yay0) staging for the code and literal sections
 size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64_t max_src_len) {
