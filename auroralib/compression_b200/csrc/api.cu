@@ -129,6 +129,11 @@ int fill_decode_params(DecodeParams& p, int format, const aurora_codec_opts* o) 
     return AURORA_OK;
 }
 
+cudaError_t launch_encode(const EncodeParams& p, int warps, cudaStream_t st) {
+    if (is_flaglz(p.format)) return launch_encode_lz(p, warps, st);
+    return launch_encode_bytelz(p, warps, st);
+}
+
 cudaError_t launch_decode(const DecodeParams& p, int sm_count, cudaStream_t st) {
     if (is_flaglz(p.format)) return launch_decode_flaglz(p, sm_count, st);
     return launch_decode_bytelz(p, sm_count, st);
@@ -432,9 +437,20 @@ int fill_encode_params(EncodeParams& p, int format, const aurora_codec_opts* o) 
             else aurora_lz_props_bits(&lz, 12, 4, 2);
             if (lz.windows_bits < 1 || lz.windows_bits > 24 || lz.length_bits < 1 || lz.length_bits > 8) return AURORA_INVALID_ARGUMENT;
             break;
+        case AURORA_FMT_LZ4:
+        case AURORA_FMT_LZ4_LEGACY:
+        case AURORA_FMT_LZ4_BLOCK: aurora_lz_props_window(&lz, 0xFFFF, 0x7FFFFFFF, 4, 0, 1); break;   // LZ4.cs:29
+        case AURORA_FMT_LZO: aurora_lz_props_window(&lz, 0xBFFF, 0x7FFFFFFF, 3, 0, 1); break;         // LZO.cs:24
+        case AURORA_FMT_SNAPPY:
+        case AURORA_FMT_SNAPPY_BLOCK: aurora_lz_props_window(&lz, 0x8000, 64, 4, 0, 1); break;        // Snappy.cs:28
+        case AURORA_FMT_PRS: aurora_lz_props_window(&lz, 0x1FFF, 0x100, 2, 0, 1); break;              // PRS.cs:21
         default: return AURORA_NOT_SUPPORTED;
     }
     p.format = format;
+    p.lz4_block_size = (o && o->lz4_block_size) ? o->lz4_block_size : 0x400000u;
+    if (format == AURORA_FMT_LZ4 && p.lz4_block_size != 0x10000 && p.lz4_block_size != 0x40000 && p.lz4_block_size != 0x100000 &&
+        p.lz4_block_size != 0x400000)
+        return AURORA_INVALID_ARGUMENT;
     p.byte_order = o ? o->byte_order : AURORA_ENDIAN_DEFAULT;
     p.max_chain = q < 6 ? q + 1 : q >= 11 ? 1 << (q - 5) : ((1 << (q >> 1)) | ((1 << (q >> 1)) >> (q & 1)));
     p.lazy_threshold = 3 + q / 3;
@@ -511,7 +527,7 @@ int encode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     P.status = reinterpret_cast<int32_t*>(dv + 5 * n);
     P.ticket = static_cast<unsigned int*>(d->ticket.p);
     P.n = uint32_t(n);
-    CU_TRY(ctx, launch_encode_lz(P, warps, st));
+    CU_TRY(ctx, launch_encode(P, warps, st));
     ctx->launches++;
     CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -897,7 +913,7 @@ int aurora_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* op
     EncodeParams probe{};
     const int rc = fill_encode_params(probe, format, opts);
     if (rc != AURORA_OK) {
-        ctx->set_error("aurora_encode_batch: this format has no GPU encoder yet (LZ10, LZ11, Yaz0, Yaz1, LZSS, MIO0, Yay0 do)");
+        ctx->set_error("aurora_encode_batch: unknown format or invalid settings");
         return rc;
     }
     const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, nullptr);
@@ -919,7 +935,7 @@ int aurora_encode_batch_device(aurora_ctx* ctx, int device, int format, const au
     EncodeParams P{};
     const int rc = fill_encode_params(P, format, opts);
     if (rc != AURORA_OK) {
-        ctx->set_error("aurora_encode_batch_device: this format has no GPU encoder yet");
+        ctx->set_error("aurora_encode_batch_device: unknown format or invalid settings");
         return rc;
     }
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
@@ -949,7 +965,7 @@ int aurora_encode_batch_device(aurora_ctx* ctx, int device, int format, const au
     P.status = d_status;
     P.ticket = static_cast<unsigned int*>(d->ticket.p);
     P.n = uint32_t(n);
-    CU_TRY(ctx, launch_encode_lz(P, warps, st));
+    CU_TRY(ctx, launch_encode(P, warps, st));
     ctx->launches++;
     return AURORA_OK;
 }

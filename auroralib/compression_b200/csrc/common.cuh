@@ -55,6 +55,7 @@ struct EncodeParams {
     int max_chain, lazy_threshold, hash_bits, chain_bits, min_length, max_length, min_distance, max_distance, no_self_overlap,
         use_min_table;
     uint32_t yaz0_alignment;
+    uint32_t lz4_block_size;
     LzssParams lzss;
     uint8_t* scratch;            // per-resident-warp match-finder tables
     uint64_t scratch_per_warp;
@@ -64,6 +65,7 @@ struct EncodeParams {
 cudaError_t launch_decode_flaglz(const DecodeParams& p, int sm_count, cudaStream_t st);
 cudaError_t launch_decode_bytelz(const DecodeParams& p, int sm_count, cudaStream_t st);
 cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st);
+cudaError_t launch_encode_bytelz(const EncodeParams& p, int warps, cudaStream_t st);
 size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64_t max_src_len);
 int encode_resident_warps(int sm_count);
 cudaError_t launch_size_order(const uint64_t* d_size, uint32_t n, uint32_t* d_hist64, uint32_t* d_order, cudaStream_t st);

@@ -243,7 +243,7 @@ class LZSS : public SizedAlgorithm {
   protected:
     void Fill(aurora_codec_opts& o, bool) const override { o.lzss = LZ; }
 };
-// Formats/Common/LZ4.cs, LZ4Legacy.cs, LZO.cs, Snappy.cs; Sega/PRS.cs (no GPU encoder for these yet: Compress throws)
+// Formats/Common/LZ4.cs, LZ4Legacy.cs, LZO.cs, Snappy.cs; Sega/PRS.cs
 class LZ4 : public CompressionAlgorithm {
   public:
     AURORA_FORMAT(LZ4, AURORA_FMT_LZ4, "LZ4 Frame Compression")
