@@ -73,6 +73,14 @@ struct GOut {
             if (uint64_t(p) < cap) dst[p] = uint8_t(lds_u8((p & kORingMask) | rb));
         flushed = written;
     }
+    // make everything decoded so far visible in global memory without disturbing the 512-byte drain cadence
+    __device__ __forceinline__ void sync_tail() {
+        const uint32_t lane = lane_id();
+        drain();
+        for (uint32_t p = flushed + lane; p < written; p += 32)
+            if (uint64_t(p) < cap) dst[p] = uint8_t(lds_u8((p & kORingMask) | rb));
+        __syncwarp();
+    }
     // LzWindows.Write / CopyFrom: `len` bytes from the staged input at relative position ipos
     __device__ __forceinline__ void lit_copy(InStream& in, uint32_t ipos, uint32_t len) {
         const uint32_t lane = lane_id();
@@ -230,8 +238,45 @@ __device__ __forceinline__ bool lz4_magic(uint32_t v) {
     return v == 0x184C2102u || v == 0x184D2204u || (v >= 0x184D2A50u && v <= 0x184D2A5Fu);
 }
 
-// LZ4.cs:50-111 + LZ4.Frame.cs:107-174
-__device__ Res lz4_container(InStream& in, GOut& out, uint32_t slen, int verify) {
+// XXH32 (seed 0) of n bytes at p in global memory, the hash the reference injects as LZ4.HashAlgorithm
+// (LZ4.Frame.cs:24-40).  The four stripe accumulators are independent: lanes 0..3 own one each; lane 0 folds them and
+// walks the tail.  The result is broadcast to the warp.
+__device__ uint32_t xxh32_warp(const uint8_t* p, uint32_t n) {
+    const uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+    const uint32_t lane = lane_id();
+    auto rd32 = [&](uint32_t o) { return uint32_t(p[o]) | (uint32_t(p[o + 1]) << 8) | (uint32_t(p[o + 2]) << 16) | (uint32_t(p[o + 3]) << 24); };
+    auto rotl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
+    uint32_t h;
+    const uint32_t stripes = n / 16;
+    if (stripes > 0) {
+        uint32_t v = lane == 0 ? P1 + P2 : lane == 1 ? P2 : lane == 2 ? 0u : 0u - P1;
+        if (lane < 4)
+            for (uint32_t s = 0; s < stripes; s++) v = rotl(v + rd32(16 * s + 4 * lane) * P2, 13) * P1;
+        const uint32_t v1 = __shfl_sync(kFull, v, 0), v2 = __shfl_sync(kFull, v, 1), v3 = __shfl_sync(kFull, v, 2), v4 = __shfl_sync(kFull, v, 3);
+        h = rotl(v1, 1) + rotl(v2, 7) + rotl(v3, 12) + rotl(v4, 18);
+    } else {
+        h = P5;
+    }
+    h += n;
+    uint32_t o = stripes * 16;
+    while (o + 4 <= n) {
+        h = rotl(h + rd32(o) * P3, 17) * P4;
+        o += 4;
+    }
+    while (o < n) {
+        h = rotl(h + uint32_t(p[o]) * P5, 11) * P1;
+        o++;
+    }
+    h ^= h >> 15;
+    h *= P2;
+    h ^= h >> 13;
+    h *= P3;
+    h ^= h >> 16;
+    return h;
+}
+
+// LZ4.cs:50-111 + LZ4.Frame.cs:107-174.  `src` is the blob in global memory (checksum verification reads it directly).
+__device__ Res lz4_container(InStream& in, GOut& out, const uint8_t* src, uint32_t slen, int verify) {
     uint32_t sp = 0;
     while (sp < slen) {
         if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
@@ -298,10 +343,12 @@ __device__ Res lz4_container(InStream& in, GOut& out, uint32_t slen, int verify)
                     if (uint64_t(sp) + sz > slen) return Res{AURORA_END_OF_STREAM, slen};
                     const uint32_t blk = sp;
                     sp += sz;
-                    if (FLG & 16) {
+                    if (FLG & 16) {   // block checksum (CheckChecksum, LZ4.Frame.cs:26-41)
                         if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                        // read from global memory: the staged input only moves forward and the block comes first
+                        const uint32_t want = uint32_t(src[sp]) | (uint32_t(src[sp + 1]) << 8) | (uint32_t(src[sp + 2]) << 16) | (uint32_t(src[sp + 3]) << 24);
                         sp += 4;
-                        if (verify) return Res{AURORA_NOT_SUPPORTED, sp};
+                        if (verify && !out.size_only && xxh32_warp(src + blk, sz) != want) return Res{AURORA_INVALID_DATA, sp};
                     }
                     if (stored) {
                         out.lit_copy(in, blk, sz);
@@ -311,10 +358,15 @@ __device__ Res lz4_container(InStream& in, GOut& out, uint32_t slen, int verify)
                     }
                 }
                 if ((FLG & 8) && uint64_t(out.written) != uint64_t(dest_start) + content) return Res{AURORA_SIZE_MISMATCH, sp};
-                if (FLG & 4) {
+                if (FLG & 4) {   // content checksum over the decoded frame
                     if (sp + 4 > slen) return Res{AURORA_END_OF_STREAM, slen};
+                    const uint32_t want = uint32_t(src[sp]) | (uint32_t(src[sp + 1]) << 8) | (uint32_t(src[sp + 2]) << 16) | (uint32_t(src[sp + 3]) << 24);
                     sp += 4;
-                    if (verify) return Res{AURORA_NOT_SUPPORTED, sp};
+                    if (verify && !out.size_only) {
+                        out.sync_tail();
+                        if (uint64_t(out.written) > out.cap) return Res{AURORA_DST_TOO_SMALL, sp};
+                        if (xxh32_warp(out.dst + dest_start, out.written - dest_start) != want) return Res{AURORA_INVALID_DATA, sp};
+                    }
                 }
                 break;
             } else if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) {   // skippable
@@ -658,7 +710,7 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream& in,
     out.size_only = P.size_only != 0;
     in.begin(P.src_base, P.src_limit, src);
     Res r;
-    if (K == B_LZ4) r = lz4_container(in, out, slen, P.lz4_verify);
+    if (K == B_LZ4) r = lz4_container(in, out, src, slen, P.lz4_verify);
     else if (K == B_LZ4_BLOCK) {
         const int st = lz4_block(in, out, 0, slen);
         r = Res{st, slen};

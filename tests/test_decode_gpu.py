@@ -170,6 +170,21 @@ def test_lz4_containers(codec, oracle, bmp):
     caps = [700000] * len(blobs)
     for fmt in (A.FMT_LZ4, A.FMT_LZ4_LEGACY):
         _compare(codec, oracle, fmt, blobs, caps, what="containers")
+    # LZ4.HashAlgorithm set (lz4_verify): XXH32 block / content checksums are verified on the device
+    import struct
+    def frame(block_ck, content_ck, nblocks=1):
+        body = b""
+        for _ in range(nblocks):
+            body += len(blk).to_bytes(4, "little") + blk + struct.pack("<I", block_ck if block_ck is not None else oracle.xxh32(blk))
+        content = raw[:50000] * nblocks
+        return (0x184D2204).to_bytes(4, "little") + bytes([0x40 | 16 | 4 | 32, 0x40, 0x00]) + body + (0).to_bytes(4, "little") + \
+            struct.pack("<I", content_ck if content_ck is not None else oracle.xxh32(content))
+    good, bad_block, bad_content = frame(None, None), frame(0x12345678, None), frame(None, 0x9ABCDEF0)
+    two = frame(None, None) + frame(None, None)
+    vblobs = [good, bad_block, bad_content, two, f64, hand]
+    _compare(codec, oracle, A.FMT_LZ4, vblobs, [200000] * len(vblobs), A.make_opts(lz4_verify=1), what="checksums")
+    outs, out_len, consumed, status = codec.decode_batch(A.FMT_LZ4, vblobs, [200000] * len(vblobs), A.make_opts(lz4_verify=1))
+    assert list(status[:4]) == [A.OK, A.INVALID_DATA, A.INVALID_DATA, A.OK] and outs[0] == raw[:50000] and outs[3] == raw[:50000] * 2
 
 
 def test_snappy_framing(codec, oracle, bmp):
