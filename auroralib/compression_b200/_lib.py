@@ -13,7 +13,7 @@ EXPORTS = [
     "aurora_init", "aurora_shutdown", "aurora_device_count", "aurora_ctx_device_count", "aurora_abi_version",
     "aurora_last_error_string", "aurora_status_string", "aurora_pinned_alloc", "aurora_pinned_free",
     "aurora_lz_props_window", "aurora_lz_props_bits", "aurora_codec_opts_init", "aurora_decoded_size_batch",
-    "aurora_is_match_batch", "aurora_decode_batch", "aurora_encode_bound", "aurora_encode_batch",
+    "aurora_is_match_batch", "aurora_scan_offsets", "aurora_decode_batch", "aurora_encode_bound", "aurora_encode_batch",
     "aurora_decode_batch_device", "aurora_encode_batch_device", "aurora_kernel_launch_count",
 ]
 
@@ -56,6 +56,8 @@ def load():
     L.aurora_decoded_size_batch.argtypes = [vp, i32, opts, sz, vp, vp, vp, i32, vp, vp]
     L.aurora_is_match_batch.restype = i32
     L.aurora_is_match_batch.argtypes = [vp, i32, opts, sz, vp, vp, vp, vp]
+    L.aurora_scan_offsets.restype = i32
+    L.aurora_scan_offsets.argtypes = [vp, i32, opts, vp, u64, vp]
     L.aurora_decode_batch.restype = i32
     L.aurora_decode_batch.argtypes = [vp, i32, opts, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.aurora_encode_bound.restype = u64

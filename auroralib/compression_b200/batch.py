@@ -116,6 +116,16 @@ class BatchCodec:
         self._check(rc, "aurora_is_match_batch")
         return m.astype(bool)
 
+    def scan_offsets(self, fmt, image, opts=None):
+        """IsMatch at every byte offset of `image` -> bool array (the data-parallel `-scan`)."""
+        opts = opts or _abi.make_opts()
+        a = np.frombuffer(bytes(image), dtype=np.uint8) if not isinstance(image, np.ndarray) else image
+        m = np.zeros(max(len(a), 1), dtype=np.uint8)
+        if len(a):
+            rc = self._L.aurora_scan_offsets(self._ctx, fmt, C.byref(opts), _ptr(a), len(a), _ptr(m))
+            self._check(rc, "aurora_scan_offsets")
+        return m[:len(a)].astype(bool)
+
     def encode_bound(self, fmt, raw_len):
         return int(self._L.aurora_encode_bound(fmt, raw_len))
 

@@ -834,6 +834,27 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
     return AURORA_OK;
 }
 
+int aurora_scan_offsets(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, const uint8_t* image, uint64_t len, uint8_t* match) {
+    (void)opts;
+    if (!ctx) return AURORA_INVALID_ARGUMENT;
+    if (len == 0) return AURORA_OK;
+    if (!image || !match || !(is_flaglz(format) || is_bytelz(format)) || format == AURORA_FMT_LZ4_BLOCK || format == AURORA_FMT_SNAPPY_BLOCK ||
+        len > 0xFFFFFFFF00ull)
+        return AURORA_INVALID_ARGUMENT;
+    DeviceCtx* d = ctx->devs[0];
+    std::lock_guard<std::mutex> guard(d->mu);
+    CU_TRY(ctx, cudaSetDevice(d->dev));
+    CU_TRY(ctx, d->src.reserve(len + 16));
+    CU_TRY(ctx, d->dst.reserve(len + 16));
+    cudaStream_t st = d->stream;
+    CU_TRY(ctx, cudaMemcpyAsync(d->src.p, image, len, cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, launch_scan(static_cast<const uint8_t*>(d->src.p), len, static_cast<uint8_t*>(d->dst.p), format, st));
+    ctx->launches++;
+    CU_TRY(ctx, cudaMemcpyAsync(match, d->dst.p, len, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return AURORA_OK;
+}
+
 int aurora_decode_batch_device(aurora_ctx* ctx, int device, int format, const aurora_codec_opts* opts, size_t n,
                                const uint8_t* d_src_base, uint64_t src_total, const uint64_t* d_src_off,
                                const uint64_t* d_src_len, uint8_t* d_dst_base, const uint64_t* d_dst_off,

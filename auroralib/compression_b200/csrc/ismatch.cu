@@ -119,24 +119,57 @@ __device__ int prs_validate(const uint8_t* p, uint64_t len, bool big) {
     return 0;
 }
 
-__global__ void is_match_kernel(const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* match, uint32_t n, int format) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t* p = src_base + src_off[i];
-    const uint64_t len = src_len[i];
-    bool m = false;
-    if (format == AURORA_FMT_LZ10) m = lz1x_validate(p, len, false);
-    else if (format == AURORA_FMT_LZ11) m = lz1x_validate(p, len, true);
-    else if (format == AURORA_FMT_PRS) {
-        if (4 < len) {   // stream.Position + 0x4 < stream.Length
+// IsMatch for one candidate stream (SURVEY.md Appendix A "IsMatch rules")
+__device__ bool is_match_one(const uint8_t* p, uint64_t len, int format) {
+    auto magic = [&](uint32_t be) {
+        return 0x10 < len && ((uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]) == be;
+    };
+    switch (format) {
+        case AURORA_FMT_YAZ0: return magic(0x59617A30u);
+        case AURORA_FMT_YAZ1: return magic(0x59617A31u);
+        case AURORA_FMT_YAY0: return magic(0x59617930u);
+        case AURORA_FMT_MIO0: return magic(0x4D494F30u);
+        case AURORA_FMT_LZSS: return magic(0x4C5A5353u);
+        case AURORA_FMT_LZ4_LEGACY: return magic(0x02214C18u);
+        case AURORA_FMT_LZ4: {
+            if (!(0x10 < len)) return false;
+            const uint32_t v = uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24);
+            return v == 0x184C2102u || v == 0x184D2204u || (v >= 0x184D2A50u && v <= 0x184D2A5Fu);
+        }
+        case AURORA_FMT_SNAPPY: {
+            const uint8_t id[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};
+            if (!(0x10 < len)) return false;
+            for (int i = 0; i < 10; i++)
+                if (p[i] != id[i]) return false;
+            return true;
+        }
+        case AURORA_FMT_LZO: return len > 0 && p[0] < 0x20;
+        case AURORA_FMT_LZ10: return lz1x_validate(p, len, false);
+        case AURORA_FMT_LZ11: return lz1x_validate(p, len, true);
+        case AURORA_FMT_PRS: {
+            if (!(4 < len)) return false;   // stream.Position + 0x4 < stream.Length
             const uint32_t flag = p[0];
             int v = 0;
             if (flag > 12 && (flag & 1)) v = prs_validate(p, len, false);
             if (v == 0 && (flag & 128)) v = prs_validate(p, len, true);
-            m = v == 1;
+            return v == 1;
         }
     }
-    match[i] = m ? 1 : 0;
+    return false;
+}
+
+__global__ void is_match_kernel(const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* match, uint32_t n, int format) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    match[i] = is_match_one(src_base + src_off[i], src_len[i], format) ? 1 : 0;
+}
+
+// Offset scan: IsMatch at EVERY byte offset of one image (the data-parallel form of the CLI's `-scan` loop,
+// Commands/ScanDecompressCommand.cs:23-39): thread i tests the stream that starts at offset i and runs to the end.
+__global__ void scan_kernel(const uint8_t* image, uint64_t len, uint8_t* match, int format) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    match[i] = is_match_one(image + i, len - i, format) ? 1 : 0;
 }
 
 // ---- largest-first stream order for batches with a wide size spread: counting sort by floor(log2(size)) ----
@@ -165,6 +198,11 @@ cudaError_t launch_size_order(const uint64_t* d_size, uint32_t n, uint32_t* d_hi
     order_hist_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_size, n, d_hist64);
     order_scan_kernel<<<1, 1, 0, st>>>(d_hist64);
     order_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_size, n, d_hist64, d_order);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan(const uint8_t* image, uint64_t len, uint8_t* match, int format, cudaStream_t st) {
+    scan_kernel<<<uint32_t((len + 255) / 256), 256, 0, st>>>(image, len, match, format);
     return cudaGetLastError();
 }
 

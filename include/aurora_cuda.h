@@ -146,6 +146,12 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
                           const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
                           uint8_t* match);
 
+/* IsMatch at EVERY byte offset of one image: match[i] = IsMatch(image[i .. len)).  The data-parallel form of the CLI's
+ * `-scan` loop (AuroraLib.Compression.CLI/Commands/ScanDecompressCommand.cs:23-39): the caller walks the bitmap, decodes
+ * at the first hit and resumes after the consumed bytes.  `image` and `match` are host buffers of `len` bytes. */
+int aurora_scan_offsets(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, const uint8_t* image, uint64_t len,
+                        uint8_t* match);
+
 /* Decompress(Stream source, Stream destination) for n streams.
  * out_len[i]  = bytes the reference would have written (may exceed dst_cap[i] on overshoot),
  * consumed[i] = source.Position after the call, relative to the start of stream i. */

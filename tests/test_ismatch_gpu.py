@@ -98,3 +98,35 @@ def test_mirror_streams_and_exceptions(codec, oracle, bmp):
     c = le.Compress(raw)
     assert c.getvalue()[4:8] == len(raw).to_bytes(4, "little")
     assert Yaz0().Decompress(c).getvalue() == raw   # default Big: the swapped-size retry (Yaz0.cs:67-78)
+
+
+def test_offset_scan_of_a_rom_like_image(codec, oracle, bmp):
+    """The CLI's `-scan` (ScanDecompressCommand.cs:23-39) as one pass: IsMatch at every offset of an image that holds a few
+    compressed assets between junk, then decode at the hits and resume after the consumed bytes."""
+    rng = np.random.default_rng(77)
+    assets = [bmp[1000:9000], bytes(3000), synth(rng, 5000, 0), synth(rng, 2500, 2)]
+    for fmt in (A.FMT_YAZ0, A.FMT_LZ10, A.FMT_LZ11, A.FMT_MIO0, A.FMT_LZ4, A.FMT_PRS):
+        image = bytearray(rng.integers(0, 256, size=700, dtype=np.uint8).tobytes())
+        starts = []
+        for a in assets:
+            c, st = oracle.encode(fmt, a, A.make_opts(quality=8))
+            assert st == 0
+            starts.append(len(image))
+            image += c + rng.integers(0, 256, size=int(rng.integers(10, 400)), dtype=np.uint8).tobytes()
+        image = bytes(image)
+        got = codec.scan_offsets(fmt, image)
+        ref = np.array([oracle.is_match(fmt, image[i:]) for i in range(len(image))])
+        assert (got == ref).all(), (fmt_id(fmt), int((got != ref).sum()))
+        if fmt in (A.FMT_YAZ0, A.FMT_MIO0, A.FMT_LZ4):   # magic formats hit every asset (the token-walk heuristics may not, like the reference)
+            assert all(got[s] for s in starts), fmt_id(fmt)
+        if fmt in (A.FMT_YAZ0, A.FMT_MIO0):   # magic formats: walk the bitmap like the CLI does
+            found, i = [], 0
+            while i < len(image):
+                if got[i]:
+                    outs, out_len, consumed, status = codec.decode_batch(fmt, [image[i:]], [1 << 16])
+                    if status[0] == 0:
+                        found.append(outs[0])
+                        i += int(consumed[0])
+                        continue
+                i += 1
+            assert found == assets
