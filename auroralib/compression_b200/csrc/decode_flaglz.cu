@@ -45,7 +45,7 @@ struct Traits {
     static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : 1;
     static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0) ? 273 : (K == K_LZSS) ? 258 : 65808;
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
-    static constexpr bool kG32 = (K != K_LZ11);   // one flag group per lane (256 tokens per iteration)
+    static constexpr bool kG32 = true;   // one flag group per lane (256 tokens per iteration)
     static constexpr int kQueueBytes = kG32 ? kQueue * 8 + 256 : 0;       // match queue + group offsets / group descriptors
     static constexpr int kSmemPerWarp = kRing + kStreams * kInStage + kQueueBytes + 64;
     static constexpr int kWarps = (113 * 1024 - kRing) / kSmemPerWarp;    // x2 blocks per SM (8 KiB ring-alignment slack per block)
@@ -375,7 +375,7 @@ __device__ __forceinline__ void ring_copy_queued(uint32_t rb, uint32_t pos, uint
 }
 
 
-// Replays the queued matches of one iteration in stream order.  Entries are {pos, len | d << 16}.
+// Replays the queued matches of one iteration in stream order.  Entries are {pos, len | d << 17} (len up to 17 bits: LZ11).
 // Run merging: encoders split a long run (or a 32-byte tile) into maximum-length matches with the same distance that
 // follow each other without a gap; such a chain is exactly one longer periodic copy out[o] = out[o - d].  A parallel
 // post-pass (one entry per lane, chains cut at 32-entry blocks) compacts every chain into one entry in place, then the
@@ -413,7 +413,7 @@ __device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint
         const bool have = q < nq;
         const uint2 e = lds_u64(qaddr + 8 * q);
         const uint32_t px = __shfl_up_sync(kFull, e.x, 1), py = __shfl_up_sync(kFull, e.y, 1);
-        const bool cont = have && lane > 0 && e.x == px + (py & 0xFFFFu) && (e.y >> 16) == (py >> 16);
+        const bool cont = have && lane > 0 && e.x == px + (py & 0x1FFFFu) && (e.y >> 17) == (py >> 17);
         const uint32_t heads = __ballot_sync(kFull, have && !cont);
         const uint32_t valid = __ballot_sync(kFull, have);
         // last entry of my chain: the lane before the next head (or the last valid lane of the block)
@@ -421,7 +421,7 @@ __device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint
         const uint32_t last = after ? uint32_t(__ffs(after) - 2) : uint32_t(31 - __clz(valid));
         const uint32_t tx = __shfl_sync(kFull, e.x, last & 31), ty = __shfl_sync(kFull, e.y, last & 31);
         __syncwarp();
-        if (have && !cont) sts_u64(qaddr + 8 * (nout + __popc(heads & lt)), e.x, (tx + (ty & 0xFFFFu) - e.x) | (e.y & 0xFFFF0000u));
+        if (have && !cont) sts_u64(qaddr + 8 * (nout + __popc(heads & lt)), e.x, (tx + (ty & 0x1FFFFu) - e.x) | (e.y & 0xFFFE0000u));
         nout += __popc(heads);
     }
     __syncwarp();
@@ -432,7 +432,7 @@ __device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint
     uint32_t q = 0;
     while (q + 1 < nout) {
         const uint2 n0 = lds_u64(qaddr + 8 * (q + 2)), n1 = lds_u64(qaddr + 8 * (q + 3));
-        const uint32_t len0 = e0.y & 0xFFFFu, d0 = e0.y >> 16, len1 = e1.y & 0xFFFFu, d1 = e1.y >> 16;
+        const uint32_t len0 = e0.y & 0x1FFFFu, d0 = e0.y >> 17, len1 = e1.y & 0x1FFFFu, d1 = e1.y >> 17;
         if (max(len0, len1) < 512 && e1.x - d1 + min(len1, d1) <= e0.x) {
             const uint32_t r0 = d0 < len0 ? c_rcp.v[d0] : 0u, r1 = d1 < len1 ? c_rcp.v[d1] : 0u;   // 0: no wrap, off = i
             const uint32_t s0 = e0.x - d0, s1 = e1.x - d1, lmax = max(len0, len1);
@@ -456,7 +456,7 @@ __device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint
         q += 2;
     }
     if (q < nout) {
-        ring_copy_any(rb, e0.x, e0.y >> 16, e0.y & 0xFFFFu);
+        ring_copy_any(rb, e0.x, e0.y >> 17, e0.y & 0x1FFFFu);
         __syncwarp();
     }
 }
@@ -541,7 +541,7 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
                         dist = rp >= offset ? rp - offset : rp - offset + ring_len;
                         if (dist == 0) dist = ring_len;
                     }
-                    sts_u64(qa, pos, len | (dist << 16));
+                    sts_u64(qa, pos, len | (dist << 17));
                     qa += 8;
                 }
                 a += ism ? 2 : 1;
@@ -610,7 +610,7 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
                             dist = rp >= offset ? rp - offset : rp - offset + ring_len;
                             if (dist == 0) dist = ring_len;
                         }
-                        sts_u64(qaddr + 8 * qi, pos, len | (dist << 16));
+                        sts_u64(qaddr + 8 * qi, pos, len | (dist << 17));
                         qi++;
                     }
                     a += ism ? 2 : 1;
@@ -639,8 +639,8 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
 }
 
 // ---------------------------------------------------------------------------------------------
-// G32 core for Yaz0/Yaz1 (Yay0.cs:110-144 through Yaz0.cs:91-92).  A match token is 2 bytes, or 3 when the high nibble
-// of its first byte is 0, so a group's size depends on its own data and the chain of group starts cannot be a pure
+// G32 core for Yaz0/Yaz1 (Yay0.cs:110-144 through Yaz0.cs:91-92) and LZ11 (LZ11.cs:83-133).  A match token is 2 bytes, or 3
+// when the high nibble of its first byte is 0 (LZ11: also 4 when it is 1), so a group's size depends on its own data and the chain of group starts cannot be a pure
 // popcount chain.  The chain is still the only serial part: per group the warp loads the flag byte, builds a ballot mask
 // E of "high nibble == 0" over the group's next 32 bytes, and walks only the MATCH tokens of the group (highest flag bit
 // first) accumulating the number of 3-byte tokens: token i starts at 1 + i + matches_before + ext_before, and its
@@ -648,7 +648,8 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
 // (A fixed-point iteration over guessed group starts was tried first; on data with many long matches it needs one
 // round per group and was slower.)
 // ---------------------------------------------------------------------------------------------
-__device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const uint32_t qaddr, const uint32_t gaddr, const uint32_t slen,
+template <int K>   // K_YAZ0 or K_LZ11
+__device__ BodyResult decode_body_g32_var(InStream* in, OutState& out, const uint32_t qaddr, const uint32_t gaddr, const uint32_t slen,
                                            const uint32_t size, const uint32_t body_off) {
     const uint32_t lane = lane_id();
     const uint32_t rb = out.rbase;
@@ -658,7 +659,7 @@ __device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const ui
     while (written < size) {
         in[0].ensure(cur, kInMirror - 16);
         const uint32_t wa = smem_u32(in[0].window(cur));
-        const uint32_t wlimit = kInMirror - 40;   // a group may start in the first 600 bytes of the window (it is <= 25 bytes)
+        const uint32_t wlimit = kInMirror - 48;   // a group may start in the first 592 bytes of the window (it is <= 33 bytes)
         // ---- exact chain of group starts
         uint32_t ca = wa, nvalid = 0;
 #pragma unroll 1
@@ -666,11 +667,14 @@ __device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const ui
             if (ca - wa > wlimit) break;
             sts_u32(gaddr + 4 * g, ca);
             const uint32_t fb = lds_u8(ca);
-            const uint32_t E = __ballot_sync(kFull, (lds_u8(ca + 1 + lane) >> 4) == 0);
-            uint32_t mm = fb ^ 0xFFu, x = 0, cnt = 0;
+            const uint32_t hi4 = lds_u8(ca + 1 + lane) >> 4;
+            const uint32_t E = __ballot_sync(kFull, hi4 == 0);                             // +1 byte
+            const uint32_t E2 = (K == K_LZ11) ? __ballot_sync(kFull, hi4 == 1) : 0u;       // +2 bytes (LZ11 4-byte tokens)
+            uint32_t mm = (K == K_YAZ0) ? (fb ^ 0xFFu) : fb, x = 0, cnt = 0;               // match bits, MSB first
             while (mm) {
                 const uint32_t hb = 31 - __clz(mm);
-                x += (E >> (7 - hb + cnt + x)) & 1u;
+                const uint32_t at = 7 - hb + cnt + x;
+                x += ((E >> at) & 1u) + 2u * ((E2 >> at) & 1u);
                 cnt++;
                 mm ^= 1u << hb;
             }
@@ -690,22 +694,32 @@ __device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const ui
             uint32_t a = mya + 1;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const bool lit = (f >> (7 - j)) & 1;
+                const bool lit = ((f >> (7 - j)) & 1) == (K == K_YAZ0 ? 1u : 0u);
                 const uint32_t b1 = lds_u8(a);
                 const uint32_t n = b1 >> 4;
-                const bool ext = !lit && n == 0;
-                const uint32_t b3 = lds_u8(a + 2);
                 b1v[j] = b1;
                 orel[j] = gsize;
-                lenv[j] = lit ? 1u : (ext ? b3 + 0x12u : n + 2u);
+                if (K == K_YAZ0) {
+                    const bool ext = !lit && n == 0;
+                    const uint32_t b3 = lds_u8(a + 2);
+                    lenv[j] = lit ? 1u : (ext ? b3 + 0x12u : n + 2u);
+                    a += lit ? 1u : (ext ? 3u : 2u);
+                } else {
+                    const uint32_t b2 = lds_u8(a + 1), b3 = lds_u8(a + 2);
+                    uint32_t l = n + 1, sz = 2;
+                    if (n == 0) { l = (((b1 & 0xF) << 4) | (b2 >> 4)) + 17; sz = 3; }
+                    if (n == 1) { l = (((b1 & 0xF) << 12) | (b2 << 4) | (b3 >> 4)) + 273; sz = 4; }
+                    lenv[j] = lit ? 1u : l;
+                    a += lit ? 1u : sz;
+                }
                 gsize += lenv[j];
-                a += lit ? 1u : (ext ? 3u : 2u);
             }
             gin = a - mya;
         }
-        const uint32_t nm = __popc(f ^ 0xFFu);
-        const uint32_t incl = warp_incl_scan(valid ? (gsize | (nm << 20)) : 0u);
-        const uint32_t gincl = incl & 0xFFFFFu, gexcl = gincl - (valid ? gsize : 0u);
+        const uint32_t nm = __popc((K == K_YAZ0) ? (f ^ 0xFFu) : f);
+        const uint32_t gclamp = min(gsize, 4095u);   // LZ11 groups can be huge; anything above kSubMaxG takes the long-group path
+        const uint32_t incl = warp_incl_scan(valid ? (gclamp | (nm << 20)) : 0u);
+        const uint32_t gincl = incl & 0xFFFFFu, gexcl = gincl - (valid ? gclamp : 0u);
         const uint32_t qexcl = (incl >> 20) - (valid ? nm : 0u);
         const uint32_t remaining = size - written;
         const uint32_t gbase = written + gexcl;
@@ -723,15 +737,22 @@ __device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const ui
             bool stop = false;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const bool lit = (f >> (7 - j)) & 1;
-                const bool ext = !lit && (b1v[j] >> 4) == 0;
-                const uint32_t need = a + (lit ? 1u : 2u);   // the extended-length byte is optional (ReadByte)
+                const bool lit = ((f >> (7 - j)) & 1) == (K == K_YAZ0 ? 1u : 0u);
+                const uint32_t n = b1v[j] >> 4;
+                uint32_t need, next_a;
+                if (K == K_YAZ0) {
+                    need = a + (lit ? 1u : 2u);   // the extended-length byte is optional (ReadByte)
+                    next_a = need + ((!lit && n == 0) ? 1u : 0u);
+                } else {
+                    need = a + (lit ? 1u : (n == 0 ? 3u : n == 1 ? 4u : 2u));
+                    next_a = need;
+                }
                 const bool want = orel[j] < lim;
                 const bool bad = gabs >= slen || need > slen;
                 if (!stop && want && bad) eos_here = true;
                 stop = stop || !want || bad;
                 if (!stop) jexec = j + 1;
-                a = need + (ext ? 1u : 0u);
+                a = next_a;
             }
         }
         if (!taken) {
@@ -745,7 +766,53 @@ __device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const ui
             status = AURORA_END_OF_STREAM;
         }
         const uint32_t nlan = __popc(__ballot_sync(kFull, jexec > 0));
-        if (nlan == 0) break;
+        if (nlan == 0) {
+            if (K == K_LZ11 && status == AURORA_OK && __shfl_sync(kFull, gsize, 0) > uint32_t(kSubMaxG)) {
+                // long-group path: the first group alone exceeds the iteration budget (matches of up to 65 808 bytes):
+                // its 8 tokens run one at a time, long matches as periodic 2 KiB segments with a drain in between
+                const uint32_t rel0 = __shfl_sync(kFull, myrel, 0), f0 = __shfl_sync(kFull, f, 0);
+                uint32_t a = rel0 + 1;   // relative to cur
+                bool done = false;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t b1 = __shfl_sync(kFull, b1v[j], 0), l = __shfl_sync(kFull, lenv[j], 0);
+                    const bool lit = ((f0 >> (7 - j)) & 1) == 0;
+                    const uint32_t n = b1 >> 4, sz = lit ? 1u : (n == 0 ? 3u : n == 1 ? 4u : 2u);
+                    if (!done && written < size) {
+                        if (cur + rel0 >= slen || cur + a + sz > slen) {
+                            status = AURORA_END_OF_STREAM;
+                            done = true;
+                        } else {
+                            if (lit) {
+                                if (lane == 0) sts_u8((written & kRingMask) | rb, b1);
+                                written += 1;
+                            } else {
+                                const uint32_t ta = wa + a;
+                                const uint32_t c2 = lds_u8(ta + 1), c3 = lds_u8(ta + 2), c4 = lds_u8(ta + 3);
+                                const uint32_t d = n == 0 ? (((c2 & 0xF) << 8) | c3) + 1 : n == 1 ? (((c3 & 0xF) << 8) | c4) + 1 : (((b1 & 0xF) << 8) | c2) + 1;
+                                for (uint32_t sgm = 0; sgm < l; sgm += 2048) {
+                                    const uint32_t seg = min(2048u, l - sgm);
+                                    ring_copy_any(rb, written, d, seg);
+                                    __syncwarp();
+                                    written += seg;
+                                    out.drain(written);
+                                }
+                            }
+                            __syncwarp();
+                            a += sz;
+                            consumed = cur + a;
+                        }
+                    } else {
+                        done = true;
+                    }
+                }
+                out.drain(written);
+                if (status != AURORA_OK) break;
+                cur += a;
+                continue;
+            }
+            break;
+        }
         const uint32_t last = nlan - 1;
         uint32_t oend = 0, qi = qexcl, aend = 0;
         {
@@ -753,22 +820,30 @@ __device__ BodyResult decode_body_g32_yaz0(InStream* in, OutState& out, const ui
             const uint32_t gabs1 = cur + myrel + 1;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const bool lit = (f >> (7 - j)) & 1;
+                const bool lit = ((f >> (7 - j)) & 1) == (K == K_YAZ0 ? 1u : 0u);
                 const bool e = uint32_t(j) < jexec;
-                const uint32_t b1 = b1v[j];
-                const bool ext = !lit && (b1 >> 4) == 0;
+                const uint32_t b1 = b1v[j], n = b1 >> 4;
                 const uint32_t pos = gbase + orel[j];
-                uint32_t len = lenv[j];
-                const uint32_t tabs = gabs1 + (a - (mya + 1));   // blob offset of this token
-                const bool have_ext = tabs + 2 < slen;
-                if (ext && !have_ext) len = 0x11;   // Stream.ReadByte() == -1 at EOF (Yay0.cs:131)
+                uint32_t len = lenv[j], sz;
+                if (K == K_YAZ0) {
+                    const bool ext = !lit && n == 0;
+                    const uint32_t tabs = gabs1 + (a - (mya + 1));   // blob offset of this token
+                    const bool have_ext = tabs + 2 < slen;
+                    if (ext && !have_ext) len = 0x11;   // Stream.ReadByte() == -1 at EOF (Yay0.cs:131)
+                    sz = lit ? 1u : ((ext && have_ext) ? 3u : 2u);
+                } else {
+                    sz = lit ? 1u : (n == 0 ? 3u : n == 1 ? 4u : 2u);
+                }
                 if (e && lit) sts_u8((pos & kRingMask) | rb, b1);
                 if (e && !lit) {
                     const uint32_t b2 = lds_u8(a + 1);
-                    sts_u64(qaddr + 8 * qi, pos, len | (((((b1 & 0xF) << 8) | b2) + 1) << 16));
+                    uint32_t dist = (((b1 & 0xF) << 8) | b2) + 1;
+                    if (K == K_LZ11 && n == 0) dist = (((b2 & 0xF) << 8) | lds_u8(a + 2)) + 1;
+                    if (K == K_LZ11 && n == 1) dist = (((lds_u8(a + 2) & 0xF) << 8) | lds_u8(a + 3)) + 1;
+                    sts_u64(qaddr + 8 * qi, pos, len | (dist << 17));
                     qi++;
                 }
-                a += lit ? 1u : ((ext && have_ext) ? 3u : 2u);
+                a += sz;
                 if (e) {
                     oend = orel[j] + len;
                     aend = a - wa;
@@ -910,7 +985,7 @@ __device__ BodyResult decode_body_g32_split(InStream* in, OutState& out, const u
                 if (e && !ism) sts_u8((pos & kRingMask) | rb, litv[j]);
                 if (e && ism) {
                     const uint32_t b2 = lds_u8(ca + 2 * (mb + k) + 1);
-                    sts_u64(qaddr + 8 * qi, pos, len | (((((c1v[j] & 0xF) << 8) | b2) + 1) << 16));
+                    sts_u64(qaddr + 8 * qi, pos, len | (((((c1v[j] & 0xF) << 8) | b2) + 1) << 17));
                     qi++;
                 }
                 k += ism ? 1 : 0;
@@ -1051,8 +1126,8 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                 if (K == K_LZSS) g32 = 8u * (((1u << P.lzss.length_bits) - 1u) + uint32_t(P.lzss.min_length)) <= uint32_t(kSubMaxG);
                 if constexpr (K == K_MIO0 || K == K_YAY0) {
                     r = decode_body_g32_split<K>(in, out, qaddr, slen, size, comp_off, lit_off);
-                } else if constexpr (K == K_YAZ0) {
-                    r = decode_body_g32_yaz0(in, out, qaddr, gaddr, slen, size, body_off);
+                } else if constexpr (K == K_YAZ0 || K == K_LZ11) {
+                    r = decode_body_g32_var<K>(in, out, qaddr, gaddr, slen, size, body_off);
                 } else if constexpr (Traits<K>::kG32) {
                     if (g32) r = decode_body_g32<K>(in, out, qaddr, gaddr, slen, size, body_off, P.lzss);
                     else r = decode_body<K>(in, out, slen, size, body_off, comp_off, lit_off, P.lzss);

@@ -133,6 +133,28 @@ def test_lzss_properties(codec, oracle, props):
         assert (status == 0).all() and all(o == r for o, r in zip(outs, raws))
 
 
+def test_lz11_long_matches(codec, oracle):
+    """LZ11 matches of up to 65 808 bytes (LZ11.cs:106-112, 4-byte tokens): long constant / periodic runs between
+    literal-heavy stretches, valid, truncated and with short destinations — the group-per-lane core's long-group path."""
+    rng = np.random.default_rng(4111)
+    raws = []
+    for i in range(48):
+        parts = []
+        for _ in range(int(rng.integers(1, 5))):
+            parts.append(rng.integers(0, 256, size=int(rng.integers(0, 300)), dtype=np.uint8).tobytes())
+            period = rng.integers(0, 256, size=int(rng.choice([1, 1, 2, 3, 17, 255, 4096])), dtype=np.uint8).tobytes()
+            n = int(rng.choice([272, 273, 274, 2303, 2304, 2305, 4000, 20000, 65807, 65808, 65809, 70000, 150000]))
+            parts.append((period * (n // len(period) + 1))[:n])
+        raws.append(b"".join(parts))
+    comps, st = oracle.encode_batch(A.FMT_LZ11, raws, A.make_opts(quality=8))
+    assert (st == 0).all()
+    outs, status = _compare(codec, oracle, A.FMT_LZ11, comps, [len(r) for r in raws], what="lz11 long")
+    assert (status == 0).all() and all(o == r for o, r in zip(outs, raws))
+    cut = [c[:int(rng.integers(5, len(c)))] for c in comps]
+    _compare(codec, oracle, A.FMT_LZ11, cut, [len(r) for r in raws], what="lz11 long truncated")
+    _compare(codec, oracle, A.FMT_LZ11, comps, [max(0, len(r) - int(rng.integers(1, 3000))) for r in raws], what="lz11 long short dst")
+
+
 def test_prehistory_references(codec, oracle):
     """Back-references before the start of the output read the window's pre-history (zeros / initialFill):
     hand-made LZ10, Yaz0 and LZSS streams whose first token is a match."""
