@@ -6,7 +6,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaurora_cuda.so")
+# AURORA_CUDA_LIB: developer override to load an alternate build of the same library (tools/build_variant.sh)
+LIB_PATH = os.environ.get("AURORA_CUDA_LIB") or os.path.join(_HERE, "libaurora_cuda.so")
 
 # every symbol include/aurora_cuda.h declares
 EXPORTS = [

@@ -34,21 +34,30 @@ constexpr int kRingMask = kRing - 1;
 constexpr int kWindow = 4096;        // largest back-reference distance of the family
 constexpr int kSubMax = 2048;        // output bytes resolved per sub-batch (ring keeps window + sub-batch + drain slack)
 constexpr int kFlush = 512;          // bytes per ring->HBM drain step (16 B per lane)
-constexpr int kQueue = 256;          // match descriptors per G32 iteration (32 groups x 8 tokens)
+constexpr int kQueue = 168;          // match descriptors per G32 iteration (an iteration is cut when its queue is full)
 constexpr int kSubMaxG = 2304;       // G32: output bytes per iteration (>= the largest single group)
+constexpr int kPairSpan = 4096;      // parser/replayer pipeline: two consecutive iterations in flight, window + both + drain slack <= ring
 
 
 enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5 };
 
+// Shared memory of one stream slot (the launcher adds 8 KiB of alignment slack for the rings):
+//   ring 8 KiB | staged sub-streams | match queue x2 (+ read slack) | group offsets | mailboxes x2 | stream descriptor | mbarriers
 template <int K>
 struct Traits {
     static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : 1;
     static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0) ? 273 : (K == K_LZSS) ? 258 : 65808;
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
-    static constexpr bool kG32 = true;   // one flag group per lane (256 tokens per iteration)
-    static constexpr int kQueueBytes = kG32 ? kQueue * 8 + 256 : 0;       // match queue + group offsets / group descriptors
-    static constexpr int kSmemPerWarp = kRing + kStreams * kInStage + kQueueBytes + 64;
-    static constexpr int kWarps = (113 * 1024 - kRing) / kSmemPerWarp;    // x2 blocks per SM (8 KiB ring-alignment slack per block)
+    static constexpr int kQueueBytes = 2 * kQueue * 8 + 32;
+    static constexpr int kAuxBytes = kStreams * kInStage + kQueueBytes + 128 + 32 + 16 + (2 * kStreams + 4) * 8;
+    static constexpr int kSmemPerSlot = kRing + kAuxBytes;
+#ifdef AURORA_FLAG_SLOTS
+    static constexpr int kSlots = AURORA_FLAG_SLOTS;                      // developer probe: stream slots per block
+#else
+    // one block per SM; slots come in fours (a parser warpgroup + a replayer warpgroup)
+    static constexpr int kSlots = ((227 * 1024 - kRing) / kSmemPerSlot) / 4 * 4;
+#endif
+    static constexpr bool kRegSplit = kSlots == 16;   // 1024 threads: 64 registers each at launch, re-split 88 / 40 by setmaxnreg
 };
 
 // out[dst+i] = out[dst-d + (i mod d)], i < len : LzWindows.BackCopy (IO/LzWindows.cs:72-100) on the flat ring.
@@ -399,11 +408,61 @@ __device__ __forceinline__ void ring_copy_any(uint32_t rb, uint32_t pos, uint32_
             sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + off) & kRingMask) | rb));
         }
     } else {
-        for (uint32_t i = lane; i < len; i += 32) sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + i % d) & kRingMask) | rb));
+        // long periodic run: i mod d kept incrementally (one division for the lane's start and one for the stride)
+        uint32_t off = lane % d;
+        const uint32_t step = 32 % d;
+        for (uint32_t i = lane; i < len; i += 32) {
+            sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + off) & kRingMask) | rb));
+            off += step;
+            off -= off >= d ? d : 0u;
+        }
     }
 }
 
-__device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint32_t nq) {
+// entries [q, qend) of the compacted queue in stream order, two per step: when the second match's source ends at or before
+// the first match's destination the two copies are independent, so both loads are issued before both stores
+__device__ __forceinline__ void replay_range(uint32_t rb, uint32_t qaddr, uint32_t q, const uint32_t qend) {
+    const uint32_t lane = lane_id();
+    while (q + 1 < qend) {
+        const uint2 e0 = lds_u64(qaddr + 8 * q), e1 = lds_u64(qaddr + 8 * q + 8);
+        const uint32_t len0 = e0.y & 0x1FFFFu, d0 = e0.y >> 17, len1 = e1.y & 0x1FFFFu, d1 = e1.y >> 17;
+        if (max(len0, len1) < 512 && e1.x - d1 + min(len1, d1) <= e0.x) {
+            const uint32_t r0 = d0 < len0 ? c_rcp.v[d0] : 0u, r1 = d1 < len1 ? c_rcp.v[d1] : 0u;   // 0: no wrap, off = i
+            const uint32_t s0 = e0.x - d0, s1 = e1.x - d1, lmax = max(len0, len1);
+            for (uint32_t i = lane; i < lmax; i += 32) {
+                const uint32_t off0 = i - ((i * r0) >> 20) * d0, off1 = i - ((i * r1) >> 20) * d1;
+                uint32_t v0 = 0, v1 = 0;
+                if (i < len0) v0 = lds_u8(((s0 + off0) & kRingMask) | rb);
+                if (i < len1) v1 = lds_u8(((s1 + off1) & kRingMask) | rb);
+                if (i < len0) sts_u8(((e0.x + i) & kRingMask) | rb, v0);
+                if (i < len1) sts_u8(((e1.x + i) & kRingMask) | rb, v1);
+            }
+            __syncwarp();
+        } else {
+            ring_copy_any(rb, e0.x, d0, len0);
+            __syncwarp();
+            ring_copy_any(rb, e1.x, d1, len1);
+            __syncwarp();
+        }
+        q += 2;
+    }
+    if (q < qend) {
+        const uint2 e0 = lds_u64(qaddr + 8 * q);
+        ring_copy_any(rb, e0.x, e0.y >> 17, e0.y & 0x1FFFFu);
+        __syncwarp();
+    }
+}
+
+constexpr uint32_t kQuadMaxLen = 64;   // longest match a quad step takes (8 lanes x 8 trips); its period is < 64: rcp table in smem
+
+// Replays the queued matches of one iteration in stream order.
+//  1. run merging (lane-parallel, see above): chains of adjacent same-distance matches become one periodic copy;
+//  2. classification (lane-parallel, one compacted entry per lane): an entry is "quad-able" when it is short
+//     (<= 64 bytes) and its source does not overlap the destination of an earlier entry of its group of four;
+//  3. groups of four quad-able entries run as ONE warp step: lanes 8g..8g+7 copy entry g, 8 bytes per trip, all loads of
+//     a batch of trips issued before the stores; the other groups fall back to the two-per-step / warp-wide copies.
+// Per-entry scalar work (unpacking, hazard tests, reciprocal fetch) is thereby done once per lane instead of once per warp.
+__device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint32_t nq, uint32_t rcp_addr) {
     const uint32_t lane = lane_id();
     if (nq == 0) return;
     const uint32_t lt = (1u << lane) - 1u;
@@ -425,51 +484,190 @@ __device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint
         nout += __popc(heads);
     }
     __syncwarp();
-    // Two entries per step: when the second match's source ends at or before the first match's destination the two
-    // copies are independent, so both loads are issued before both stores (one barrier, twice the ILP); the slots
-    // past the end of the queue are readable (slack behind the queue).
-    uint2 e0 = lds_u64(qaddr), e1 = lds_u64(qaddr + 8);
-    uint32_t q = 0;
-    while (q + 1 < nout) {
-        const uint2 n0 = lds_u64(qaddr + 8 * (q + 2)), n1 = lds_u64(qaddr + 8 * (q + 3));
-        const uint32_t len0 = e0.y & 0x1FFFFu, d0 = e0.y >> 17, len1 = e1.y & 0x1FFFFu, d1 = e1.y >> 17;
-        if (max(len0, len1) < 512 && e1.x - d1 + min(len1, d1) <= e0.x) {
-            const uint32_t r0 = d0 < len0 ? c_rcp.v[d0] : 0u, r1 = d1 < len1 ? c_rcp.v[d1] : 0u;   // 0: no wrap, off = i
-            const uint32_t s0 = e0.x - d0, s1 = e1.x - d1, lmax = max(len0, len1);
-            for (uint32_t i = lane; i < lmax; i += 32) {
-                const uint32_t off0 = i - ((i * r0) >> 20) * d0, off1 = i - ((i * r1) >> 20) * d1;
-                uint32_t v0 = 0, v1 = 0;
-                if (i < len0) v0 = lds_u8(((s0 + off0) & kRingMask) | rb);
-                if (i < len1) v1 = lds_u8(((s1 + off1) & kRingMask) | rb);
-                if (i < len0) sts_u8(((e0.x + i) & kRingMask) | rb, v0);
-                if (i < len1) sts_u8(((e1.x + i) & kRingMask) | rb, v1);
-            }
-            __syncwarp();
-        } else {
-            ring_copy_any(rb, e0.x, d0, len0);
-            __syncwarp();
-            ring_copy_any(rb, e1.x, d1, len1);
-            __syncwarp();
+    const uint32_t g8 = 8 * (lane >> 3), sub = lane & 7;
+    for (uint32_t base = 0; base < nout; base += 32) {
+        // ---- classification of the block's entries (slots past the end of the queue are readable)
+        const uint32_t j = base + lane;
+        const uint2 e = lds_u64(qaddr + 8 * j);
+        const uint32_t len = e.y & 0x1FFFFu, d = e.y >> 17;
+        const uint32_t s = e.x - d, send = s + min(len, d);   // source bytes [s, send)
+        bool bad = j >= nout || len > kQuadMaxLen;
+#pragma unroll
+        for (int k = 1; k <= 3; k++) {
+            const uint32_t px = __shfl_up_sync(kFull, e.x, k), pl = __shfl_up_sync(kFull, len, k);
+            if (int(lane & 3) >= k && s < px + pl && send > px) bad = true;
         }
-        e0 = n0;
-        e1 = n1;
-        q += 2;
-    }
-    if (q < nout) {
-        ring_copy_any(rb, e0.x, e0.y >> 17, e0.y & 0x1FFFFu);
-        __syncwarp();
+        const uint32_t badmask = __ballot_sync(kFull, bad);
+        const uint32_t trips = (__reduce_max_sync(kFull, bad ? 0u : len) + 7) >> 3;
+        const uint32_t nblk = min(32u, nout - base);
+        for (uint32_t k = 0; k < nblk; k += 4) {
+            if (((badmask >> k) & 0xFu) == 0) {
+                const uint2 m = lds_u64(qaddr + 8 * (base + k) + g8);   // my group's entry
+                const uint32_t ml = m.y & 0x1FFFFu, md = m.y >> 17, ms = m.x - md;
+                const uint32_t r = md < ml ? lds_u32(rcp_addr + 4 * md) : 0u;   // 0: no wrap, off = i
+                for (uint32_t t0 = 0; t0 < trips; t0 += 4) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const uint32_t i = sub + 8 * (t0 + t);
+                        const uint32_t off = i - ((i * r) >> 20) * md;
+                        v[t] = 0;
+                        if (i < ml) v[t] = lds_u8(((ms + off) & kRingMask) | rb);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const uint32_t i = sub + 8 * (t0 + t);
+                        if (i < ml) sts_u8(((m.x + i) & kRingMask) | rb, v[t]);
+                    }
+                }
+                __syncwarp();
+            } else {
+                replay_range(rb, qaddr, base + k, min(base + k + 4, nout));
+            }
+        }
     }
 }
 
-template <int K>
-__device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_t qaddr, const uint32_t gaddr, const uint32_t slen,
+// ---------------------------------------------------------------------------------------------
+// Parser / replayer pipeline.  A stream slot is served by TWO warps: the parser walks the flag-byte chain, sizes the
+// tokens, scatters the literals into the ring and queues the matches of one iteration; the replayer merges and replays
+// the queued matches and drains the ring to HBM.  They overlap on consecutive iterations through two queue buffers, a
+// 16-byte mailbox per buffer and full/empty mbarriers (arrive = release.cta, try_wait = acquire.cta), so the slot keeps
+// two dependent instruction streams in flight instead of one (the kernel is latency bound, profiles/).
+//   ring safety: while the replayer works on iteration i (positions [w, w + t_i), sources >= w - 4096, undrained bytes
+//   >= w - 511) the parser may write iteration i+1 up to position w + t_i + t_{i+1}; the slots it overwrites hold
+//   positions 8192 lower, so t_i + t_{i+1} <= kPairSpan = 4096 keeps them below the window.  The parser acquires
+//   buffer (i+1) & 1 first, i.e. iteration i-1 is replayed and drained before anything of i+1 is written.
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { kMsgBegin = 1u, kMsgFinish = 2u, kMsgLong = 4u, kMsgExit = 8u };
+
+// one (possibly very long) match in segments of 2 KiB with a drain in between (LZ11: up to 65 808 bytes)
+__device__ __forceinline__ void long_match_copy(OutState& out, uint32_t pos, uint32_t d, uint32_t len) {
+    for (uint32_t sgm = 0; sgm < len; sgm += 2048) {
+        const uint32_t seg = min(2048u, len - sgm);
+        ring_copy_any(out.rbase, pos + sgm, d, seg);
+        __syncwarp();
+        out.drain(pos + sgm + seg);
+    }
+}
+
+// parser side of the pipeline (all members warp-uniform)
+struct PipeSink {
+    uint32_t rbase;        // shared address of the slot's ring
+    uint32_t qbase;        // shared address of queue buffer 0 (buffer 1 follows)
+    uint32_t mail;         // shared address of mailbox 0 (mailbox 1 follows), then the stream descriptor
+    uint64_t* full;        // [2]
+    uint64_t* empty;       // [2]
+    uint32_t it;           // messages sent over the lifetime of the warp
+    uint32_t prev_total;   // decoded bytes of the latest message, possibly still being replayed
+    uint32_t flags_next;
+
+    __device__ __forceinline__ void wait_idle() {   // every message sent so far has been consumed
+        if (it >= 2) mbar_wait(&empty[it & 1], ((it - 2) >> 1) & 1);
+        if (it >= 1) mbar_wait(&empty[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        prev_total = 0;
+    }
+    // new stream (or Yaz0's second attempt): the replayer is idle, so the ring and the descriptor are ours
+    __device__ __forceinline__ void begin(uint8_t* ring, uint32_t fill, uint8_t* dst, uint32_t limit) {
+        wait_idle();
+        const uint32_t w = fill * 0x01010101u;
+        const uint4 v = make_uint4(w, w, w, w);
+        uint4* p = reinterpret_cast<uint4*>(ring + (kRing - kWindow));
+        for (int i = lane_id(); i < kWindow / 16; i += 32) p[i] = v;
+        if (lane_id() == 0) {
+            const uint64_t a = reinterpret_cast<uint64_t>(dst);
+            sts_u128(mail + 32, uint32_t(a), uint32_t(a >> 32), limit, (a & 15) == 0 ? 1u : 0u);
+        }
+        flags_next = kMsgBegin;
+        __syncwarp();
+    }
+    __device__ __forceinline__ uint32_t cap() const { return min(uint32_t(kSubMaxG), uint32_t(kPairSpan) - prev_total); }
+    // the budget was cut by the iteration still in flight: wait for it and offer the full budget once
+    __device__ __forceinline__ bool retry_full() {
+        if (prev_total == 0) return false;
+        wait_idle();
+        return true;
+    }
+    __device__ __forceinline__ uint32_t acquire() {
+        mbar_wait(&empty[it & 1], ((it >> 1) & 1) ^ 1);
+        return qbase + (it & 1) * (kQueue * 8);
+    }
+    __device__ __forceinline__ void submit(uint32_t nq, uint32_t produced, uint32_t total, uint32_t flags = 0) {
+        __syncwarp();   // every lane's ring / queue stores are ordered before lane 0's releasing arrive
+        if (lane_id() == 0) {
+            sts_u128(mail + 16 * (it & 1), nq, produced, flags | flags_next, 0u);
+            mbar_arrive(&full[it & 1]);
+        }
+        it++;
+        prev_total = total;
+        flags_next = 0;
+    }
+    __device__ __forceinline__ void finish(uint32_t produced) {
+        acquire();
+        submit(0, produced, 0, kMsgFinish);
+    }
+    // LZ11 long-group path: tokens one at a time while the replayer is idle
+    __device__ __forceinline__ void single_literal(uint32_t pos, uint32_t b) {
+        wait_idle();
+        if (lane_id() == 0) sts_u8((pos & kRingMask) | rbase, b);
+    }
+    __device__ __forceinline__ void long_match(uint32_t pos, uint32_t d, uint32_t len) {
+        const uint32_t q = acquire();
+        if (lane_id() == 0) sts_u64(q, pos, len | (d << 17));
+        submit(1, pos + len, 0, kMsgLong);
+        wait_idle();
+    }
+    __device__ __forceinline__ void exit() {
+        acquire();
+        submit(0, 0, 0, kMsgExit);
+    }
+};
+
+// replayer side of the pipeline: consumes messages until the parser says exit
+__device__ void replayer_role(uint8_t* ring, uint32_t qbase, uint32_t mail, uint64_t* full, uint64_t* empty, uint32_t rcp_addr) {
+    OutState out;
+    out.ring = ring;
+    out.rbase = smem_u32(ring);
+    out.dst = nullptr;
+    out.limit = 0;
+    out.flushed = 0;
+    out.aligned = false;
+    for (uint32_t m = 0;; m++) {
+        const uint32_t b = m & 1;
+        mbar_wait(&full[b], (m >> 1) & 1);
+        const uint4 msg = lds_u128(mail + 16 * b);   // {nq, produced, flags, -}
+        if (msg.z & kMsgExit) break;
+        if (msg.z & kMsgBegin) {
+            const uint4 d = lds_u128(mail + 32);
+            out.dst = reinterpret_cast<uint8_t*>(uint64_t(d.x) | (uint64_t(d.y) << 32));
+            out.limit = d.z;
+            out.aligned = d.w != 0;
+            out.flushed = 0;
+        }
+        const uint32_t q = qbase + b * (kQueue * 8);
+        if (msg.z & kMsgLong) {
+            const uint2 e = lds_u64(q);
+            long_match_copy(out, e.x, e.y >> 17, e.y & 0x1FFFFu);
+        } else {
+#ifndef AURORA_EXP_NOREPLAY   // developer probe: parser-bound speed (output is wrong)
+            replay_matches(out.rbase, q, msg.x, rcp_addr);
+#endif
+        }
+        if (msg.z & kMsgFinish) out.finish(msg.y);
+        else out.drain(msg.y);
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&empty[b]);
+    }
+}
+
+template <int K, class Sink>
+__device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t gaddr, const uint32_t slen,
                                       const uint32_t size, const uint32_t body_off, const LzssParams& lz) {
     const uint32_t lane = lane_id();
-    const uint32_t rb = out.rbase;
+    const uint32_t rb = sink.rbase;
     uint32_t written = 0, cur = body_off, consumed = body_off;
     int status = AURORA_OK;
     const uint32_t lmask = (1u << lz.length_bits) - 1u;
-    constexpr bool kShort = (K == K_LZ10);
 
     while (written < size) {
         in[0].ensure(cur, kInMirror - 16);
@@ -516,8 +714,12 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
         const uint32_t total_all = all & 0xFFFFFu;
         const uint32_t gbase = written + gexcl;
         uint32_t total, nq, nlan;
+        const uint32_t qaddr = sink.acquire();   // the first ring / queue store of the iteration is below
+        bool stuck = false;
 
-        if (total_all <= min(remaining, uint32_t(kSubMaxG)) && cur + chain_end <= slen) {
+      for (;;) {
+        const uint32_t cap = sink.cap();
+        if (total_all <= min(remaining, cap) && (all >> 20) <= uint32_t(kQueue) && cur + chain_end <= slen) {
             // ---- fast path: all 256 tokens execute
             uint32_t a = mya + 1, qa = qaddr + 8 * qexcl;
 #pragma unroll
@@ -552,7 +754,7 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
             consumed = cur + chain_end;
         } else {
             // ---- slow path (end of the output, end of the input, or an oversized iteration): cut token by token
-            const bool taken = gexcl < remaining && gincl <= uint32_t(kSubMaxG);
+            const bool taken = gexcl < remaining && gincl <= cap && (incl >> 20) <= uint32_t(kQueue);
             const uint32_t lim = remaining - gexcl;   // only meaningful when taken
             uint32_t jexec = 0;
             bool eos_here = false;
@@ -583,7 +785,11 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
                 status = AURORA_END_OF_STREAM;
             }
             nlan = __popc(__ballot_sync(kFull, jexec > 0));   // a prefix of the lanes
-            if (nlan == 0) break;
+            if (nlan == 0) {
+                if (status == AURORA_OK && sink.retry_full()) continue;   // the budget was cut by the iteration in flight
+                stuck = true;
+                break;
+            }
             const uint32_t last = nlan - 1;
             uint32_t oend = 0, qi = qexcl, aend = 0;
             {
@@ -624,14 +830,15 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
             nq = __shfl_sync(kFull, qi, last);
             consumed = cur + __shfl_sync(kFull, aend, last);
         }
-        __syncwarp();
-        replay_matches(rb, qaddr, nq);
-        out.drain(written + total);
+        break;
+      }
+        if (stuck) break;
+        sink.submit(nq, written + total, total);
         written += total;
         if (status != AURORA_OK) break;
         cur += (nlan == 32) ? chain_end : __shfl_sync(kFull, myrel, nlan & 31);
     }
-    out.finish(written);
+    sink.finish(written);
     if (status == AURORA_OK) {
         if (K == K_LZSS ? written != size : written > size) status = AURORA_SIZE_MISMATCH;
     }
@@ -648,11 +855,11 @@ __device__ BodyResult decode_body_g32(InStream* in, OutState& out, const uint32_
 // (A fixed-point iteration over guessed group starts was tried first; on data with many long matches it needs one
 // round per group and was slower.)
 // ---------------------------------------------------------------------------------------------
-template <int K>   // K_YAZ0 or K_LZ11
-__device__ BodyResult decode_body_g32_var(InStream* in, OutState& out, const uint32_t qaddr, const uint32_t gaddr, const uint32_t slen,
+template <int K, class Sink>   // K_YAZ0 or K_LZ11
+__device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32_t gaddr, const uint32_t slen,
                                            const uint32_t size, const uint32_t body_off) {
     const uint32_t lane = lane_id();
-    const uint32_t rb = out.rbase;
+    const uint32_t rb = sink.rbase;
     uint32_t written = 0, cur = body_off, consumed = body_off;
     int status = AURORA_OK;
 
@@ -723,14 +930,18 @@ __device__ BodyResult decode_body_g32_var(InStream* in, OutState& out, const uin
         const uint32_t qexcl = (incl >> 20) - (valid ? nm : 0u);
         const uint32_t remaining = size - written;
         const uint32_t gbase = written + gexcl;
-        // ---- which of my tokens execute (end of output, end of input, iteration byte budget)
-        const bool taken = valid && gexcl < remaining && gincl <= uint32_t(kSubMaxG);
+        const uint32_t qaddr = sink.acquire();   // the first ring / queue store of the iteration is below
+        uint32_t jexec, nlan;
+      for (;;) {
+        // ---- which of my tokens execute (end of output, end of input, iteration byte budget, queue capacity)
+        const uint32_t cap = sink.cap();
+        const bool taken = valid && gexcl < remaining && gincl <= cap && (incl >> 20) <= uint32_t(kQueue);
         const uint32_t lim = remaining - gexcl;
-        uint32_t jexec = 8;
+        jexec = 8;
         bool eos_here = false;
         // fast path: every token of every valid group executes (not the end of the output, all input bytes present)
-        const uint32_t all_out = __shfl_sync(kFull, gincl, 31);
-        if (!(all_out <= min(remaining, uint32_t(kSubMaxG)) && cur + (ca - wa) <= slen)) {
+        const uint32_t all_incl = __shfl_sync(kFull, incl, 31);
+        if (!((all_incl & 0xFFFFFu) <= min(remaining, cap) && (all_incl >> 20) <= uint32_t(kQueue) && cur + (ca - wa) <= slen)) {
             jexec = 0;
             const uint32_t gabs = cur + myrel;
             uint32_t a = gabs + 1;
@@ -765,7 +976,10 @@ __device__ BodyResult decode_body_g32_var(InStream* in, OutState& out, const uin
             if (lane > gb) jexec = 0;
             status = AURORA_END_OF_STREAM;
         }
-        const uint32_t nlan = __popc(__ballot_sync(kFull, jexec > 0));
+        nlan = __popc(__ballot_sync(kFull, jexec > 0));
+        if (nlan == 0 && status == AURORA_OK && sink.retry_full()) continue;   // the budget was cut by the iteration in flight
+        break;
+      }
         if (nlan == 0) {
             if (K == K_LZ11 && status == AURORA_OK && __shfl_sync(kFull, gsize, 0) > uint32_t(kSubMaxG)) {
                 // long-group path: the first group alone exceeds the iteration budget (matches of up to 65 808 bytes):
@@ -784,19 +998,14 @@ __device__ BodyResult decode_body_g32_var(InStream* in, OutState& out, const uin
                             done = true;
                         } else {
                             if (lit) {
-                                if (lane == 0) sts_u8((written & kRingMask) | rb, b1);
+                                sink.single_literal(written, b1);
                                 written += 1;
                             } else {
                                 const uint32_t ta = wa + a;
                                 const uint32_t c2 = lds_u8(ta + 1), c3 = lds_u8(ta + 2), c4 = lds_u8(ta + 3);
                                 const uint32_t d = n == 0 ? (((c2 & 0xF) << 8) | c3) + 1 : n == 1 ? (((c3 & 0xF) << 8) | c4) + 1 : (((b1 & 0xF) << 8) | c2) + 1;
-                                for (uint32_t sgm = 0; sgm < l; sgm += 2048) {
-                                    const uint32_t seg = min(2048u, l - sgm);
-                                    ring_copy_any(rb, written, d, seg);
-                                    __syncwarp();
-                                    written += seg;
-                                    out.drain(written);
-                                }
+                                sink.long_match(written, d, l);
+                                written += l;
                             }
                             __syncwarp();
                             a += sz;
@@ -806,7 +1015,6 @@ __device__ BodyResult decode_body_g32_var(InStream* in, OutState& out, const uin
                         done = true;
                     }
                 }
-                out.drain(written);
                 if (status != AURORA_OK) break;
                 cur += a;
                 continue;
@@ -853,16 +1061,14 @@ __device__ BodyResult decode_body_g32_var(InStream* in, OutState& out, const uin
         const uint32_t total = __shfl_sync(kFull, gexcl + oend, last);
         const uint32_t nq = __shfl_sync(kFull, qi, last);
         consumed = cur + __shfl_sync(kFull, aend, last);
-        __syncwarp();
-        replay_matches(rb, qaddr, nq);
-        out.drain(written + total);
+        sink.submit(nq, written + total, total);
         written += total;
         if (status != AURORA_OK) break;
         // resume at the first group that was not executed (its start is exact: it follows exact groups)
         const uint32_t next_rel = __shfl_sync(kFull, myrel + gin, last);
         cur += next_rel;
     }
-    out.finish(written);
+    sink.finish(written);
     if (status == AURORA_OK && written > size) status = AURORA_SIZE_MISMATCH;
     return BodyResult{status, written, consumed};
 }
@@ -874,11 +1080,11 @@ __device__ BodyResult decode_body_g32_var(InStream* in, OutState& out, const uin
 // literal cursor, and a third scan of the group output sizes gives its output base.
 //   in[0] flags (relative to blob offset 0x10), in[1] codes (relative to comp_off), in[2] literals (relative to lit_off)
 // ---------------------------------------------------------------------------------------------
-template <int K>
-__device__ BodyResult decode_body_g32_split(InStream* in, OutState& out, const uint32_t qaddr, const uint32_t slen, const uint32_t size,
+template <int K, class Sink>
+__device__ BodyResult decode_body_g32_split(InStream* in, Sink& sink, const uint32_t slen, const uint32_t size,
                                             const uint32_t comp_off, const uint32_t lit_off) {
     const uint32_t lane = lane_id();
-    const uint32_t rb = out.rbase;
+    const uint32_t rb = sink.rbase;
     uint32_t written = 0, cur = 0, ccur = 0, lcur = 0;
     int status = AURORA_OK;
 
@@ -931,15 +1137,19 @@ __device__ BodyResult decode_body_g32_split(InStream* in, OutState& out, const u
         const uint32_t gincl = warp_incl_scan(gsize), gexcl = gincl - gsize;
         const uint32_t remaining = size - written;
         const uint32_t gbase = written + gexcl;
-        const bool taken = gexcl < remaining && gincl <= uint32_t(kSubMaxG);
+        const uint32_t qaddr = sink.acquire();   // the first ring / queue store of the iteration is below
+        uint32_t jexec, nlan;
+      for (;;) {
+        const uint32_t cap = sink.cap();
+        const bool taken = gexcl < remaining && gincl <= cap && mincl <= uint32_t(kQueue);
         const uint32_t lim = remaining - gexcl;
         // ---- which of my tokens execute
-        uint32_t jexec = 8;
+        jexec = 8;
         bool eos_here = false;
         // fast path: all 256 tokens execute (not the end of the output, all three sub-streams have their bytes)
         const uint32_t all_out = __shfl_sync(kFull, gincl, 31), all_m = __shfl_sync(kFull, mincl, 31);
         const uint32_t all_l = 256 - all_m + ((K == K_YAY0) ? __shfl_sync(kFull, eb + next, 31) : 0u);
-        if (!(all_out <= min(remaining, uint32_t(kSubMaxG)) && 0x10 + cur + 32 <= slen && comp_off + ccur + 2 * all_m <= slen &&
+        if (!(all_out <= min(remaining, cap) && all_m <= uint32_t(kQueue) && 0x10 + cur + 32 <= slen && comp_off + ccur + 2 * all_m <= slen &&
               lit_off + lcur + all_l <= slen)) {
             jexec = 0;
             const bool fbad = 0x10 + cur + lane >= slen;
@@ -968,7 +1178,10 @@ __device__ BodyResult decode_body_g32_split(InStream* in, OutState& out, const u
             if (lane > gb) jexec = 0;
             status = AURORA_END_OF_STREAM;
         }
-        const uint32_t nlan = __popc(__ballot_sync(kFull, jexec > 0));
+        nlan = __popc(__ballot_sync(kFull, jexec > 0));
+        if (nlan == 0 && status == AURORA_OK && sink.retry_full()) continue;   // the budget was cut by the iteration in flight
+        break;
+      }
         if (nlan == 0) break;
         const uint32_t last = nlan - 1;
         // ---- pass 2
@@ -1000,9 +1213,7 @@ __device__ BodyResult decode_body_g32_split(InStream* in, OutState& out, const u
         const uint32_t total = __shfl_sync(kFull, gexcl + oend, last);
         const uint32_t nq = __shfl_sync(kFull, kend, last);
         const uint32_t nl = __shfl_sync(kFull, lend, last);
-        __syncwarp();
-        replay_matches(rb, qaddr, nq);
-        out.drain(written + total);
+        sink.submit(nq, written + total, total);
         written += total;
         ccur += 2 * nq;
         {
@@ -1012,7 +1223,7 @@ __device__ BodyResult decode_body_g32_split(InStream* in, OutState& out, const u
         cur += nlan;
         if (status != AURORA_OK) break;
     }
-    out.finish(written);
+    sink.finish(written);
     if (status == AURORA_OK && written > size) status = AURORA_SIZE_MISMATCH;
     return BodyResult{status, written, max(comp_off + ccur, lit_off + lcur)};
 }
@@ -1026,8 +1237,8 @@ __device__ __forceinline__ void ring_prefill(uint8_t* ring, uint32_t fill) {
     __syncwarp();
 }
 
-template <int K>
-__device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in, uint8_t* ring, uint32_t qaddr, uint32_t gaddr) {
+template <int K, class Sink>
+__device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in, uint8_t* ring, Sink& sink, uint32_t gaddr) {
     const uint32_t lane = lane_id();
     const uint8_t* src = P.src_base + P.src_off[idx];
     const uint64_t slen64 = P.src_len[idx];
@@ -1106,14 +1317,8 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                 written = 0;
                 consumed = (K == K_MIO0 || K == K_YAY0) ? slen : body_off;
             } else {
-                ring_prefill(ring, K == K_LZSS ? uint32_t(P.lzss.initial_fill) & 0xFFu : 0u);
-                OutState out;
-                out.ring = ring;
-                out.rbase = smem_u32(ring);
-                out.dst = dst;
-                out.limit = uint32_t(min(uint64_t(0xFFFFFFFFu), cap));
-                out.flushed = 0;
-                out.aligned = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+                const uint32_t fill = K == K_LZSS ? uint32_t(P.lzss.initial_fill) & 0xFFu : 0u;
+                const uint32_t limit = uint32_t(min(uint64_t(0xFFFFFFFFu), cap));
                 if constexpr (K == K_MIO0 || K == K_YAY0) {
                     in[0].begin(P.src_base, P.src_limit, src + 0x10);
                     in[1].begin(P.src_base, P.src_limit, src + comp_off);
@@ -1122,16 +1327,24 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                     in[0].begin(P.src_base, P.src_limit, src);
                 }
                 BodyResult r;
-                bool g32 = Traits<K>::kG32;
+                bool g32 = true;
                 if (K == K_LZSS) g32 = 8u * (((1u << P.lzss.length_bits) - 1u) + uint32_t(P.lzss.min_length)) <= uint32_t(kSubMaxG);
-                if constexpr (K == K_MIO0 || K == K_YAY0) {
-                    r = decode_body_g32_split<K>(in, out, qaddr, slen, size, comp_off, lit_off);
-                } else if constexpr (K == K_YAZ0 || K == K_LZ11) {
-                    r = decode_body_g32_var<K>(in, out, qaddr, gaddr, slen, size, body_off);
-                } else if constexpr (Traits<K>::kG32) {
-                    if (g32) r = decode_body_g32<K>(in, out, qaddr, gaddr, slen, size, body_off, P.lzss);
-                    else r = decode_body<K>(in, out, slen, size, body_off, comp_off, lit_off, P.lzss);
-                } else {
+                if (g32) {
+                    sink.begin(ring, fill, dst, limit);
+                    if constexpr (K == K_MIO0 || K == K_YAY0) r = decode_body_g32_split<K>(in, sink, slen, size, comp_off, lit_off);
+                    else if constexpr (K == K_YAZ0 || K == K_LZ11) r = decode_body_g32_var<K>(in, sink, gaddr, slen, size, body_off);
+                    else r = decode_body_g32<K>(in, sink, gaddr, slen, size, body_off, P.lzss);
+                } else if constexpr (K == K_LZSS) {
+                    // LzProperties whose largest group exceeds an iteration: the token-per-lane core, run by this warp alone
+                    sink.wait_idle();
+                    ring_prefill(ring, fill);
+                    OutState out;
+                    out.ring = ring;
+                    out.rbase = smem_u32(ring);
+                    out.dst = dst;
+                    out.limit = limit;
+                    out.flushed = 0;
+                    out.aligned = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
                     r = decode_body<K>(in, out, slen, size, body_off, comp_off, lit_off, P.lzss);
                 }
                 status = r.status;
@@ -1154,39 +1367,73 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
 }
 
 template <int K>
-__global__ void __launch_bounds__(Traits<K>::kWarps * 32, 2) decode_flaglz_kernel(const DecodeParams P) {
+__global__ void __launch_bounds__(Traits<K>::kSlots * 64, 1) decode_flaglz_kernel(const DecodeParams P) {
+    using T = Traits<K>;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
+    // warpgroups alternate parser / replayer; slot s is served by parser warp (s / 4) * 8 + s % 4 and the warp 4 above it
+    const int role = (warp >> 2) & 1;
+    const int slot = (warp >> 3) * 4 + (warp & 3);
     // rings first, 8 KiB aligned in the shared window (wrapped ring addresses become one LOP3); the launcher adds 8 KiB of slack
     const uint32_t s0 = smem_u32(smem);
     uint8_t* aligned = smem + (((s0 + kRing - 1) & ~uint32_t(kRing - 1)) - s0);
-    uint8_t* ring = aligned + size_t(warp) * kRing;
-    uint8_t* wbase = aligned + size_t(Traits<K>::kWarps) * kRing + size_t(warp) * (Traits<K>::kSmemPerWarp - kRing);
-    uint8_t* qbase = wbase + Traits<K>::kStreams * kInStage;
-    const uint32_t qaddr = smem_u32(qbase), gaddr = qaddr + kQueue * 8;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qbase + Traits<K>::kQueueBytes);
-    InStream in[Traits<K>::kStreams];
-#pragma unroll
-    for (int s = 0; s < Traits<K>::kStreams; s++) in[s].init(wbase + s * kInStage, bars + 2 * s);
-    __syncwarp();
-    fence_proxy_async();
-
-    for (;;) {
-        uint32_t t = 0;
-        if (lane_id() == 0) t = atomicAdd(P.ticket, 1u);
-        t = __shfl_sync(kFull, t, 0);
-        if (t >= P.n) break;
-        const uint32_t idx = P.order ? P.order[t] : t;
-        decode_stream<K>(P, idx, in, ring, qaddr, gaddr);
+    uint8_t* ring = aligned + size_t(slot) * kRing;
+    uint8_t* aux = aligned + size_t(T::kSlots) * kRing + size_t(slot) * T::kAuxBytes;
+    uint8_t* qptr = aux + T::kStreams * kInStage;
+    const uint32_t qbase = smem_u32(qptr), gaddr = qbase + T::kQueueBytes, mail = gaddr + 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qptr + T::kQueueBytes + 128 + 32 + 16);
+    uint64_t* full = bars + 2 * T::kStreams;
+    uint64_t* empty = full + 2;
+    // block-shared copy of the reciprocal table's first 64 entries (lane-divergent lookups in the quad replay)
+    const uint32_t rcp_addr = smem_u32(aligned + size_t(T::kSlots) * T::kSmemPerSlot);
+    if (threadIdx.x < kQuadMaxLen) sts_u32(rcp_addr + 4 * threadIdx.x, c_rcp.v[threadIdx.x]);
+    if (role == 0 && lane_id() == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&empty[0], 1);
+        mbar_init(&empty[1], 1);
     }
+    InStream in[T::kStreams];
+    if (role == 0) {
 #pragma unroll
-    for (int s = 0; s < Traits<K>::kStreams; s++) in[s].drain_inflight();
+        for (int s = 0; s < T::kStreams; s++) in[s].init(aux + s * kInStage, bars + 2 * s);
+        fence_proxy_async();
+    }
+    __syncthreads();   // the only block-wide barrier: the slots' mbarriers are initialised
+
+    if (role == 0) {
+        if constexpr (T::kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        PipeSink sink;
+        sink.rbase = smem_u32(ring);
+        sink.qbase = qbase;
+        sink.mail = mail;
+        sink.full = full;
+        sink.empty = empty;
+        sink.it = 0;
+        sink.prev_total = 0;
+        sink.flags_next = 0;
+        for (;;) {
+            uint32_t t = 0;
+            if (lane_id() == 0) t = atomicAdd(P.ticket, 1u);
+            t = __shfl_sync(kFull, t, 0);
+            if (t >= P.n) break;
+            const uint32_t idx = P.order ? P.order[t] : t;
+            decode_stream<K>(P, idx, in, ring, sink, gaddr);
+        }
+        sink.exit();
+#pragma unroll
+        for (int s = 0; s < T::kStreams; s++) in[s].drain_inflight();
+    } else {
+        if constexpr (T::kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        replayer_role(ring, qbase, mail, full, empty, rcp_addr);
+    }
 }
 
 template <int K>
 cudaError_t launch(const DecodeParams& p, int sm_count, cudaStream_t st) {
-    const int threads = Traits<K>::kWarps * 32;
-    const size_t smem = size_t(Traits<K>::kWarps) * Traits<K>::kSmemPerWarp + kRing;   // + alignment slack for the rings
+    using T = Traits<K>;
+    const int threads = T::kSlots * 64;
+    const size_t smem = size_t(T::kSlots) * T::kSmemPerSlot + kRing + 4 * kQuadMaxLen;   // + alignment slack for the rings + rcp table
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1195,9 +1442,8 @@ cudaError_t launch(const DecodeParams& p, int sm_count, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    const uint32_t warps_needed = p.n;
-    int blocks = sm_count * 2;
-    const int needed_blocks = int((warps_needed + Traits<K>::kWarps - 1) / Traits<K>::kWarps);
+    int blocks = sm_count;
+    const int needed_blocks = int((p.n + T::kSlots - 1) / T::kSlots);
     if (needed_blocks < blocks) blocks = needed_blocks > 0 ? needed_blocks : 1;
     decode_flaglz_kernel<K><<<blocks, threads, smem, st>>>(p);
     return cudaGetLastError();

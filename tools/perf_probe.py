@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--classes", default="T,M,X,mix")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--quality", type=int, default=8)
+    ap.add_argument("--no-verify", action="store_true", help="skip the byte comparison (experimental kernel variants)")
     args = ap.parse_args()
     peak = 6551.7
     try:
@@ -84,7 +85,7 @@ def main():
             ok = d_st == 0
             if fname not in ("lzo", "prs"):   # the reference's LZO encoder / PRS order heuristic have known self-inconsistencies
                 assert bool(ok.all()), "decode status"
-            if fname not in ("lzo", "prs"):
+            if fname not in ("lzo", "prs") and not args.no_verify:
                 assert torch.equal(d_dst[:n * args.size].view(n, args.size)[ok], raw[ok]), "decode mismatch"
             ms = float(np.median(times))
             out_b, in_b = n * args.size, int(clen.sum())
