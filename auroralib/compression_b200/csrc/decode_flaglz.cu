@@ -34,8 +34,12 @@ constexpr int kRingMask = kRing - 1;
 constexpr int kWindow = 4096;        // largest back-reference distance of the family
 constexpr int kSubMax = 2048;        // output bytes resolved per sub-batch (ring keeps window + sub-batch + drain slack)
 constexpr int kFlush = 512;          // bytes per ring->HBM drain step (16 B per lane)
+constexpr int kQueueSplit = 168;     // same for the three-sub-stream formats (128 would give 12 slots per SM at 80 registers: measured slower, spills)
 constexpr int kQueue = 168;          // match descriptors per G32 iteration (an iteration is cut when its queue is full)
 constexpr int kSubMaxG = 2304;       // G32: output bytes per iteration (>= the largest single group)
+#ifndef AURORA_REG_DELTA
+#define AURORA_REG_DELTA 24
+#endif
 constexpr int kPairSpan = 4096;      // parser/replayer pipeline: two consecutive iterations in flight, window + both + drain slack <= ring
 
 
@@ -48,7 +52,8 @@ struct Traits {
     static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : 1;
     static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0) ? 273 : (K == K_LZSS) ? 258 : 65808;
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
-    static constexpr int kQueueBytes = 2 * kQueue * 8 + 32;
+    static constexpr int kQueueLen = kStreams == 3 ? kQueueSplit : kQueue;
+    static constexpr int kQueueBytes = 2 * kQueueLen * 8 + 32;
     static constexpr int kAuxBytes = kStreams * kInStage + kQueueBytes + 128 + 32 + 16 + (2 * kStreams + 4) * 8;
     static constexpr int kSmemPerSlot = kRing + kAuxBytes;
 #ifdef AURORA_FLAG_SLOTS
@@ -57,7 +62,11 @@ struct Traits {
     // one block per SM; slots come in fours (a parser warpgroup + a replayer warpgroup)
     static constexpr int kSlots = ((227 * 1024 - kRing) / kSmemPerSlot) / 4 * 4;
 #endif
-    static constexpr bool kRegSplit = kSlots == 16;   // 1024 threads: 64 registers each at launch, re-split 88 / 40 by setmaxnreg
+    // registers: the launch gives every thread kLaunchRegs (what ptxas derives from the launch bounds); the parser
+    // warpgroups then grow by kRegDelta and the replayer warpgroups shrink by it (setmaxnreg; the sum stays in the block's pool)
+    static constexpr int kLaunchRegs = (65536 / (kSlots * 64)) / 8 * 8 > 128 ? 128 : (65536 / (kSlots * 64)) / 8 * 8;
+    static constexpr bool kRegSplit = kLaunchRegs < 128;
+    static constexpr int kParserRegs = kLaunchRegs + AURORA_REG_DELTA, kReplayerRegs = kLaunchRegs - AURORA_REG_DELTA;
 };
 
 // out[dst+i] = out[dst-d + (i mod d)], i < len : LzWindows.BackCopy (IO/LzWindows.cs:72-100) on the flat ring.
@@ -419,50 +428,11 @@ __device__ __forceinline__ void ring_copy_any(uint32_t rb, uint32_t pos, uint32_
     }
 }
 
-// entries [q, qend) of the compacted queue in stream order, two per step: when the second match's source ends at or before
-// the first match's destination the two copies are independent, so both loads are issued before both stores
-__device__ __forceinline__ void replay_range(uint32_t rb, uint32_t qaddr, uint32_t q, const uint32_t qend) {
-    const uint32_t lane = lane_id();
-    while (q + 1 < qend) {
-        const uint2 e0 = lds_u64(qaddr + 8 * q), e1 = lds_u64(qaddr + 8 * q + 8);
-        const uint32_t len0 = e0.y & 0x1FFFFu, d0 = e0.y >> 17, len1 = e1.y & 0x1FFFFu, d1 = e1.y >> 17;
-        if (max(len0, len1) < 512 && e1.x - d1 + min(len1, d1) <= e0.x) {
-            const uint32_t r0 = d0 < len0 ? c_rcp.v[d0] : 0u, r1 = d1 < len1 ? c_rcp.v[d1] : 0u;   // 0: no wrap, off = i
-            const uint32_t s0 = e0.x - d0, s1 = e1.x - d1, lmax = max(len0, len1);
-            for (uint32_t i = lane; i < lmax; i += 32) {
-                const uint32_t off0 = i - ((i * r0) >> 20) * d0, off1 = i - ((i * r1) >> 20) * d1;
-                uint32_t v0 = 0, v1 = 0;
-                if (i < len0) v0 = lds_u8(((s0 + off0) & kRingMask) | rb);
-                if (i < len1) v1 = lds_u8(((s1 + off1) & kRingMask) | rb);
-                if (i < len0) sts_u8(((e0.x + i) & kRingMask) | rb, v0);
-                if (i < len1) sts_u8(((e1.x + i) & kRingMask) | rb, v1);
-            }
-            __syncwarp();
-        } else {
-            ring_copy_any(rb, e0.x, d0, len0);
-            __syncwarp();
-            ring_copy_any(rb, e1.x, d1, len1);
-            __syncwarp();
-        }
-        q += 2;
-    }
-    if (q < qend) {
-        const uint2 e0 = lds_u64(qaddr + 8 * q);
-        ring_copy_any(rb, e0.x, e0.y >> 17, e0.y & 0x1FFFFu);
-        __syncwarp();
-    }
-}
-
-constexpr uint32_t kQuadMaxLen = 64;   // longest match a quad step takes (8 lanes x 8 trips); its period is < 64: rcp table in smem
-
-// Replays the queued matches of one iteration in stream order.
-//  1. run merging (lane-parallel, see above): chains of adjacent same-distance matches become one periodic copy;
-//  2. classification (lane-parallel, one compacted entry per lane): an entry is "quad-able" when it is short
-//     (<= 64 bytes) and its source does not overlap the destination of an earlier entry of its group of four;
-//  3. groups of four quad-able entries run as ONE warp step: lanes 8g..8g+7 copy entry g, 8 bytes per trip, all loads of
-//     a batch of trips issued before the stores; the other groups fall back to the two-per-step / warp-wide copies.
-// Per-entry scalar work (unpacking, hazard tests, reciprocal fetch) is thereby done once per lane instead of once per warp.
-__device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint32_t nq, uint32_t rcp_addr) {
+// Replays the queued matches of one iteration in stream order (see the comment above ring_copy_any).
+// (Measured and rejected, round 1: groups of four independent short matches as one warp step, 8 lanes per match, with a
+// lane-parallel hazard classification; it removed ~30 % of the replayer's instructions but lost the entry prefetch and
+// was 10 % slower end to end: the replayer is bound by its dependent instruction chain, not by its instruction count.)
+__device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint32_t nq) {
     const uint32_t lane = lane_id();
     if (nq == 0) return;
     const uint32_t lt = (1u << lane) - 1u;
@@ -484,47 +454,39 @@ __device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint
         nout += __popc(heads);
     }
     __syncwarp();
-    const uint32_t g8 = 8 * (lane >> 3), sub = lane & 7;
-    for (uint32_t base = 0; base < nout; base += 32) {
-        // ---- classification of the block's entries (slots past the end of the queue are readable)
-        const uint32_t j = base + lane;
-        const uint2 e = lds_u64(qaddr + 8 * j);
-        const uint32_t len = e.y & 0x1FFFFu, d = e.y >> 17;
-        const uint32_t s = e.x - d, send = s + min(len, d);   // source bytes [s, send)
-        bool bad = j >= nout || len > kQuadMaxLen;
-#pragma unroll
-        for (int k = 1; k <= 3; k++) {
-            const uint32_t px = __shfl_up_sync(kFull, e.x, k), pl = __shfl_up_sync(kFull, len, k);
-            if (int(lane & 3) >= k && s < px + pl && send > px) bad = true;
-        }
-        const uint32_t badmask = __ballot_sync(kFull, bad);
-        const uint32_t trips = (__reduce_max_sync(kFull, bad ? 0u : len) + 7) >> 3;
-        const uint32_t nblk = min(32u, nout - base);
-        for (uint32_t k = 0; k < nblk; k += 4) {
-            if (((badmask >> k) & 0xFu) == 0) {
-                const uint2 m = lds_u64(qaddr + 8 * (base + k) + g8);   // my group's entry
-                const uint32_t ml = m.y & 0x1FFFFu, md = m.y >> 17, ms = m.x - md;
-                const uint32_t r = md < ml ? lds_u32(rcp_addr + 4 * md) : 0u;   // 0: no wrap, off = i
-                for (uint32_t t0 = 0; t0 < trips; t0 += 4) {
-                    uint32_t v[4];
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const uint32_t i = sub + 8 * (t0 + t);
-                        const uint32_t off = i - ((i * r) >> 20) * md;
-                        v[t] = 0;
-                        if (i < ml) v[t] = lds_u8(((ms + off) & kRingMask) | rb);
-                    }
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const uint32_t i = sub + 8 * (t0 + t);
-                        if (i < ml) sts_u8(((m.x + i) & kRingMask) | rb, v[t]);
-                    }
-                }
-                __syncwarp();
-            } else {
-                replay_range(rb, qaddr, base + k, min(base + k + 4, nout));
+    // Two entries per step: when the second match's source ends at or before the first match's destination the two
+    // copies are independent, so both loads are issued before both stores (one barrier, twice the ILP); the slots
+    // past the end of the queue are readable (slack behind the queue).
+    uint2 e0 = lds_u64(qaddr), e1 = lds_u64(qaddr + 8);
+    uint32_t q = 0;
+    while (q + 1 < nout) {
+        const uint2 n0 = lds_u64(qaddr + 8 * (q + 2)), n1 = lds_u64(qaddr + 8 * (q + 3));
+        const uint32_t len0 = e0.y & 0x1FFFFu, d0 = e0.y >> 17, len1 = e1.y & 0x1FFFFu, d1 = e1.y >> 17;
+        if (max(len0, len1) < 512 && e1.x - d1 + min(len1, d1) <= e0.x) {
+            const uint32_t r0 = d0 < len0 ? c_rcp.v[d0] : 0u, r1 = d1 < len1 ? c_rcp.v[d1] : 0u;   // 0: no wrap, off = i
+            const uint32_t s0 = e0.x - d0, s1 = e1.x - d1, lmax = max(len0, len1);
+            for (uint32_t i = lane; i < lmax; i += 32) {
+                const uint32_t off0 = i - ((i * r0) >> 20) * d0, off1 = i - ((i * r1) >> 20) * d1;
+                uint32_t v0 = 0, v1 = 0;
+                if (i < len0) v0 = lds_u8(((s0 + off0) & kRingMask) | rb);
+                if (i < len1) v1 = lds_u8(((s1 + off1) & kRingMask) | rb);
+                if (i < len0) sts_u8(((e0.x + i) & kRingMask) | rb, v0);
+                if (i < len1) sts_u8(((e1.x + i) & kRingMask) | rb, v1);
             }
+            __syncwarp();
+        } else {
+            ring_copy_any(rb, e0.x, d0, len0);
+            __syncwarp();
+            ring_copy_any(rb, e1.x, d1, len1);
+            __syncwarp();
         }
+        e0 = n0;
+        e1 = n1;
+        q += 2;
+    }
+    if (q < nout) {
+        ring_copy_any(rb, e0.x, e0.y >> 17, e0.y & 0x1FFFFu);
+        __syncwarp();
     }
 }
 
@@ -554,7 +516,8 @@ __device__ __forceinline__ void long_match_copy(OutState& out, uint32_t pos, uin
 // parser side of the pipeline (all members warp-uniform)
 struct PipeSink {
     uint32_t rbase;        // shared address of the slot's ring
-    uint32_t qbase;        // shared address of queue buffer 0 (buffer 1 follows)
+    uint32_t qbase;        // shared address of queue buffer 0 (buffer 1 follows qstride bytes later)
+    uint32_t qstride;
     uint32_t mail;         // shared address of mailbox 0 (mailbox 1 follows), then the stream descriptor
     uint64_t* full;        // [2]
     uint64_t* empty;       // [2]
@@ -590,7 +553,7 @@ struct PipeSink {
     }
     __device__ __forceinline__ uint32_t acquire() {
         mbar_wait(&empty[it & 1], ((it >> 1) & 1) ^ 1);
-        return qbase + (it & 1) * (kQueue * 8);
+        return qbase + (it & 1) * qstride;
     }
     __device__ __forceinline__ void submit(uint32_t nq, uint32_t produced, uint32_t total, uint32_t flags = 0) {
         __syncwarp();   // every lane's ring / queue stores are ordered before lane 0's releasing arrive
@@ -624,7 +587,7 @@ struct PipeSink {
 };
 
 // replayer side of the pipeline: consumes messages until the parser says exit
-__device__ void replayer_role(uint8_t* ring, uint32_t qbase, uint32_t mail, uint64_t* full, uint64_t* empty, uint32_t rcp_addr) {
+__device__ void replayer_role(uint8_t* ring, uint32_t qbase, uint32_t qstride, uint32_t mail, uint64_t* full, uint64_t* empty) {
     OutState out;
     out.ring = ring;
     out.rbase = smem_u32(ring);
@@ -644,13 +607,13 @@ __device__ void replayer_role(uint8_t* ring, uint32_t qbase, uint32_t mail, uint
             out.aligned = d.w != 0;
             out.flushed = 0;
         }
-        const uint32_t q = qbase + b * (kQueue * 8);
+        const uint32_t q = qbase + b * qstride;
         if (msg.z & kMsgLong) {
             const uint2 e = lds_u64(q);
             long_match_copy(out, e.x, e.y >> 17, e.y & 0x1FFFFu);
         } else {
 #ifndef AURORA_EXP_NOREPLAY   // developer probe: parser-bound speed (output is wrong)
-            replay_matches(out.rbase, q, msg.x, rcp_addr);
+            replay_matches(out.rbase, q, msg.x);
 #endif
         }
         if (msg.z & kMsgFinish) out.finish(msg.y);
@@ -710,8 +673,6 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
         const uint32_t gincl = incl & 0xFFFFFu, gexcl = gincl - gsize;
         const uint32_t qexcl = (incl >> 20) - nm;
         const uint32_t remaining = size - written;
-        const uint32_t all = __shfl_sync(kFull, incl, 31);
-        const uint32_t total_all = all & 0xFFFFFu;
         const uint32_t gbase = written + gexcl;
         uint32_t total, nq, nlan;
         const uint32_t qaddr = sink.acquire();   // the first ring / queue store of the iteration is below
@@ -719,9 +680,15 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
 
       for (;;) {
         const uint32_t cap = sink.cap();
-        if (total_all <= min(remaining, cap) && (all >> 20) <= uint32_t(kQueue) && cur + chain_end <= slen) {
-            // ---- fast path: all 256 tokens execute
+        // groups that fit the byte budget and the queue (a prefix of the lanes): all of their tokens execute unless
+        // the output or the input ends inside them
+        const uint32_t nl = __popc(__ballot_sync(kFull, gincl <= cap && (incl >> 20) <= uint32_t(kQueue)));
+        const uint32_t cut = __shfl_sync(kFull, incl, (nl + 31) & 31);
+        const uint32_t end_rel = nl == 32 ? chain_end : __shfl_sync(kFull, myrel, nl & 31);
+        if (nl > 0 && (cut & 0xFFFFFu) <= remaining && cur + end_rel <= slen) {
+            // ---- fast path: every token of the first nl groups executes
             uint32_t a = mya + 1, qa = qaddr + 8 * qexcl;
+            if (lane < nl) {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
@@ -748,10 +715,11 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
                 }
                 a += ism ? 2 : 1;
             }
-            total = total_all;
-            nq = all >> 20;
-            nlan = 32;
-            consumed = cur + chain_end;
+            }
+            total = cut & 0xFFFFFu;
+            nq = cut >> 20;
+            nlan = nl;
+            consumed = cur + end_rel;
         } else {
             // ---- slow path (end of the output, end of the input, or an oversized iteration): cut token by token
             const bool taken = gexcl < remaining && gincl <= cap && (incl >> 20) <= uint32_t(kQueue);
@@ -862,17 +830,26 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
     const uint32_t rb = sink.rbase;
     uint32_t written = 0, cur = body_off, consumed = body_off;
     int status = AURORA_OK;
+    // Chain reuse: an iteration cut by the byte budget executes only its first groups; the starts of the others stay
+    // exact, so they are carried (as offsets relative to the next window) instead of being walked again.
+    uint32_t nkeep = 0, chain_rel = 0;   // carried groups; offset at which the walk continues
 
     while (written < size) {
         in[0].ensure(cur, kInMirror - 16);
         const uint32_t wa = smem_u32(in[0].window(cur));
         const uint32_t wlimit = kInMirror - 48;   // a group may start in the first 592 bytes of the window (it is <= 33 bytes)
-        // ---- exact chain of group starts
-        uint32_t ca = wa, nvalid = 0;
+        // ---- exact chain of group starts (offsets relative to the window)
+        uint32_t nvalid;
+        {
+            const uint32_t rel = lane < nkeep ? lds_u32(gaddr + 4 * lane) : 0xFFFFFFFFu;
+            nvalid = __popc(__ballot_sync(kFull, rel <= wlimit));       // carried groups that start inside this window (a prefix)
+            if (nvalid < nkeep) chain_rel = __shfl_sync(kFull, rel, nvalid);
+        }
+        uint32_t ca = wa + chain_rel;
 #pragma unroll 1
-        for (int g = 0; g < 32; g++) {
+        for (uint32_t g = nvalid; g < 32; g++) {
             if (ca - wa > wlimit) break;
-            sts_u32(gaddr + 4 * g, ca);
+            sts_u32(gaddr + 4 * g, ca - wa);
             const uint32_t fb = lds_u8(ca);
             const uint32_t hi4 = lds_u8(ca + 1 + lane) >> 4;
             const uint32_t E = __ballot_sync(kFull, hi4 == 0);                             // +1 byte
@@ -890,8 +867,8 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
         }
         __syncwarp();
         const bool valid = lane < nvalid;
-        const uint32_t mya = valid ? lds_u32(gaddr + 4 * lane) : wa;
-        const uint32_t myrel = mya - wa;
+        const uint32_t myrel = valid ? lds_u32(gaddr + 4 * lane) : 0u;
+        const uint32_t mya = wa + myrel;
 
         // ---- pass 1: my 8 tokens
         uint32_t b1v[8], lenv[8], orel[8];
@@ -1017,6 +994,8 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
                 }
                 if (status != AURORA_OK) break;
                 cur += a;
+                nkeep = 0;
+                chain_rel = 0;
                 continue;
             }
             break;
@@ -1067,6 +1046,14 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
         // resume at the first group that was not executed (its start is exact: it follows exact groups)
         const uint32_t next_rel = __shfl_sync(kFull, myrel + gin, last);
         cur += next_rel;
+        {   // carry the starts of the groups that did not execute
+            const uint32_t carry = __shfl_down_sync(kFull, myrel, nlan & 31);
+            nkeep = nvalid - nlan;
+            __syncwarp();
+            if (lane < nkeep) sts_u32(gaddr + 4 * lane, carry - next_rel);
+            chain_rel = (ca - wa) - next_rel;
+            __syncwarp();
+        }
     }
     sink.finish(written);
     if (status == AURORA_OK && written > size) status = AURORA_SIZE_MISMATCH;
@@ -1141,7 +1128,7 @@ __device__ BodyResult decode_body_g32_split(InStream* in, Sink& sink, const uint
         uint32_t jexec, nlan;
       for (;;) {
         const uint32_t cap = sink.cap();
-        const bool taken = gexcl < remaining && gincl <= cap && mincl <= uint32_t(kQueue);
+        const bool taken = gexcl < remaining && gincl <= cap && mincl <= uint32_t(kQueueSplit);
         const uint32_t lim = remaining - gexcl;
         // ---- which of my tokens execute
         jexec = 8;
@@ -1149,7 +1136,7 @@ __device__ BodyResult decode_body_g32_split(InStream* in, Sink& sink, const uint
         // fast path: all 256 tokens execute (not the end of the output, all three sub-streams have their bytes)
         const uint32_t all_out = __shfl_sync(kFull, gincl, 31), all_m = __shfl_sync(kFull, mincl, 31);
         const uint32_t all_l = 256 - all_m + ((K == K_YAY0) ? __shfl_sync(kFull, eb + next, 31) : 0u);
-        if (!(all_out <= min(remaining, cap) && all_m <= uint32_t(kQueue) && 0x10 + cur + 32 <= slen && comp_off + ccur + 2 * all_m <= slen &&
+        if (!(all_out <= min(remaining, cap) && all_m <= uint32_t(kQueueSplit) && 0x10 + cur + 32 <= slen && comp_off + ccur + 2 * all_m <= slen &&
               lit_off + lcur + all_l <= slen)) {
             jexec = 0;
             const bool fbad = 0x10 + cur + lane >= slen;
@@ -1384,9 +1371,6 @@ __global__ void __launch_bounds__(Traits<K>::kSlots * 64, 1) decode_flaglz_kerne
     uint64_t* bars = reinterpret_cast<uint64_t*>(qptr + T::kQueueBytes + 128 + 32 + 16);
     uint64_t* full = bars + 2 * T::kStreams;
     uint64_t* empty = full + 2;
-    // block-shared copy of the reciprocal table's first 64 entries (lane-divergent lookups in the quad replay)
-    const uint32_t rcp_addr = smem_u32(aligned + size_t(T::kSlots) * T::kSmemPerSlot);
-    if (threadIdx.x < kQuadMaxLen) sts_u32(rcp_addr + 4 * threadIdx.x, c_rcp.v[threadIdx.x]);
     if (role == 0 && lane_id() == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
@@ -1402,10 +1386,11 @@ __global__ void __launch_bounds__(Traits<K>::kSlots * 64, 1) decode_flaglz_kerne
     __syncthreads();   // the only block-wide barrier: the slots' mbarriers are initialised
 
     if (role == 0) {
-        if constexpr (T::kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        if constexpr (T::kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T::kParserRegs));
         PipeSink sink;
         sink.rbase = smem_u32(ring);
         sink.qbase = qbase;
+        sink.qstride = T::kQueueLen * 8;
         sink.mail = mail;
         sink.full = full;
         sink.empty = empty;
@@ -1424,8 +1409,8 @@ __global__ void __launch_bounds__(Traits<K>::kSlots * 64, 1) decode_flaglz_kerne
 #pragma unroll
         for (int s = 0; s < T::kStreams; s++) in[s].drain_inflight();
     } else {
-        if constexpr (T::kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        replayer_role(ring, qbase, mail, full, empty, rcp_addr);
+        if constexpr (T::kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T::kReplayerRegs));
+        replayer_role(ring, qbase, T::kQueueLen * 8, mail, full, empty);
     }
 }
 
@@ -1433,7 +1418,7 @@ template <int K>
 cudaError_t launch(const DecodeParams& p, int sm_count, cudaStream_t st) {
     using T = Traits<K>;
     const int threads = T::kSlots * 64;
-    const size_t smem = size_t(T::kSlots) * T::kSmemPerSlot + kRing + 4 * kQuadMaxLen;   // + alignment slack for the rings + rcp table
+    const size_t smem = size_t(T::kSlots) * T::kSmemPerSlot + kRing;   // + alignment slack for the rings
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
