@@ -29,6 +29,8 @@ struct InStream {
     uint32_t kbase, cbase;  // load number / stream chunk of the current mapping
     uint32_t issued, ready; // running load counters
     uint32_t rbias;         // ring index of relative byte 0 under the current mapping
+    uint32_t ready_end;     // bytes (from gbase) below this are staged and waited for
+    uint32_t issue_trig;    // cursor (from gbase) at which the next chunk has to be issued
 
     __device__ __forceinline__ void init(uint8_t* r, uint64_t* b) {
         ring = r;
@@ -50,6 +52,8 @@ struct InStream {
         kbase = issued;
         cbase = chunk;
         rbias = skew + ((kbase - cbase) & 1u) * kInChunk;
+        ready_end = 0;
+        issue_trig = 0;
     }
     __device__ __forceinline__ void begin(const uint8_t* src_base, uint64_t src_limit, const uint8_t* p) {
         skew = uint32_t(reinterpret_cast<uintptr_t>(p) & 15);
@@ -61,6 +65,11 @@ struct InStream {
     }
     // make relative bytes [pos, pos + span) readable (span <= kInChunk); pos never moves backwards
     __device__ __forceinline__ void ensure(uint32_t pos, uint32_t span = kLookahead) {
+        // fast path (two compares): the bytes are staged and the cursor has not reached the next issue point
+        if (pos + skew + span < ready_end && pos + skew < issue_trig) return;
+        ensure_slow(pos, span);
+    }
+    __device__ __forceinline__ void ensure_slow(uint32_t pos, uint32_t span) {
         const uint32_t lo = (pos + skew) / kInChunk;
         const uint32_t hi = (pos + skew + span) / kInChunk;
         uint32_t cend = cbase + (issued - kbase);   // next stream chunk to issue
@@ -92,8 +101,17 @@ struct InStream {
                 ready++;
             }
         }
+        // limits of the fast path under the current mapping
+        const uint32_t rchunks = cbase + (ready - kbase);                  // stream chunks [cbase, rchunks) are complete
+        ready_end = rchunks >= nchunks ? 0xFFFFFFFFu : rchunks * kInChunk;  // nothing to wait for past the last chunk
+        const uint32_t nend = cbase + (issued - kbase);                    // next stream chunk to issue
+        issue_trig = nend >= nchunks ? 0xFFFFFFFFu : (nend - 1) * kInChunk;
     }
-    __device__ __forceinline__ uint32_t at(uint32_t pos) const { return ring[(pos + rbias) & kInMask]; }
+    __device__ __forceinline__ uint32_t at(uint32_t pos) const {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(smem_u32(ring) + ((pos + rbias) & kInMask)) : "memory");
+        return v;
+    }
     // pointer to relative byte `pos`, contiguous for kInMirror bytes (after ensure(pos, <= kInMirror))
     __device__ __forceinline__ const uint8_t* window(uint32_t pos) const { return ring + ((pos + rbias) & kInMask); }
 };
