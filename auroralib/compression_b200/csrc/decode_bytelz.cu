@@ -204,13 +204,21 @@ __device__ int lz4_block(InStream& in, GOut& out, uint32_t sp, uint32_t end) {
     while (sp < end) {
         in.ensure(sp, 64);
         const uint32_t token = in.at(sp);
-        if ((token >> 4) != 15 && (token & 15) != 15 && sp + 3 + (token >> 4) <= end && (token >> 4) + (token & 15) + 4 <= 32) {
-            // fast path: no extension bytes, literals + match fit one warp step (the vast majority of sequences)
+        if ((token >> 4) != 15 && sp + 4 + (token >> 4) <= end) {
+            // fast path: no literal extension, at most one match-length extension byte, literals + match fit one warp step
+            // (the vast majority of sequences; a 32-byte tile copy is token 0x0F + one extension byte)
             const uint32_t lit = token >> 4, off = sp + 1 + lit;
-            const uint32_t d = in.at(off) | (in.at(off + 1) << 8);
-            out.seq_copy_small(in, sp + 1, lit, d, (token & 15) + 4);
-            sp = off + 2;
-            continue;
+            uint32_t ml = token & 15, nx = off + 2;
+            if (ml == 15) {
+                ml += in.at(nx);   // 255 (more extension bytes follow) fails the size test below
+                nx++;
+            }
+            if (lit + ml + 4 <= 32) {
+                const uint32_t d = in.at(off) | (in.at(off + 1) << 8);
+                out.seq_copy_small(in, sp + 1, lit, d, ml + 4);
+                sp = nx;
+                continue;
+            }
         }
         sp++;
         uint32_t plain = token >> 4;
