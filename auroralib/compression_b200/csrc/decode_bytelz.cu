@@ -215,6 +215,7 @@ __device__ int lz4_block(InStream& in, GOut& out, uint32_t sp, uint32_t end) {
             }
             if (lit + ml + 4 <= 32) {
                 const uint32_t d = in.at(off) | (in.at(off + 1) << 8);
+                // (measured and rejected: an L1 prefetch of the NEXT sequence's far source here — 8 % slower, the kernel is issue bound)
                 out.seq_copy_small(in, sp + 1, lit, d, ml + 4);
                 sp = nx;
                 continue;
