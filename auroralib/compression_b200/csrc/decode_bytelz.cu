@@ -100,6 +100,24 @@ struct GOut {
     __device__ __forceinline__ void match_copy(uint32_t d, uint32_t len) {
         const uint32_t lane = lane_id();
         if (d == 0) d = ring_len;   // BackCopy(0, n) re-reads the ring slot it writes: one window back
+        if (len <= 32) {
+            // short match (the common case): one warp step, no piece loop
+            const uint32_t base = written;
+            const uint32_t r = d < len ? c_rcp.v[d & 511] : 0u;
+            if (lane < len) {
+                const int32_t s = int32_t(base) - int32_t(d) + int32_t(lane - ((lane * r) >> 20) * d);
+                uint32_t v = 0;
+                if (s >= int32_t(win_base)) {
+                    if (d <= uint32_t(kOKeep)) v = lds_u8((uint32_t(s) & kORingMask) | rb);
+                    else if (uint64_t(s) < cap) v = dst[s];
+                }
+                sts_u8(((base + lane) & kORingMask) | rb, v);
+            }
+            written = base + len;
+            __syncwarp();
+            drain();
+            return;
+        }
         uint32_t done = 0;
         while (done < len) {
             const uint32_t piece = min(len - done, uint32_t(kOPiece));
