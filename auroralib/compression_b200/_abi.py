@@ -12,10 +12,14 @@ STATUS_NAMES = ["OK", "END_OF_STREAM", "INVALID_IDENTIFIER", "SIZE_MISMATCH", "D
 # aurora_format
 FMT_YAZ0, FMT_YAZ1, FMT_YAY0, FMT_MIO0, FMT_LZ10, FMT_LZ11, FMT_LZSS, FMT_LZ4, FMT_LZ4_BLOCK, \
     FMT_LZ4_LEGACY, FMT_LZO, FMT_SNAPPY, FMT_SNAPPY_BLOCK, FMT_PRS = range(1, 15)
+# wrapper formats (a header around one of the cores above; host entry points only)
+FMT_GCLZ, FMT_CXLZ, FMT_COMP, FMT_LZ_3DS, FMT_LZ77, FMT_LEVEL5, FMT_LZON, FMT_LEVEL5_LZSS = range(15, 23)
+WRAPPER_FORMATS = list(range(15, 23))
 FORMAT_NAMES = {FMT_YAZ0: "Yaz0", FMT_YAZ1: "Yaz1", FMT_YAY0: "Yay0", FMT_MIO0: "MIO0", FMT_LZ10: "LZ10",
                 FMT_LZ11: "LZ11", FMT_LZSS: "LZSS", FMT_LZ4: "LZ4", FMT_LZ4_BLOCK: "LZ4Block",
                 FMT_LZ4_LEGACY: "LZ4Legacy", FMT_LZO: "LZO", FMT_SNAPPY: "Snappy",
-                FMT_SNAPPY_BLOCK: "SnappyBlock", FMT_PRS: "PRS"}
+                FMT_SNAPPY_BLOCK: "SnappyBlock", FMT_PRS: "PRS", FMT_GCLZ: "GCLZ", FMT_CXLZ: "CXLZ", FMT_COMP: "COMP",
+                FMT_LZ_3DS: "3DS-LZ", FMT_LZ77: "LZ77", FMT_LEVEL5: "Level5", FMT_LZON: "LZOn", FMT_LEVEL5_LZSS: "Level5LZSS"}
 
 ENDIAN_LITTLE, ENDIAN_BIG, ENDIAN_DEFAULT = 0, 1, 2
 
@@ -31,11 +35,13 @@ class CodecOpts(C.Structure):
                 ("max_window_bits", C.c_int32), ("strategy", C.c_int32), ("vram_mode", C.c_int32),
                 ("lzss", LzProps), ("lzss_initial_fill", C.c_int32), ("lz4_block_size", C.c_uint32),
                 ("lz4_verify", C.c_int32), ("yaz0_alignment", C.c_uint32), ("balance", C.c_uint32),
-                ("reserved", C.c_uint32 * 5)]
+                ("lz77_type", C.c_uint32), ("lz77_chunk_size", C.c_uint32), ("level5_type", C.c_uint32),
+                ("reserved", C.c_uint32 * 2)]
 
 
 def make_opts(byte_order=ENDIAN_DEFAULT, quality=-1, max_window_bits=0, strategy=0, vram_mode=-1,
-              lzss=None, lzss_initial_fill=0, lz4_block_size=0, lz4_verify=0, yaz0_alignment=0, balance=0):
+              lzss=None, lzss_initial_fill=0, lz4_block_size=0, lz4_verify=0, yaz0_alignment=0, balance=0,
+              lz77_type=0, lz77_chunk_size=0, level5_type=0):
     o = CodecOpts()
     o.struct_size = C.sizeof(CodecOpts)
     o.byte_order = byte_order
@@ -50,6 +56,9 @@ def make_opts(byte_order=ENDIAN_DEFAULT, quality=-1, max_window_bits=0, strategy
     o.lz4_verify = lz4_verify
     o.yaz0_alignment = yaz0_alignment
     o.balance = balance
+    o.lz77_type = lz77_type
+    o.lz77_chunk_size = lz77_chunk_size
+    o.level5_type = level5_type
     return o
 
 

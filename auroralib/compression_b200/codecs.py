@@ -322,4 +322,74 @@ class PRS(_Codec, _EndianCodec):
         return o
 
 
-ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS]
+# ---- wrapper formats: a header around one of the cores above (AuroraLib.Compression.Nintendo) ----
+class GCLZ(_SizedCodec):
+    """Nintendo/GCLZ.cs: "GCLZ" + LZ10 (Pandora's Tower)"""
+    FORMAT, Name = _abi.FMT_GCLZ, "GCLZ"
+
+
+class CXLZ(_SizedCodec):
+    """Sega/CXLZ.cs: "CXLZ" + LZ10"""
+    FORMAT, Name = _abi.FMT_CXLZ, "CXLZ"
+
+
+class COMP(_SizedCodec):
+    """Sega/COMP.cs: "COMP" + LZ11"""
+    FORMAT, Name = _abi.FMT_COMP, "COMP"
+
+
+class LZ_3DS(_SizedCodec):
+    """Nintendo/3DS-LZ.cs: "3DS-LZ\r\n" + LZ10"""
+    FORMAT, Name = _abi.FMT_LZ_3DS, "3DS-LZ"
+
+
+class LZ77(_SizedCodec):
+    """Nintendo/LZ77.cs: "LZ77" + LZ10 / LZ11 / ChunkLZ10 (Type, ChunkSize :30-35)"""
+    FORMAT, Name = _abi.FMT_LZ77, "Nintendo LZ77"
+    LZ10_TYPE, LZ11_TYPE, CHUNK_LZ10_TYPE = 0x10, 0x11, 0xF7
+
+    def __init__(self):
+        self.Type = LZ77.LZ10_TYPE
+        self.ChunkSize = 0x1000
+
+    def _opts(self, settings=None):
+        o = super()._opts(settings)
+        o.lz77_type = self.Type
+        o.lz77_chunk_size = self.ChunkSize
+        return o
+
+
+class Level5(_SizedCodec):
+    """Level5/Level5.cs: u32 (type | size << 3) + OnlySave / LZ10 body (the Huffman, RLE and zlib types are not LZ codecs)"""
+    FORMAT, Name = _abi.FMT_LEVEL5, "Level5 compression"
+    ONLY_SAVE, LZ10_TYPE = 0, 1
+
+    def __init__(self):
+        self.Type = Level5.LZ10_TYPE
+
+    def _opts(self, settings=None):
+        o = super()._opts(settings)
+        o.level5_type = self.Type
+        return o
+
+    def Compress(self, source, destination=None, settings=None):
+        if settings is not None and settings.Quality == 0:
+            self.Type = Level5.ONLY_SAVE   # Level5.cs:124-125 mutates the instance
+        return super().Compress(source, destination, settings)
+
+    def IsMatch(self, stream, fileNameAndExtension=None):
+        raise NotSupportedException("Level5.IsMatch depends on zlib and the file extension (Level5.cs:35-50): not on the LZ hot path")
+
+
+class LZOn(_SizedCodec):
+    """Nintendo/LZOn.cs: "LZOn" header + LZO"""
+    FORMAT, Name = _abi.FMT_LZON, "LZOn"
+
+
+class Level5LZSS(_SizedCodec):
+    """Level5/Level5LZSS.cs: "SSZL" header + LZSS with LZSS.Lzss0Properties"""
+    FORMAT, Name = _abi.FMT_LEVEL5_LZSS, "Level5 lzss"
+
+
+WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS]
+ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS] + WRAPPERS

@@ -11,6 +11,7 @@
 #include <thread>
 #include <vector>
 
+#include "api_internal.hpp"
 #include "common.cuh"
 
 using namespace aurora;
@@ -209,7 +210,7 @@ Layout plan_layout(const uint64_t* off, const uint64_t* len, size_t b, size_t e)
 int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_opts* opts, size_t b, size_t e,
                  const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
                  const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t* out_len, uint64_t* consumed, int32_t* status,
-                 int size_only) {
+                 int size_only, const uint64_t* raw_size = nullptr) {
     const size_t n = e - b;
     if (n == 0) return AURORA_OK;
     std::lock_guard<std::mutex> guard(d->mu);
@@ -225,6 +226,7 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
         return AURORA_OK;
     }
     P.size_only = size_only;
+    P.headerless = raw_size != nullptr;
     const Layout S = plan_layout(src_off, src_len, b, e);
     Layout D;
     if (!size_only) D = plan_layout(dst_off, dst_cap, b, e);
@@ -244,6 +246,8 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
         h[n + i] = src_len[b + i];
         h[2 * n + i] = D.dev_off[i];
         h[3 * n + i] = size_only ? 0 : dst_cap[b + i];
+        // headerless bodies: the decoded size travels in the upper half of the capacity word (DecodeParams::headerless)
+        if (raw_size) h[3 * n + i] = (raw_size[b + i] << 32) | std::min<uint64_t>(dst_cap[b + i], 0xFFFFFFFFull);
     }
     cudaStream_t st = d->stream;
     CU_TRY(ctx, cudaMemcpyAsync(dv, h, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -675,16 +679,15 @@ int aurora_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* op
                         const uint64_t* dst_cap, uint64_t* out_len, uint64_t* consumed, int32_t* status) {
     if (!ctx) return AURORA_INVALID_ARGUMENT;
     if (n == 0) return AURORA_OK;
-    if (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_cap || !status || !(is_flaglz(format) || is_bytelz(format))) {
+    if (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_cap || !status ||
+        !(is_flaglz(format) || is_bytelz(format) || aurora::is_wrapper_format(format))) {
         ctx->set_error("aurora_decode_batch: null argument or unknown format");
         return AURORA_INVALID_ARGUMENT;
     }
     if (n > 0xFFFFFFF0ull) return AURORA_INVALID_ARGUMENT;
-    const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, dst_cap);
-    return for_each_shard(ctx, ranges, [&](DeviceCtx* d, Range r) {
-        return decode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
-                            out_len, consumed, status, 0);
-    });
+    if (aurora::is_wrapper_format(format))
+        return aurora::wrapped_decode_batch(ctx, format, opts, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, consumed, status);
+    return aurora::decode_core_batch(ctx, format, opts, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, nullptr, out_len, consumed, status);
 }
 
 int aurora_decoded_size_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
@@ -693,6 +696,10 @@ int aurora_decoded_size_batch(aurora_ctx* ctx, int format, const aurora_codec_op
     if (!ctx) return AURORA_INVALID_ARGUMENT;
     if (n == 0) return AURORA_OK;
     if (!src_base || !src_off || !src_len || !out_size || !status) return AURORA_INVALID_ARGUMENT;
+    if (aurora::is_wrapper_format(format)) {   // header peeks of the wrapper formats (wrappers.cu)
+        for (size_t i = 0; i < n; i++) status[i] = aurora::wrapped_decoded_size(format, src_base + src_off[i], src_len[i], &out_size[i]);
+        return AURORA_OK;
+    }
     const int bo = opts ? opts->byte_order : AURORA_ENDIAN_DEFAULT;
     auto be32 = [](const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; };
     auto le32 = [](const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); };
@@ -771,6 +778,46 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
         return 0x10 < src_len[i] && src_len[i] >= k && std::memcmp(src_base + src_off[i], m, k) == 0;
     };
     static const uint8_t snappy_id[10] = {0xff, 0x06, 0x00, 0x00, 0x73, 0x4e, 0x61, 0x50, 0x70, 0x59};
+    if (aurora::is_wrapper_format(format)) {
+        // IsMatchStatic of the wrapper formats: identifier (+ a minimum length), then, for GCLZ / CXLZ / COMP, the
+        // LZ10 / LZ11 heuristic on the bytes behind it (GCLZ.cs:30-31, CXLZ.cs:31-32, COMP.cs:30-31, 3DS-LZ.cs:29-30,
+        // LZ77.cs:46-47, LZOn.cs:29-30, Level5LZSS.cs:29-30).  Level5.IsMatch needs zlib and the file name: not provided.
+        static const uint8_t lzon_id[8] = {'L', 'Z', 'O', 'n', 0x00, 0x2F, 0xF1, 0x71};
+        std::vector<size_t> idx;
+        std::vector<uint64_t> so, sl;
+        for (size_t i = 0; i < n; i++) {
+            const uint8_t* p = src_base + src_off[i];
+            const uint64_t len = src_len[i];
+            bool m = false;
+            switch (format) {
+                case AURORA_FMT_GCLZ: m = 0x8 < len && std::memcmp(p, "GCLZ", 4) == 0; break;
+                case AURORA_FMT_CXLZ: m = 0x8 < len && std::memcmp(p, "CXLZ", 4) == 0; break;
+                case AURORA_FMT_COMP: m = 0x8 < len && std::memcmp(p, "COMP", 4) == 0; break;
+                case AURORA_FMT_LZ_3DS: m = 0x10 < len && std::memcmp(p, "3DS-LZ\r\n", 8) == 0; break;
+                case AURORA_FMT_LZON: m = 0x10 < len && std::memcmp(p, lzon_id, 8) == 0; break;
+                case AURORA_FMT_LEVEL5_LZSS: m = 0x10 < len && std::memcmp(p, "SSZL", 4) == 0 && (p[4] | p[5] | p[6] | p[7]) == 0; break;
+                case AURORA_FMT_LZ77:
+                    m = 0x8 < len && std::memcmp(p, "LZ77", 4) == 0 &&
+                        (p[4] == 0x10 || p[4] == 0x11 || p[4] == 0x24 || p[4] == 0x28 || p[4] == 0x30 || p[4] == 0xF7);
+                    break;
+                default: return AURORA_NOT_SUPPORTED;   // Level5
+            }
+            match[i] = m ? 1 : 0;
+            if (m && (format == AURORA_FMT_GCLZ || format == AURORA_FMT_CXLZ || format == AURORA_FMT_COMP)) {
+                idx.push_back(i);
+                so.push_back(src_off[i] + 4);
+                sl.push_back(len - 4);
+            }
+        }
+        if (!idx.empty()) {
+            std::vector<uint8_t> mm(idx.size());
+            const int rc = aurora_is_match_batch(ctx, format == AURORA_FMT_COMP ? AURORA_FMT_LZ11 : AURORA_FMT_LZ10, opts, idx.size(),
+                                                 src_base, so.data(), sl.data(), mm.data());
+            if (rc != AURORA_OK) return rc;
+            for (size_t k = 0; k < idx.size(); k++) match[idx[k]] = mm[k];
+        }
+        return AURORA_OK;
+    }
     if (format == AURORA_FMT_LZ10 || format == AURORA_FMT_LZ11 || format == AURORA_FMT_PRS) {
         // token-walk heuristics run on the device, one thread per candidate stream (csrc/ismatch.cu)
         if (n > 0xFFFFFFF0ull) return AURORA_INVALID_ARGUMENT;
@@ -910,6 +957,7 @@ int aurora_decode_batch_device(aurora_ctx* ctx, int device, int format, const au
 extern "C" {
 
 uint64_t aurora_encode_bound(int format, uint64_t raw_len) {
+    if (aurora::is_wrapper_format(format)) return aurora::wrapped_encode_bound(format, raw_len, nullptr);
     // worst case of every token writer on the hot path: all literals + flag bits + headers / chunk framing
     switch (format) {
         case AURORA_FMT_LZ4:
@@ -931,6 +979,30 @@ int aurora_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* op
         ctx->set_error("aurora_encode_batch: null argument");
         return AURORA_INVALID_ARGUMENT;
     }
+    if (aurora::is_wrapper_format(format))
+        return aurora::wrapped_encode_batch(ctx, format, opts, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status);
+    return aurora::encode_core_batch(ctx, format, opts, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status);
+}
+
+}  // extern "C"
+
+namespace aurora {
+
+int decode_core_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
+                      const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
+                      const uint64_t* dst_cap, const uint64_t* raw_size, uint64_t* out_len, uint64_t* consumed, int32_t* status) {
+    if (n == 0) return AURORA_OK;
+    const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, dst_cap);
+    return for_each_shard(ctx, ranges, [&](DeviceCtx* d, Range r) {
+        return decode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
+                            out_len, consumed, status, 0, raw_size);
+    });
+}
+
+int encode_core_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
+                      const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
+                      const uint64_t* dst_cap, uint64_t* out_len, int32_t* status) {
+    if (n == 0) return AURORA_OK;
     EncodeParams probe{};
     const int rc = fill_encode_params(probe, format, opts);
     if (rc != AURORA_OK) {
@@ -942,6 +1014,10 @@ int aurora_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* op
         return encode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status);
     });
 }
+
+}  // namespace aurora
+
+extern "C" {
 
 int aurora_encode_batch_device(aurora_ctx* ctx, int device, int format, const aurora_codec_opts* opts, size_t n,
                                const uint8_t* d_src_base, uint64_t src_total, const uint64_t* d_src_off,

@@ -34,6 +34,8 @@ struct DecodeParams {
     int byte_order;              // aurora_endian
     int size_only;               // parse without copying (decoded_size_batch size_scan)
     int lz4_verify;              // LZ4.HashAlgorithm set: verify XXH32 checksums
+    int headerless;              // LZ10/LZ11/LZSS DecompressHeaderless(source, destination, size): the stream is the bare token
+                                 // body and dst_cap[i] carries (size << 32) | min(capacity, 2^32 - 1)  (wrapper formats)
     LzssParams lzss;
 };
 

@@ -1231,7 +1231,10 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
     const uint64_t slen64 = P.src_len[idx];
     const uint32_t slen = slen64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : uint32_t(slen64);
     uint8_t* dst = P.dst_base + P.dst_off[idx];
-    const uint64_t cap = P.dst_cap[idx];
+    uint64_t cap = P.dst_cap[idx];
+    const bool headerless = P.headerless != 0 && (K == K_LZ10 || K == K_LZ11 || K == K_LZSS);
+    const uint32_t given_size = uint32_t(cap >> 32);
+    if (headerless) cap &= 0xFFFFFFFFull;
 
     // ---- header (<= 16 bytes), read straight from global memory
     const uint32_t hb = (lane < 16 && lane < slen) ? src[lane] : 0u;
@@ -1243,7 +1246,9 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
     uint32_t size = 0, body_off = 0, comp_off = 0, lit_off = 0, consumed = 0;
     bool yaz_retry = false;
 
-    if (K == K_LZ10 || K == K_LZ11) {
+    if (headerless) {
+        size = given_size;   // DecompressHeaderless(source, destination, decomLength): LZ10.cs:82, LZ11.cs:83, LZSS.cs:91
+    } else if (K == K_LZ10 || K == K_LZ11) {
         const uint32_t id = (K == K_LZ10) ? 0x10 : 0x11;
         if (slen < 1) { status = AURORA_END_OF_STREAM; consumed = slen; }
         else if (H(0) != id) { status = AURORA_INVALID_IDENTIFIER; consumed = 1; }

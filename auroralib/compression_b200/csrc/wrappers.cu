@@ -1,0 +1,469 @@
+// wrappers.cu — the wrapper formats of AuroraLib.Compression.Nintendo: a header around one of the
+// cores the kernels decode.  The headers are a few bytes per stream and are resolved on the host; every stream becomes
+// one (ChunkLZ10: several independent) sub-stream of a core batch that runs on the device exactly like a direct call.
+//
+// Reference semantics restated (paths under /root/reference/src/AuroraLib.Compression.Nintendo):
+//   Nintendo/GCLZ.cs:39-53, Sega/CXLZ.cs:41-55, Nintendo/3DS-LZ.cs:37-50   magic + LZ10.Decompress / Compress
+//   Sega/COMP.cs:39-53                                                    magic + LZ11
+//   Nintendo/LZ77.cs:59-158   "LZ77", type byte, u24 size (u32 when 0): LZ10 / LZ11 headerless, or ChunkLZ10 = u16 end
+//                             offsets + independent LZ10 streams of ChunkSize bytes each
+//   Level5/Level5.cs:63-148   u32 LE (type | size << 3): OnlySave (stored) or LZ10 headerless; a payload starting with
+//                             0x78 is zlib.  Huffman / RLE / zlib are not LZ hot-path codecs: NOT_SUPPORTED
+//   Nintendo/LZOn.cs:41-80    "LZOn" 00 2F F1 71, BE size, BE compressed size, LZO headerless, ThrowIfMismatch(size)
+//   Level5/Level5LZSS.cs:41-72 "SSZL", u32, compressed size, size, LZSS headerless with LZSS.Lzss0Properties
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "api_internal.hpp"
+
+namespace aurora {
+
+namespace {
+
+const uint8_t kLzonMagic[8] = {'L', 'Z', 'O', 'n', 0x00, 0x2F, 0xF1, 0x71};
+
+inline uint32_t le32(const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); }
+inline uint32_t be32(const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
+inline void put_le32(uint8_t* p, uint32_t v) { p[0] = uint8_t(v); p[1] = uint8_t(v >> 8); p[2] = uint8_t(v >> 16); p[3] = uint8_t(v >> 24); }
+inline void put_be32(uint8_t* p, uint32_t v) { p[3] = uint8_t(v); p[2] = uint8_t(v >> 8); p[1] = uint8_t(v >> 16); p[0] = uint8_t(v >> 24); }
+
+constexpr uint64_t kParseHeader = ~0ull;   // raw size "none": the core parses its own header
+
+// one core sub-stream of a wrapped stream
+struct Sub {
+    size_t stream;      // index of the wrapped stream
+    int core;           // AURORA_FMT_LZ10 / LZ11 / LZSS / LZO
+    uint64_t off, len;  // source bytes, relative to the wrapped stream
+    uint64_t doff;      // destination offset inside the wrapped stream's slot
+    uint64_t raw;       // kParseHeader or the decoded size of a headerless body
+};
+
+struct Plan {
+    int status = AURORA_OK;      // header-level result (the core statuses are merged in afterwards)
+    uint64_t consumed = 0;       // source position when a header-level error was raised
+    uint64_t out_len = 0;        // bytes written by the host (stored payloads)
+    uint64_t expect = 0;         // LZ77 chunked / LZOn: the size the header promises
+    uint64_t end_consumed = 0;   // LZ77 chunked: source position after the last chunk
+    size_t first_sub = 0, n_sub = 0;
+};
+
+// Magic check with the stream semantics of MatchThrow: short stream -> END_OF_STREAM (position at the end), wrong
+// bytes -> INVALID_IDENTIFIER (position after the identifier)
+bool match_throw(Plan& pl, const uint8_t* p, uint64_t len, const void* magic, uint64_t k) {
+    if (len < k) {
+        pl.status = AURORA_END_OF_STREAM;
+        pl.consumed = len;
+        return false;
+    }
+    if (std::memcmp(p, magic, k) != 0) {
+        pl.status = AURORA_INVALID_IDENTIFIER;
+        pl.consumed = k;
+        return false;
+    }
+    return true;
+}
+
+void eos(Plan& pl, uint64_t len) {
+    pl.status = AURORA_END_OF_STREAM;
+    pl.consumed = len;
+}
+
+// resolve one wrapped stream into core sub-streams
+void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst, uint64_t cap, Plan& pl, std::vector<Sub>& subs) {
+    pl.first_sub = subs.size();
+    auto one = [&](int core, uint64_t off, uint64_t raw) { subs.push_back(Sub{i, core, off, len - off, 0, raw}); };
+    switch (format) {
+        case AURORA_FMT_GCLZ:
+            if (match_throw(pl, p, len, "GCLZ", 4)) one(AURORA_FMT_LZ10, 4, kParseHeader);
+            break;
+        case AURORA_FMT_CXLZ:
+            if (match_throw(pl, p, len, "CXLZ", 4)) one(AURORA_FMT_LZ10, 4, kParseHeader);
+            break;
+        case AURORA_FMT_COMP:
+            if (match_throw(pl, p, len, "COMP", 4)) one(AURORA_FMT_LZ11, 4, kParseHeader);
+            break;
+        case AURORA_FMT_LZ_3DS:
+            if (match_throw(pl, p, len, "3DS-LZ\r\n", 8)) one(AURORA_FMT_LZ10, 8, kParseHeader);
+            break;
+        case AURORA_FMT_LZON:
+            if (!match_throw(pl, p, len, kLzonMagic, 8)) break;
+            if (len < 16) { eos(pl, len); break; }
+            pl.expect = be32(p + 8);
+            one(AURORA_FMT_LZO, 16, kParseHeader);
+            break;
+        case AURORA_FMT_LEVEL5_LZSS:
+            if (!match_throw(pl, p, len, "SSZL", 4)) break;
+            if (len < 16) { eos(pl, len); break; }
+            one(AURORA_FMT_LZSS, 16, le32(p + 12));
+            break;
+        case AURORA_FMT_LEVEL5: {
+            if (len < 5) { eos(pl, len); break; }   // ReadUInt32 + Peek<byte>()
+            const uint32_t v = le32(p);
+            if (p[4] == 0x78) { pl.status = AURORA_NOT_SUPPORTED; pl.consumed = 4; break; }   // zlib payload
+            const uint32_t type = v & 7, size = v >> 3;
+            if (type == 0) {   // OnlySave: ReadExactly + Write
+                if (uint64_t(size) > len - 4) { eos(pl, len); break; }
+                std::memcpy(dst, p + 4, size_t(std::min<uint64_t>(size, cap)));
+                pl.out_len = size;
+                pl.consumed = 4 + uint64_t(size);
+                if (size > cap) pl.status = AURORA_DST_TOO_SMALL;
+            } else if (type == 1) {
+                one(AURORA_FMT_LZ10, 4, size);
+            } else {
+                pl.status = AURORA_NOT_SUPPORTED;
+                pl.consumed = 4;
+            }
+            break;
+        }
+        case AURORA_FMT_LZ77: {
+            if (!match_throw(pl, p, len, "LZ77", 4)) break;
+            if (len < 8) { eos(pl, len); break; }   // type byte + u24
+            const uint8_t type = p[4];
+            uint64_t pos = 8;
+            uint32_t size = uint32_t(p[5]) | (uint32_t(p[6]) << 8) | (uint32_t(p[7]) << 16);
+            if (size == 0) {
+                if (len < 12) { eos(pl, len); break; }
+                size = le32(p + 8);
+                pos = 12;
+            }
+            if (type == 0x10 || type == 0x11) {
+                // type byte + size are exactly an LZ10 / LZ11 header: DecompressHeaderless(size) == Decompress from offset 4
+                one(type == 0x10 ? AURORA_FMT_LZ10 : AURORA_FMT_LZ11, 4, kParseHeader);
+            } else if (type == 0xF7) {
+                // u16 end offsets until one of them, added to the position behind it, is the end of the stream
+                std::vector<uint32_t> ends;
+                for (;;) {
+                    if (pos + 2 > len) { eos(pl, len); break; }
+                    ends.push_back(uint32_t(p[pos]) | (uint32_t(p[pos + 1]) << 8));
+                    pos += 2;
+                    if (uint64_t(ends.back()) + pos == len) break;
+                }
+                if (pl.status != AURORA_OK) break;
+                pl.expect = size;
+                // every chunk is a complete LZ10 stream; its header gives the size that places the next one
+                uint64_t start = pos, doff = 0;
+                for (size_t k = 0; k < ends.size(); k++) {
+                    const uint64_t avail = start <= len ? len - start : 0;
+                    subs.push_back(Sub{i, AURORA_FMT_LZ10, std::min(start, len), avail, doff, kParseHeader});
+                    uint64_t csize = 0;
+                    const uint8_t* c = p + std::min(start, len);
+                    if (avail >= 4 && c[0] == 0x10) {
+                        csize = uint32_t(c[1]) | (uint32_t(c[2]) << 8) | (uint32_t(c[3]) << 16);
+                        if (csize == 0 && avail >= 8) csize = le32(c + 4);
+                    }
+                    doff += csize;
+                    start = pos + ends[k];
+                }
+                pl.end_consumed = pos + ends.back();
+            } else {
+                pl.status = AURORA_NOT_SUPPORTED;   // HUF20 / RLE30 sub-types, undefined values
+                pl.consumed = pos;
+            }
+            break;
+        }
+        default: pl.status = AURORA_INVALID_ARGUMENT; break;
+    }
+    pl.n_sub = subs.size() - pl.first_sub;
+}
+
+}  // namespace
+
+bool is_wrapper_format(int f) { return f >= AURORA_FMT_GCLZ && f <= AURORA_FMT_LEVEL5_LZSS; }
+
+int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
+                         const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
+                         const uint64_t* dst_cap, uint64_t* out_len, uint64_t* consumed, int32_t* status) {
+    std::vector<Plan> plans(n);
+    std::vector<Sub> subs;
+    subs.reserve(n);
+    for (size_t i = 0; i < n; i++)
+        resolve(format, i, src_base + src_off[i], src_len[i], dst_base + dst_off[i], dst_cap[i], plans[i], subs);
+
+    // one core batch per core format
+    std::vector<uint64_t> r_out(subs.size(), 0), r_cons(subs.size(), 0);
+    std::vector<int32_t> r_st(subs.size(), AURORA_OK);
+    aurora_codec_opts o;
+    if (opts) o = *opts;
+    else aurora_codec_opts_init(&o);
+    if (format == AURORA_FMT_LEVEL5_LZSS) aurora_lz_props_window(&o.lzss, 0x1000, 0xF + 3, 3, 0xFEE, 1);   // LZSS.Lzss0Properties
+    for (int key = 0; key < 8; key++) {   // one batch per (core format, headerless or not)
+        static const int kCores[4] = {AURORA_FMT_LZ10, AURORA_FMT_LZ11, AURORA_FMT_LZSS, AURORA_FMT_LZO};
+        const int core = kCores[key >> 1];
+        const bool want_raw = (key & 1) != 0;
+        std::vector<size_t> idx;
+        for (size_t k = 0; k < subs.size(); k++)
+            if (subs[k].core == core && (subs[k].raw != kParseHeader) == want_raw) idx.push_back(k);
+        if (idx.empty()) continue;
+        const size_t m = idx.size();
+        std::vector<uint64_t> so(m), sl(m), dof(m), dc(m), raw(m), ol(m), cs(m);
+        std::vector<int32_t> st(m);
+        for (size_t j = 0; j < m; j++) {
+            const Sub& s = subs[idx[j]];
+            so[j] = src_off[s.stream] + s.off;
+            sl[j] = s.len;
+            const uint64_t cap = dst_cap[s.stream];
+            dof[j] = dst_off[s.stream] + std::min(s.doff, cap);
+            dc[j] = s.doff < cap ? cap - s.doff : 0;
+            raw[j] = s.raw;
+        }
+        const int rc = decode_core_batch(ctx, core, &o, m, src_base, so.data(), sl.data(), dst_base, dof.data(), dc.data(),
+                                         want_raw ? raw.data() : nullptr, ol.data(), cs.data(), st.data());
+        if (rc != AURORA_OK) return rc;
+        for (size_t j = 0; j < m; j++) {
+            r_out[idx[j]] = ol[j];
+            r_cons[idx[j]] = cs[j];
+            r_st[idx[j]] = st[j];
+        }
+    }
+
+    for (size_t i = 0; i < n; i++) {
+        const Plan& pl = plans[i];
+        uint64_t ol = pl.out_len, cs = pl.consumed;
+        int st = pl.status;
+        if (st == AURORA_OK && pl.n_sub > 0) {
+            if (format == AURORA_FMT_LZ77 && pl.end_consumed) {
+                // chunks decode one after the other: the first failure ends the stream
+                for (size_t k = 0; k < pl.n_sub; k++) {
+                    const size_t q = pl.first_sub + k;
+                    ol = subs[q].doff + r_out[q];
+                    cs = subs[q].off + r_cons[q];
+                    if (r_st[q] != AURORA_OK) { st = r_st[q]; break; }
+                    // a chunk that decodes to a size other than its header's would shift the following ones
+                    if (k + 1 < pl.n_sub && subs[q + 1].doff != ol) { st = AURORA_INVALID_DATA; break; }
+                }
+                if (st == AURORA_OK) {
+                    cs = pl.end_consumed;
+                    if (ol > pl.expect) st = AURORA_SIZE_MISMATCH;
+                }
+            } else {
+                const size_t q = pl.first_sub;
+                ol = r_out[q];
+                cs = subs[q].off + r_cons[q];
+                st = r_st[q];
+                // ThrowIfMismatch runs before the destination's overflow is noticed
+                if (format == AURORA_FMT_LZON && (st == AURORA_OK || st == AURORA_DST_TOO_SMALL) && ol != pl.expect) st = AURORA_SIZE_MISMATCH;
+            }
+        }
+        if (out_len) out_len[i] = ol;
+        if (consumed) consumed[i] = cs;
+        status[i] = st;
+    }
+    return AURORA_OK;
+}
+
+// GetDecompressedSize of the wrapper formats: a header peek
+int wrapped_decoded_size(int format, const uint8_t* p, uint64_t len, uint64_t* out_size) {
+    *out_size = 0;
+    Plan pl;
+    uint64_t at = 0;
+    uint8_t id = 0x10;
+    switch (format) {
+        case AURORA_FMT_GCLZ: if (!match_throw(pl, p, len, "GCLZ", 4)) return pl.status; at = 4; break;
+        case AURORA_FMT_CXLZ: if (!match_throw(pl, p, len, "CXLZ", 4)) return pl.status; at = 4; break;
+        case AURORA_FMT_COMP: if (!match_throw(pl, p, len, "COMP", 4)) return pl.status; at = 4; id = 0x11; break;
+        case AURORA_FMT_LZ_3DS: if (!match_throw(pl, p, len, "3DS-LZ\r\n", 8)) return pl.status; at = 8; break;
+        case AURORA_FMT_LZ77: {
+            if (!match_throw(pl, p, len, "LZ77", 4)) return pl.status;
+            if (len < 8) return AURORA_END_OF_STREAM;
+            uint32_t v = uint32_t(p[5]) | (uint32_t(p[6]) << 8) | (uint32_t(p[7]) << 16);
+            if (v == 0) {
+                if (len < 12) return AURORA_END_OF_STREAM;
+                v = le32(p + 8);
+            }
+            *out_size = v;
+            return AURORA_OK;
+        }
+        case AURORA_FMT_LEVEL5:
+            if (len < 5) return AURORA_END_OF_STREAM;
+            *out_size = p[4] == 0x78 ? le32(p) : le32(p) >> 3;
+            return AURORA_OK;
+        case AURORA_FMT_LZON:
+            if (!match_throw(pl, p, len, kLzonMagic, 8)) return pl.status;
+            if (len < 12) return AURORA_END_OF_STREAM;
+            *out_size = be32(p + 8);
+            return AURORA_OK;
+        case AURORA_FMT_LEVEL5_LZSS:
+            if (!match_throw(pl, p, len, "SSZL", 4)) return pl.status;
+            if (len < 16) return AURORA_END_OF_STREAM;
+            *out_size = le32(p + 12);
+            return AURORA_OK;
+        default: return AURORA_INVALID_ARGUMENT;
+    }
+    // the prefixed LZ10 / LZ11 stream: type byte + u24 (LZ10.cs:47-57)
+    if (len < at + 1) return AURORA_END_OF_STREAM;
+    if (p[at] != id) return AURORA_INVALID_IDENTIFIER;
+    if (len < at + 4) return AURORA_END_OF_STREAM;
+    uint32_t v = uint32_t(p[at + 1]) | (uint32_t(p[at + 2]) << 8) | (uint32_t(p[at + 3]) << 16);
+    if (v == 0) {
+        if (len < at + 8) return AURORA_END_OF_STREAM;
+        v = le32(p + at + 4);
+    }
+    *out_size = v;
+    return AURORA_OK;
+}
+
+uint64_t wrapped_encode_bound(int format, uint64_t raw_len, const aurora_codec_opts* opts) {
+    switch (format) {
+        case AURORA_FMT_GCLZ: case AURORA_FMT_CXLZ: return 4 + aurora_encode_bound(AURORA_FMT_LZ10, raw_len);
+        case AURORA_FMT_COMP: return 4 + aurora_encode_bound(AURORA_FMT_LZ11, raw_len);
+        case AURORA_FMT_LZ_3DS: return 8 + aurora_encode_bound(AURORA_FMT_LZ10, raw_len);
+        case AURORA_FMT_LZ77: {
+            const uint64_t chunk = (opts && opts->lz77_chunk_size) ? opts->lz77_chunk_size : 0x1000;
+            const uint64_t segs = (raw_len + chunk - 1) / chunk + 1;
+            return 8 + 2 * segs + segs * aurora_encode_bound(AURORA_FMT_LZ10, chunk) +
+                   std::max(aurora_encode_bound(AURORA_FMT_LZ10, raw_len), aurora_encode_bound(AURORA_FMT_LZ11, raw_len));
+        }
+        case AURORA_FMT_LEVEL5: return 8 + std::max<uint64_t>(raw_len, aurora_encode_bound(AURORA_FMT_LZ10, raw_len));
+        case AURORA_FMT_LZON: return 16 + aurora_encode_bound(AURORA_FMT_LZO, raw_len);
+        case AURORA_FMT_LEVEL5_LZSS: return 16 + aurora_encode_bound(AURORA_FMT_LZSS, raw_len);
+        default: return 0;
+    }
+}
+
+// Compress of the wrapper formats: the core encoder writes at the offset the wrapper header leaves free, the header
+// bytes are written (or the core's own header is rewritten in place) on the host afterwards.
+int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
+                         const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
+                         const uint64_t* dst_cap, uint64_t* out_len, int32_t* status) {
+    aurora_codec_opts o;
+    if (opts) o = *opts;
+    else aurora_codec_opts_init(&o);
+    const bool has_ext = o.struct_size >= sizeof(aurora_codec_opts);
+    const uint32_t lz77_type = (has_ext && o.lz77_type) ? o.lz77_type : 0x10;
+    const uint64_t chunk = (has_ext && o.lz77_chunk_size) ? o.lz77_chunk_size : 0x1000;
+    const uint32_t level5_type = (o.quality == 0) ? 0 : ((has_ext && o.level5_type) ? o.level5_type : 1);
+
+    int core = AURORA_FMT_LZ10;
+    uint64_t head = 4;   // bytes in front of the core's output
+    switch (format) {
+        case AURORA_FMT_GCLZ: case AURORA_FMT_CXLZ: break;
+        case AURORA_FMT_COMP: core = AURORA_FMT_LZ11; break;
+        case AURORA_FMT_LZ_3DS: head = 8; break;
+        case AURORA_FMT_LZ77:
+            if (lz77_type == 0x11) core = AURORA_FMT_LZ11;
+            else if (lz77_type != 0x10 && lz77_type != 0xF7) {
+                for (size_t i = 0; i < n; i++) { status[i] = AURORA_NOT_SUPPORTED; out_len[i] = 0; }
+                return AURORA_OK;
+            }
+            break;
+        case AURORA_FMT_LEVEL5:
+            if (level5_type > 1) {
+                for (size_t i = 0; i < n; i++) { status[i] = AURORA_NOT_SUPPORTED; out_len[i] = 0; }
+                return AURORA_OK;
+            }
+            head = 0;   // the LZ10 header is rewritten in place
+            break;
+        case AURORA_FMT_LZON: core = AURORA_FMT_LZO; head = 16; break;
+        case AURORA_FMT_LEVEL5_LZSS:
+            core = AURORA_FMT_LZSS;
+            head = 0;   // the 16-byte LZSS header is rewritten in place
+            aurora_lz_props_window(&o.lzss, 0x1000, 0xF + 3, 3, 0xFEE, 1);
+            break;
+        default: return AURORA_INVALID_ARGUMENT;
+    }
+
+    // sub-buffers: one per stream, or one per chunk for LZ77 ChunkLZ10 with more than one chunk
+    struct Piece { size_t stream; uint64_t soff, slen, doff; };
+    std::vector<Piece> pieces;
+    std::vector<uint64_t> table_at(n, 0);   // chunked: offset of the u16 table inside the stream's slot
+    for (size_t i = 0; i < n; i++) {
+        status[i] = AURORA_OK;
+        out_len[i] = 0;
+        const uint64_t len = src_len[i];
+        if (format == AURORA_FMT_LEVEL5 && level5_type == 0) continue;   // stored on the host below
+        if (format == AURORA_FMT_LZ77 && lz77_type == 0xF7 && chunk < len) {
+            const uint64_t segs = (len + chunk - 1) / chunk;
+            const uint64_t body = 8 + 2 * segs;
+            const uint64_t per = aurora_encode_bound(AURORA_FMT_LZ10, chunk);
+            if (body + segs * per > dst_cap[i]) { status[i] = AURORA_DST_TOO_SMALL; continue; }
+            table_at[i] = 8;
+            for (uint64_t k = 0; k < segs; k++)   // encode every chunk into its own worst-case slot, compact afterwards
+                pieces.push_back(Piece{i, k * chunk, std::min(chunk, len - k * chunk), body + k * per});
+        } else {
+            if (dst_cap[i] < head) { status[i] = AURORA_DST_TOO_SMALL; continue; }
+            pieces.push_back(Piece{i, 0, len, head});
+        }
+    }
+    const size_t m = pieces.size();
+    std::vector<uint64_t> so(m), sl(m), dof(m), dc(m), ol(m);
+    std::vector<int32_t> st(m);
+    for (size_t j = 0; j < m; j++) {
+        const Piece& pc = pieces[j];
+        so[j] = src_off[pc.stream] + pc.soff;
+        sl[j] = pc.slen;
+        dof[j] = dst_off[pc.stream] + pc.doff;
+        dc[j] = table_at[pc.stream] ? aurora_encode_bound(AURORA_FMT_LZ10, chunk) : dst_cap[pc.stream] - pc.doff;
+    }
+    if (m) {
+        const int rc = encode_core_batch(ctx, core, &o, m, src_base, so.data(), sl.data(), dst_base, dof.data(), dc.data(), ol.data(), st.data());
+        if (rc != AURORA_OK) return rc;
+    }
+
+    // headers
+    size_t j = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint8_t* d = dst_base + dst_off[i];
+        const uint64_t len = src_len[i];
+        if (format == AURORA_FMT_LEVEL5 && level5_type == 0) {
+            if (dst_cap[i] < 4 + len) { status[i] = AURORA_DST_TOO_SMALL; continue; }
+            put_le32(d, uint32_t(len) << 3);
+            std::memcpy(d + 4, src_base + src_off[i], size_t(len));
+            out_len[i] = 4 + len;
+            continue;
+        }
+        if (status[i] != AURORA_OK) continue;
+        if (table_at[i]) {
+            const uint64_t segs = (len + chunk - 1) / chunk;
+            const uint64_t body = 8 + 2 * segs;
+            std::memcpy(d, "LZ77", 4);
+            put_le32(d + 4, 0xF7u | (uint32_t(len) << 8));
+            uint64_t end = 0;
+            for (uint64_t k = 0; k < segs; k++, j++) {
+                if (st[j] != AURORA_OK && status[i] == AURORA_OK) status[i] = st[j];
+                if (status[i] != AURORA_OK) continue;
+                std::memmove(d + body + end, d + pieces[j].doff, size_t(ol[j]));
+                end += ol[j];
+                if (end > 0xFFFF) { status[i] = AURORA_INVALID_ARGUMENT; continue; }   // "chunks too large to process"
+                d[8 + 2 * k] = uint8_t(end);
+                d[8 + 2 * k + 1] = uint8_t(end >> 8);
+            }
+            if (status[i] == AURORA_OK) out_len[i] = body + end;
+            continue;
+        }
+        const uint64_t clen = ol[j];
+        const int cst = st[j];
+        j++;
+        if (cst != AURORA_OK) { status[i] = cst; continue; }
+        switch (format) {
+            case AURORA_FMT_GCLZ: std::memcpy(d, "GCLZ", 4); break;
+            case AURORA_FMT_CXLZ: std::memcpy(d, "CXLZ", 4); break;
+            case AURORA_FMT_COMP: std::memcpy(d, "COMP", 4); break;
+            case AURORA_FMT_LZ77: std::memcpy(d, "LZ77", 4); break;
+            case AURORA_FMT_LZ_3DS: std::memcpy(d, "3DS-LZ\r\n", 8); break;
+            case AURORA_FMT_LZON:
+                std::memcpy(d, kLzonMagic, 8);
+                put_be32(d + 8, uint32_t(len));
+                put_be32(d + 12, uint32_t(clen));
+                break;
+            case AURORA_FMT_LEVEL5: {
+                // LZ10.Compress wrote 0x10 + u24 (or 0x10 00 00 00 + u32): CompressHeaderless is the same bytes without it
+                const uint64_t h = (d[1] | d[2] | d[3]) == 0 ? 8 : 4;
+                if (h == 8) std::memmove(d + 4, d + 8, size_t(clen - 8));
+                put_le32(d, 1u | (uint32_t(len) << 3));
+                out_len[i] = clen - h + 4;
+                continue;
+            }
+            case AURORA_FMT_LEVEL5_LZSS:
+                std::memcpy(d, "SSZL", 4);
+                put_le32(d + 4, 0);
+                put_le32(d + 8, uint32_t(clen - 16));
+                put_le32(d + 12, uint32_t(len));
+                break;
+        }
+        out_len[i] = head + clen;
+    }
+    return AURORA_OK;
+}
+
+}  // namespace aurora

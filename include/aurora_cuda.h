@@ -59,7 +59,17 @@ typedef enum aurora_format {
     AURORA_FMT_LZO          = 11, /* Formats/Common/LZO.cs (headerless LZO1X)                */
     AURORA_FMT_SNAPPY       = 12, /* Snappy.cs framing format                                */
     AURORA_FMT_SNAPPY_BLOCK = 13, /* Snappy.DecompressHeaderless / CompressHeaderless        */
-    AURORA_FMT_PRS          = 14  /* Sega/PRS.cs                                             */
+    AURORA_FMT_PRS          = 14, /* Sega/PRS.cs                                             */
+    /* wrapper formats: a header around one of the cores above (paths under
+     * src/AuroraLib.Compression.Nintendo).  Host entry points only (the headers are resolved on the host). */
+    AURORA_FMT_GCLZ         = 15, /* Nintendo/GCLZ.cs: "GCLZ" + LZ10                         */
+    AURORA_FMT_CXLZ         = 16, /* Sega/CXLZ.cs: "CXLZ" + LZ10                             */
+    AURORA_FMT_COMP         = 17, /* Sega/COMP.cs: "COMP" + LZ11                             */
+    AURORA_FMT_LZ_3DS       = 18, /* Nintendo/3DS-LZ.cs: "3DS-LZ\r\n" + LZ10                 */
+    AURORA_FMT_LZ77         = 19, /* Nintendo/LZ77.cs: "LZ77" + LZ10 / LZ11 / ChunkLZ10      */
+    AURORA_FMT_LEVEL5       = 20, /* Level5/Level5.cs: u32 type|size<<3 + stored / LZ10 body */
+    AURORA_FMT_LZON         = 21, /* Nintendo/LZOn.cs: "LZOn" header + LZO                   */
+    AURORA_FMT_LEVEL5_LZSS  = 22  /* Level5/Level5LZSS.cs: "SSZL" header + LZSS (Lzss0)      */
 } aurora_format;
 
 typedef enum aurora_endian {
@@ -100,7 +110,11 @@ typedef struct aurora_codec_opts {
     uint32_t yaz0_alignment;   /* Yaz0.MemoryAlignment written by the encoder                          */
     uint32_t balance;          /* decode: hand streams to warps largest first (device counting sort by size class):
                                   0 = auto (host path: when max size > 2 x mean; device path: off), 1 = on, 2 = off */
-    uint32_t reserved[5];
+    /* wrapper formats (encode) */
+    uint32_t lz77_type;        /* LZ77.Type: 0 -> 0x10 (LZ10); 0x11 (LZ11); 0xF7 (ChunkLZ10)            */
+    uint32_t lz77_chunk_size;  /* LZ77.ChunkSize: 0 -> 0x1000                                           */
+    uint32_t level5_type;      /* Level5.Type: 0 -> 1 (LZ10); quality 0 always stores (OnlySave)        */
+    uint32_t reserved[2];
 } aurora_codec_opts;
 
 typedef struct aurora_ctx aurora_ctx;

@@ -38,6 +38,11 @@ static CodecOpts to_opts(const aurora_codec_opts* c) {
     o.lz4BlockSize = c->lz4_block_size ? c->lz4_block_size : 0x400000;
     o.lz4Verify = c->lz4_verify != 0;
     o.yaz0Alignment = c->yaz0_alignment;
+    if (c->struct_size >= sizeof(aurora_codec_opts)) {
+        o.lz77Type = c->lz77_type ? int(c->lz77_type) : 0x10;
+        o.lz77ChunkSize = c->lz77_chunk_size ? int(c->lz77_chunk_size) : 0x1000;
+        o.level5Type = c->level5_type ? int(c->level5_type) : 1;
+    }
     return o;
 }
 
@@ -62,7 +67,9 @@ DecodeResult decode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t
             case FMT_SNAPPY: snappy_decode(s, d); break;
             case FMT_SNAPPY_BLOCK: snappy_block_decode(s, d); break;
             case FMT_PRS: prs_decode(s, d); break;
-            default: fail(INVALID_ARGUMENT);
+            default:
+                if (!is_wrapper_format(fmt)) fail(INVALID_ARGUMENT);
+                wrapper_decode(fmt, s, d, o);
         }
         if (d.pos > d.cap) r.status = DST_TOO_SMALL;
     } catch (const Error& e) {
@@ -93,7 +100,9 @@ int encode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t n64, std
             case FMT_SNAPPY: snappy_encode(src, n, b, o); break;
             case FMT_SNAPPY_BLOCK: snappy_block_encode(src, n, b, o); break;
             case FMT_PRS: prs_encode(src, n, b, o); break;
-            default: return INVALID_ARGUMENT;
+            default:
+                if (!is_wrapper_format(fmt)) return INVALID_ARGUMENT;
+                wrapper_encode(fmt, src, n, b, o, o.lz77Type, o.lz77ChunkSize, o.level5Type);
         }
     } catch (const Error& e) {
         return e.status;
@@ -113,6 +122,7 @@ uint32_t decoded_size(int fmt, Src& s, const CodecOpts& o) {
             s.MatchThrow("LZSS", 4);
             return s.ReadUInt32(Endian::Big);
     }
+    if (is_wrapper_format(fmt)) return wrapper_decoded_size(fmt, s);
     fail(NOT_SUPPORTED);
 }
 
@@ -144,6 +154,22 @@ bool is_match(int fmt, Src& s, const CodecOpts&) {
             return (flag > 11 && flag < 0x20) || (flag != -1 && flag < 0x10);
         }
         case FMT_PRS: return s.pos + 0x4 < s.len && prs_get_byte_order(s) >= 0;   // PRS.cs:31-32
+        // wrapper formats (GCLZ.cs:30-31, CXLZ.cs:31-32, COMP.cs:30-31, 3DS-LZ.cs:29-30, LZ77.cs:46-47, LZOn.cs:29-30,
+        // Level5LZSS.cs:29-30); Level5.IsMatch needs zlib and the file name: not restated
+        case FMT_GCLZ: return s.pos + 0x8 < s.len && s.Match("GCLZ", 4) && s.pos + 0x8 < s.len && lz1x_validate(s, false);
+        case FMT_CXLZ: return s.pos + 0x8 < s.len && s.Match("CXLZ", 4) && s.pos + 0x8 < s.len && lz1x_validate(s, false);
+        case FMT_COMP: return s.pos + 0x8 < s.len && s.Match("COMP", 4) && s.pos + 0x8 < s.len && lz1x_validate(s, true);
+        case FMT_LZ_3DS: return s.pos + 0x10 < s.len && s.Match("3DS-LZ\r\n", 8);
+        case FMT_LZON: {
+            static const uint8_t id[8] = {'L', 'Z', 'O', 'n', 0x00, 0x2F, 0xF1, 0x71};
+            return s.pos + 0x10 < s.len && s.Match(id, 8);
+        }
+        case FMT_LEVEL5_LZSS: return s.pos + 0x10 < s.len && s.Match("SSZL", 4) && s.ReadUInt32() == 0;
+        case FMT_LZ77: {
+            if (!(s.pos + 0x8 < s.len && s.Match("LZ77", 4))) return false;
+            uint8_t t = s.ReadUInt8();
+            return t == 0x10 || t == 0x11 || t == 0x24 || t == 0x28 || t == 0x30 || t == 0xF7;
+        }
     }
     fail(NOT_SUPPORTED);
 }

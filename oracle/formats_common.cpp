@@ -7,7 +7,7 @@ namespace ora {
 
 // ================================================================== LZSS
 // LZSS.cs:91-130
-static void lzss_headerless(Src& source, Sink& destination, uint32_t decomLength, const LzProps& lz, uint8_t initialFill) {
+void lzss_headerless(Src& source, Sink& destination, uint32_t decomLength, const LzProps& lz, uint8_t initialFill) {
     int64_t endPosition = destination.pos + decomLength;
     destination.SetLength(endPosition);
     FlagReader flag(&source, Endian::Little);

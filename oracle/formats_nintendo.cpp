@@ -21,7 +21,7 @@ static uint32_t lz1x_size(Src& s, uint8_t id) {
 }
 
 // LZ10.cs:82-111
-static void lz10_headerless(Src& source, Sink& destination, uint32_t decomLength) {
+void lz10_headerless(Src& source, Sink& destination, uint32_t decomLength) {
     int64_t endPosition = destination.pos + decomLength;
     destination.SetLength(endPosition);
     {
@@ -78,7 +78,7 @@ void lz10_encode(const uint8_t* source, int n, OutBuf& destination, const CodecO
 
 // ------------------------------------------------------------------ LZ11
 // LZ11.cs:83-133
-static void lz11_headerless(Src& source, Sink& destination, uint32_t decomLength) {
+void lz11_headerless(Src& source, Sink& destination, uint32_t decomLength) {
     int64_t endPosition = destination.pos + decomLength;
     destination.SetLength(endPosition);
     {

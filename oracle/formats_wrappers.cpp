@@ -1,0 +1,206 @@
+// formats_wrappers.cpp — CPU ORACLE (test infrastructure, NOT product code).
+// Restatement of the wrapper formats of src/AuroraLib.Compression.Nintendo that put a header around a core this
+// repository already has:
+//   Nintendo/GCLZ.cs:39-53      "GCLZ" + LZ10            Sega/CXLZ.cs:41-55       "CXLZ" + LZ10
+//   Sega/COMP.cs:39-53          "COMP" + LZ11            Nintendo/3DS-LZ.cs:37-50 "3DS-LZ\r\n" + LZ10
+//   Nintendo/LZ77.cs:59-158     "LZ77" + type byte + u24 size: LZ10 / LZ11 / ChunkLZ10 (independent LZ10 chunks)
+//   Level5/Level5.cs:63-148     u32 (type | size << 3): OnlySave / LZ10 headerless
+//   Nintendo/LZOn.cs:41-80      "LZOn" 00 2F F1 71 + BE size + BE compressed size + LZO headerless
+//   Level5/Level5LZSS.cs:41-72  "SSZL" + u32 + compressed size + size + LZSS headerless, Lzss0Properties
+// The Huffman / RLE / zlib sub-types of LZ77 and Level5 are outside the LZ hot path: NOT_SUPPORTED here and on the GPU.
+#include "oracle_core.hpp"
+
+namespace ora {
+
+void lz10_headerless(Src& source, Sink& destination, uint32_t decomLength);
+void lz11_headerless(Src& source, Sink& destination, uint32_t decomLength);
+void lzss_headerless(Src& source, Sink& destination, uint32_t decomLength, const LzProps& lz, uint8_t initialFill);
+
+static const uint8_t kLzonMagic[8] = {'L', 'Z', 'O', 'n', 0x00, 0x2F, 0xF1, 0x71};
+static const LzProps kLzss0 = LzProps::Window(0x1000, 0xF + 3, 3, 0xFEE);   // LZSS.cs:34
+
+static void prefixed(Src& s, Sink& d, const char* magic, int n, bool lz11) {
+    s.MatchThrow(magic, n);
+    if (lz11) lz11_decode(s, d);
+    else lz10_decode(s, d);
+}
+
+// LZ77.cs:108-157
+static void lz77_decode(Src& source, Sink& destination) {
+    source.MatchThrow("LZ77", 4);
+    uint8_t type = source.ReadUInt8();
+    uint32_t decompressedSize = source.ReadUInt24();
+    if (decompressedSize == 0) decompressedSize = source.ReadUInt32();
+    switch (type) {
+        case 0x10: lz10_headerless(source, destination, decompressedSize); break;
+        case 0x11: lz11_headerless(source, destination, decompressedSize); break;
+        case 0xF7: {
+            int64_t destinationEndPosition = destination.pos + decompressedSize;
+            std::vector<uint16_t> segmentEndOffsets;
+            do {
+                segmentEndOffsets.push_back(source.ReadUInt16(Endian::Little));
+            } while (int64_t(segmentEndOffsets.back()) + source.pos != source.len);
+            int64_t headerEndOffset = source.pos;
+            for (size_t i = 0; i < segmentEndOffsets.size(); i++) {
+                lz10_decode(source, destination);
+                source.pos = segmentEndOffsets[i] + headerEndOffset;
+            }
+            if (destination.pos > destinationEndPosition)
+                fail(SIZE_MISMATCH, decompressedSize, destination.pos - (destinationEndPosition - decompressedSize));
+            break;
+        }
+        default: fail(NOT_SUPPORTED);   // HUF20 / RLE30 sub-types and undefined values
+    }
+}
+
+// Level5.cs:63-113
+static void level5_decode(Src& source, Sink& destination) {
+    uint32_t typeAndSize = source.ReadUInt32();
+    if (source.pos >= source.len) fail(END_OF_STREAM);    // Peek<byte>() at the end of the stream
+    if (source.PeekByte() == 0x78) fail(NOT_SUPPORTED);   // zlib payload
+    uint32_t type = typeAndSize & 7, decompressedSize = typeAndSize >> 3;
+    switch (type) {
+        case 0: {   // OnlySave
+            source.need(decompressedSize);
+            destination.Write(source.p + source.pos, decompressedSize);
+            source.pos += decompressedSize;
+            break;
+        }
+        case 1: lz10_headerless(source, destination, decompressedSize); break;
+        default: fail(NOT_SUPPORTED);
+    }
+}
+
+// LZOn.cs:41-61
+static void lzon_decode(Src& source, Sink& destination) {
+    source.MatchThrow(kLzonMagic, 8);
+    uint32_t decompressedSize = source.ReadUInt32(Endian::Big);
+    (void)source.ReadUInt32(Endian::Big);
+    int64_t start = destination.pos;
+    lzo_decode(source, destination);
+    if (destination.pos - start != int64_t(decompressedSize)) fail(SIZE_MISMATCH, decompressedSize, destination.pos - start);
+}
+
+// Level5LZSS.cs:41-57
+static void sszl_decode(Src& source, Sink& destination, const CodecOpts& o) {
+    source.MatchThrow("SSZL", 4);
+    (void)source.ReadUInt32();
+    (void)source.ReadUInt32();
+    uint32_t decompressedSize = source.ReadUInt32();
+    lzss_headerless(source, destination, decompressedSize, kLzss0, uint8_t(o.lzssInitialFill));
+}
+
+bool is_wrapper_format(int fmt) { return fmt >= FMT_GCLZ && fmt <= FMT_LEVEL5_LZSS; }
+
+void wrapper_decode(int fmt, Src& s, Sink& d, const CodecOpts& o) {
+    switch (fmt) {
+        case FMT_GCLZ: prefixed(s, d, "GCLZ", 4, false); break;
+        case FMT_CXLZ: prefixed(s, d, "CXLZ", 4, false); break;
+        case FMT_COMP: prefixed(s, d, "COMP", 4, true); break;
+        case FMT_LZ_3DS: prefixed(s, d, "3DS-LZ\r\n", 8, false); break;
+        case FMT_LZ77: lz77_decode(s, d); break;
+        case FMT_LEVEL5: level5_decode(s, d); break;
+        case FMT_LZON: lzon_decode(s, d); break;
+        case FMT_LEVEL5_LZSS: sszl_decode(s, d, o); break;
+        default: fail(INVALID_ARGUMENT);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- encoders
+static void strip_lz1x_header(const OutBuf& core, OutBuf& out) {   // CompressHeaderless == Compress minus the 4/8-byte header
+    size_t h = (core.v.size() >= 4 && (core.v[1] | core.v[2] | core.v[3]) == 0) ? 8 : 4;
+    out.Write(core.v.data() + h, core.v.size() - h);
+}
+
+void wrapper_encode(int fmt, const uint8_t* src, int n, OutBuf& out, const CodecOpts& o, int lz77_type, int chunk_size, int level5_type) {
+    switch (fmt) {
+        case FMT_GCLZ: out.Write(reinterpret_cast<const uint8_t*>("GCLZ"), 4); lz10_encode(src, n, out, o); break;
+        case FMT_CXLZ: out.Write(reinterpret_cast<const uint8_t*>("CXLZ"), 4); lz10_encode(src, n, out, o); break;
+        case FMT_COMP: out.Write(reinterpret_cast<const uint8_t*>("COMP"), 4); lz11_encode(src, n, out, o); break;
+        case FMT_LZ_3DS: out.Write(reinterpret_cast<const uint8_t*>("3DS-LZ\r\n"), 8); lz10_encode(src, n, out, o); break;
+        case FMT_LZ77: {   // LZ77.cs:59-105
+            out.Write(reinterpret_cast<const uint8_t*>("LZ77"), 4);
+            if (lz77_type == 0x11) { lz11_encode(src, n, out, o); break; }
+            if (lz77_type == 0x10 || (lz77_type == 0xF7 && chunk_size >= n)) { lz10_encode(src, n, out, o); break; }
+            if (lz77_type != 0xF7) fail(NOT_SUPPORTED);
+            out.WriteU32(0xF7u | (uint32_t(n) << 8));
+            int segments = (n + chunk_size - 1) / chunk_size;
+            size_t table = out.size();
+            for (int i = 0; i < segments; i++) out.WriteU16(0, Endian::Little);
+            size_t headerEnd = out.size();
+            for (int i = 0; i < segments; i++) {
+                int start = i * chunk_size, size = std::min(chunk_size, n - start);
+                lz10_encode(src + start, size, out, o);
+                size_t end = out.size() - headerEnd;
+                if (end > 0xFFFF) fail(INVALID_ARGUMENT);   // ArgumentOutOfRangeException: chunks too large
+                out.v[table + 2 * i] = uint8_t(end);
+                out.v[table + 2 * i + 1] = uint8_t(end >> 8);
+            }
+            break;
+        }
+        case FMT_LEVEL5: {   // Level5.cs:116-148
+            int type = o.settings.Quality == 0 ? 0 : level5_type;
+            out.WriteU32(uint32_t(type) | (uint32_t(n) << 3));
+            if (type == 0) out.Write(src, size_t(n));
+            else if (type == 1) {
+                OutBuf core;
+                lz10_encode(src, n, core, o);
+                strip_lz1x_header(core, out);
+            } else fail(NOT_SUPPORTED);
+            break;
+        }
+        case FMT_LZON: {   // LZOn.cs:64-79
+            out.Write(kLzonMagic, 8);
+            out.WriteU32(uint32_t(n), Endian::Big);
+            size_t at = out.size();
+            out.WriteU32(0);
+            lzo_encode(src, n, out, o);
+            out.PatchU32(at, uint32_t(out.size() - 0x10), Endian::Big);
+            break;
+        }
+        case FMT_LEVEL5_LZSS: {   // Level5LZSS.cs:60-72
+            CodecOpts oo = o;
+            oo.lzss = kLzss0;
+            OutBuf core;
+            lzss_encode(src, n, core, oo);
+            out.Write(reinterpret_cast<const uint8_t*>("SSZL"), 4);
+            out.WriteU32(0);
+            out.WriteU32(uint32_t(core.size() - 0x10));
+            out.WriteU32(uint32_t(n));
+            out.Write(core.v.data() + 0x10, core.size() - 0x10);
+            break;
+        }
+        default: fail(INVALID_ARGUMENT);
+    }
+}
+
+// GetDecompressedSize of the wrappers (a Peek)
+uint32_t wrapper_decoded_size(int fmt, Src& s) {
+    switch (fmt) {
+        case FMT_GCLZ: s.MatchThrow("GCLZ", 4); break;
+        case FMT_CXLZ: s.MatchThrow("CXLZ", 4); break;
+        case FMT_COMP: s.MatchThrow("COMP", 4); break;
+        case FMT_LZ_3DS: s.MatchThrow("3DS-LZ\r\n", 8); break;
+        case FMT_LZ77: {
+            s.MatchThrow("LZ77", 4);
+            s.need(1);
+            s.pos += 1;
+            uint32_t v = s.ReadUInt24();
+            return v ? v : s.ReadUInt32();
+        }
+        case FMT_LEVEL5: {
+            uint32_t v = s.ReadUInt32();
+            return s.PeekByte() == 0x78 ? v : v >> 3;
+        }
+        case FMT_LZON: s.MatchThrow(kLzonMagic, 8); return s.ReadUInt32(Endian::Big);
+        case FMT_LEVEL5_LZSS: s.MatchThrow("SSZL", 4); s.need(8); s.pos += 8; return s.ReadUInt32();
+        default: fail(INVALID_ARGUMENT);
+    }
+    // the prefixed LZ10 / LZ11 streams: type byte + u24 (LZ10.cs:47-57)
+    uint8_t id = s.ReadUInt8();
+    if (id != (fmt == FMT_COMP ? 0x11 : 0x10)) fail(INVALID_IDENTIFIER);
+    uint32_t v = s.ReadUInt24();
+    return v ? v : s.ReadUInt32();
+}
+
+}  // namespace ora

@@ -33,7 +33,8 @@ enum Status : int {
 enum Format : int {
     FMT_YAZ0 = 1, FMT_YAZ1 = 2, FMT_YAY0 = 3, FMT_MIO0 = 4, FMT_LZ10 = 5, FMT_LZ11 = 6, FMT_LZSS = 7,
     FMT_LZ4 = 8, FMT_LZ4_BLOCK = 9, FMT_LZ4_LEGACY = 10, FMT_LZO = 11, FMT_SNAPPY = 12,
-    FMT_SNAPPY_BLOCK = 13, FMT_PRS = 14
+    FMT_SNAPPY_BLOCK = 13, FMT_PRS = 14,
+    FMT_GCLZ = 15, FMT_CXLZ = 16, FMT_COMP = 17, FMT_LZ_3DS = 18, FMT_LZ77 = 19, FMT_LEVEL5 = 20, FMT_LZON = 21, FMT_LEVEL5_LZSS = 22
 };
 
 struct Error {
@@ -424,6 +425,7 @@ struct CodecOpts {
     uint32_t lz4BlockSize = 0x400000;
     bool lz4Verify = false;
     uint32_t yaz0Alignment = 0;
+    int lz77Type = 0x10, lz77ChunkSize = 0x1000, level5Type = 1;   // LZ77.Type / LZ77.ChunkSize / Level5.Type
 };
 
 struct DecodeResult {
@@ -433,6 +435,10 @@ struct DecodeResult {
 };
 
 // per-format entry points (formats_*.cpp).  Decoders throw ora::Error; the dispatcher catches.
+bool is_wrapper_format(int fmt);
+void wrapper_decode(int fmt, Src& s, Sink& d, const CodecOpts& o);
+void wrapper_encode(int fmt, const uint8_t* src, int n, OutBuf& out, const CodecOpts& o, int lz77_type, int chunk_size, int level5_type);
+uint32_t wrapper_decoded_size(int fmt, Src& s);
 void lz10_decode(Src& s, Sink& d);
 void lz11_decode(Src& s, Sink& d);
 void yaz0_decode(Src& s, Sink& d, const CodecOpts& o, const char* magic);
