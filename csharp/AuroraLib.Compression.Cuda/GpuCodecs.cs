@@ -132,6 +132,77 @@ namespace AuroraLib.Compression.Cuda
         public uint GetDecompressedSize(Stream source) => PeekSize(source);
     }
 
+    // ---- wrapper formats (AuroraLib.Compression.Nintendo): the header is resolved by libaurora_cuda.so on the host, the core
+    // runs on the device; ChunkLZ10 chunks decode as independent streams of one batch
+    public sealed class GpuGCLZ : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Nintendo.GCLZ _managed = new Formats.Nintendo.GCLZ();
+        protected override AuroraFormat Format => AuroraFormat.GCLZ;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuCXLZ : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Nintendo.CXLZ _managed = new Formats.Nintendo.CXLZ();
+        protected override AuroraFormat Format => AuroraFormat.CXLZ;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuCOMP : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Nintendo.COMP _managed = new Formats.Nintendo.COMP();
+        protected override AuroraFormat Format => AuroraFormat.COMP;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuLZ_3DS : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Nintendo.LZ_3DS _managed = new Formats.Nintendo.LZ_3DS();
+        protected override AuroraFormat Format => AuroraFormat.LZ_3DS;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuLZ77 : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Nintendo.LZ77 _managed = new Formats.Nintendo.LZ77();
+        protected override AuroraFormat Format => AuroraFormat.LZ77;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public Formats.Nintendo.LZ77.CompressionType Type { get; set; } = Formats.Nintendo.LZ77.CompressionType.LZ10;
+        public uint ChunkSize { get; set; } = 0x1000;
+        protected override void FillOptions(ref AuroraCodecOpts o, CompressionSettings s) { o.Lz77Type = (uint)Type; o.Lz77ChunkSize = ChunkSize; }
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuLevel5 : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Level5.Level5 _managed = new Formats.Level5.Level5();
+        protected override AuroraFormat Format => AuroraFormat.Level5;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public Formats.Level5.Level5.CompressionType Type { get; set; } = Formats.Level5.Level5.CompressionType.LZ10;
+        protected override void FillOptions(ref AuroraCodecOpts o, CompressionSettings s) { o.Level5Type = (uint)Type; }
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuLZOn : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Nintendo.LZOn _managed = new Formats.Nintendo.LZOn();
+        protected override AuroraFormat Format => AuroraFormat.LZOn;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuLevel5LZSS : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Level5.Level5LZSS _managed = new Formats.Level5.Level5LZSS();
+        protected override AuroraFormat Format => AuroraFormat.Level5LZSS;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
     public sealed class GpuLZ4 : GpuCodec
     {
         private readonly Formats.Common.LZ4 _managed = new Formats.Common.LZ4();

@@ -14,7 +14,9 @@ namespace AuroraLib.Compression.Cuda
     public enum AuroraFormat : int
     {
         Yaz0 = 1, Yaz1 = 2, Yay0 = 3, MIO0 = 4, LZ10 = 5, LZ11 = 6, LZSS = 7, LZ4 = 8, LZ4Block = 9,
-        LZ4Legacy = 10, LZO = 11, Snappy = 12, SnappyBlock = 13, PRS = 14
+        LZ4Legacy = 10, LZO = 11, Snappy = 12, SnappyBlock = 13, PRS = 14,
+        // wrapper formats (AuroraLib.Compression.Nintendo): a header around one of the cores above
+        GCLZ = 15, CXLZ = 16, COMP = 17, LZ_3DS = 18, LZ77 = 19, Level5 = 20, LZOn = 21, Level5LZSS = 22
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -38,7 +40,10 @@ namespace AuroraLib.Compression.Cuda
         public int Lz4Verify;
         public uint Yaz0Alignment;
         public uint Balance;           // 0 auto, 1 largest-first on, 2 off
-        public fixed uint Reserved[5];
+        public uint Lz77Type;          // LZ77.Type: 0 -> 0x10; 0x11; 0xF7 (ChunkLZ10)
+        public uint Lz77ChunkSize;     // LZ77.ChunkSize: 0 -> 0x1000
+        public uint Level5Type;        // Level5.Type: 0 -> 1 (LZ10)
+        public fixed uint Reserved[2];
     }
 
     internal static unsafe class Native

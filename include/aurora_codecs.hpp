@@ -268,6 +268,53 @@ class PRS : public CompressionAlgorithm {
   protected:
     void Fill(aurora_codec_opts& o, bool) const override { o.byte_order = int(FormatByteOrder); }
 };
+// Wrapper formats of AuroraLib.Compression.Nintendo: a header around one of the cores above (aurora_cuda.h, formats 15-22)
+class GCLZ : public SizedAlgorithm {   // Nintendo/GCLZ.cs
+  public:
+    AURORA_FORMAT(GCLZ, AURORA_FMT_GCLZ, "GCLZ")
+};
+class CXLZ : public SizedAlgorithm {   // Sega/CXLZ.cs
+  public:
+    AURORA_FORMAT(CXLZ, AURORA_FMT_CXLZ, "CXLZ")
+};
+class COMP : public SizedAlgorithm {   // Sega/COMP.cs
+  public:
+    AURORA_FORMAT(COMP, AURORA_FMT_COMP, "COMP")
+};
+class LZ_3DS : public SizedAlgorithm {   // Nintendo/3DS-LZ.cs
+  public:
+    AURORA_FORMAT(LZ_3DS, AURORA_FMT_LZ_3DS, "3DS-LZ")
+};
+class LZ77 : public SizedAlgorithm {   // Nintendo/LZ77.cs: Type (:30) and ChunkSize (:35)
+  public:
+    AURORA_FORMAT(LZ77, AURORA_FMT_LZ77, "Nintendo LZ77")
+    enum CompressionType : uint32_t { LZ10_ = 0x10, LZ11_ = 0x11, ChunkLZ10 = 0xF7 };
+    uint32_t Type = LZ10_;
+    uint32_t ChunkSize = 0x1000;
+
+  protected:
+    void Fill(aurora_codec_opts& o, bool) const override {
+        o.lz77_type = Type;
+        o.lz77_chunk_size = ChunkSize;
+    }
+};
+class Level5 : public SizedAlgorithm {   // Level5/Level5.cs: OnlySave / LZ10 (the Huffman, RLE and zlib types are not LZ codecs)
+  public:
+    AURORA_FORMAT(Level5, AURORA_FMT_LEVEL5, "Level5 compression")
+    enum CompressionType : uint32_t { OnlySave = 0, LZ10_ = 1 };
+    uint32_t Type = LZ10_;
+
+  protected:
+    void Fill(aurora_codec_opts& o, bool) const override { o.level5_type = Type; }
+};
+class LZOn : public SizedAlgorithm {   // Nintendo/LZOn.cs
+  public:
+    AURORA_FORMAT(LZOn, AURORA_FMT_LZON, "LZOn")
+};
+class Level5LZSS : public SizedAlgorithm {   // Level5/Level5LZSS.cs
+  public:
+    AURORA_FORMAT(Level5LZSS, AURORA_FMT_LEVEL5_LZSS, "Level5 lzss")
+};
 #undef AURORA_FORMAT
 
 // The new batch entry point: many independent blobs at once, sharded over all GPUs of the box.

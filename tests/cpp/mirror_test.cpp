@@ -46,6 +46,21 @@ int main(int argc, char** argv) {
         bad += round_trip(LZO(), raw, CompressionSettings::Balanced(), false);
         bad += round_trip(Snappy(), raw, CompressionSettings::Balanced(), false);
         bad += round_trip(PRS(), raw, CompressionSettings::Balanced(), false);
+        // wrapper formats (headers resolved on the host, cores on the device)
+        bad += round_trip(GCLZ(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(CXLZ(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(COMP(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(LZ_3DS(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(LZ77(), raw, CompressionSettings::Balanced(), true);
+        {
+            LZ77 chunked;
+            chunked.Type = LZ77::ChunkLZ10;
+            chunked.ChunkSize = 0x800;
+            bad += round_trip(chunked, raw, CompressionSettings::Balanced(), true);
+        }
+        bad += round_trip(Level5(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(LZOn(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(Level5LZSS(), raw, CompressionSettings::Balanced(), true);
         // GetDecompressedSize (DataRecognitionTest: 256 zero bytes)
         {
             std::string zeros(0x100, '\0');
