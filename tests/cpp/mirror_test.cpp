@@ -12,11 +12,11 @@
 using namespace aurora;
 
 template <typename T>
-static int round_trip(T&& algo, const std::string& raw, const CompressionSettings& s, bool sized) {
+static int round_trip(T&& algo, const std::string& raw, const CompressionSettings& s, bool sized, bool check_match = true) {
     std::stringstream comp, out;
     algo.Compress(reinterpret_cast<const uint8_t*>(raw.data()), raw.size(), comp, s);
     comp.seekg(0);
-    if (!algo.IsMatch(comp)) { std::printf("%s: IsMatch false\n", algo.Name()); return 1; }
+    if (check_match && !algo.IsMatch(comp)) { std::printf("%s: IsMatch false\n", algo.Name()); return 1; }
     if (comp.tellg() != std::streampos(0)) { std::printf("%s: IsMatch moved the stream\n", algo.Name()); return 1; }
     algo.Decompress(comp, out);
     if (out.str() != raw) { std::printf("%s: round trip differs\n", algo.Name()); return 1; }
@@ -58,7 +58,7 @@ int main(int argc, char** argv) {
             chunked.ChunkSize = 0x800;
             bad += round_trip(chunked, raw, CompressionSettings::Balanced(), true);
         }
-        bad += round_trip(Level5(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(Level5(), raw, CompressionSettings::Balanced(), true, false);   // Level5.IsMatch is not provided (zlib, file name)
         bad += round_trip(LZOn(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(Level5LZSS(), raw, CompressionSettings::Balanced(), true);
         // GetDecompressedSize (DataRecognitionTest: 256 zero bytes)
