@@ -391,5 +391,45 @@ class Level5LZSS(_SizedCodec):
     FORMAT, Name = _abi.FMT_LEVEL5_LZSS, "Level5 lzss"
 
 
-WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS]
+class _NoIdentifier:
+    def IsMatch(self, stream, fileNameAndExtension=None):
+        raise NotSupportedException(f"{type(self).__name__}.IsMatch is a heuristic on lengths / the file name, not an identifier: not on the LZ hot path")
+
+
+class AKLZ(_SizedCodec):
+    """Sega/AKLZ.cs: 12-byte identifier + BE size + LZSS body (DefaultProperties)"""
+    FORMAT, Name = _abi.FMT_AKLZ, "AKLZ"
+
+
+class LZ01(_SizedCodec):
+    """Sega/LZ01.cs: "LZ01" + file length + size + 0 + LZSS body (Lzss0Properties)"""
+    FORMAT, Name = _abi.FMT_LZ01, "LZ01"
+
+
+class FCMP(_SizedCodec):
+    """Extended/Marvelous/FCMP.cs: "FCMP" + size + constant + LZSS body (Lzss0Properties)"""
+    FORMAT, Name = _abi.FMT_FCMP, "FCMP"
+
+
+class IECP(_SizedCodec):
+    """Extended/Marvelous/IECP.cs: "IECP" + size + LZSS body (Lzss0Properties)"""
+    FORMAT, Name = _abi.FMT_IECP, "IECP"
+
+
+class MDB4(_SizedCodec):
+    """Extended/Specialized/MDB4.cs: 32-byte header + LZSS body (DefaultProperties)"""
+    FORMAT, Name = _abi.FMT_MDB4, "MDB4"
+
+
+class LZSega(_NoIdentifier, _SizedCodec):
+    """Sega/LZSega.cs: compressed size + size + LZSS body (DefaultProperties)"""
+    FORMAT, Name = _abi.FMT_LZSEGA, "LZSega"
+
+
+class GCZ(_NoIdentifier, _SizedCodec):
+    """Extended/Konami/GCZ.cs: size + LZSS body (Lzss0Properties)"""
+    FORMAT, Name = _abi.FMT_GCZ, "Konami GCZ"
+
+
+WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ]
 ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS] + WRAPPERS

@@ -800,7 +800,13 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
                     m = 0x8 < len && std::memcmp(p, "LZ77", 4) == 0 &&
                         (p[4] == 0x10 || p[4] == 0x11 || p[4] == 0x24 || p[4] == 0x28 || p[4] == 0x30 || p[4] == 0xF7);
                     break;
-                default: return AURORA_NOT_SUPPORTED;   // Level5
+                // the LZSS-property family with an identifier (AKLZ.cs:31-32, LZ01.cs:33-34, FCMP.cs:31-32, IECP.cs:30-31, MDB4.cs:28-29)
+                case AURORA_FMT_AKLZ: m = 0x10 < len && std::memcmp(p, "AKLZ~?Qd=\xCC\xCC\xCD", 12) == 0; break;
+                case AURORA_FMT_LZ01: m = 0x10 < len && std::memcmp(p, "LZ01", 4) == 0; break;
+                case AURORA_FMT_FCMP: m = 0x10 < len && std::memcmp(p, "FCMP", 4) == 0; break;
+                case AURORA_FMT_IECP: m = 0x10 < len && std::memcmp(p, "IECP", 4) == 0; break;
+                case AURORA_FMT_MDB4: m = 0x10 < len && std::memcmp(p, "MDB4", 4) == 0; break;
+                default: return AURORA_NOT_SUPPORTED;   // Level5 (zlib, file name), LZSega / GCZ (no identifier)
             }
             match[i] = m ? 1 : 0;
             if (m && (format == AURORA_FMT_GCLZ || format == AURORA_FMT_CXLZ || format == AURORA_FMT_COMP)) {

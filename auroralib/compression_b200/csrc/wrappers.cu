@@ -11,6 +11,9 @@
 //                             0x78 is zlib.  Huffman / RLE / zlib are not LZ hot-path codecs: NOT_SUPPORTED
 //   Nintendo/LZOn.cs:41-80    "LZOn" 00 2F F1 71, BE size, BE compressed size, LZO headerless, ThrowIfMismatch(size)
 //   Level5/Level5LZSS.cs:41-72 "SSZL", u32, compressed size, size, LZSS headerless with LZSS.Lzss0Properties
+// The LZSS-property family (a fixed header + LZSS.DecompressHeaderless with DefaultProperties or Lzss0Properties) is table
+// driven (kFamily below): Sega/AKLZ.cs:43-56, Sega/LZ01.cs:47-82, Sega/LZSega.cs:49-67 (src/AuroraLib.Compression.Sega),
+// Marvelous/FCMP.cs:43-59, Marvelous/IECP.cs:42-55, Konami/GCZ.cs:40-51, Specialized/MDB4.cs:41-80 (…-Extended).
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -29,6 +32,33 @@ inline void put_le32(uint8_t* p, uint32_t v) { p[0] = uint8_t(v); p[1] = uint8_t
 inline void put_be32(uint8_t* p, uint32_t v) { p[3] = uint8_t(v); p[2] = uint8_t(v >> 8); p[1] = uint8_t(v >> 16); p[0] = uint8_t(v >> 24); }
 
 constexpr uint64_t kParseHeader = ~0ull;   // raw size "none": the core parses its own header
+
+// LZSS-property family: identifier, header bytes that are READ (a short stream is END_OF_STREAM), bytes skipped by a seek
+// after them, where the decoded size sits, and which LzProperties the body uses
+struct Family {
+    int format;
+    const char* magic;
+    uint32_t magic_len, read_len, skip_len, size_off;
+    bool size_big, lzss0;
+};
+const Family kFamily[] = {
+    {AURORA_FMT_AKLZ, "AKLZ~?Qd=\xCC\xCC\xCD", 12, 16, 0, 12, true, false},
+    {AURORA_FMT_LZ01, "LZ01", 4, 16, 0, 8, false, true},
+    {AURORA_FMT_FCMP, "FCMP", 4, 12, 0, 4, false, true},
+    {AURORA_FMT_IECP, "IECP", 4, 8, 0, 4, false, true},
+    {AURORA_FMT_MDB4, "MDB4", 4, 16, 16, 8, false, false},
+    {AURORA_FMT_LZSEGA, "", 0, 8, 0, 4, false, false},
+    {AURORA_FMT_GCZ, "", 0, 4, 0, 0, false, true},
+};
+const Family* family_of(int format) {
+    for (const Family& f : kFamily)
+        if (f.format == format) return &f;
+    return nullptr;
+}
+void family_props(const Family& f, aurora_lz_props* lz) {
+    if (f.lzss0) aurora_lz_props_window(lz, 0x1000, 0xF + 3, 3, 0xFEE, 1);   // LZSS.Lzss0Properties (LZSS.cs:34)
+    else aurora_lz_props_bits(lz, 12, 4, 2);                                 // LZSS.DefaultProperties (LZSS.cs:33)
+}
 
 // one core sub-stream of a wrapped stream
 struct Sub {
@@ -162,14 +192,22 @@ void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst,
             }
             break;
         }
-        default: pl.status = AURORA_INVALID_ARGUMENT; break;
+        default: {
+            const Family* f = family_of(format);
+            if (!f) { pl.status = AURORA_INVALID_ARGUMENT; break; }
+            if (f->magic_len && !match_throw(pl, p, len, f->magic, f->magic_len)) break;
+            if (len < f->read_len) { eos(pl, len); break; }
+            const uint32_t size = f->size_big ? be32(p + f->size_off) : le32(p + f->size_off);
+            one(AURORA_FMT_LZSS, std::min<uint64_t>(f->read_len + f->skip_len, len), size);   // Skip() is a seek: it may pass the end
+            break;
+        }
     }
     pl.n_sub = subs.size() - pl.first_sub;
 }
 
 }  // namespace
 
-bool is_wrapper_format(int f) { return f >= AURORA_FMT_GCLZ && f <= AURORA_FMT_LEVEL5_LZSS; }
+bool is_wrapper_format(int f) { return f >= AURORA_FMT_GCLZ && f <= AURORA_FMT_GCZ; }
 
 int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
                          const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
@@ -187,6 +225,7 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
     if (opts) o = *opts;
     else aurora_codec_opts_init(&o);
     if (format == AURORA_FMT_LEVEL5_LZSS) aurora_lz_props_window(&o.lzss, 0x1000, 0xF + 3, 3, 0xFEE, 1);   // LZSS.Lzss0Properties
+    if (const Family* f = family_of(format)) family_props(*f, &o.lzss);
     for (int key = 0; key < 8; key++) {   // one batch per (core format, headerless or not)
         static const int kCores[4] = {AURORA_FMT_LZ10, AURORA_FMT_LZ11, AURORA_FMT_LZSS, AURORA_FMT_LZO};
         const int core = kCores[key >> 1];
@@ -288,7 +327,14 @@ int wrapped_decoded_size(int format, const uint8_t* p, uint64_t len, uint64_t* o
             if (len < 16) return AURORA_END_OF_STREAM;
             *out_size = le32(p + 12);
             return AURORA_OK;
-        default: return AURORA_INVALID_ARGUMENT;
+        default: {
+            const Family* f = family_of(format);
+            if (!f) return AURORA_INVALID_ARGUMENT;
+            if (f->magic_len && !match_throw(pl, p, len, f->magic, f->magic_len)) return pl.status;
+            if (len < uint64_t(f->size_off) + 4) return AURORA_END_OF_STREAM;
+            *out_size = f->size_big ? be32(p + f->size_off) : le32(p + f->size_off);
+            return AURORA_OK;
+        }
     }
     // the prefixed LZ10 / LZ11 stream: type byte + u24 (LZ10.cs:47-57)
     if (len < at + 1) return AURORA_END_OF_STREAM;
@@ -317,7 +363,7 @@ uint64_t wrapped_encode_bound(int format, uint64_t raw_len, const aurora_codec_o
         case AURORA_FMT_LEVEL5: return 8 + std::max<uint64_t>(raw_len, aurora_encode_bound(AURORA_FMT_LZ10, raw_len));
         case AURORA_FMT_LZON: return 16 + aurora_encode_bound(AURORA_FMT_LZO, raw_len);
         case AURORA_FMT_LEVEL5_LZSS: return 16 + aurora_encode_bound(AURORA_FMT_LZSS, raw_len);
-        default: return 0;
+        default: return family_of(format) ? 32 + aurora_encode_bound(AURORA_FMT_LZSS, raw_len) : 0;
     }
 }
 
@@ -360,7 +406,17 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
             head = 0;   // the 16-byte LZSS header is rewritten in place
             aurora_lz_props_window(&o.lzss, 0x1000, 0xF + 3, 3, 0xFEE, 1);
             break;
-        default: return AURORA_INVALID_ARGUMENT;
+        default: {
+            const Family* f = family_of(format);
+            if (!f) return AURORA_INVALID_ARGUMENT;
+            // The LZSS core writes its own 16-byte header in front of the body.  It is placed so that the body starts right
+            // behind the family's header (header >= 16 bytes), or the body is moved down afterwards (header < 16 bytes).
+            core = AURORA_FMT_LZSS;
+            const uint64_t hlen = f->read_len + f->skip_len;
+            head = hlen >= 16 ? hlen - 16 : 0;
+            family_props(*f, &o.lzss);
+            break;
+        }
     }
 
     // sub-buffers: one per stream, or one per chunk for LZ77 ChunkLZ10 with more than one chunk
@@ -460,6 +516,24 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
                 put_le32(d + 8, uint32_t(clen - 16));
                 put_le32(d + 12, uint32_t(len));
                 break;
+            default: {
+                const Family* f = family_of(format);
+                const uint64_t hlen = f->read_len + f->skip_len, blen = clen - 16;   // body bytes (CompressHeaderless)
+                if (hlen < 16) std::memmove(d + hlen, d + 16, size_t(blen));
+                std::memset(d, 0, size_t(hlen));
+                if (f->magic_len) std::memcpy(d, f->magic, f->magic_len);
+                switch (format) {
+                    case AURORA_FMT_AKLZ: put_be32(d + 12, uint32_t(len)); break;
+                    case AURORA_FMT_LZ01: put_le32(d + 4, uint32_t(16 + blen)); put_le32(d + 8, uint32_t(len)); break;   // LZ01.cs:80-81: the whole file
+                    case AURORA_FMT_FCMP: put_le32(d + 4, uint32_t(len)); put_le32(d + 8, 305397760u); break;
+                    case AURORA_FMT_IECP: put_le32(d + 4, uint32_t(len)); break;
+                    case AURORA_FMT_MDB4: put_le32(d + 4, uint32_t(len) + 1); put_le32(d + 8, uint32_t(len)); put_le32(d + 12, uint32_t(32 + blen - 0x10)); break;   // MDB4.cs:78
+                    case AURORA_FMT_LZSEGA: put_le32(d, uint32_t(blen)); put_le32(d + 4, uint32_t(len)); break;
+                    case AURORA_FMT_GCZ: put_le32(d, uint32_t(len)); break;
+                }
+                out_len[i] = hlen + blen;
+                continue;
+            }
         }
         out_len[i] = head + clen;
     }

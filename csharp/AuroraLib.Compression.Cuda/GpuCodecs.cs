@@ -203,6 +203,62 @@ namespace AuroraLib.Compression.Cuda
         public uint GetDecompressedSize(Stream source) => PeekSize(source);
     }
 
+    public sealed class GpuAKLZ : GpuCodec, IProvidesDecompressedSize   // header + LZSS.DecompressHeaderless (wrappers.cu, kFamily)
+    {
+        private readonly Formats.Sega.AKLZ _managed = new Formats.Sega.AKLZ();
+        protected override AuroraFormat Format => AuroraFormat.AKLZ;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuLZ01 : GpuCodec, IProvidesDecompressedSize   // header + LZSS.DecompressHeaderless (wrappers.cu, kFamily)
+    {
+        private readonly Formats.Sega.LZ01 _managed = new Formats.Sega.LZ01();
+        protected override AuroraFormat Format => AuroraFormat.LZ01;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuFCMP : GpuCodec, IProvidesDecompressedSize   // header + LZSS.DecompressHeaderless (wrappers.cu, kFamily)
+    {
+        private readonly Formats.Marvelous.FCMP _managed = new Formats.Marvelous.FCMP();
+        protected override AuroraFormat Format => AuroraFormat.FCMP;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuIECP : GpuCodec, IProvidesDecompressedSize   // header + LZSS.DecompressHeaderless (wrappers.cu, kFamily)
+    {
+        private readonly Formats.Marvelous.IECP _managed = new Formats.Marvelous.IECP();
+        protected override AuroraFormat Format => AuroraFormat.IECP;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuMDB4 : GpuCodec, IProvidesDecompressedSize   // header + LZSS.DecompressHeaderless (wrappers.cu, kFamily)
+    {
+        private readonly Formats.Specialized.MDB4 _managed = new Formats.Specialized.MDB4();
+        protected override AuroraFormat Format => AuroraFormat.MDB4;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuLZSega : GpuCodec, IProvidesDecompressedSize   // header + LZSS.DecompressHeaderless (wrappers.cu, kFamily)
+    {
+        private readonly Formats.Sega.LZSega _managed = new Formats.Sega.LZSega();
+        protected override AuroraFormat Format => AuroraFormat.LZSega;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuGCZ : GpuCodec, IProvidesDecompressedSize   // header + LZSS.DecompressHeaderless (wrappers.cu, kFamily)
+    {
+        private readonly Formats.Konami.GCZ _managed = new Formats.Konami.GCZ();
+        protected override AuroraFormat Format => AuroraFormat.GCZ;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
     public sealed class GpuLZ4 : GpuCodec
     {
         private readonly Formats.Common.LZ4 _managed = new Formats.Common.LZ4();

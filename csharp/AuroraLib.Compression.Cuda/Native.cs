@@ -16,7 +16,9 @@ namespace AuroraLib.Compression.Cuda
         Yaz0 = 1, Yaz1 = 2, Yay0 = 3, MIO0 = 4, LZ10 = 5, LZ11 = 6, LZSS = 7, LZ4 = 8, LZ4Block = 9,
         LZ4Legacy = 10, LZO = 11, Snappy = 12, SnappyBlock = 13, PRS = 14,
         // wrapper formats (AuroraLib.Compression.Nintendo): a header around one of the cores above
-        GCLZ = 15, CXLZ = 16, COMP = 17, LZ_3DS = 18, LZ77 = 19, Level5 = 20, LZOn = 21, Level5LZSS = 22
+        GCLZ = 15, CXLZ = 16, COMP = 17, LZ_3DS = 18, LZ77 = 19, Level5 = 20, LZOn = 21, Level5LZSS = 22,
+        // the LZSS-property family (AuroraLib.Compression.Sega, AuroraLib.Compression-Extended)
+        AKLZ = 23, LZ01 = 24, FCMP = 25, IECP = 26, MDB4 = 27, LZSega = 28, GCZ = 29
     }
 
     [StructLayout(LayoutKind.Sequential)]

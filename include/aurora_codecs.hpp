@@ -315,6 +315,35 @@ class Level5LZSS : public SizedAlgorithm {   // Level5/Level5LZSS.cs
   public:
     AURORA_FORMAT(Level5LZSS, AURORA_FMT_LEVEL5_LZSS, "Level5 lzss")
 };
+// The LZSS-property family: a fixed header + LZSS.DecompressHeaderless (aurora_cuda.h, formats 23-29)
+class AKLZ : public SizedAlgorithm {   // Sega/AKLZ.cs
+  public:
+    AURORA_FORMAT(AKLZ, AURORA_FMT_AKLZ, "AKLZ")
+};
+class LZ01 : public SizedAlgorithm {   // Sega/LZ01.cs
+  public:
+    AURORA_FORMAT(LZ01, AURORA_FMT_LZ01, "LZ01")
+};
+class FCMP : public SizedAlgorithm {   // Extended/Marvelous/FCMP.cs
+  public:
+    AURORA_FORMAT(FCMP, AURORA_FMT_FCMP, "FCMP")
+};
+class IECP : public SizedAlgorithm {   // Extended/Marvelous/IECP.cs
+  public:
+    AURORA_FORMAT(IECP, AURORA_FMT_IECP, "IECP")
+};
+class MDB4 : public SizedAlgorithm {   // Extended/Specialized/MDB4.cs
+  public:
+    AURORA_FORMAT(MDB4, AURORA_FMT_MDB4, "MDB4")
+};
+class LZSega : public SizedAlgorithm {   // Sega/LZSega.cs (no identifier: IsMatch is not provided)
+  public:
+    AURORA_FORMAT(LZSega, AURORA_FMT_LZSEGA, "LZSega")
+};
+class GCZ : public SizedAlgorithm {   // Extended/Konami/GCZ.cs (no identifier: IsMatch is not provided)
+  public:
+    AURORA_FORMAT(GCZ, AURORA_FMT_GCZ, "Konami GCZ")
+};
 #undef AURORA_FORMAT
 
 // The new batch entry point: many independent blobs at once, sharded over all GPUs of the box.

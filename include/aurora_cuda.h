@@ -69,7 +69,16 @@ typedef enum aurora_format {
     AURORA_FMT_LZ77         = 19, /* Nintendo/LZ77.cs: "LZ77" + LZ10 / LZ11 / ChunkLZ10      */
     AURORA_FMT_LEVEL5       = 20, /* Level5/Level5.cs: u32 type|size<<3 + stored / LZ10 body */
     AURORA_FMT_LZON         = 21, /* Nintendo/LZOn.cs: "LZOn" header + LZO                   */
-    AURORA_FMT_LEVEL5_LZSS  = 22  /* Level5/Level5LZSS.cs: "SSZL" header + LZSS (Lzss0)      */
+    AURORA_FMT_LEVEL5_LZSS  = 22, /* Level5/Level5LZSS.cs: "SSZL" header + LZSS (Lzss0)      */
+    /* the LZSS-property family: a fixed header + LZSS.DecompressHeaderless with DefaultProperties or Lzss0Properties
+     * (src/AuroraLib.Compression.Sega/Sega, src/AuroraLib.Compression-Extended) */
+    AURORA_FMT_AKLZ         = 23, /* Sega/AKLZ.cs: 12-byte identifier + BE size, Default     */
+    AURORA_FMT_LZ01         = 24, /* Sega/LZ01.cs: "LZ01" + length + size + 0, Lzss0         */
+    AURORA_FMT_FCMP         = 25, /* Marvelous/FCMP.cs: "FCMP" + size + constant, Lzss0      */
+    AURORA_FMT_IECP         = 26, /* Marvelous/IECP.cs: "IECP" + size, Lzss0                 */
+    AURORA_FMT_MDB4         = 27, /* Specialized/MDB4.cs: 32-byte header, Default            */
+    AURORA_FMT_LZSEGA       = 28, /* Sega/LZSega.cs: compressed size + size, Default         */
+    AURORA_FMT_GCZ          = 29  /* Konami/GCZ.cs: size, Lzss0                              */
 } aurora_format;
 
 typedef enum aurora_endian {

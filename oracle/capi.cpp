@@ -165,6 +165,16 @@ bool is_match(int fmt, Src& s, const CodecOpts&) {
             return s.pos + 0x10 < s.len && s.Match(id, 8);
         }
         case FMT_LEVEL5_LZSS: return s.pos + 0x10 < s.len && s.Match("SSZL", 4) && s.ReadUInt32() == 0;
+        // the LZSS-property family: identifier only (AKLZ.cs:31-32, LZ01.cs:33-34, FCMP.cs:31-32, IECP.cs:30-31, MDB4.cs:28-29);
+        // LZSega / GCZ have no identifier (length heuristic / file extension): not restated
+        case FMT_AKLZ: {
+            static const uint8_t id[12] = {'A', 'K', 'L', 'Z', '~', '?', 'Q', 'd', '=', 0xCC, 0xCC, 0xCD};
+            return s.pos + 0x10 < s.len && s.Match(id, 12);
+        }
+        case FMT_LZ01: return s.pos + 0x10 < s.len && s.Match("LZ01", 4);
+        case FMT_FCMP: return s.pos + 0x10 < s.len && s.Match("FCMP", 4);
+        case FMT_IECP: return s.pos + 0x10 < s.len && s.Match("IECP", 4);
+        case FMT_MDB4: return s.pos + 0x10 < s.len && s.Match("MDB4", 4);
         case FMT_LZ77: {
             if (!(s.pos + 0x8 < s.len && s.Match("LZ77", 4))) return false;
             uint8_t t = s.ReadUInt8();

@@ -7,6 +7,9 @@
 //   Level5/Level5.cs:63-148     u32 (type | size << 3): OnlySave / LZ10 headerless
 //   Nintendo/LZOn.cs:41-80      "LZOn" 00 2F F1 71 + BE size + BE compressed size + LZO headerless
 //   Level5/Level5LZSS.cs:41-72  "SSZL" + u32 + compressed size + size + LZSS headerless, Lzss0Properties
+// and the LZSS-property family (a fixed header + LZSS.DecompressHeaderless / CompressHeaderless):
+//   src/AuroraLib.Compression.Sega/Sega/AKLZ.cs:43-56, LZ01.cs:47-82, LZSega.cs:49-67
+//   src/AuroraLib.Compression-Extended/Marvelous/FCMP.cs:43-59, IECP.cs:42-55, Konami/GCZ.cs:40-51, Specialized/MDB4.cs:41-80
 // The Huffman / RLE / zlib sub-types of LZ77 and Level5 are outside the LZ hot path: NOT_SUPPORTED here and on the GPU.
 #include "oracle_core.hpp"
 
@@ -90,7 +93,88 @@ static void sszl_decode(Src& source, Sink& destination, const CodecOpts& o) {
     lzss_headerless(source, destination, decompressedSize, kLzss0, uint8_t(o.lzssInitialFill));
 }
 
-bool is_wrapper_format(int fmt) { return fmt >= FMT_GCLZ && fmt <= FMT_LEVEL5_LZSS; }
+bool is_wrapper_format(int fmt) { return fmt >= FMT_GCLZ && fmt <= FMT_GCZ; }
+
+static const uint8_t kAklzMagic[12] = {'A', 'K', 'L', 'Z', '~', '?', 'Q', 'd', '=', 0xCC, 0xCC, 0xCD};   // Identifier("AKLZ~?Qd=ÌÌÍ")
+static const LzProps kLzssDefault = LzProps::Bits(12, 4, 2);   // LZSS.cs:33
+
+static void lzss_family_decode(int fmt, Src& source, Sink& destination, const CodecOpts& o) {
+    uint32_t decompressedSize = 0;
+    const LzProps* lz = &kLzss0;
+    switch (fmt) {
+        case FMT_AKLZ:   // AKLZ.cs:43-48
+            source.MatchThrow(kAklzMagic, 12);
+            decompressedSize = source.ReadUInt32(Endian::Big);
+            lz = &kLzssDefault;
+            break;
+        case FMT_LZ01:   // LZ01.cs:47-62
+            source.MatchThrow("LZ01", 4);
+            (void)source.ReadUInt32();
+            decompressedSize = source.ReadUInt32();
+            (void)source.ReadUInt32();
+            break;
+        case FMT_FCMP:   // FCMP.cs:43-49
+            source.MatchThrow("FCMP", 4);
+            decompressedSize = source.ReadUInt32();
+            (void)source.ReadUInt32();
+            break;
+        case FMT_IECP:   // IECP.cs:42-47
+            source.MatchThrow("IECP", 4);
+            decompressedSize = source.ReadUInt32();
+            break;
+        case FMT_MDB4:   // MDB4.cs:41-58
+            source.MatchThrow("MDB4", 4);
+            (void)source.ReadUInt32();
+            decompressedSize = source.ReadUInt32();
+            (void)source.ReadUInt32();
+            source.pos += 16;   // Skip(4 * 4): a seek, not a read
+            lz = &kLzssDefault;
+            break;
+        case FMT_LZSEGA:   // LZSega.cs:49-54
+            (void)source.ReadUInt32();
+            decompressedSize = source.ReadUInt32();
+            lz = &kLzssDefault;
+            break;
+        case FMT_GCZ:   // GCZ.cs:40-44
+            decompressedSize = source.ReadUInt32();
+            break;
+    }
+    lzss_headerless(source, destination, decompressedSize, *lz, uint8_t(o.lzssInitialFill));
+}
+
+static void lzss_family_encode(int fmt, const uint8_t* src, int n, OutBuf& out, const CodecOpts& o) {
+    CodecOpts oo = o;
+    oo.lzss = (fmt == FMT_AKLZ || fmt == FMT_MDB4 || fmt == FMT_LZSEGA) ? kLzssDefault : kLzss0;
+    OutBuf core;
+    lzss_encode(src, n, core, oo);   // "LZSS" header (16 bytes) + body; CompressHeaderless is the body
+    const uint8_t* body = core.v.data() + 0x10;
+    const size_t blen = core.size() - 0x10;
+    switch (fmt) {
+        case FMT_AKLZ: out.Write(kAklzMagic, 12); out.WriteU32(uint32_t(n), Endian::Big); break;
+        case FMT_LZ01:
+            out.Write(reinterpret_cast<const uint8_t*>("LZ01"), 4);
+            out.WriteU32(uint32_t(16 + blen));   // the whole file (LZ01.cs:80-81)
+            out.WriteU32(uint32_t(n));
+            out.WriteU32(0);
+            break;
+        case FMT_FCMP:
+            out.Write(reinterpret_cast<const uint8_t*>("FCMP"), 4);
+            out.WriteU32(uint32_t(n));
+            out.WriteU32(305397760u);
+            break;
+        case FMT_IECP: out.Write(reinterpret_cast<const uint8_t*>("IECP"), 4); out.WriteU32(uint32_t(n)); break;
+        case FMT_MDB4:
+            out.Write(reinterpret_cast<const uint8_t*>("MDB4"), 4);
+            out.WriteU32(uint32_t(n) + 1);
+            out.WriteU32(uint32_t(n));
+            out.WriteU32(uint32_t(32 + blen - 0x10));   // Position - start - 0x10 (MDB4.cs:78)
+            for (int i = 0; i < 4; i++) out.WriteU32(0);
+            break;
+        case FMT_LZSEGA: out.WriteU32(uint32_t(blen)); out.WriteU32(uint32_t(n)); break;
+        case FMT_GCZ: out.WriteU32(uint32_t(n)); break;
+    }
+    out.Write(body, blen);
+}
 
 void wrapper_decode(int fmt, Src& s, Sink& d, const CodecOpts& o) {
     switch (fmt) {
@@ -102,7 +186,9 @@ void wrapper_decode(int fmt, Src& s, Sink& d, const CodecOpts& o) {
         case FMT_LEVEL5: level5_decode(s, d); break;
         case FMT_LZON: lzon_decode(s, d); break;
         case FMT_LEVEL5_LZSS: sszl_decode(s, d, o); break;
-        default: fail(INVALID_ARGUMENT);
+        default:
+            if (fmt < FMT_AKLZ || fmt > FMT_GCZ) fail(INVALID_ARGUMENT);
+            lzss_family_decode(fmt, s, d, o);
     }
 }
 
@@ -113,6 +199,7 @@ static void strip_lz1x_header(const OutBuf& core, OutBuf& out) {   // CompressHe
 }
 
 void wrapper_encode(int fmt, const uint8_t* src, int n, OutBuf& out, const CodecOpts& o, int lz77_type, int chunk_size, int level5_type) {
+    if (fmt >= FMT_AKLZ && fmt <= FMT_GCZ) return lzss_family_encode(fmt, src, n, out, o);
     switch (fmt) {
         case FMT_GCLZ: out.Write(reinterpret_cast<const uint8_t*>("GCLZ"), 4); lz10_encode(src, n, out, o); break;
         case FMT_CXLZ: out.Write(reinterpret_cast<const uint8_t*>("CXLZ"), 4); lz10_encode(src, n, out, o); break;
@@ -194,6 +281,13 @@ uint32_t wrapper_decoded_size(int fmt, Src& s) {
         }
         case FMT_LZON: s.MatchThrow(kLzonMagic, 8); return s.ReadUInt32(Endian::Big);
         case FMT_LEVEL5_LZSS: s.MatchThrow("SSZL", 4); s.need(8); s.pos += 8; return s.ReadUInt32();
+        case FMT_AKLZ: s.MatchThrow(kAklzMagic, 12); return s.ReadUInt32(Endian::Big);        // AKLZ.cs:35-40
+        case FMT_LZ01: s.MatchThrow("LZ01", 4); s.pos += 4; return s.ReadUInt32();             // LZ01.cs:37-43
+        case FMT_FCMP: s.MatchThrow("FCMP", 4); return s.ReadUInt32();                         // FCMP.cs:35-40
+        case FMT_IECP: s.MatchThrow("IECP", 4); return s.ReadUInt32();                         // IECP.cs:34-39
+        case FMT_MDB4: s.MatchThrow("MDB4", 4); (void)s.ReadUInt32(); return s.ReadUInt32();   // MDB4.cs:32-38
+        case FMT_LZSEGA: s.pos = 4; return s.ReadUInt32();                                     // LZSega.cs:41-46 (Position = +4)
+        case FMT_GCZ: return s.ReadUInt32();                                                   // GCZ.cs:37
         default: fail(INVALID_ARGUMENT);
     }
     // the prefixed LZ10 / LZ11 streams: type byte + u24 (LZ10.cs:47-57)

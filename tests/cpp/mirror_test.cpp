@@ -61,6 +61,13 @@ int main(int argc, char** argv) {
         bad += round_trip(Level5(), raw, CompressionSettings::Balanced(), true, false);   // Level5.IsMatch is not provided (zlib, file name)
         bad += round_trip(LZOn(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(Level5LZSS(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(AKLZ(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(LZ01(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(FCMP(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(IECP(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(MDB4(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(LZSega(), raw, CompressionSettings::Balanced(), true, false);
+        bad += round_trip(GCZ(), raw, CompressionSettings::Balanced(), true, false);
         // GetDecompressedSize (DataRecognitionTest: 256 zero bytes)
         {
             std::string zeros(0x100, '\0');

@@ -13,6 +13,7 @@ from auroralib.compression_b200 import _abi as A
 from tests.util import corrupt, fmt_id, synth
 
 WRAPPERS = A.WRAPPER_FORMATS
+NO_IDENTIFIER = (A.FMT_LEVEL5, A.FMT_LZSEGA, A.FMT_GCZ)   # no magic: IsMatch is a heuristic on zlib / lengths / the file name
 LZON_MAGIC = b"LZOn\x00\x2f\xf1\x71"
 
 
@@ -46,6 +47,17 @@ def test_oracle_wrapper_layouts(oracle, bmp):
     # Level5LZSS.cs:60-72: "SSZL", 0, compressed size, size (LE) + LZSS body with Lzss0Properties (0x1000, 18, 3, 0xFEE)
     lzss0, _ = oracle.encode(A.FMT_LZSS, raw, A.make_opts(quality=8, lzss=A.lz_props_window(0x1000, 0xF + 3, 3, 0xFEE)))
     assert enc(A.FMT_LEVEL5_LZSS) == b"SSZL" + bytes(4) + (len(lzss0) - 16).to_bytes(4, "little") + len(raw).to_bytes(4, "little") + lzss0[16:]
+    # the LZSS-property family: fixed headers around the headerless LZSS body (Default (12,4,2) or Lzss0 properties)
+    lzssd, _ = oracle.encode(A.FMT_LZSS, raw, q8)
+    bd, b0, n = lzssd[16:], lzss0[16:], len(raw)
+    le = lambda v: v.to_bytes(4, "little")
+    assert enc(A.FMT_AKLZ) == b"AKLZ~?Qd=\xcc\xcc\xcd" + n.to_bytes(4, "big") + bd                       # AKLZ.cs:51-56
+    assert enc(A.FMT_LZ01) == b"LZ01" + le(16 + len(b0)) + le(n) + le(0) + b0                                # LZ01.cs:65-82
+    assert enc(A.FMT_FCMP) == b"FCMP" + le(n) + le(305397760) + b0                                           # FCMP.cs:52-59
+    assert enc(A.FMT_IECP) == b"IECP" + le(n) + b0                                                           # IECP.cs:50-55
+    assert enc(A.FMT_MDB4) == b"MDB4" + le(n + 1) + le(n) + le(16 + len(bd)) + bytes(16) + bd                # MDB4.cs:61-80
+    assert enc(A.FMT_LZSEGA) == le(len(bd)) + le(n) + bd                                                     # LZSega.cs:57-67
+    assert enc(A.FMT_GCZ) == le(n) + b0                                                                      # GCZ.cs:47-51
     # ChunkLZ10 (LZ77.cs:75-100): 0xF7 | size << 8, u16 end offsets, independent LZ10 streams of ChunkSize bytes
     ch = enc(A.FMT_LZ77, lz77_type=0xF7)
     nseg = (len(raw) + 0xFFF) // 0x1000
@@ -76,11 +88,11 @@ def test_oracle_wrapper_roundtrip_and_errors(oracle, bmp, fmt):
                 continue   # the LZO encoder's dropped-first-match quirk
             assert dst[0] == 0 and outs[0] == raw and cons[0] == len(c), (fmt_id(fmt), kw, n, dst[0])
             assert oracle.decoded_size(fmt, c, opts) == (n, 0)
-            if fmt not in (A.FMT_LEVEL5, A.FMT_GCLZ, A.FMT_CXLZ, A.FMT_COMP) and len(c) > 0x11:
+            if fmt not in NO_IDENTIFIER + (A.FMT_GCLZ, A.FMT_CXLZ, A.FMT_COMP) and len(c) > 0x11:
                 assert oracle.is_match(fmt, c, opts)   # (GCLZ / CXLZ / COMP add the LZ10 / LZ11 token-walk heuristic)
     # wrong identifier / truncated header
     c, _ = oracle.encode(fmt, bmp[:3000], A.make_opts(quality=8))
-    if fmt != A.FMT_LEVEL5:
+    if fmt not in NO_IDENTIFIER:
         bad = b"XXXX" + c[4:]
         _, _, cons, dst = oracle.decode_batch(fmt, [bad], [3000])
         assert dst[0] == A.INVALID_IDENTIFIER
@@ -155,7 +167,7 @@ def test_gpu_wrapper_encode_parity(codec, oracle, fmt):
         assert not bad, f"{fmt_id(fmt)} {kw}: {len(bad)} streams differ from the oracle encoder, first #{bad[0]} ({len(raws[bad[0]])} bytes)"
         size, sst = codec.decoded_size_batch(fmt, got, opts)
         assert (sst == 0).all() and [int(x) for x in size] == [len(r) for r in raws]
-        if fmt != A.FMT_LEVEL5:
+        if fmt not in NO_IDENTIFIER:
             m = codec.is_match_batch(fmt, got, opts)
             assert [bool(x) for x in m] == [bool(oracle.is_match(fmt, g, opts)) for g in got]
 
@@ -163,10 +175,10 @@ def test_gpu_wrapper_encode_parity(codec, oracle, fmt):
 @pytest.mark.gpu
 def test_gpu_wrapper_mirror_classes(bmp):
     """The reference-facing classes: Compress / Decompress / GetDecompressedSize / IsMatch over streams."""
-    from auroralib.compression_b200 import (COMP, CXLZ, GCLZ, LZ77, LZ_3DS, CompressionSettings, InvalidIdentifierException, Level5,
-                                            Level5LZSS, LZOn)
+    from auroralib.compression_b200 import (AKLZ, COMP, CXLZ, FCMP, GCLZ, GCZ, IECP, LZ01, LZ77, LZ_3DS, MDB4, CompressionSettings,
+                                            InvalidIdentifierException, Level5, Level5LZSS, LZOn, LZSega)
     raw = bmp[:30000]
-    for cls in (GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS):
+    for cls in (GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ):
         alg = cls()
         blob = alg.Compress(raw, settings=CompressionSettings(8)).getvalue()
         src = io.BytesIO(b"pad" + blob + b"tail")
@@ -175,7 +187,7 @@ def test_gpu_wrapper_mirror_classes(bmp):
         dst = io.BytesIO()
         alg.Decompress(src, dst)
         assert dst.getvalue() == raw and src.tell() == 3 + len(blob)
-        if cls is not Level5:
+        if cls not in (Level5, LZSega, GCZ):
             assert alg.IsMatch(io.BytesIO(blob)) and not alg.IsMatch(io.BytesIO(b"nope" + blob[4:]))
             with pytest.raises(InvalidIdentifierException):
                 alg.Decompress(io.BytesIO(b"nope" + blob[4:]), io.BytesIO())
