@@ -17,6 +17,12 @@
 // comparison of every chain candidate (32 bytes per step, ballot for the first mismatch) and the table reset.
 // The one-thread-per-window-position search with a shared-memory hash table is the planned replacement
 // ("what comes next").
+// Measured and rejected (round 1): one stream per THREAD with the same tables (32 streams per warp instruction, 32 table
+// lookups in flight per warp, epoch-stamped entries instead of per-stream resets).  Byte-identical, but 2.1 GB/s against
+// 8.1 GB/s here: the reference-sized tables (2.3 MiB per stream at quality 8) cap the resident streams at ~19 000
+// threads = 4 warps per SM, and those warps diverge through the chain walk and the prefix comparison.  A faster exact
+// encoder needs compact tables first (e.g. window-sized bucket heads / bucket chains that reproduce head[h] by
+// re-hashing the candidates), so that thousands of streams per SM can be resident.
 #include "common.cuh"
 #include "finder.cuh"
 
