@@ -15,14 +15,15 @@ FMT_YAZ0, FMT_YAZ1, FMT_YAY0, FMT_MIO0, FMT_LZ10, FMT_LZ11, FMT_LZSS, FMT_LZ4, F
 # wrapper formats (a header around one of the cores above; host entry points only)
 FMT_GCLZ, FMT_CXLZ, FMT_COMP, FMT_LZ_3DS, FMT_LZ77, FMT_LEVEL5, FMT_LZON, FMT_LEVEL5_LZSS = range(15, 23)
 FMT_AKLZ, FMT_LZ01, FMT_FCMP, FMT_IECP, FMT_MDB4, FMT_LZSEGA, FMT_GCZ = range(23, 30)   # header + LZSS headerless
-WRAPPER_FORMATS = list(range(15, 30))
+FMT_SDPC = 30   # "SDPC" + size + LZO headerless
+WRAPPER_FORMATS = list(range(15, 31))
 FORMAT_NAMES = {FMT_YAZ0: "Yaz0", FMT_YAZ1: "Yaz1", FMT_YAY0: "Yay0", FMT_MIO0: "MIO0", FMT_LZ10: "LZ10",
                 FMT_LZ11: "LZ11", FMT_LZSS: "LZSS", FMT_LZ4: "LZ4", FMT_LZ4_BLOCK: "LZ4Block",
                 FMT_LZ4_LEGACY: "LZ4Legacy", FMT_LZO: "LZO", FMT_SNAPPY: "Snappy",
                 FMT_SNAPPY_BLOCK: "SnappyBlock", FMT_PRS: "PRS", FMT_GCLZ: "GCLZ", FMT_CXLZ: "CXLZ", FMT_COMP: "COMP",
                 FMT_LZ_3DS: "3DS-LZ", FMT_LZ77: "LZ77", FMT_LEVEL5: "Level5", FMT_LZON: "LZOn", FMT_LEVEL5_LZSS: "Level5LZSS",
                 FMT_AKLZ: "AKLZ", FMT_LZ01: "LZ01", FMT_FCMP: "FCMP", FMT_IECP: "IECP", FMT_MDB4: "MDB4", FMT_LZSEGA: "LZSega",
-                FMT_GCZ: "GCZ"}
+                FMT_GCZ: "GCZ", FMT_SDPC: "SDPC"}
 
 ENDIAN_LITTLE, ENDIAN_BIG, ENDIAN_DEFAULT = 0, 1, 2
 

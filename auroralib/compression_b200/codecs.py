@@ -431,5 +431,10 @@ class GCZ(_NoIdentifier, _SizedCodec):
     FORMAT, Name = _abi.FMT_GCZ, "Konami GCZ"
 
 
-WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ]
+class SDPC(_SizedCodec):
+    """Extended/Specialized/SDPC.cs: "SDPC" + size + LZO"""
+    FORMAT, Name = _abi.FMT_SDPC, "SDPC"
+
+
+WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC]
 ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS] + WRAPPERS

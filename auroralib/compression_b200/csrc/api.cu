@@ -802,6 +802,7 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
                     break;
                 // the LZSS-property family with an identifier (AKLZ.cs:31-32, LZ01.cs:33-34, FCMP.cs:31-32, IECP.cs:30-31, MDB4.cs:28-29)
                 case AURORA_FMT_AKLZ: m = 0x10 < len && std::memcmp(p, "AKLZ~?Qd=\xCC\xCC\xCD", 12) == 0; break;
+                case AURORA_FMT_SDPC: m = 0x10 < len && std::memcmp(p, "SDPC", 4) == 0 && (p[4] | p[5] | p[6] | p[7]) != 0; break;   // SDPC.cs:31-32
                 case AURORA_FMT_LZ01: m = 0x10 < len && std::memcmp(p, "LZ01", 4) == 0; break;
                 case AURORA_FMT_FCMP: m = 0x10 < len && std::memcmp(p, "FCMP", 4) == 0; break;
                 case AURORA_FMT_IECP: m = 0x10 < len && std::memcmp(p, "IECP", 4) == 0; break;

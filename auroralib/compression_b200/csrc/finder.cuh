@@ -54,7 +54,7 @@ __device__ __forceinline__ int match_length(const uint8_t* data, int a, int b, i
 }
 
 // :214-282
-static __device__ void match_search(Finder& f, const uint8_t* data, int data_len, int pos, int& best_dist, int& best_len) {
+static __device__ __forceinline__ void match_search(Finder& f, const uint8_t* data, int data_len, int pos, int& best_dist, int& best_len) {
     int h4, hm;
     compute_hash(f, data + pos, h4, hm);
     int cur = __shfl_sync(kFull, lane_id() == 0 ? f.head[h4] : 0, 0);
@@ -102,7 +102,7 @@ struct Match {
 };
 
 // :157-212
-static __device__ Match find_next_best_match(Finder& f, const uint8_t* data, int length) {
+static __device__ __forceinline__ Match find_next_best_match(Finder& f, const uint8_t* data, int length) {
     const int limit = length - 4;
     while (f.position <= limit) {
         int best_dist, best_len;

@@ -122,6 +122,14 @@ void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst,
             pl.expect = be32(p + 8);
             one(AURORA_FMT_LZO, 16, kParseHeader);
             break;
+        case AURORA_FMT_SDPC: {   // -Extended/Specialized/SDPC.cs:43-56: SetLength(size) up front, overshoot check afterwards
+            if (!match_throw(pl, p, len, "SDPC", 4)) break;
+            if (len < 8) { eos(pl, len); break; }
+            pl.expect = le32(p + 4);
+            if (pl.expect > cap) { pl.status = AURORA_DST_TOO_SMALL; pl.consumed = 8; break; }
+            one(AURORA_FMT_LZO, 8, kParseHeader);
+            break;
+        }
         case AURORA_FMT_LEVEL5_LZSS:
             if (!match_throw(pl, p, len, "SSZL", 4)) break;
             if (len < 16) { eos(pl, len); break; }
@@ -207,7 +215,7 @@ void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst,
 
 }  // namespace
 
-bool is_wrapper_format(int f) { return f >= AURORA_FMT_GCLZ && f <= AURORA_FMT_GCZ; }
+bool is_wrapper_format(int f) { return f >= AURORA_FMT_GCLZ && f <= AURORA_FMT_SDPC; }
 
 int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
                          const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
@@ -282,6 +290,7 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
                 st = r_st[q];
                 // ThrowIfMismatch runs before the destination's overflow is noticed
                 if (format == AURORA_FMT_LZON && (st == AURORA_OK || st == AURORA_DST_TOO_SMALL) && ol != pl.expect) st = AURORA_SIZE_MISMATCH;
+                if (format == AURORA_FMT_SDPC && (st == AURORA_OK || st == AURORA_DST_TOO_SMALL) && ol > pl.expect) st = AURORA_SIZE_MISMATCH;
             }
         }
         if (out_len) out_len[i] = ol;
@@ -316,6 +325,11 @@ int wrapped_decoded_size(int format, const uint8_t* p, uint64_t len, uint64_t* o
         case AURORA_FMT_LEVEL5:
             if (len < 5) return AURORA_END_OF_STREAM;
             *out_size = p[4] == 0x78 ? le32(p) : le32(p) >> 3;
+            return AURORA_OK;
+        case AURORA_FMT_SDPC:
+            if (!match_throw(pl, p, len, "SDPC", 4)) return pl.status;
+            if (len < 8) return AURORA_END_OF_STREAM;
+            *out_size = le32(p + 4);
             return AURORA_OK;
         case AURORA_FMT_LZON:
             if (!match_throw(pl, p, len, kLzonMagic, 8)) return pl.status;
@@ -362,6 +376,7 @@ uint64_t wrapped_encode_bound(int format, uint64_t raw_len, const aurora_codec_o
         }
         case AURORA_FMT_LEVEL5: return 8 + std::max<uint64_t>(raw_len, aurora_encode_bound(AURORA_FMT_LZ10, raw_len));
         case AURORA_FMT_LZON: return 16 + aurora_encode_bound(AURORA_FMT_LZO, raw_len);
+        case AURORA_FMT_SDPC: return 8 + aurora_encode_bound(AURORA_FMT_LZO, raw_len);
         case AURORA_FMT_LEVEL5_LZSS: return 16 + aurora_encode_bound(AURORA_FMT_LZSS, raw_len);
         default: return family_of(format) ? 32 + aurora_encode_bound(AURORA_FMT_LZSS, raw_len) : 0;
     }
@@ -401,6 +416,7 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
             head = 0;   // the LZ10 header is rewritten in place
             break;
         case AURORA_FMT_LZON: core = AURORA_FMT_LZO; head = 16; break;
+        case AURORA_FMT_SDPC: core = AURORA_FMT_LZO; head = 8; break;
         case AURORA_FMT_LEVEL5_LZSS:
             core = AURORA_FMT_LZSS;
             head = 0;   // the 16-byte LZSS header is rewritten in place
@@ -497,6 +513,10 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
             case AURORA_FMT_COMP: std::memcpy(d, "COMP", 4); break;
             case AURORA_FMT_LZ77: std::memcpy(d, "LZ77", 4); break;
             case AURORA_FMT_LZ_3DS: std::memcpy(d, "3DS-LZ\r\n", 8); break;
+            case AURORA_FMT_SDPC:
+                std::memcpy(d, "SDPC", 4);
+                put_le32(d + 4, uint32_t(len));
+                break;
             case AURORA_FMT_LZON:
                 std::memcpy(d, kLzonMagic, 8);
                 put_be32(d + 8, uint32_t(len));

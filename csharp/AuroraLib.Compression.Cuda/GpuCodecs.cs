@@ -259,6 +259,14 @@ namespace AuroraLib.Compression.Cuda
         public uint GetDecompressedSize(Stream source) => PeekSize(source);
     }
 
+    public sealed class GpuSDPC : GpuCodec, IProvidesDecompressedSize   // "SDPC" + size + LZO.DecompressHeaderless
+    {
+        private readonly Formats.Specialized.SDPC _managed = new Formats.Specialized.SDPC();
+        protected override AuroraFormat Format => AuroraFormat.SDPC;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
     public sealed class GpuLZ4 : GpuCodec
     {
         private readonly Formats.Common.LZ4 _managed = new Formats.Common.LZ4();

@@ -18,7 +18,7 @@ namespace AuroraLib.Compression.Cuda
         // wrapper formats (AuroraLib.Compression.Nintendo): a header around one of the cores above
         GCLZ = 15, CXLZ = 16, COMP = 17, LZ_3DS = 18, LZ77 = 19, Level5 = 20, LZOn = 21, Level5LZSS = 22,
         // the LZSS-property family (AuroraLib.Compression.Sega, AuroraLib.Compression-Extended)
-        AKLZ = 23, LZ01 = 24, FCMP = 25, IECP = 26, MDB4 = 27, LZSega = 28, GCZ = 29
+        AKLZ = 23, LZ01 = 24, FCMP = 25, IECP = 26, MDB4 = 27, LZSega = 28, GCZ = 29, SDPC = 30
     }
 
     [StructLayout(LayoutKind.Sequential)]

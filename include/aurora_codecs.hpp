@@ -344,6 +344,10 @@ class GCZ : public SizedAlgorithm {   // Extended/Konami/GCZ.cs (no identifier: 
   public:
     AURORA_FORMAT(GCZ, AURORA_FMT_GCZ, "Konami GCZ")
 };
+class SDPC : public SizedAlgorithm {   // Extended/Specialized/SDPC.cs: "SDPC" + size + LZO
+  public:
+    AURORA_FORMAT(SDPC, AURORA_FMT_SDPC, "SDPC")
+};
 #undef AURORA_FORMAT
 
 // The new batch entry point: many independent blobs at once, sharded over all GPUs of the box.

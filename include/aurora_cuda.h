@@ -78,7 +78,8 @@ typedef enum aurora_format {
     AURORA_FMT_IECP         = 26, /* Marvelous/IECP.cs: "IECP" + size, Lzss0                 */
     AURORA_FMT_MDB4         = 27, /* Specialized/MDB4.cs: 32-byte header, Default            */
     AURORA_FMT_LZSEGA       = 28, /* Sega/LZSega.cs: compressed size + size, Default         */
-    AURORA_FMT_GCZ          = 29  /* Konami/GCZ.cs: size, Lzss0                              */
+    AURORA_FMT_GCZ          = 29, /* Konami/GCZ.cs: size, Lzss0                              */
+    AURORA_FMT_SDPC         = 30  /* -Extended/Specialized/SDPC.cs: "SDPC" + size + LZO      */
 } aurora_format;
 
 typedef enum aurora_endian {

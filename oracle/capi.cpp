@@ -171,6 +171,7 @@ bool is_match(int fmt, Src& s, const CodecOpts&) {
             static const uint8_t id[12] = {'A', 'K', 'L', 'Z', '~', '?', 'Q', 'd', '=', 0xCC, 0xCC, 0xCD};
             return s.pos + 0x10 < s.len && s.Match(id, 12);
         }
+        case FMT_SDPC: return s.pos + 0x10 < s.len && s.Match("SDPC", 4) && s.ReadUInt32() != 0;   // SDPC.cs:31-32
         case FMT_LZ01: return s.pos + 0x10 < s.len && s.Match("LZ01", 4);
         case FMT_FCMP: return s.pos + 0x10 < s.len && s.Match("FCMP", 4);
         case FMT_IECP: return s.pos + 0x10 < s.len && s.Match("IECP", 4);

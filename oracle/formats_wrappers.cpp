@@ -84,6 +84,16 @@ static void lzon_decode(Src& source, Sink& destination) {
     if (destination.pos - start != int64_t(decompressedSize)) fail(SIZE_MISMATCH, decompressedSize, destination.pos - start);
 }
 
+// AuroraLib.Compression-Extended/Specialized/SDPC.cs:43-56
+static void sdpc_decode(Src& source, Sink& destination) {
+    source.MatchThrow("SDPC", 4);
+    uint32_t decompressedSize = source.ReadUInt32();
+    int64_t endPosition = destination.pos + decompressedSize;
+    destination.SetLength(endPosition);
+    lzo_decode(source, destination);
+    if (destination.pos > endPosition) fail(SIZE_MISMATCH, decompressedSize, destination.pos - (endPosition - decompressedSize));
+}
+
 // Level5LZSS.cs:41-57
 static void sszl_decode(Src& source, Sink& destination, const CodecOpts& o) {
     source.MatchThrow("SSZL", 4);
@@ -93,7 +103,7 @@ static void sszl_decode(Src& source, Sink& destination, const CodecOpts& o) {
     lzss_headerless(source, destination, decompressedSize, kLzss0, uint8_t(o.lzssInitialFill));
 }
 
-bool is_wrapper_format(int fmt) { return fmt >= FMT_GCLZ && fmt <= FMT_GCZ; }
+bool is_wrapper_format(int fmt) { return fmt >= FMT_GCLZ && fmt <= FMT_SDPC; }
 
 static const uint8_t kAklzMagic[12] = {'A', 'K', 'L', 'Z', '~', '?', 'Q', 'd', '=', 0xCC, 0xCC, 0xCD};   // Identifier("AKLZ~?Qd=ÌÌÍ")
 static const LzProps kLzssDefault = LzProps::Bits(12, 4, 2);   // LZSS.cs:33
@@ -186,6 +196,7 @@ void wrapper_decode(int fmt, Src& s, Sink& d, const CodecOpts& o) {
         case FMT_LEVEL5: level5_decode(s, d); break;
         case FMT_LZON: lzon_decode(s, d); break;
         case FMT_LEVEL5_LZSS: sszl_decode(s, d, o); break;
+        case FMT_SDPC: sdpc_decode(s, d); break;
         default:
             if (fmt < FMT_AKLZ || fmt > FMT_GCZ) fail(INVALID_ARGUMENT);
             lzss_family_decode(fmt, s, d, o);
@@ -236,6 +247,11 @@ void wrapper_encode(int fmt, const uint8_t* src, int n, OutBuf& out, const Codec
             } else fail(NOT_SUPPORTED);
             break;
         }
+        case FMT_SDPC:   // SDPC.cs:59-64
+            out.Write(reinterpret_cast<const uint8_t*>("SDPC"), 4);
+            out.WriteU32(uint32_t(n));
+            lzo_encode(src, n, out, o);
+            break;
         case FMT_LZON: {   // LZOn.cs:64-79
             out.Write(kLzonMagic, 8);
             out.WriteU32(uint32_t(n), Endian::Big);
@@ -288,6 +304,7 @@ uint32_t wrapper_decoded_size(int fmt, Src& s) {
         case FMT_MDB4: s.MatchThrow("MDB4", 4); (void)s.ReadUInt32(); return s.ReadUInt32();   // MDB4.cs:32-38
         case FMT_LZSEGA: s.pos = 4; return s.ReadUInt32();                                     // LZSega.cs:41-46 (Position = +4)
         case FMT_GCZ: return s.ReadUInt32();                                                   // GCZ.cs:37
+        case FMT_SDPC: s.MatchThrow("SDPC", 4); return s.ReadUInt32();                         // SDPC.cs:35-40
         default: fail(INVALID_ARGUMENT);
     }
     // the prefixed LZ10 / LZ11 streams: type byte + u24 (LZ10.cs:47-57)

@@ -35,7 +35,7 @@ enum Format : int {
     FMT_LZ4 = 8, FMT_LZ4_BLOCK = 9, FMT_LZ4_LEGACY = 10, FMT_LZO = 11, FMT_SNAPPY = 12,
     FMT_SNAPPY_BLOCK = 13, FMT_PRS = 14,
     FMT_GCLZ = 15, FMT_CXLZ = 16, FMT_COMP = 17, FMT_LZ_3DS = 18, FMT_LZ77 = 19, FMT_LEVEL5 = 20, FMT_LZON = 21, FMT_LEVEL5_LZSS = 22,
-    FMT_AKLZ = 23, FMT_LZ01 = 24, FMT_FCMP = 25, FMT_IECP = 26, FMT_MDB4 = 27, FMT_LZSEGA = 28, FMT_GCZ = 29
+    FMT_AKLZ = 23, FMT_LZ01 = 24, FMT_FCMP = 25, FMT_IECP = 26, FMT_MDB4 = 27, FMT_LZSEGA = 28, FMT_GCZ = 29, FMT_SDPC = 30
 };
 
 struct Error {

@@ -68,6 +68,7 @@ int main(int argc, char** argv) {
         bad += round_trip(MDB4(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(LZSega(), raw, CompressionSettings::Balanced(), true, false);
         bad += round_trip(GCZ(), raw, CompressionSettings::Balanced(), true, false);
+        bad += round_trip(SDPC(), raw, CompressionSettings::Balanced(), true);
         // GetDecompressedSize (DataRecognitionTest: 256 zero bytes)
         {
             std::string zeros(0x100, '\0');

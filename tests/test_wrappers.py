@@ -58,6 +58,7 @@ def test_oracle_wrapper_layouts(oracle, bmp):
     assert enc(A.FMT_MDB4) == b"MDB4" + le(n + 1) + le(n) + le(16 + len(bd)) + bytes(16) + bd                # MDB4.cs:61-80
     assert enc(A.FMT_LZSEGA) == le(len(bd)) + le(n) + bd                                                     # LZSega.cs:57-67
     assert enc(A.FMT_GCZ) == le(n) + b0                                                                      # GCZ.cs:47-51
+    assert enc(A.FMT_SDPC) == b"SDPC" + le(n) + lzo                                                          # SDPC.cs:59-64
     # ChunkLZ10 (LZ77.cs:75-100): 0xF7 | size << 8, u16 end offsets, independent LZ10 streams of ChunkSize bytes
     ch = enc(A.FMT_LZ77, lz77_type=0xF7)
     nseg = (len(raw) + 0xFFF) // 0x1000
@@ -84,7 +85,7 @@ def test_oracle_wrapper_roundtrip_and_errors(oracle, bmp, fmt):
             c, st = oracle.encode(fmt, raw, opts)
             assert st == 0
             outs, olen, cons, dst = oracle.decode_batch(fmt, [c], [n], opts)
-            if fmt == A.FMT_LZON and not (dst[0] == 0 and outs[0] == raw):
+            if fmt in (A.FMT_LZON, A.FMT_SDPC) and not (dst[0] == 0 and outs[0] == raw):
                 continue   # the LZO encoder's dropped-first-match quirk
             assert dst[0] == 0 and outs[0] == raw and cons[0] == len(c), (fmt_id(fmt), kw, n, dst[0])
             assert oracle.decoded_size(fmt, c, opts) == (n, 0)
@@ -136,7 +137,7 @@ def test_gpu_wrapper_decode_parity(codec, oracle, fmt):
         comps = [c for c, s_ in zip(comps, st) if s_ == 0]
         outs, status = _compare(codec, oracle, fmt, comps, [len(r) for r in raws], opts, what=f"valid {kw}")
         ok = sum(1 for i, r in enumerate(raws) if status[i] == 0 and outs[i] == r)
-        assert ok >= len(raws) - (6 if fmt == A.FMT_LZON else 0)
+        assert ok >= len(raws) - (6 if fmt in (A.FMT_LZON, A.FMT_SDPC) else 0)
         # truncated / bit-flipped / padded / empty / header-cut inputs, and short destinations
         bad = [corrupt(rng, c, i % 5) for i, c in enumerate(comps)]
         _compare(codec, oracle, fmt, bad, [len(r) + int(rng.choice([0, 0, 64])) for r in raws], opts, what=f"fuzz {kw}")
@@ -176,9 +177,9 @@ def test_gpu_wrapper_encode_parity(codec, oracle, fmt):
 def test_gpu_wrapper_mirror_classes(bmp):
     """The reference-facing classes: Compress / Decompress / GetDecompressedSize / IsMatch over streams."""
     from auroralib.compression_b200 import (AKLZ, COMP, CXLZ, FCMP, GCLZ, GCZ, IECP, LZ01, LZ77, LZ_3DS, MDB4, CompressionSettings,
-                                            InvalidIdentifierException, Level5, Level5LZSS, LZOn, LZSega)
+                                            InvalidIdentifierException, Level5, Level5LZSS, LZOn, LZSega, SDPC)
     raw = bmp[:30000]
-    for cls in (GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ):
+    for cls in (GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC):
         alg = cls()
         blob = alg.Compress(raw, settings=CompressionSettings(8)).getvalue()
         src = io.BytesIO(b"pad" + blob + b"tail")
