@@ -217,9 +217,158 @@ __device__ __forceinline__ bool lz4_ext(InStream& in, uint32_t& sp, uint32_t end
     return true;
 }
 
+// Sequence-per-lane batch (LZ4.cs:176-200 for up to 32 consecutive "regular" sequences: at most one literal-length and one
+// match-length extension byte, the match present inside the block).  The token walk of LZ4 is uniform work —
+// 32 lanes computing the same scalars — and the kernel is issue bound, so everything that can be is moved to one lane per
+// sequence:
+//   1. chain (uniform, ~16 instructions per sequence): only the sequence starts — token, literal count, extension byte;
+//   2. lane k decodes sequence k (literal source, distance, match length); one warp scan places all of them;
+//   3. literals: every lane copies its own (<= 14) literal bytes, all sequences at once; longer runs warp-cooperatively;
+//   4. far matches — the source was drained to HBM before the batch began, so it depends on nothing in the batch —
+//      run four at a time with all four global loads issued before the stores (four L2 round trips in flight);
+//   5. the other matches replay in stream order from the output ring (their sources are at most ~800 bytes behind the
+//      batch: the ring still holds them), periodic when distance < length.
+// A batch decodes at most kBatchOut = 1024 bytes: the last byte it writes maps to the ring slot 2048 below it, which is
+// older than anything a match of the batch may still read (>= batch start - 1024).
+// Returns the number of sequences consumed (0: the sequence at sp is not regular, the caller decodes it alone).
+constexpr uint32_t kBatchOut = 1024;
+__device__ __forceinline__ uint32_t lz4_batch32(InStream& in, GOut& out, uint32_t& sp, const uint32_t end) {
+    const uint32_t lane = lane_id();
+    in.ensure(sp, kInMirror - 16);
+    const uint32_t wa = smem_u32(in.window(sp));
+    const uint32_t blk = end - sp;   // bytes of the block from sp
+    // ---- 1. chain of sequence starts
+    constexpr uint32_t kWin = kInMirror - 16;   // contiguous staged bytes from sp
+    uint32_t r = 0, cum = 0, n = 0, myr = 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < 32; k++) {
+        if (r + 2 > blk || r + 2 > kWin) break;
+        const uint32_t token = lds_u8(wa + r);
+        uint32_t lit = token >> 4, ml = token & 15;
+        uint32_t q = r + 1;
+        if (lit == 15) {   // one literal-length extension byte (runs of 15..269 literals)
+            const uint32_t e = lds_u8(wa + q);
+            if (e == 255) break;
+            lit += e;
+            q++;
+        }
+        q += lit + 2;                        // behind the distance
+        if (q > blk || q + 1 > kWin) break;  // no match inside the block, or the sequence leaves the staged window
+        if (ml == 15) {
+            if (q >= blk) break;
+            const uint32_t e = lds_u8(wa + q);
+            if (e == 255) break;             // a second extension byte follows
+            ml += e;
+            q++;
+        }
+        const uint32_t o = lit + ml + 4;
+        if (cum + o > kBatchOut) break;
+        if (lane == k) myr = r;
+        cum += o;
+        r = q;
+        n = k + 1;
+    }
+    if (n < 3) return 0;   // not worth a batch: the caller's one-sequence paths take it
+    // ---- 2. my sequence
+    uint32_t lit = 0, mlen = 0, d = 0;
+    uint32_t la = wa + myr + 1;   // shared address of my literals
+    if (lane < n) {
+        const uint32_t token = lds_u8(wa + myr);
+        lit = token >> 4;
+        uint32_t ml = token & 15;
+        if (lit == 15) {
+            lit += lds_u8(la);
+            la++;
+        }
+        d = lds_u8(la + lit) | (lds_u8(la + lit + 1) << 8);
+        if (ml == 15) ml += lds_u8(la + lit + 2);
+        mlen = ml + 4;
+    }
+    const uint32_t incl = warp_incl_scan(lit + mlen);
+    const uint32_t base = out.written;
+    const uint32_t lpos = base + incl - (lit + mlen), mpos = lpos + lit;
+    const uint32_t dd = d ? d : out.ring_len;
+    const uint32_t rb = out.rb;
+    // ---- 3. literals: short runs one lane per sequence, long runs (15..269 bytes) warp-cooperatively
+    {
+        const bool shortl = lit <= 14;
+        const uint32_t maxlit = __reduce_max_sync(kFull, shortl ? lit : 0u);
+        for (uint32_t j = 0; j < maxlit; j++)
+            if (shortl && j < lit) sts_u8(((lpos + j) & kORingMask) | rb, lds_u8(la + j));
+        uint32_t lm = __ballot_sync(kFull, !shortl);
+        while (lm) {
+            const int k = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const uint32_t kp = __shfl_sync(kFull, lpos, k), kl = __shfl_sync(kFull, lit, k), ka = __shfl_sync(kFull, la, k);
+            for (uint32_t i = lane; i < kl; i += 32) sts_u8(((kp + i) & kORingMask) | rb, lds_u8(ka + i));
+        }
+    }
+    // ---- 4. far matches: the source is in HBM already
+    const bool has = lane < n;
+    const bool far = has && int32_t(mpos - dd + mlen) <= int32_t(out.flushed) && dd >= mlen;
+    uint32_t fm = __ballot_sync(kFull, far);
+    while (fm) {
+        uint32_t v[4], dp[4], ln[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            v[t] = 0;
+            ln[t] = 0;
+            dp[t] = 0;
+            if (fm) {
+                const int k = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const uint32_t kp = __shfl_sync(kFull, mpos, k), kl = __shfl_sync(kFull, mlen, k), kd = __shfl_sync(kFull, dd, k);
+                dp[t] = kp;
+                ln[t] = kl;
+                const int32_t sidx = int32_t(kp) - int32_t(kd) + int32_t(lane);
+                if (lane < kl && sidx >= int32_t(out.win_base) && uint64_t(sidx) < out.cap) v[t] = out.dst[sidx];
+                if (kl > 32) {   // the rest of a long match right away (rare)
+                    for (uint32_t i = lane + 32; i < kl; i += 32) {
+                        const int32_t s2 = int32_t(kp) - int32_t(kd) + int32_t(i);
+                        uint32_t w = 0;
+                        if (s2 >= int32_t(out.win_base) && uint64_t(s2) < out.cap) w = out.dst[s2];
+                        sts_u8(((kp + i) & kORingMask) | rb, w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            if (lane < ln[t]) sts_u8(((dp[t] + lane) & kORingMask) | rb, v[t]);
+    }
+    // ---- 5. the other matches, in stream order, from the ring
+    uint32_t nm = __ballot_sync(kFull, has && !far);
+    while (nm) {
+        const int k = __ffs(nm) - 1;
+        nm &= nm - 1;
+        const uint32_t kp = __shfl_sync(kFull, mpos, k), kl = __shfl_sync(kFull, mlen, k), kd = __shfl_sync(kFull, dd, k);
+        __syncwarp();
+        const uint32_t rr = kd < kl ? c_rcp.v[kd & 511] : 0u;   // kd < kl <= 273: the reciprocal table applies
+        for (uint32_t i = lane; i < kl; i += 32) {
+            const int32_t sidx = int32_t(kp) - int32_t(kd) + int32_t(i - ((i * rr) >> 20) * kd);
+            uint32_t w = 0;
+            if (sidx >= int32_t(out.win_base)) w = lds_u8((uint32_t(sidx) & kORingMask) | rb);
+            sts_u8(((kp + i) & kORingMask) | rb, w);
+        }
+    }
+    out.written = base + cum;
+    __syncwarp();
+    out.drain();
+    sp += r;
+    return n;
+}
+
 // LZ4.cs:176-200.  The block occupies relative input bytes [sp, end).
 __device__ int lz4_block(InStream& in, GOut& out, uint32_t sp, uint32_t end) {
+    uint32_t hold = 0;   // sequences to decode one at a time after a batch attempt that found too few regular ones
     while (sp < end) {
+#ifndef AURORA_NO_LZ4_BATCH
+        if (hold == 0) {
+            if (lz4_batch32(in, out, sp, end)) continue;
+            hold = 4;
+        }
+        hold--;
+#endif
         in.ensure(sp, 64);
         const uint32_t token = in.at(sp);
         if ((token >> 4) != 15 && sp + 4 + (token >> 4) <= end) {
@@ -754,8 +903,18 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream& in,
     }
 }
 
+#ifndef AURORA_LZ4_WARPS
+#define AURORA_LZ4_WARPS 20
+#endif
+// resident warps per block (x2 blocks per SM): the LZ4 kernels trade warps for the registers of the sequence-per-lane batch
 template <int K>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) decode_bytelz_kernel(const DecodeParams P) {
+struct BlockShape {
+    static constexpr int kWarps = (K == B_LZ4 || K == B_LZ4_BLOCK) ? AURORA_LZ4_WARPS : kWarpsPerBlock;
+};
+
+template <int K>
+__global__ void __launch_bounds__(BlockShape<K>::kWarps * 32, 2) decode_bytelz_kernel(const DecodeParams P) {
+    constexpr int kWarpsPerBlock = BlockShape<K>::kWarps;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     const uint32_t s0 = smem_u32(smem);
@@ -779,6 +938,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) decode_bytelz_kernel(c
 
 template <int K>
 cudaError_t launch(const DecodeParams& p, int sm_count, cudaStream_t st) {
+    constexpr int kWarpsPerBlock = BlockShape<K>::kWarps;
     const int threads = kWarpsPerBlock * 32;
     const size_t smem = size_t(kWarpsPerBlock) * kSmemPerWarp + kORing;   // + alignment slack for the rings
     static bool configured[64] = {};
