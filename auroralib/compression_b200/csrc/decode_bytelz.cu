@@ -217,6 +217,87 @@ __device__ __forceinline__ bool lz4_ext(InStream& in, uint32_t& sp, uint32_t end
     return true;
 }
 
+// Commit of an element-per-lane batch (shared by the LZ4 and Snappy front ends): lane k < n holds one element = `lit`
+// literal bytes at shared address `la` followed by a match of `mlen` bytes at distance `d` (either part may be empty); the
+// batch decodes `cum` <= kBatchOut bytes in total.  Order of the parts is stream order: a warp scan places every element,
+// literals and far matches (source drained to HBM before the batch: independent of everything in it) are stored first,
+// then the remaining matches replay in stream order from the output ring.
+constexpr uint32_t kBatchOut = 1024;
+__device__ __forceinline__ void batch_commit(GOut& out, const uint32_t n, const uint32_t cum, const uint32_t lit, const uint32_t la,
+                                             const uint32_t mlen, const uint32_t d) {
+    const uint32_t lane = lane_id();
+    const uint32_t incl = warp_incl_scan(lit + mlen);
+    const uint32_t base = out.written;
+    const uint32_t lpos = base + incl - (lit + mlen), mpos = lpos + lit;
+    const uint32_t dd = d ? d : out.ring_len;
+    const uint32_t rb = out.rb;
+    // ---- 3. literals: short runs one lane per sequence, long runs (15..269 bytes) warp-cooperatively
+    {
+        const bool shortl = lit <= 14;
+        const uint32_t maxlit = __reduce_max_sync(kFull, shortl ? lit : 0u);
+        for (uint32_t j = 0; j < maxlit; j++)
+            if (shortl && j < lit) sts_u8(((lpos + j) & kORingMask) | rb, lds_u8(la + j));
+        uint32_t lm = __ballot_sync(kFull, !shortl);
+        while (lm) {
+            const int k = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const uint32_t kp = __shfl_sync(kFull, lpos, k), kl = __shfl_sync(kFull, lit, k), ka = __shfl_sync(kFull, la, k);
+            for (uint32_t i = lane; i < kl; i += 32) sts_u8(((kp + i) & kORingMask) | rb, lds_u8(ka + i));
+        }
+    }
+    // ---- 4. far matches: the source is in HBM already
+    const bool has = lane < n && mlen > 0;
+    const bool far = has && int32_t(mpos - dd + mlen) <= int32_t(out.flushed) && dd >= mlen;
+    uint32_t fm = __ballot_sync(kFull, far);
+    while (fm) {
+        uint32_t v[4], dp[4], ln[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            v[t] = 0;
+            ln[t] = 0;
+            dp[t] = 0;
+            if (fm) {
+                const int k = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const uint32_t kp = __shfl_sync(kFull, mpos, k), kl = __shfl_sync(kFull, mlen, k), kd = __shfl_sync(kFull, dd, k);
+                dp[t] = kp;
+                ln[t] = kl;
+                const int32_t sidx = int32_t(kp) - int32_t(kd) + int32_t(lane);
+                if (lane < kl && sidx >= int32_t(out.win_base) && uint64_t(sidx) < out.cap) v[t] = out.dst[sidx];
+                if (kl > 32) {   // the rest of a long match right away (rare)
+                    for (uint32_t i = lane + 32; i < kl; i += 32) {
+                        const int32_t s2 = int32_t(kp) - int32_t(kd) + int32_t(i);
+                        uint32_t w = 0;
+                        if (s2 >= int32_t(out.win_base) && uint64_t(s2) < out.cap) w = out.dst[s2];
+                        sts_u8(((kp + i) & kORingMask) | rb, w);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            if (lane < ln[t]) sts_u8(((dp[t] + lane) & kORingMask) | rb, v[t]);
+    }
+    // ---- 5. the other matches, in stream order, from the ring
+    uint32_t nm = __ballot_sync(kFull, has && !far);
+    while (nm) {
+        const int k = __ffs(nm) - 1;
+        nm &= nm - 1;
+        const uint32_t kp = __shfl_sync(kFull, mpos, k), kl = __shfl_sync(kFull, mlen, k), kd = __shfl_sync(kFull, dd, k);
+        __syncwarp();
+        const uint32_t rr = kd < kl ? c_rcp.v[kd & 511] : 0u;   // kd < kl <= 273: the reciprocal table applies
+        for (uint32_t i = lane; i < kl; i += 32) {
+            const int32_t sidx = int32_t(kp) - int32_t(kd) + int32_t(i - ((i * rr) >> 20) * kd);
+            uint32_t w = 0;
+            if (sidx >= int32_t(out.win_base)) w = lds_u8((uint32_t(sidx) & kORingMask) | rb);
+            sts_u8(((kp + i) & kORingMask) | rb, w);
+        }
+    }
+    out.written = base + cum;
+    __syncwarp();
+    out.drain();
+}
+
 // Sequence-per-lane batch (LZ4.cs:176-200 for up to 32 consecutive "regular" sequences: at most one literal-length and one
 // match-length extension byte, the match present inside the block).  The token walk of LZ4 is uniform work —
 // 32 lanes computing the same scalars — and the kernel is issue bound, so everything that can be is moved to one lane per
@@ -231,7 +312,6 @@ __device__ __forceinline__ bool lz4_ext(InStream& in, uint32_t& sp, uint32_t end
 // A batch decodes at most kBatchOut = 1024 bytes: the last byte it writes maps to the ring slot 2048 below it, which is
 // older than anything a match of the batch may still read (>= batch start - 1024).
 // Returns the number of sequences consumed (0: the sequence at sp is not regular, the caller decodes it alone).
-constexpr uint32_t kBatchOut = 1024;
 __device__ __forceinline__ uint32_t lz4_batch32(InStream& in, GOut& out, uint32_t& sp, const uint32_t end) {
     const uint32_t lane = lane_id();
     in.ensure(sp, kInMirror - 16);
@@ -284,76 +364,7 @@ __device__ __forceinline__ uint32_t lz4_batch32(InStream& in, GOut& out, uint32_
         if (ml == 15) ml += lds_u8(la + lit + 2);
         mlen = ml + 4;
     }
-    const uint32_t incl = warp_incl_scan(lit + mlen);
-    const uint32_t base = out.written;
-    const uint32_t lpos = base + incl - (lit + mlen), mpos = lpos + lit;
-    const uint32_t dd = d ? d : out.ring_len;
-    const uint32_t rb = out.rb;
-    // ---- 3. literals: short runs one lane per sequence, long runs (15..269 bytes) warp-cooperatively
-    {
-        const bool shortl = lit <= 14;
-        const uint32_t maxlit = __reduce_max_sync(kFull, shortl ? lit : 0u);
-        for (uint32_t j = 0; j < maxlit; j++)
-            if (shortl && j < lit) sts_u8(((lpos + j) & kORingMask) | rb, lds_u8(la + j));
-        uint32_t lm = __ballot_sync(kFull, !shortl);
-        while (lm) {
-            const int k = __ffs(lm) - 1;
-            lm &= lm - 1;
-            const uint32_t kp = __shfl_sync(kFull, lpos, k), kl = __shfl_sync(kFull, lit, k), ka = __shfl_sync(kFull, la, k);
-            for (uint32_t i = lane; i < kl; i += 32) sts_u8(((kp + i) & kORingMask) | rb, lds_u8(ka + i));
-        }
-    }
-    // ---- 4. far matches: the source is in HBM already
-    const bool has = lane < n;
-    const bool far = has && int32_t(mpos - dd + mlen) <= int32_t(out.flushed) && dd >= mlen;
-    uint32_t fm = __ballot_sync(kFull, far);
-    while (fm) {
-        uint32_t v[4], dp[4], ln[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            v[t] = 0;
-            ln[t] = 0;
-            dp[t] = 0;
-            if (fm) {
-                const int k = __ffs(fm) - 1;
-                fm &= fm - 1;
-                const uint32_t kp = __shfl_sync(kFull, mpos, k), kl = __shfl_sync(kFull, mlen, k), kd = __shfl_sync(kFull, dd, k);
-                dp[t] = kp;
-                ln[t] = kl;
-                const int32_t sidx = int32_t(kp) - int32_t(kd) + int32_t(lane);
-                if (lane < kl && sidx >= int32_t(out.win_base) && uint64_t(sidx) < out.cap) v[t] = out.dst[sidx];
-                if (kl > 32) {   // the rest of a long match right away (rare)
-                    for (uint32_t i = lane + 32; i < kl; i += 32) {
-                        const int32_t s2 = int32_t(kp) - int32_t(kd) + int32_t(i);
-                        uint32_t w = 0;
-                        if (s2 >= int32_t(out.win_base) && uint64_t(s2) < out.cap) w = out.dst[s2];
-                        sts_u8(((kp + i) & kORingMask) | rb, w);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-            if (lane < ln[t]) sts_u8(((dp[t] + lane) & kORingMask) | rb, v[t]);
-    }
-    // ---- 5. the other matches, in stream order, from the ring
-    uint32_t nm = __ballot_sync(kFull, has && !far);
-    while (nm) {
-        const int k = __ffs(nm) - 1;
-        nm &= nm - 1;
-        const uint32_t kp = __shfl_sync(kFull, mpos, k), kl = __shfl_sync(kFull, mlen, k), kd = __shfl_sync(kFull, dd, k);
-        __syncwarp();
-        const uint32_t rr = kd < kl ? c_rcp.v[kd & 511] : 0u;   // kd < kl <= 273: the reciprocal table applies
-        for (uint32_t i = lane; i < kl; i += 32) {
-            const int32_t sidx = int32_t(kp) - int32_t(kd) + int32_t(i - ((i * rr) >> 20) * kd);
-            uint32_t w = 0;
-            if (sidx >= int32_t(out.win_base)) w = lds_u8((uint32_t(sidx) & kORingMask) | rb);
-            sts_u8(((kp + i) & kORingMask) | rb, w);
-        }
-    }
-    out.written = base + cum;
-    __syncwarp();
-    out.drain();
+    batch_commit(out, n, cum, lit, la, mlen, d);
     sp += r;
     return n;
 }
@@ -561,6 +572,63 @@ __device__ Res lz4_container(InStream& in, GOut& out, const uint8_t* src, uint32
 }
 
 // ------------------------------------------------------------------------------------------------ Snappy
+// Element-per-lane batch of Snappy elements (Snappy.cs:216-247): literals of 1..60 bytes and the 2- and 3-byte copies;
+// literals with length bytes and 5-byte copies end the batch and go through the element-at-a-time path.  `room` = bytes
+// the block may still decode: an element that would reach or pass it is left to that path, too (it ends the loop).
+__device__ __forceinline__ uint32_t snappy_batch32(InStream& in, GOut& out, uint32_t& sp, const uint32_t slen, const uint64_t room) {
+    const uint32_t lane = lane_id();
+    in.ensure(sp, kInMirror - 16);
+    const uint32_t wa = smem_u32(in.window(sp));
+    constexpr uint32_t kWin = kInMirror - 16;
+    const uint32_t avail = min(slen - sp, kWin);
+    const uint32_t cap_out = uint32_t(min(uint64_t(kBatchOut), room));
+    uint32_t r = 0, cum = 0, n = 0, myr = 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < 32; k++) {
+        if (r >= avail) break;
+        const uint32_t tag = lds_u8(wa + r);
+        const uint32_t type = tag & 3, L = tag >> 2;
+        uint32_t size, o;
+        if (type == 0) {
+            if (L >= 60) break;
+            o = L + 1;
+            size = 1 + o;
+        } else if (type == 1) {
+            o = (L & 7) + 4;
+            size = 2;
+        } else if (type == 2) {
+            o = L + 1;
+            size = 3;
+        } else {
+            break;
+        }
+        if (r + size > avail || cum + o >= cap_out) break;
+        if (lane == k) myr = r;
+        cum += o;
+        r += size;
+        n = k + 1;
+    }
+    if (n < 3) return 0;
+    uint32_t lit = 0, mlen = 0, d = 0;
+    const uint32_t a = wa + myr;
+    if (lane < n) {
+        const uint32_t tag = lds_u8(a);
+        const uint32_t type = tag & 3, L = tag >> 2;
+        if (type == 0) {
+            lit = L + 1;
+        } else if (type == 1) {
+            mlen = (L & 7) + 4;
+            d = ((tag >> 5) << 8) | lds_u8(a + 1);
+        } else {
+            mlen = L + 1;
+            d = lds_u8(a + 1) | (lds_u8(a + 2) << 8);
+        }
+    }
+    batch_commit(out, n, cum, lit, a + 1, mlen, d);
+    sp += r;
+    return n;
+}
+
 // Snappy.cs:205-250 on relative input starting at sp; returns the position after the block's last token
 __device__ Res snappy_block(InStream& in, GOut& out, uint32_t sp, uint32_t slen) {
     // ReadDecompressedSize (:109-122)
@@ -575,8 +643,16 @@ __device__ Res snappy_block(InStream& in, GOut& out, uint32_t sp, uint32_t slen)
     const uint64_t end_position = uint64_t(out.written) + size;
     if (!out.size_only && end_position > out.cap) return Res{AURORA_DST_TOO_SMALL, sp};   // SetLength on a fixed destination
     out.new_window();
+    uint32_t hold = 0;   // elements to decode one at a time after a batch attempt that found too few regular ones
     while (out.written < end_position) {
         if (sp >= slen) return Res{AURORA_END_OF_STREAM, slen};
+#ifndef AURORA_NO_SNAPPY_BATCH
+        if (hold == 0) {
+            if (snappy_batch32(in, out, sp, slen, end_position - out.written)) continue;
+            hold = 4;
+        }
+        hold--;
+#endif
         in.ensure(sp, 16);
         const uint32_t tag = in.at(sp++);
         const uint32_t type = tag & 3;
@@ -909,7 +985,9 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream& in,
 // resident warps per block (x2 blocks per SM): the LZ4 kernels trade warps for the registers of the sequence-per-lane batch
 template <int K>
 struct BlockShape {
-    static constexpr int kWarps = (K == B_LZ4 || K == B_LZ4_BLOCK) ? AURORA_LZ4_WARPS : kWarpsPerBlock;
+    // block kernels with an element-per-lane batch: 20 warps (48 registers); the framed kernels inline two block decoders:
+    // 16 warps (64 registers); LZO and PRS walk uniformly: 23 warps (40 registers)
+    static constexpr int kWarps = (K == B_LZ4_BLOCK || K == B_SNAPPY_BLOCK) ? AURORA_LZ4_WARPS : (K == B_LZ4 || K == B_SNAPPY) ? 16 : kWarpsPerBlock;
 };
 
 template <int K>
