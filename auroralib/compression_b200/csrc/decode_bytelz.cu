@@ -223,12 +223,14 @@ __device__ __forceinline__ bool lz4_ext(InStream& in, uint32_t& sp, uint32_t end
 // literals and far matches (source drained to HBM before the batch: independent of everything in it) are stored first,
 // then the remaining matches replay in stream order from the output ring.
 constexpr uint32_t kBatchOut = 1024;
+template <bool kLitAfter = false>   // LZO: an element is a match FOLLOWED by its 0..3 trailing literals
 __device__ __forceinline__ void batch_commit(GOut& out, const uint32_t n, const uint32_t cum, const uint32_t lit, const uint32_t la,
                                              const uint32_t mlen, const uint32_t d) {
     const uint32_t lane = lane_id();
     const uint32_t incl = warp_incl_scan(lit + mlen);
     const uint32_t base = out.written;
-    const uint32_t lpos = base + incl - (lit + mlen), mpos = lpos + lit;
+    const uint32_t epos = base + incl - (lit + mlen);
+    const uint32_t lpos = kLitAfter ? epos + mlen : epos, mpos = kLitAfter ? epos : epos + lit;
     const uint32_t dd = d ? d : out.ring_len;
     const uint32_t rb = out.rb;
     // ---- 3. literals: short runs one lane per sequence, long runs (15..269 bytes) warp-cooperatively
@@ -371,12 +373,18 @@ __device__ __forceinline__ uint32_t lz4_batch32(InStream& in, GOut& out, uint32_
 
 // LZ4.cs:176-200.  The block occupies relative input bytes [sp, end).
 __device__ int lz4_block(InStream& in, GOut& out, uint32_t sp, uint32_t end) {
-    uint32_t hold = 0;   // sequences to decode one at a time after a batch attempt that found too few regular ones
+    // sequences to decode one at a time after a batch attempt that found too few regular ones (doubling back-off:
+    // long literal runs and long matches never batch, and a failed attempt costs a chain walk)
+    uint32_t hold = 0, backoff = 4;
     while (sp < end) {
 #ifndef AURORA_NO_LZ4_BATCH
         if (hold == 0) {
-            if (lz4_batch32(in, out, sp, end)) continue;
-            hold = 4;
+            if (lz4_batch32(in, out, sp, end)) {
+                backoff = 4;
+                continue;
+            }
+            hold = backoff;
+            backoff = min(backoff * 2, 64u);
         }
         hold--;
 #endif
@@ -643,13 +651,17 @@ __device__ Res snappy_block(InStream& in, GOut& out, uint32_t sp, uint32_t slen)
     const uint64_t end_position = uint64_t(out.written) + size;
     if (!out.size_only && end_position > out.cap) return Res{AURORA_DST_TOO_SMALL, sp};   // SetLength on a fixed destination
     out.new_window();
-    uint32_t hold = 0;   // elements to decode one at a time after a batch attempt that found too few regular ones
+    uint32_t hold = 0, backoff = 4;   // elements to decode one at a time after a failed batch attempt (doubling back-off)
     while (out.written < end_position) {
         if (sp >= slen) return Res{AURORA_END_OF_STREAM, slen};
 #ifndef AURORA_NO_SNAPPY_BATCH
         if (hold == 0) {
-            if (snappy_batch32(in, out, sp, slen, end_position - out.written)) continue;
-            hold = 4;
+            if (snappy_batch32(in, out, sp, slen, end_position - out.written)) {
+                backoff = 4;
+                continue;
+            }
+            hold = backoff;
+            backoff = min(backoff * 2, 64u);
         }
         hold--;
 #endif
@@ -744,6 +756,127 @@ __device__ __forceinline__ bool lzo_ext(InStream& in, uint32_t& sp, uint32_t sle
     return true;
 }
 
+// Element-per-lane batch of LZO instructions (LZO.cs:62-137).  The interpretation of an instruction depends on the
+// trailing-literal count of the one before (`plain`), which the uniform chain carries along: per instruction it only
+// derives the size, the output bytes and the next `plain`; lane k then decodes instruction k completely.  An element is a
+// literal run, or a match followed by its 0..3 trailing literals.  Length extensions of more than one byte, the end
+// marker and instructions that leave the staged window end the batch.  `at` = position of the first flag byte.
+__device__ __forceinline__ uint32_t lzo_batch32(InStream& in, GOut& out, uint32_t& at, uint32_t& plain_io, const uint32_t slen) {
+    const uint32_t lane = lane_id();
+    in.ensure(at, kInMirror - 16);
+    const uint32_t wa = smem_u32(in.window(at));
+    constexpr uint32_t kWin = kInMirror - 16;
+    const uint32_t avail = min(slen - at, kWin);
+    uint32_t r = 0, cum = 0, n = 0, myr = 0, myplain = 0, plain = plain_io;
+#pragma unroll 1
+    for (uint32_t k = 0; k < 32; k++) {
+        if (r + 4 > avail) break;   // flag + up to three header bytes must be readable (the tail of the stream goes one by one)
+        const uint32_t flag = lds_u8(wa + r);
+        const uint32_t code = flag >> 4;
+        uint32_t size, o, np;
+        if (code == 0 && plain == 0) {
+            uint32_t len = 3 + flag, hdr = 1;
+            if (len == 3) {
+                const uint32_t e = lds_u8(wa + r + 1);
+                if (e == 0) break;          // more extension bytes
+                len = 18 + e;
+                hdr = 2;
+            }
+            size = hdr + len;
+            o = len;
+            np = 4;
+        } else {
+            uint32_t ml, hdr, pb = flag;    // pb: the byte whose low two bits give the trailing literals
+            if (code == 0) {
+                ml = plain <= 3 ? 2 : 3;
+                hdr = 2;
+            } else if (code <= 3) {
+                const uint32_t mask = code == 1 ? 7u : 31u;
+                ml = 2 + (flag & mask);
+                hdr = 3;
+                if (ml == 2) {
+                    const uint32_t e = lds_u8(wa + r + 1);
+                    if (e == 0) break;
+                    ml = (code == 1 ? 9u : 33u) + e;
+                    hdr = 4;
+                }
+                pb = lds_u8(wa + r + hdr - 2);
+                if (code == 1) {
+                    const uint32_t dist = (16384u + ((flag & 8) << 11)) | (lds_u8(wa + r + hdr - 1) << 6) | (pb >> 2);
+                    if (dist == 16384u) break;   // end marker
+                }
+            } else if (code <= 7) {
+                ml = 3 + ((flag >> 5) & 1);
+                hdr = 2;
+            } else {
+                ml = 5 + ((flag >> 5) & 3);
+                hdr = 2;
+            }
+            np = pb & 3;
+            size = hdr + np;
+            o = ml + np;
+        }
+        if (r + size > avail || cum + o > kBatchOut) break;
+        if (lane == k) {
+            myr = r;
+            myplain = plain;
+        }
+        cum += o;
+        r += size;
+        plain = np;
+        n = k + 1;
+    }
+    if (n < 3) return 0;
+    // ---- lane k decodes instruction k
+    uint32_t lit = 0, mlen = 0, d = 1, la = 0;
+    if (lane < n) {
+        const uint32_t a = wa + myr;
+        const uint32_t flag = lds_u8(a);
+        const uint32_t code = flag >> 4;
+        if (code == 0 && myplain == 0) {
+            lit = 3 + flag;
+            la = a + 1;
+            if (lit == 3) {
+                lit = 18 + lds_u8(a + 1);
+                la = a + 2;
+            }
+        } else {
+            uint32_t hdr, pb = flag;
+            if (code == 0) {
+                mlen = myplain <= 3 ? 2 : 3;
+                d = (lds_u8(a + 1) << 2) + (flag >> 2) + (myplain <= 3 ? 1u : 2049u);
+                hdr = 2;
+            } else if (code <= 3) {
+                const uint32_t mask = code == 1 ? 7u : 31u;
+                mlen = 2 + (flag & mask);
+                hdr = 3;
+                if (mlen == 2) {
+                    mlen = (code == 1 ? 9u : 33u) + lds_u8(a + 1);
+                    hdr = 4;
+                }
+                pb = lds_u8(a + hdr - 2);
+                const uint32_t b1 = lds_u8(a + hdr - 1);
+                if (code == 1) d = (16384u + ((flag & 8) << 11)) | (b1 << 6) | (pb >> 2);
+                else d = ((b1 << 6) | (pb >> 2)) + 1;
+            } else if (code <= 7) {
+                mlen = 3 + ((flag >> 5) & 1);
+                d = (lds_u8(a + 1) << 3) + ((flag >> 2) & 7) + 1;
+                hdr = 2;
+            } else {
+                mlen = 5 + ((flag >> 5) & 3);
+                d = (lds_u8(a + 1) << 3) + ((flag & 0x1c) >> 2) + 1;
+                hdr = 2;
+            }
+            lit = pb & 3;
+            la = a + hdr;
+        }
+    }
+    batch_commit<true>(out, n, cum, lit, la, mlen, d);
+    at += r;
+    plain_io = plain;
+    return n;
+}
+
 // LZO.cs:49-139
 __device__ Res lzo_decode(InStream& in, GOut& out, uint32_t slen) {
     uint32_t sp = 0, plain = 0, length, distance;
@@ -759,7 +892,24 @@ __device__ Res lzo_decode(InStream& in, GOut& out, uint32_t slen) {
         in.ensure(sp, 16);
         flag = in.at(sp++);
     }
+    uint32_t hold = 0, backoff = 4;   // instructions to decode one at a time after a failed batch attempt (doubling back-off)
     for (;;) {
+#ifndef AURORA_NO_LZO_BATCH
+        if (hold == 0) {
+            uint32_t at = sp - 1;   // the flag byte just read
+            if (lzo_batch32(in, out, at, plain, slen)) {
+                backoff = 4;
+                sp = at;
+                if (sp >= slen) return eos;   // while ((flag = ReadByte()) != -1) ... throw EndOfStream
+                in.ensure(sp, 16);
+                flag = in.at(sp++);
+                continue;
+            }
+            hold = backoff;
+            backoff = min(backoff * 2, 64u);
+        }
+        hold--;
+#endif
         in.ensure(sp, 16);
         const uint32_t code = flag >> 4;
         bool literal_run = false;
@@ -986,8 +1136,8 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream& in,
 template <int K>
 struct BlockShape {
     // block kernels with an element-per-lane batch: 20 warps (48 registers); the framed kernels inline two block decoders:
-    // 16 warps (64 registers); LZO and PRS walk uniformly: 23 warps (40 registers)
-    static constexpr int kWarps = (K == B_LZ4_BLOCK || K == B_SNAPPY_BLOCK) ? AURORA_LZ4_WARPS : (K == B_LZ4 || K == B_SNAPPY) ? 16 : kWarpsPerBlock;
+    // 16 warps (64 registers); PRS walks uniformly: 23 warps (40 registers)
+    static constexpr int kWarps = (K == B_LZ4_BLOCK || K == B_SNAPPY_BLOCK || K == B_LZO) ? AURORA_LZ4_WARPS : (K == B_LZ4 || K == B_SNAPPY) ? 16 : kWarpsPerBlock;
 };
 
 template <int K>
