@@ -155,6 +155,34 @@ def test_lz11_long_matches(codec, oracle):
     _compare(codec, oracle, A.FMT_LZ11, comps, [max(0, len(r) - int(rng.integers(1, 3000))) for r in raws], what="lz11 long short dst")
 
 
+@pytest.mark.parametrize("fmt", [A.FMT_LZ4_BLOCK, A.FMT_LZ4, A.FMT_SNAPPY_BLOCK, A.FMT_SNAPPY, A.FMT_LZO], ids=fmt_id)
+def test_bytelz_batch_boundaries(codec, oracle, fmt):
+    """Element-per-lane batches: literal runs and matches at the eligibility edges (14/15/16 and 268..271 literals, matches
+    of 18/19/273/274 bytes, near / far / self-overlapping distances), long stretches of tiny sequences, and truncations
+    inside a batch."""
+    rng = np.random.default_rng(5200 + fmt)
+    raws = []
+    for i in range(64):
+        out = bytearray(rng.integers(0, 256, size=int(rng.integers(8, 3000)), dtype=np.uint8).tobytes())
+        for _ in range(int(rng.integers(20, 400))):
+            lit = int(rng.choice([0, 0, 1, 2, 3, 13, 14, 15, 16, 17, 59, 60, 61, 268, 269, 270, 271, 300]))
+            out += rng.integers(0, 256, size=lit, dtype=np.uint8).tobytes()
+            mlen = int(rng.choice([4, 5, 8, 11, 12, 18, 19, 20, 32, 33, 64, 65, 272, 273, 274, 275, 600]))
+            dist = int(rng.choice([1, 2, 3, 7, 31, 32, 100, 1023, 1024, 1025, 2048, 5000, 40000]))
+            dist = min(dist, len(out))
+            for k in range(mlen):
+                out.append(out[len(out) - dist])
+        raws.append(bytes(out))
+    comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=8))
+    assert (st == 0).all()
+    outs, status = _compare(codec, oracle, fmt, comps, [len(r) for r in raws], what="batch boundaries")
+    ok = sum(1 for o, r, s_ in zip(outs, raws, status) if s_ == 0 and o == r)
+    assert ok >= len(raws) - (8 if fmt == A.FMT_LZO else 0)
+    cut = [c[:int(rng.integers(1, len(c)))] for c in comps]
+    _compare(codec, oracle, fmt, cut, [len(r) for r in raws], what="batch boundaries truncated")
+    _compare(codec, oracle, fmt, comps, [max(0, len(r) - int(rng.integers(1, 2000))) for r in raws], what="batch boundaries short dst")
+
+
 def test_prehistory_references(codec, oracle):
     """Back-references before the start of the output read the window's pre-history (zeros / initialFill):
     hand-made LZ10, Yaz0 and LZSS streams whose first token is a match."""
