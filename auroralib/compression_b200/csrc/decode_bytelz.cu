@@ -981,21 +981,119 @@ __device__ Res lzo_decode(InStream& in, GOut& out, uint32_t slen) {
 
 // ------------------------------------------------------------------------------------------------ PRS
 struct PrsBits {
-    uint32_t cur, left;
+    uint32_t cur, left;   // the unread bits of the current flag byte in READ order, next bit = bit 0 (an MSB-first byte is reversed on fetch)
     bool msb;
     // FlagReader.Readbit (IO/FlagReader.cs:53-65): the flag byte is fetched lazily from the same stream
     __device__ __forceinline__ int bit(InStream& in, uint32_t& sp, uint32_t slen) {
         if (left == 0) {
             if (sp >= slen) return -1;
             in.ensure(sp, 8);
-            cur = in.at(sp++);
+            const uint32_t b = in.at(sp++);
+            cur = msb ? __brev(b) >> 24 : b;
             left = 8;
         }
-        const uint32_t sh = msb ? left - 1 : 8 - left;
+        const int v = int(cur & 1u);
+        cur >>= 1;
         left--;
-        return (cur >> sh) & 1;
+        return v;
     }
 };
+
+// Element-per-lane batch of PRS tokens (PRS.cs:59-102).  An element = the literal bits that follow each other inside ONE
+// flag byte (their data bytes are contiguous in the input) plus the match token behind them, if the flag byte has a bit
+// left.  The chain is the bit walk itself (flag bytes are fetched lazily between the data bytes, so every position
+// depends on every bit before it) and is uniform work; lane k keeps element k as the chain passes it, and the shared
+// batch commit places and copies all elements.  The end token, a token that needs input bytes past the staged window /
+// the end of the input, and an element that would pass kBatchOut decoded bytes end the batch BEFORE that element (the
+// state is rolled back to the element's start); the token-at-a-time path in prs_walk decodes it with the reference's
+// exact error behaviour.  Returns the number of elements consumed.
+__device__ __forceinline__ uint32_t prs_batch32(InStream& in, GOut& out, PrsBits& fr, uint32_t& sp, const uint32_t slen) {
+    const uint32_t lane = lane_id();
+    in.ensure(sp, kInMirror - 16);
+    const uint32_t wa = smem_u32(in.window(sp));
+    constexpr uint32_t kWin = kInMirror - 16;
+    const uint32_t avail = min(slen - sp, kWin);
+    const bool big = fr.msb;
+    uint32_t bits = fr.cur, left = fr.left, r = 0;          // running state
+    uint32_t cbits = bits, cleft = left, cr = 0;            // state after the last committed element
+    uint32_t cum = 0, n = 0;
+    uint32_t my_la = wa, my_lit = 0, my_len = 0, my_d = 0;
+#define PRS_FETCH()                                   \
+    {                                                 \
+        if (r >= avail) break;                        \
+        const uint32_t fb = lds_u8(wa + r);           \
+        r++;                                          \
+        bits = big ? __brev(fb) >> 24 : fb;           \
+        left = 8;                                     \
+    }
+#pragma unroll 1
+    for (uint32_t k = 0; k < 32; k++) {
+        if (left == 0) PRS_FETCH();
+        const uint32_t ones = uint32_t(__ffs(int(~bits))) - 1u;   // literal bits; bits < 2^left, so ones <= left
+        const uint32_t e_la = wa + r;
+        r += ones;
+        bits >>= ones;
+        left -= ones;
+        if (r > avail) break;
+        uint32_t mlen = 0, d = 0;
+        if (left != 0) {
+            bits >>= 1;   // the 0 bit that opens a match token
+            left--;
+            if (left == 0) PRS_FETCH();
+            const uint32_t b = bits & 1u;
+            bits >>= 1;
+            left--;
+            if (b) {
+                if (r + 3 > avail) break;   // u16 + a possible length byte
+                const uint32_t x0 = lds_u8(wa + r), x1 = lds_u8(wa + r + 1);
+                const uint32_t v = big ? (x0 << 8) | x1 : x0 | (x1 << 8);
+                r += 2;
+                if (v == 0) break;          // end token
+                mlen = v & 7u;
+                d = 0x2000u - (v >> 3);
+                if (mlen == 0) {
+                    mlen = lds_u8(wa + r) + 1u;
+                    r++;
+                } else {
+                    mlen += 2;
+                }
+            } else {
+                if (left == 0) PRS_FETCH();
+                const uint32_t b1 = bits & 1u;
+                bits >>= 1;
+                left--;
+                if (left == 0) PRS_FETCH();
+                const uint32_t b0 = bits & 1u;
+                bits >>= 1;
+                left--;
+                if (r >= avail) break;
+                mlen = b1 * 2 + b0 + 2;
+                d = 0x100u - lds_u8(wa + r);
+                r++;
+            }
+        }
+        const uint32_t o = ones + mlen;
+        if (cum + o > kBatchOut) break;
+        if (lane == k) {
+            my_la = e_la;
+            my_lit = ones;
+            my_len = mlen;
+            my_d = d;
+        }
+        cum += o;
+        n = k + 1;
+        cbits = bits;
+        cleft = left;
+        cr = r;
+    }
+#undef PRS_FETCH
+    if (n < 3) return 0;
+    batch_commit(out, n, cum, my_lit, my_la, my_len, my_d);
+    fr.cur = cbits;
+    fr.left = cleft;
+    sp += cr;
+    return n;
+}
 
 // PRS.cs:59-102 (copy == true) and ValidateByteOrder :172-218 (copy == false; status kPrsValid / kPrsInvalid)
 constexpr int kPrsValid = 100, kPrsInvalid = 101;
@@ -1006,7 +1104,21 @@ __device__ Res prs_walk(InStream& in, GOut& out, uint32_t slen, bool big) {
     uint32_t produced = 0;
     int budget = 3;
     const Res eos{AURORA_END_OF_STREAM, slen};
+    uint32_t hold = 0, backoff = 4;   // tokens to decode one at a time after a failed batch attempt (doubling back-off)
     while (sp < slen) {
+#ifndef AURORA_NO_PRS_BATCH
+        if (kCopy) {
+            if (hold == 0) {
+                if (prs_batch32(in, out, fr, sp, slen)) {
+                    backoff = 4;
+                    continue;
+                }
+                hold = backoff;
+                backoff = min(backoff * 2, 64u);
+            }
+            hold--;
+        }
+#endif
         int b = fr.bit(in, sp, slen);
         if (b < 0) return eos;
         if (b) {
@@ -1014,8 +1126,9 @@ __device__ Res prs_walk(InStream& in, GOut& out, uint32_t slen, bool big) {
             if (kCopy) {
                 // the literal bits that follow in the SAME flag byte govern the next input bytes: copy the run at once
                 uint32_t n = 1;
-                while (fr.left > 0 && ((fr.cur >> (fr.msb ? fr.left - 1 : 8 - fr.left)) & 1u)) {
+                while (fr.left > 0 && (fr.cur & 1u)) {
                     n++;
+                    fr.cur >>= 1;
                     fr.left--;
                 }
                 const uint32_t avail = slen - sp;
@@ -1086,14 +1199,17 @@ __device__ Res prs_decode(InStream& in, GOut& out, uint32_t slen, const uint8_t*
         in.begin(P.src_base, P.src_limit, src);
     }
     const bool first_big = detected == 1;
-    out.new_window();
-    Res r = prs_walk<true>(in, out, slen, first_big);
-    if (r.status != AURORA_OK) {
-        in.begin(P.src_base, P.src_limit, src);
-        out.written = 0;
-        out.flushed = 0;
+    Res r{AURORA_OK, 0};
+#pragma unroll 1   // one inlined copy of the walk: the retry with the other order (PRS.cs:49-56) is the second trip
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (attempt) {
+            in.begin(P.src_base, P.src_limit, src);
+            out.written = 0;
+            out.flushed = 0;
+        }
         out.new_window();
-        r = prs_walk<true>(in, out, slen, !first_big);
+        r = prs_walk<true>(in, out, slen, attempt ? !first_big : first_big);
+        if (r.status == AURORA_OK) break;
     }
     return r;
 }
@@ -1139,11 +1255,14 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream& in,
 template <int K>
 struct BlockShape {
     // block kernels with an element-per-lane batch: 20 warps (48 registers); the framed kernels inline two block decoders:
-    // 16 warps (64 registers); PRS walks uniformly: 23 warps (40 registers)
+    // 16 warps (64 registers); PRS: 16 warps (64 registers: the element-per-lane batch spills below that; measured 12 / 14 / 16 / 20 / 23 warps: 88 / 94 / 97 / 74 / 57 GB/s)
 #ifndef AURORA_LZO_WARPS
 #define AURORA_LZO_WARPS 23
 #endif
-    static constexpr int kWarps = (K == B_LZ4_BLOCK || K == B_SNAPPY_BLOCK) ? AURORA_LZ4_WARPS : K == B_LZO ? AURORA_LZO_WARPS : (K == B_LZ4 || K == B_SNAPPY) ? 16 : kWarpsPerBlock;
+#ifndef AURORA_PRS_WARPS
+#define AURORA_PRS_WARPS 16
+#endif
+    static constexpr int kWarps = (K == B_LZ4_BLOCK || K == B_SNAPPY_BLOCK) ? AURORA_LZ4_WARPS : K == B_LZO ? AURORA_LZO_WARPS : (K == B_LZ4 || K == B_SNAPPY) ? 16 : K == B_PRS ? AURORA_PRS_WARPS : kWarpsPerBlock;
 };
 
 template <int K>

@@ -85,8 +85,11 @@ def main():
             ok = d_st == 0
             if fname not in ("lzo", "prs"):   # the reference's LZO encoder / PRS order heuristic have known self-inconsistencies
                 assert bool(ok.all()), "decode status"
-            if fname not in ("lzo", "prs") and not args.no_verify:
+            # PRS: the reference's order heuristic can pick the wrong order and still "succeed" (parity tests compare with the oracle)
+            if fname != "prs" and not args.no_verify:
                 assert torch.equal(d_dst[:n * args.size].view(n, args.size)[ok], raw[ok]), "decode mismatch"
+                if not bool(ok.all()):
+                    print(f"  ({int((~ok).sum())} of {n} streams not OK by design of the reference's encoder / order heuristic)")
             ms = float(np.median(times))
             out_b, in_b = n * args.size, int(clen.sum())
             print(f"{fname:8s} class {cname:3s} n={n} ratio {in_b / out_b:.3f}  {ms:8.3f} ms  out {out_b / ms / 1e6:8.1f} GB/s  "
