@@ -16,14 +16,16 @@ FMT_YAZ0, FMT_YAZ1, FMT_YAY0, FMT_MIO0, FMT_LZ10, FMT_LZ11, FMT_LZSS, FMT_LZ4, F
 FMT_GCLZ, FMT_CXLZ, FMT_COMP, FMT_LZ_3DS, FMT_LZ77, FMT_LEVEL5, FMT_LZON, FMT_LEVEL5_LZSS = range(15, 23)
 FMT_AKLZ, FMT_LZ01, FMT_FCMP, FMT_IECP, FMT_MDB4, FMT_LZSEGA, FMT_GCZ = range(23, 30)   # header + LZSS headerless
 FMT_SDPC = 30   # "SDPC" + size + LZO headerless
-WRAPPER_FORMATS = list(range(15, 31))
+FMT_ECD = 31    # "ECD" header + plain bytes + LZSS(0x400, 0x42, 3, 0x3BE), or stored
+FMT_LZ00 = 32   # 64-byte header + LZSS (Lzss0) under a per-byte LCG keystream
+WRAPPER_FORMATS = list(range(15, 33))
 FORMAT_NAMES = {FMT_YAZ0: "Yaz0", FMT_YAZ1: "Yaz1", FMT_YAY0: "Yay0", FMT_MIO0: "MIO0", FMT_LZ10: "LZ10",
                 FMT_LZ11: "LZ11", FMT_LZSS: "LZSS", FMT_LZ4: "LZ4", FMT_LZ4_BLOCK: "LZ4Block",
                 FMT_LZ4_LEGACY: "LZ4Legacy", FMT_LZO: "LZO", FMT_SNAPPY: "Snappy",
                 FMT_SNAPPY_BLOCK: "SnappyBlock", FMT_PRS: "PRS", FMT_GCLZ: "GCLZ", FMT_CXLZ: "CXLZ", FMT_COMP: "COMP",
                 FMT_LZ_3DS: "3DS-LZ", FMT_LZ77: "LZ77", FMT_LEVEL5: "Level5", FMT_LZON: "LZOn", FMT_LEVEL5_LZSS: "Level5LZSS",
                 FMT_AKLZ: "AKLZ", FMT_LZ01: "LZ01", FMT_FCMP: "FCMP", FMT_IECP: "IECP", FMT_MDB4: "MDB4", FMT_LZSEGA: "LZSega",
-                FMT_GCZ: "GCZ", FMT_SDPC: "SDPC"}
+                FMT_GCZ: "GCZ", FMT_SDPC: "SDPC", FMT_ECD: "ECD", FMT_LZ00: "LZ00"}
 
 ENDIAN_LITTLE, ENDIAN_BIG, ENDIAN_DEFAULT = 0, 1, 2
 
@@ -40,12 +42,12 @@ class CodecOpts(C.Structure):
                 ("lzss", LzProps), ("lzss_initial_fill", C.c_int32), ("lz4_block_size", C.c_uint32),
                 ("lz4_verify", C.c_int32), ("yaz0_alignment", C.c_uint32), ("balance", C.c_uint32),
                 ("lz77_type", C.c_uint32), ("lz77_chunk_size", C.c_uint32), ("level5_type", C.c_uint32),
-                ("reserved", C.c_uint32 * 2)]
+                ("lz00_key", C.c_uint32), ("ecd_plain_size", C.c_uint32)]
 
 
 def make_opts(byte_order=ENDIAN_DEFAULT, quality=-1, max_window_bits=0, strategy=0, vram_mode=-1,
               lzss=None, lzss_initial_fill=0, lz4_block_size=0, lz4_verify=0, yaz0_alignment=0, balance=0,
-              lz77_type=0, lz77_chunk_size=0, level5_type=0):
+              lz77_type=0, lz77_chunk_size=0, level5_type=0, lz00_key=0, ecd_plain_size=0):
     o = CodecOpts()
     o.struct_size = C.sizeof(CodecOpts)
     o.byte_order = byte_order
@@ -63,6 +65,8 @@ def make_opts(byte_order=ENDIAN_DEFAULT, quality=-1, max_window_bits=0, strategy
     o.lz77_type = lz77_type
     o.lz77_chunk_size = lz77_chunk_size
     o.level5_type = level5_type
+    o.lz00_key = lz00_key
+    o.ecd_plain_size = ecd_plain_size
     return o
 
 

@@ -436,5 +436,55 @@ class SDPC(_SizedCodec):
     FORMAT, Name = _abi.FMT_SDPC, "SDPC"
 
 
-WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC]
+class _WholeHeaderPeek:
+    # GetDecompressedSize looks past the first 16 bytes (LZ00: size at 48) or at the stream length (ECD)
+    def GetDecompressedSize(self, source):
+        _, data = _remaining(source)
+        size, st = default_codec().decoded_size_batch(self.FORMAT, [data], self._opts())
+        _raise_for(int(st[0]))
+        return int(size[0])
+
+
+class ECD(_WholeHeaderPeek, _SizedCodec):
+    """Extended/Specialized/ECD.cs: "ECD" + flag + plain size + compressed size + size (BE), PlainSize stored bytes + LZSS
+    body with LzProperties(0x400, 0x42, 3, 0x3BE); quality 0, inputs of at most 16 bytes and incompressible inputs are stored"""
+    FORMAT, Name = _abi.FMT_ECD, "ECD lzss"
+
+    def __init__(self):
+        self.PlainSize = 4   # ECD.cs:33
+
+    def _opts(self, settings=None):
+        o = super()._opts(settings)
+        o.ecd_plain_size = self.PlainSize
+        return o
+
+    def _capacity(self, size, data):
+        # GetDecompressedSize answers 0 when the compressed-size field does not fit the stream (ECD.cs:48-49); Decompress
+        # does not look at that field, so the destination is sized by the header's size field (stored: by the payload)
+        if len(data) >= 16:
+            return max(size, int.from_bytes(data[12:16], "big"), len(data) - 16 if data[3] != 1 else 0)
+        return size
+
+
+class LZ00(_WholeHeaderPeek, _SizedCodec):
+    """Sega/LZ00.cs: 64-byte header (file length, name, size, key) + LZSS body (Lzss0Properties) under a per-byte LCG
+    keystream; the header's name field is always the reference's default "Temp.dat" """
+    FORMAT, Name = _abi.FMT_LZ00, "LZ00"
+
+    def Compress(self, source, destination=None, settings=None, key=None):
+        # LZ00.cs:75-80: without a key the reference takes the Unix time of the call
+        if key is None:
+            import time
+            key = int(time.time())
+        o = self._opts(settings)
+        o.lz00_key = key & 0xFFFFFFFF
+        outs, status = default_codec().encode_batch(self.FORMAT, [bytes(source)], o)
+        _raise_for(int(status[0]))
+        if destination is None:
+            return io.BytesIO(outs[0])
+        destination.write(outs[0])
+        return None
+
+
+WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC, ECD, LZ00]
 ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS] + WRAPPERS

@@ -210,7 +210,7 @@ Layout plan_layout(const uint64_t* off, const uint64_t* len, size_t b, size_t e)
 int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_opts* opts, size_t b, size_t e,
                  const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
                  const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t* out_len, uint64_t* consumed, int32_t* status,
-                 int size_only, const uint64_t* raw_size = nullptr) {
+                 int size_only, const uint64_t* raw_size = nullptr, const uint32_t* xor_key = nullptr) {
     const size_t n = e - b;
     if (n == 0) return AURORA_OK;
     std::lock_guard<std::mutex> guard(d->mu);
@@ -235,12 +235,15 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     CU_TRY(ctx, d->src.reserve(S.bytes + 16));
     CU_TRY(ctx, d->dst.reserve(D.bytes + 16));
     // descriptors: src_off, src_len, dst_off, dst_cap | out_len, consumed | status
-    const size_t desc_bytes = n * (6 * sizeof(uint64_t) + sizeof(int32_t)) + 64;
+    // (+ LZ00: one keystream key per stream behind the status array)
+    const size_t desc_bytes = n * (6 * sizeof(uint64_t) + 2 * sizeof(int32_t)) + 64;
     CU_TRY(ctx, d->desc.reserve(desc_bytes));
     CU_TRY(ctx, d->hdesc.reserve(desc_bytes));
     CU_TRY(ctx, d->ticket.reserve(256));
     uint64_t* h = static_cast<uint64_t*>(d->hdesc.p);
     uint64_t* dv = static_cast<uint64_t*>(d->desc.p);
+    uint32_t* dkey = reinterpret_cast<uint32_t*>(dv + 6 * n) + n;
+    if (xor_key) std::memcpy(reinterpret_cast<uint32_t*>(h + 6 * n) + n, xor_key + b, n * sizeof(uint32_t));
     for (size_t i = 0; i < n; i++) {
         h[i] = S.dev_off[i];
         h[n + i] = src_len[b + i];
@@ -251,6 +254,7 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     }
     cudaStream_t st = d->stream;
     CU_TRY(ctx, cudaMemcpyAsync(dv, h, 4 * n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (xor_key) CU_TRY(ctx, cudaMemcpyAsync(dkey, reinterpret_cast<uint32_t*>(h + 6 * n) + n, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     uint8_t* dsrc = static_cast<uint8_t*>(d->src.p);
     uint8_t* ddst = static_cast<uint8_t*>(d->dst.p);
     P.src_base = dsrc;
@@ -274,7 +278,9 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     // k decodes and piece k-1 is downloaded (D2H engine), so end-to-end time tends to max(H2D, D2H) instead of their sum.
     uint64_t total_bytes = S.bytes + D.bytes;
     size_t pieces = 1;
-    if (S.span && (size_only || D.span) && total_bytes > (64ull << 20) && n >= 64) pieces = std::min<size_t>(16, std::max<size_t>(2, total_bytes >> 28));
+    // (not with a keystream pass: piece k+1's upload starts at a 16-byte boundary and may rewrite the tail of piece k's
+    //  last stream, harmless only as long as the device copy still equals the host bytes)
+    if (S.span && (size_only || D.span) && total_bytes > (64ull << 20) && n >= 64 && !xor_key) pieces = std::min<size_t>(16, std::max<size_t>(2, total_bytes >> 28));
     if (pieces > 1) {
         while (d->ev_in.size() < pieces) {
             cudaEvent_t e1, e2;
@@ -326,6 +332,10 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
                 ctx->launches += 3;
                 Q.order = ord;
             }
+            if (xor_key) {   // LZ00: lift the keystream off this piece's bodies (device copy, in place)
+                CU_TRY(ctx, launch_lcg_xor(dsrc, Q.src_off, Q.src_len, nullptr, dkey + i0, 0, Q.n, st));
+                ctx->launches++;
+            }
             CU_TRY(ctx, launch_decode(Q, d->sm_count, st));
             ctx->launches++;
             if (!size_only) {
@@ -365,6 +375,10 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
             CU_TRY(ctx, launch_size_order(P.dst_cap, P.n, hist, hist + 64, st));
             ctx->launches += 3;
             P.order = hist + 64;
+        }
+        if (xor_key) {   // LZ00: lift the keystream off the bodies (device copy, in place)
+            CU_TRY(ctx, launch_lcg_xor(dsrc, P.src_off, P.src_len, nullptr, dkey, 0, P.n, st));
+            ctx->launches++;
         }
         CU_TRY(ctx, launch_decode(P, d->sm_count, st));
         ctx->launches++;
@@ -478,7 +492,8 @@ int fill_encode_params(EncodeParams& p, int format, const aurora_codec_opts* o) 
 
 int encode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_opts* opts, size_t b, size_t e,
                  const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
-                 const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t* out_len, int32_t* status) {
+                 const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t* out_len, int32_t* status,
+                 const uint32_t* xor_key = nullptr, uint32_t xor_skip = 0) {
     const size_t n = e - b;
     if (n == 0) return AURORA_OK;
     std::lock_guard<std::mutex> guard(d->mu);
@@ -494,7 +509,7 @@ int encode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     CU_TRY(ctx, d->scratch.reserve(size_t(warps) * P.scratch_per_warp));
     CU_TRY(ctx, d->src.reserve(S.bytes + 16));
     CU_TRY(ctx, d->dst.reserve(D.bytes + 16));
-    const size_t desc_bytes = n * (5 * sizeof(uint64_t) + sizeof(int32_t)) + 64;
+    const size_t desc_bytes = n * (5 * sizeof(uint64_t) + 2 * sizeof(int32_t)) + 64;   // (+ LZ00 keys behind the status array)
     CU_TRY(ctx, d->desc.reserve(desc_bytes));
     CU_TRY(ctx, d->hdesc.reserve(desc_bytes));
     CU_TRY(ctx, d->ticket.reserve(256));
@@ -533,6 +548,14 @@ int encode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     P.n = uint32_t(n);
     CU_TRY(ctx, launch_encode(P, warps, st));
     ctx->launches++;
+    if (xor_key) {   // LZ00: the body the encoder just wrote goes under the keystream (bytes [skip, out_len) of every stream)
+        uint32_t* hkey = reinterpret_cast<uint32_t*>(h + 5 * n) + n;
+        uint32_t* dkey = reinterpret_cast<uint32_t*>(dv + 5 * n) + n;
+        std::memcpy(hkey, xor_key + b, n * sizeof(uint32_t));
+        CU_TRY(ctx, cudaMemcpyAsync(dkey, hkey, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, launch_lcg_xor(ddst, P.dst_off, P.out_len, P.dst_cap, dkey, xor_skip, P.n, st));
+        ctx->launches++;
+    }
     CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(ctx, cudaStreamSynchronize(st));
     const int32_t* hs = reinterpret_cast<const int32_t*>(h + 5 * n);
@@ -807,6 +830,12 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
                 case AURORA_FMT_FCMP: m = 0x10 < len && std::memcmp(p, "FCMP", 4) == 0; break;
                 case AURORA_FMT_IECP: m = 0x10 < len && std::memcmp(p, "IECP", 4) == 0; break;
                 case AURORA_FMT_MDB4: m = 0x10 < len && std::memcmp(p, "MDB4", 4) == 0; break;
+                case AURORA_FMT_LZ00: m = 0x40 < len && std::memcmp(p, "LZ00", 4) == 0; break;   // LZ00.cs:37-38
+                case AURORA_FMT_ECD: {   // ECD.cs:37-38: identifier, the compressed size fits the stream, a non-zero decoded size
+                    auto be = [&](size_t at) { return (uint32_t(p[at]) << 24) | (uint32_t(p[at + 1]) << 16) | (uint32_t(p[at + 2]) << 8) | p[at + 3]; };
+                    m = 0x10 < len && std::memcmp(p, "ECD", 3) == 0 && uint64_t(be(8)) + 0x10 <= len && be(12) != 0;
+                    break;
+                }
                 default: return AURORA_NOT_SUPPORTED;   // Level5 (zlib, file name), LZSega / GCZ (no identifier)
             }
             match[i] = m ? 1 : 0;
@@ -997,18 +1026,19 @@ namespace aurora {
 
 int decode_core_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
                       const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
-                      const uint64_t* dst_cap, const uint64_t* raw_size, uint64_t* out_len, uint64_t* consumed, int32_t* status) {
+                      const uint64_t* dst_cap, const uint64_t* raw_size, uint64_t* out_len, uint64_t* consumed, int32_t* status,
+                      const uint32_t* xor_key) {
     if (n == 0) return AURORA_OK;
     const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, dst_cap);
     return for_each_shard(ctx, ranges, [&](DeviceCtx* d, Range r) {
         return decode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
-                            out_len, consumed, status, 0, raw_size);
+                            out_len, consumed, status, 0, raw_size, xor_key);
     });
 }
 
 int encode_core_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
                       const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
-                      const uint64_t* dst_cap, uint64_t* out_len, int32_t* status) {
+                      const uint64_t* dst_cap, uint64_t* out_len, int32_t* status, const uint32_t* xor_key, uint32_t xor_skip) {
     if (n == 0) return AURORA_OK;
     EncodeParams probe{};
     const int rc = fill_encode_params(probe, format, opts);
@@ -1018,7 +1048,8 @@ int encode_core_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts
     }
     const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, nullptr);
     return for_each_shard(ctx, ranges, [&](DeviceCtx* d, Range r) {
-        return encode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status);
+        return encode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status,
+                            xor_key, xor_skip);
     });
 }
 

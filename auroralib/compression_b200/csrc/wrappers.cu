@@ -14,6 +14,11 @@
 // The LZSS-property family (a fixed header + LZSS.DecompressHeaderless with DefaultProperties or Lzss0Properties) is table
 // driven (kFamily below): Sega/AKLZ.cs:43-56, Sega/LZ01.cs:47-82, Sega/LZSega.cs:49-67 (src/AuroraLib.Compression.Sega),
 // Marvelous/FCMP.cs:43-59, Marvelous/IECP.cs:42-55, Konami/GCZ.cs:40-51, Specialized/MDB4.cs:41-80 (…-Extended).
+// Two more LZSS wrappers do a little work around the core:
+//   Specialized/ECD.cs:56-121 (…-Extended)  "ECD" + flag + plain size + compressed size + size (BE); the first `plain size`
+//                             bytes are stored, the rest is LZSS(0x400, 0x42, 3, 0x3BE) headerless; or the whole payload is stored
+//   Sega/LZ00.cs:50-203 (…Sega)  64-byte header with the decoded size and a key; the LZSS (Lzss0) body is XORed byte by byte
+//                             with an LCG keystream: a device pass over the body (keystream.cu) before / after the LZSS kernel
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -49,6 +54,8 @@ const Family kFamily[] = {
     {AURORA_FMT_MDB4, "MDB4", 4, 16, 16, 8, false, false},
     {AURORA_FMT_LZSEGA, "", 0, 8, 0, 4, false, false},
     {AURORA_FMT_GCZ, "", 0, 4, 0, 0, false, true},
+    // LZ00.cs:56-63: magic, length, 8 skipped (a seek), 32-byte name, size, key are READ up to byte 56; 8 more are skipped
+    {AURORA_FMT_LZ00, "LZ00", 4, 56, 8, 48, false, true},
 };
 const Family* family_of(int format) {
     for (const Family& f : kFamily)
@@ -67,6 +74,7 @@ struct Sub {
     uint64_t off, len;  // source bytes, relative to the wrapped stream
     uint64_t doff;      // destination offset inside the wrapped stream's slot
     uint64_t raw;       // kParseHeader or the decoded size of a headerless body
+    uint32_t key;       // LZ00: keystream key of the body
 };
 
 struct Plan {
@@ -76,6 +84,10 @@ struct Plan {
     uint64_t expect = 0;         // LZ77 chunked / LZOn: the size the header promises
     uint64_t end_consumed = 0;   // LZ77 chunked: source position after the last chunk
     size_t first_sub = 0, n_sub = 0;
+    // bytes the host writes at the start of the destination slot (stored payloads, ECD's plain prefix), applied AFTER the
+    // core batch: its device-to-host copy of a contiguous destination span also covers the gaps between its streams
+    const uint8_t* host_src = nullptr;
+    uint64_t host_copy = 0, host_fill = 0;   // copy host_copy bytes from host_src, then host_fill bytes of 0xFF
 };
 
 // Magic check with the stream semantics of MatchThrow: short stream -> END_OF_STREAM (position at the end), wrong
@@ -102,7 +114,7 @@ void eos(Plan& pl, uint64_t len) {
 // resolve one wrapped stream into core sub-streams
 void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst, uint64_t cap, Plan& pl, std::vector<Sub>& subs) {
     pl.first_sub = subs.size();
-    auto one = [&](int core, uint64_t off, uint64_t raw) { subs.push_back(Sub{i, core, off, len - off, 0, raw}); };
+    auto one = [&](int core, uint64_t off, uint64_t raw) { subs.push_back(Sub{i, core, off, len - off, 0, raw, 0u}); };
     switch (format) {
         case AURORA_FMT_GCLZ:
             if (match_throw(pl, p, len, "GCLZ", 4)) one(AURORA_FMT_LZ10, 4, kParseHeader);
@@ -142,7 +154,8 @@ void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst,
             const uint32_t type = v & 7, size = v >> 3;
             if (type == 0) {   // OnlySave: ReadExactly + Write
                 if (uint64_t(size) > len - 4) { eos(pl, len); break; }
-                std::memcpy(dst, p + 4, size_t(std::min<uint64_t>(size, cap)));
+                pl.host_src = p + 4;
+                pl.host_copy = std::min<uint64_t>(size, cap);
                 pl.out_len = size;
                 pl.consumed = 4 + uint64_t(size);
                 if (size > cap) pl.status = AURORA_DST_TOO_SMALL;
@@ -183,7 +196,7 @@ void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst,
                 uint64_t start = pos, doff = 0;
                 for (size_t k = 0; k < ends.size(); k++) {
                     const uint64_t avail = start <= len ? len - start : 0;
-                    subs.push_back(Sub{i, AURORA_FMT_LZ10, std::min(start, len), avail, doff, kParseHeader});
+                    subs.push_back(Sub{i, AURORA_FMT_LZ10, std::min(start, len), avail, doff, kParseHeader, 0u});
                     uint64_t csize = 0;
                     const uint8_t* c = p + std::min(start, len);
                     if (avail >= 4 && c[0] == 0x10) {
@@ -200,6 +213,36 @@ void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst,
             }
             break;
         }
+        case AURORA_FMT_ECD: {   // ECD.cs:56-86
+            if (!match_throw(pl, p, len, "ECD", 3)) break;
+            if (len < 16) { eos(pl, len); break; }   // ReadByte() is -1 at the end, the three ReadUInt32 throw
+            const bool compressed = p[3] == 1;
+            const uint64_t plain = be32(p + 4), size = be32(p + 12);
+            if (!compressed) {   // source.CopyTo(destination)
+                const uint64_t rest = len - 16;
+                pl.host_src = p + 16;
+                pl.host_copy = std::min(rest, cap);
+                pl.out_len = rest;
+                pl.consumed = len;
+                if (rest > cap) pl.status = AURORA_DST_TOO_SMALL;
+                break;
+            }
+            // destination.WriteByte((byte)source.ReadByte()) plain times: past the end of the source that is 0xFF; a
+            // fixed-size destination refuses the first byte past its capacity
+            const uint64_t have = std::min(plain, len - 16), fits = std::min(plain, cap);
+            pl.host_src = p + 16;
+            pl.host_copy = std::min(have, fits);
+            pl.host_fill = fits > have ? fits - have : 0;
+            if (plain > cap) {
+                pl.status = AURORA_DST_TOO_SMALL;
+                pl.out_len = cap;
+                pl.consumed = 16 + std::min(cap, len - 16);
+                break;
+            }
+            pl.out_len = plain;
+            subs.push_back(Sub{i, AURORA_FMT_LZSS, 16 + have, len - 16 - have, plain, uint64_t(uint32_t(size - plain)), 0u});
+            break;
+        }
         default: {
             const Family* f = family_of(format);
             if (!f) { pl.status = AURORA_INVALID_ARGUMENT; break; }
@@ -207,6 +250,7 @@ void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst,
             if (len < f->read_len) { eos(pl, len); break; }
             const uint32_t size = f->size_big ? be32(p + f->size_off) : le32(p + f->size_off);
             one(AURORA_FMT_LZSS, std::min<uint64_t>(f->read_len + f->skip_len, len), size);   // Skip() is a seek: it may pass the end
+            if (format == AURORA_FMT_LZ00) subs.back().key = le32(p + 52);
             break;
         }
     }
@@ -215,7 +259,7 @@ void resolve(int format, size_t i, const uint8_t* p, uint64_t len, uint8_t* dst,
 
 }  // namespace
 
-bool is_wrapper_format(int f) { return f >= AURORA_FMT_GCLZ && f <= AURORA_FMT_SDPC; }
+bool is_wrapper_format(int f) { return f >= AURORA_FMT_GCLZ && f <= AURORA_FMT_LZ00; }
 
 int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
                          const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
@@ -234,6 +278,7 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
     else aurora_codec_opts_init(&o);
     if (format == AURORA_FMT_LEVEL5_LZSS) aurora_lz_props_window(&o.lzss, 0x1000, 0xF + 3, 3, 0xFEE, 1);   // LZSS.Lzss0Properties
     if (const Family* f = family_of(format)) family_props(*f, &o.lzss);
+    if (format == AURORA_FMT_ECD) aurora_lz_props_window(&o.lzss, 0x400, 0x42, 3, 0x3BE, 1);   // ECD.cs:18
     for (int key = 0; key < 8; key++) {   // one batch per (core format, headerless or not)
         static const int kCores[4] = {AURORA_FMT_LZ10, AURORA_FMT_LZ11, AURORA_FMT_LZSS, AURORA_FMT_LZO};
         const int core = kCores[key >> 1];
@@ -245,6 +290,8 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
         const size_t m = idx.size();
         std::vector<uint64_t> so(m), sl(m), dof(m), dc(m), raw(m), ol(m), cs(m);
         std::vector<int32_t> st(m);
+        std::vector<uint32_t> keys;
+        if (format == AURORA_FMT_LZ00) keys.resize(m);
         for (size_t j = 0; j < m; j++) {
             const Sub& s = subs[idx[j]];
             so[j] = src_off[s.stream] + s.off;
@@ -253,9 +300,11 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
             dof[j] = dst_off[s.stream] + std::min(s.doff, cap);
             dc[j] = s.doff < cap ? cap - s.doff : 0;
             raw[j] = s.raw;
+            if (!keys.empty()) keys[j] = s.key;
         }
         const int rc = decode_core_batch(ctx, core, &o, m, src_base, so.data(), sl.data(), dst_base, dof.data(), dc.data(),
-                                         want_raw ? raw.data() : nullptr, ol.data(), cs.data(), st.data());
+                                         want_raw ? raw.data() : nullptr, ol.data(), cs.data(), st.data(),
+                                         keys.empty() ? nullptr : keys.data());
         if (rc != AURORA_OK) return rc;
         for (size_t j = 0; j < m; j++) {
             r_out[idx[j]] = ol[j];
@@ -285,7 +334,7 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
                 }
             } else {
                 const size_t q = pl.first_sub;
-                ol = r_out[q];
+                ol = subs[q].doff + r_out[q];   // doff: ECD's plain bytes in front of the LZSS output
                 cs = subs[q].off + r_cons[q];
                 st = r_st[q];
                 // ThrowIfMismatch runs before the destination's overflow is noticed
@@ -293,6 +342,8 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
                 if (format == AURORA_FMT_SDPC && (st == AURORA_OK || st == AURORA_DST_TOO_SMALL) && ol > pl.expect) st = AURORA_SIZE_MISMATCH;
             }
         }
+        if (pl.host_copy) std::memcpy(dst_base + dst_off[i], pl.host_src, size_t(pl.host_copy));
+        if (pl.host_fill) std::memset(dst_base + dst_off[i] + pl.host_copy, 0xFF, size_t(pl.host_fill));
         if (out_len) out_len[i] = ol;
         if (consumed) consumed[i] = cs;
         status[i] = st;
@@ -341,6 +392,13 @@ int wrapped_decoded_size(int format, const uint8_t* p, uint64_t len, uint64_t* o
             if (len < 16) return AURORA_END_OF_STREAM;
             *out_size = le32(p + 12);
             return AURORA_OK;
+        case AURORA_FMT_ECD:   // ECD.cs:43-51: 0 when the compressed size does not fit the stream
+            if (!match_throw(pl, p, len, "ECD", 3)) return pl.status;
+            if (len < 12) return AURORA_END_OF_STREAM;
+            if (uint64_t(be32(p + 8)) + 0x10 > len) return AURORA_OK;
+            if (len < 16) return AURORA_END_OF_STREAM;
+            *out_size = be32(p + 12);
+            return AURORA_OK;
         default: {
             const Family* f = family_of(format);
             if (!f) return AURORA_INVALID_ARGUMENT;
@@ -378,7 +436,8 @@ uint64_t wrapped_encode_bound(int format, uint64_t raw_len, const aurora_codec_o
         case AURORA_FMT_LZON: return 16 + aurora_encode_bound(AURORA_FMT_LZO, raw_len);
         case AURORA_FMT_SDPC: return 8 + aurora_encode_bound(AURORA_FMT_LZO, raw_len);
         case AURORA_FMT_LEVEL5_LZSS: return 16 + aurora_encode_bound(AURORA_FMT_LZSS, raw_len);
-        default: return family_of(format) ? 32 + aurora_encode_bound(AURORA_FMT_LZSS, raw_len) : 0;
+        case AURORA_FMT_ECD: return 16 + std::max<uint64_t>(raw_len, 16 + aurora_encode_bound(AURORA_FMT_LZSS, raw_len));
+        default: return family_of(format) ? 64 + aurora_encode_bound(AURORA_FMT_LZSS, raw_len) : 0;
     }
 }
 
@@ -394,6 +453,10 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
     const uint32_t lz77_type = (has_ext && o.lz77_type) ? o.lz77_type : 0x10;
     const uint64_t chunk = (has_ext && o.lz77_chunk_size) ? o.lz77_chunk_size : 0x1000;
     const uint32_t level5_type = (o.quality == 0) ? 0 : ((has_ext && o.level5_type) ? o.level5_type : 1);
+
+    const uint64_t ecd_plain = (has_ext && o.ecd_plain_size) ? o.ecd_plain_size : 4;   // ECD.PlainSize
+    auto ecd_stored = [&](uint64_t len) { return o.quality == 0 || len <= 0x10; };    // ECD.cs:91
+    const uint32_t lz00_key = has_ext ? o.lz00_key : 0;
 
     int core = AURORA_FMT_LZ10;
     uint64_t head = 4;   // bytes in front of the core's output
@@ -422,6 +485,12 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
             head = 0;   // the 16-byte LZSS header is rewritten in place
             aurora_lz_props_window(&o.lzss, 0x1000, 0xF + 3, 3, 0xFEE, 1);
             break;
+        case AURORA_FMT_ECD:
+            // header (16) + plain bytes, then the body: the LZSS core's own 16-byte header lands on [plain, plain + 16)
+            core = AURORA_FMT_LZSS;
+            head = ecd_plain;
+            aurora_lz_props_window(&o.lzss, 0x400, 0x42, 3, 0x3BE, 1);
+            break;
         default: {
             const Family* f = family_of(format);
             if (!f) return AURORA_INVALID_ARGUMENT;
@@ -444,6 +513,13 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
         out_len[i] = 0;
         const uint64_t len = src_len[i];
         if (format == AURORA_FMT_LEVEL5 && level5_type == 0) continue;   // stored on the host below
+        if (format == AURORA_FMT_ECD) {
+            if (ecd_stored(len)) continue;                                   // stored on the host below
+            if (ecd_plain > len) { status[i] = AURORA_INVALID_ARGUMENT; continue; }   // source.Slice(0, plainSize)
+            if (dst_cap[i] < head) { status[i] = AURORA_DST_TOO_SMALL; continue; }
+            pieces.push_back(Piece{i, ecd_plain, len - ecd_plain, head});
+            continue;
+        }
         if (format == AURORA_FMT_LZ77 && lz77_type == 0xF7 && chunk < len) {
             const uint64_t segs = (len + chunk - 1) / chunk;
             const uint64_t body = 8 + 2 * segs;
@@ -468,7 +544,10 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
         dc[j] = table_at[pc.stream] ? aurora_encode_bound(AURORA_FMT_LZ10, chunk) : dst_cap[pc.stream] - pc.doff;
     }
     if (m) {
-        const int rc = encode_core_batch(ctx, core, &o, m, src_base, so.data(), sl.data(), dst_base, dof.data(), dc.data(), ol.data(), st.data());
+        std::vector<uint32_t> keys;
+        if (format == AURORA_FMT_LZ00) keys.assign(m, lz00_key);   // the body goes under the keystream on the device
+        const int rc = encode_core_batch(ctx, core, &o, m, src_base, so.data(), sl.data(), dst_base, dof.data(), dc.data(), ol.data(),
+                                         st.data(), keys.empty() ? nullptr : keys.data(), 16);
         if (rc != AURORA_OK) return rc;
     }
 
@@ -482,6 +561,33 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
             put_le32(d, uint32_t(len) << 3);
             std::memcpy(d + 4, src_base + src_off[i], size_t(len));
             out_len[i] = 4 + len;
+            continue;
+        }
+        if (format == AURORA_FMT_ECD) {   // ECD.cs:88-121
+            auto store = [&]() {
+                if (dst_cap[i] < 16 + len) { status[i] = AURORA_DST_TOO_SMALL; return; }
+                std::memcpy(d, "ECD", 4);   // identifier + flag 0
+                put_be32(d + 4, 0);
+                put_be32(d + 8, uint32_t(len));
+                put_be32(d + 12, uint32_t(len));
+                std::memcpy(d + 16, src_base + src_off[i], size_t(len));
+                status[i] = AURORA_OK;
+                out_len[i] = 16 + len;
+            };
+            if (ecd_stored(len)) { store(); continue; }
+            if (status[i] != AURORA_OK) continue;
+            const uint64_t clen = ol[j];
+            const int cst = st[j];
+            j++;
+            // compressed size = plain bytes + body; not smaller than the input (or no room for it): stored instead
+            if (cst == AURORA_DST_TOO_SMALL || (cst == AURORA_OK && ecd_plain + (clen - 16) >= len)) { store(); continue; }
+            if (cst != AURORA_OK) { status[i] = cst; continue; }
+            std::memmove(d + 16, src_base + src_off[i], size_t(ecd_plain));   // overwrites the LZSS core's header
+            std::memcpy(d, "ECD\x01", 4);
+            put_be32(d + 4, uint32_t(ecd_plain));
+            put_be32(d + 8, uint32_t(ecd_plain + clen - 16));
+            put_be32(d + 12, uint32_t(len));
+            out_len[i] = 16 + ecd_plain + clen - 16;
             continue;
         }
         if (status[i] != AURORA_OK) continue;
@@ -550,6 +656,12 @@ int wrapped_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
                     case AURORA_FMT_MDB4: put_le32(d + 4, uint32_t(len) + 1); put_le32(d + 8, uint32_t(len)); put_le32(d + 12, uint32_t(32 + blen - 0x10)); break;   // MDB4.cs:78
                     case AURORA_FMT_LZSEGA: put_le32(d, uint32_t(blen)); put_le32(d + 4, uint32_t(len)); break;
                     case AURORA_FMT_GCZ: put_le32(d, uint32_t(len)); break;
+                    case AURORA_FMT_LZ00:   // LZ00.cs:86-110
+                        put_le32(d + 4, uint32_t(64 + blen));
+                        std::memcpy(d + 16, "Temp.dat", 8);   // LZ00.Name default, zero padded to 32 bytes
+                        put_le32(d + 48, uint32_t(len));
+                        put_le32(d + 52, lz00_key);
+                        break;
                 }
                 out_len[i] = hlen + blen;
                 continue;

@@ -93,10 +93,12 @@ namespace AuroraLib.Compression.Cuda
             destination.Write(dst, 0, (int)outLen);
         }
 
+        protected virtual long PeekBytes => 16;   // header bytes GetDecompressedSize looks at
+
         protected uint PeekSize(Stream source)
         {
             long start = source.Position;
-            byte[] head = new byte[Math.Min(16, source.Length - start)];
+            byte[] head = new byte[Math.Min(PeekBytes, source.Length - start)];
             source.ReadExactly(head, 0, head.Length);
             source.Position = start;
             AuroraCodecOpts o;
@@ -264,6 +266,30 @@ namespace AuroraLib.Compression.Cuda
         private readonly Formats.Specialized.SDPC _managed = new Formats.Specialized.SDPC();
         protected override AuroraFormat Format => AuroraFormat.SDPC;
         protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuECD : GpuCodec, IProvidesDecompressedSize   // plain bytes + LZSS(0x400, 0x42, 3, 0x3BE), or stored
+    {
+        private readonly Formats.Specialized.ECD _managed = new Formats.Specialized.ECD();
+        protected override AuroraFormat Format => AuroraFormat.ECD;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public byte PlainSize { get; set; } = 4;
+        protected override void FillOptions(ref AuroraCodecOpts o, CompressionSettings s) { o.EcdPlainSize = PlainSize; }
+        protected override long PeekBytes => long.MaxValue;   // the compressed size is compared with the stream length
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuLZ00 : GpuCodec, IProvidesDecompressedSize   // LZSS (Lzss0) under the StreamTransformer keystream (device pass)
+    {
+        private readonly Formats.Sega.LZ00 _managed = new Formats.Sega.LZ00();
+        protected override AuroraFormat Format => AuroraFormat.LZ00;
+        protected override ICompressionAlgorithm Managed => _managed;
+        /// <summary>Key written by <see cref="Compress"/>; null = the Unix time of the call, like the reference.</summary>
+        public uint? Key { get; set; }
+        protected override void FillOptions(ref AuroraCodecOpts o, CompressionSettings s)
+            => o.Lz00Key = Key ?? (uint)DateTimeOffset.UtcNow.ToUnixTimeSeconds();
+        protected override long PeekBytes => 64;
         public uint GetDecompressedSize(Stream source) => PeekSize(source);
     }
 

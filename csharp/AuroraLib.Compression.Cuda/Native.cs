@@ -18,7 +18,9 @@ namespace AuroraLib.Compression.Cuda
         // wrapper formats (AuroraLib.Compression.Nintendo): a header around one of the cores above
         GCLZ = 15, CXLZ = 16, COMP = 17, LZ_3DS = 18, LZ77 = 19, Level5 = 20, LZOn = 21, Level5LZSS = 22,
         // the LZSS-property family (AuroraLib.Compression.Sega, AuroraLib.Compression-Extended)
-        AKLZ = 23, LZ01 = 24, FCMP = 25, IECP = 26, MDB4 = 27, LZSega = 28, GCZ = 29, SDPC = 30
+        AKLZ = 23, LZ01 = 24, FCMP = 25, IECP = 26, MDB4 = 27, LZSega = 28, GCZ = 29, SDPC = 30,
+        // LZSS wrappers with extra work around the core: stored prefix / stored fallback (ECD), LCG keystream on the device (LZ00)
+        ECD = 31, LZ00 = 32
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -45,7 +47,8 @@ namespace AuroraLib.Compression.Cuda
         public uint Lz77Type;          // LZ77.Type: 0 -> 0x10; 0x11; 0xF7 (ChunkLZ10)
         public uint Lz77ChunkSize;     // LZ77.ChunkSize: 0 -> 0x1000
         public uint Level5Type;        // Level5.Type: 0 -> 1 (LZ10)
-        public fixed uint Reserved[2];
+        public uint Lz00Key;           // LZ00.Compress(source, destination, key, settings)
+        public uint EcdPlainSize;      // ECD.PlainSize: 0 -> 4
     }
 
     internal static unsafe class Native

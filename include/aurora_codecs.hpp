@@ -162,7 +162,7 @@ class SizedAlgorithm : public CompressionAlgorithm {
   public:
     uint32_t GetDecompressedSize(std::istream& source) const {
         std::vector<uint8_t> data = Remaining(source, true);
-        data.resize(std::min<size_t>(data.size(), 16));
+        data.resize(std::min<size_t>(data.size(), PeekBytes()));
         aurora_codec_opts o = Options(nullptr);
         const uint8_t dummy = 0;
         const uint64_t off = 0, len = data.size();
@@ -172,6 +172,9 @@ class SizedAlgorithm : public CompressionAlgorithm {
         ThrowFor(st);
         return uint32_t(size);
     }
+
+  protected:
+    virtual size_t PeekBytes() const { return 16; }   // header bytes GetDecompressedSize looks at
 };
 
 #define AURORA_FORMAT(cls, fmt, name)             \
@@ -347,6 +350,24 @@ class GCZ : public SizedAlgorithm {   // Extended/Konami/GCZ.cs (no identifier: 
 class SDPC : public SizedAlgorithm {   // Extended/Specialized/SDPC.cs: "SDPC" + size + LZO
   public:
     AURORA_FORMAT(SDPC, AURORA_FMT_SDPC, "SDPC")
+};
+class ECD : public SizedAlgorithm {   // Extended/Specialized/ECD.cs: plain bytes + LZSS(0x400, 0x42, 3, 0x3BE), or stored
+  public:
+    AURORA_FORMAT(ECD, AURORA_FMT_ECD, "ECD lzss")
+    uint8_t PlainSize = 4;   // ECD.cs:33
+
+  protected:
+    void Fill(aurora_codec_opts& o, bool) const override { o.ecd_plain_size = PlainSize; }
+    size_t PeekBytes() const override { return SIZE_MAX; }   // GetDecompressedSize compares the compressed size with the stream length
+};
+class LZ00 : public SizedAlgorithm {   // Sega/LZ00.cs: 64-byte header + LZSS (Lzss0) under a per-byte LCG keystream
+  public:
+    AURORA_FORMAT(LZ00, AURORA_FMT_LZ00, "LZ00")
+    uint32_t Key = 0;   // Compress(source, destination, key, settings); the reference's keyless overload takes the Unix time
+
+  protected:
+    void Fill(aurora_codec_opts& o, bool) const override { o.lz00_key = Key; }
+    size_t PeekBytes() const override { return 64; }
 };
 #undef AURORA_FORMAT
 

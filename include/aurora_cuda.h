@@ -79,7 +79,9 @@ typedef enum aurora_format {
     AURORA_FMT_MDB4         = 27, /* Specialized/MDB4.cs: 32-byte header, Default            */
     AURORA_FMT_LZSEGA       = 28, /* Sega/LZSega.cs: compressed size + size, Default         */
     AURORA_FMT_GCZ          = 29, /* Konami/GCZ.cs: size, Lzss0                              */
-    AURORA_FMT_SDPC         = 30  /* -Extended/Specialized/SDPC.cs: "SDPC" + size + LZO      */
+    AURORA_FMT_SDPC         = 30, /* -Extended/Specialized/SDPC.cs: "SDPC" + size + LZO      */
+    AURORA_FMT_ECD          = 31, /* -Extended/Specialized/ECD.cs: "ECD" header + plain bytes + LZSS(0x400, 0x42, 3, 0x3BE) / stored */
+    AURORA_FMT_LZ00         = 32  /* Sega/LZ00.cs: 64-byte header + LZSS (Lzss0) under a per-byte LCG keystream (on the device) */
 } aurora_format;
 
 typedef enum aurora_endian {
@@ -124,7 +126,8 @@ typedef struct aurora_codec_opts {
     uint32_t lz77_type;        /* LZ77.Type: 0 -> 0x10 (LZ10); 0x11 (LZ11); 0xF7 (ChunkLZ10)            */
     uint32_t lz77_chunk_size;  /* LZ77.ChunkSize: 0 -> 0x1000                                           */
     uint32_t level5_type;      /* Level5.Type: 0 -> 1 (LZ10); quality 0 always stores (OnlySave)        */
-    uint32_t reserved[2];
+    uint32_t lz00_key;         /* LZ00 encode: the key written to the header (the reference uses the Unix time)  */
+    uint32_t ecd_plain_size;   /* ECD.PlainSize (encode): 0 -> 4                                        */
 } aurora_codec_opts;
 
 typedef struct aurora_ctx aurora_ctx;

@@ -42,6 +42,8 @@ static CodecOpts to_opts(const aurora_codec_opts* c) {
         o.lz77Type = c->lz77_type ? int(c->lz77_type) : 0x10;
         o.lz77ChunkSize = c->lz77_chunk_size ? int(c->lz77_chunk_size) : 0x1000;
         o.level5Type = c->level5_type ? int(c->level5_type) : 1;
+        o.lz00Key = c->lz00_key;
+        o.ecdPlainSize = c->ecd_plain_size ? int(c->ecd_plain_size) : 4;
     }
     return o;
 }
@@ -172,6 +174,13 @@ bool is_match(int fmt, Src& s, const CodecOpts&) {
             return s.pos + 0x10 < s.len && s.Match(id, 12);
         }
         case FMT_SDPC: return s.pos + 0x10 < s.len && s.Match("SDPC", 4) && s.ReadUInt32() != 0;   // SDPC.cs:31-32
+        case FMT_ECD: {   // ECD.cs:37-38 + GetDecompressedSizeStatic :43-51
+            if (!(s.pos + 0x10 < s.len && s.Match("ECD", 3))) return false;
+            s.pos += 5;
+            if (uint64_t(s.ReadUInt32(Endian::Big)) + 0x10 > uint64_t(s.len)) return false;
+            return s.ReadUInt32(Endian::Big) != 0;
+        }
+        case FMT_LZ00: return s.pos + 0x40 < s.len && s.Match("LZ00", 4);   // LZ00.cs:37-38
         case FMT_LZ01: return s.pos + 0x10 < s.len && s.Match("LZ01", 4);
         case FMT_FCMP: return s.pos + 0x10 < s.len && s.Match("FCMP", 4);
         case FMT_IECP: return s.pos + 0x10 < s.len && s.Match("IECP", 4);

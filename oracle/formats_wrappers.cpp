@@ -10,6 +10,11 @@
 // and the LZSS-property family (a fixed header + LZSS.DecompressHeaderless / CompressHeaderless):
 //   src/AuroraLib.Compression.Sega/Sega/AKLZ.cs:43-56, LZ01.cs:47-82, LZSega.cs:49-67
 //   src/AuroraLib.Compression-Extended/Marvelous/FCMP.cs:43-59, IECP.cs:42-55, Konami/GCZ.cs:40-51, Specialized/MDB4.cs:41-80
+// and two LZSS wrappers with extra work around the core:
+//   src/AuroraLib.Compression-Extended/Specialized/ECD.cs:56-121   "ECD" + flag + plain size + compressed size + size (BE),
+//                                     plain bytes + LZSS(0x400, 0x42, 3, 0x3BE) headerless, or the stored payload
+//   src/AuroraLib.Compression.Sega/Sega/LZ00.cs:50-203             64-byte header, LZSS (Lzss0) body under StreamTransformer:
+//                                     every byte is XORed with a value derived from a 32-bit LCG key that steps per byte
 // The Huffman / RLE / zlib sub-types of LZ77 and Level5 are outside the LZ hot path: NOT_SUPPORTED here and on the GPU.
 #include "oracle_core.hpp"
 
@@ -103,7 +108,116 @@ static void sszl_decode(Src& source, Sink& destination, const CodecOpts& o) {
     lzss_headerless(source, destination, decompressedSize, kLzss0, uint8_t(o.lzssInitialFill));
 }
 
-bool is_wrapper_format(int fmt) { return fmt >= FMT_GCLZ && fmt <= FMT_SDPC; }
+bool is_wrapper_format(int fmt) { return fmt >= FMT_GCLZ && fmt <= FMT_LZ00; }
+
+// ---- ECD (ECD.cs)
+static const LzProps kEcdProps = LzProps::Window(0x400, 0x42, 3, 0x3BE);   // ECD.cs:18
+
+static void ecd_decode(Src& source, Sink& destination) {   // ECD.cs:56-86
+    source.MatchThrow("ECD", 3);
+    bool isCompressed = source.ReadByte() == 1;
+    uint32_t plainSize = source.ReadUInt32(Endian::Big);
+    (void)source.ReadUInt32(Endian::Big);   // compressed size: only traced on mismatch
+    uint32_t decompressedSize = source.ReadUInt32(Endian::Big);
+    if (isCompressed) {
+        // destination.WriteByte((byte)source.ReadByte()): past the end of the source ReadByte() is -1, i.e. 0xFF is written.
+        // A fixed-size destination refuses the first byte past its capacity (NotSupportedException).
+        for (uint32_t i = 0; i < plainSize; i++) {
+            if (destination.pos >= destination.cap && !destination.size_only) fail(DST_TOO_SMALL);
+            destination.WriteByte(uint8_t(source.ReadByte()));
+        }
+        lzss_headerless(source, destination, decompressedSize - plainSize, kEcdProps, 0);
+    } else {
+        // source.CopyTo(destination): everything that is left
+        const int64_t rest = source.len - source.pos;
+        if (rest > 0) {
+            destination.Write(source.p + source.pos, rest);
+            source.pos = source.len;
+        }
+    }
+}
+
+static void ecd_encode(const uint8_t* src, int n, OutBuf& out, const CodecOpts& o) {   // ECD.cs:88-121
+    bool isCompressed = o.settings.Quality != 0 && n > 0x10;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const size_t start = out.size();
+        const int plainSize = isCompressed ? o.ecdPlainSize : 0;
+        if (plainSize > n) fail(INVALID_ARGUMENT);   // source.Slice(0, plainSize): ArgumentOutOfRangeException
+        out.Write(reinterpret_cast<const uint8_t*>("ECD"), 3);
+        out.WriteByte(isCompressed ? 1 : 0);
+        out.WriteU32(uint32_t(plainSize), Endian::Big);
+        out.WriteU32(isCompressed ? 0u : uint32_t(n), Endian::Big);
+        out.WriteU32(uint32_t(n), Endian::Big);
+        if (!isCompressed) {
+            out.Write(src, size_t(n));
+            return;
+        }
+        out.Write(src, size_t(plainSize));
+        CodecOpts oo = o;
+        oo.lzss = kEcdProps;
+        OutBuf core;
+        lzss_encode(src + plainSize, n - plainSize, core, oo);   // "LZSS" header (16 bytes) + body
+        out.Write(core.v.data() + 0x10, core.size() - 0x10);
+        const uint32_t compressedSize = uint32_t(out.size() - start - 0x10);
+        out.PatchU32(start + 8, compressedSize, Endian::Big);
+        if (compressedSize < uint32_t(n)) return;
+        out.v.resize(start);   // ineffective: store (Compress(source, destination, CompressionLevel.NoCompression))
+        isCompressed = false;
+    }
+}
+
+// ---- LZ00 (LZ00.cs)
+// StreamTransformer.GenerateNextKey (LZ00.cs:125-131): the shifts and subtractions multiply by 1103515245
+static inline uint32_t lz00_next_key(uint32_t key) {
+    uint32_t x = (((((((key << 1) + key) << 5) - key) << 5) + key) << 7) - key;
+    x = (x << 6) - x;
+    x = (x << 4) - x;
+    return (x << 2) - x + 12345u;
+}
+static inline uint8_t lz00_transform(uint32_t& key, uint8_t value) {   // LZ00.cs:133-138
+    key = lz00_next_key(key);
+    const uint32_t t = (key >> 16) & 0x7FFF;
+    return uint8_t(value ^ (((t << 8) - t) >> 15));
+}
+
+static void lz00_decode(Src& source, Sink& destination, const CodecOpts& o) {   // LZ00.cs:50-72
+    source.MatchThrow("LZ00", 4);
+    (void)source.ReadUInt32();   // sourceLength: only traced on mismatch
+    source.pos += 8;
+    source.need(32);             // Name = ReadString(32)
+    source.pos += 32;
+    uint32_t decompressedSize = source.ReadUInt32();
+    uint32_t key = source.ReadUInt32();
+    source.pos += 8;
+    // the LZSS decoder reads the transformed stream strictly byte by byte, front to back: transforming the rest of
+    // the source up front is the same thing
+    const int64_t at = std::min(source.pos, source.len);
+    std::vector<uint8_t> plain(source.p + at, source.p + source.len);
+    for (auto& b : plain) b = lz00_transform(key, b);
+    Src inner(plain.data(), int64_t(plain.size()));
+    struct Sync { Src& outer; Src& in; int64_t base; ~Sync() { outer.pos = base + in.pos; } } sync{source, inner, source.pos};
+    lzss_headerless(inner, destination, decompressedSize, kLzss0, uint8_t(o.lzssInitialFill));
+}
+
+static void lz00_encode(const uint8_t* src, int n, OutBuf& out, const CodecOpts& o) {   // LZ00.cs:83-110
+    CodecOpts oo = o;
+    oo.lzss = kLzss0;
+    OutBuf core;
+    lzss_encode(src, n, core, oo);
+    const size_t blen = core.size() - 0x10;
+    out.Write(reinterpret_cast<const uint8_t*>("LZ00"), 4);
+    out.WriteU32(uint32_t(64 + blen));
+    out.WriteU32(0);
+    out.WriteU32(0);
+    uint8_t name[32] = {'T', 'e', 'm', 'p', '.', 'd', 'a', 't'};   // LZ00.Name default, zero padded (WriteString(Name, 32, 0))
+    out.Write(name, 32);
+    out.WriteU32(uint32_t(n));
+    out.WriteU32(o.lz00Key);
+    out.WriteU32(0);
+    out.WriteU32(0);
+    uint32_t key = o.lz00Key;
+    for (size_t i = 0; i < blen; i++) out.WriteByte(lz00_transform(key, core.v[0x10 + i]));
+}
 
 static const uint8_t kAklzMagic[12] = {'A', 'K', 'L', 'Z', '~', '?', 'Q', 'd', '=', 0xCC, 0xCC, 0xCD};   // Identifier("AKLZ~?Qd=ÌÌÍ")
 static const LzProps kLzssDefault = LzProps::Bits(12, 4, 2);   // LZSS.cs:33
@@ -197,6 +311,8 @@ void wrapper_decode(int fmt, Src& s, Sink& d, const CodecOpts& o) {
         case FMT_LZON: lzon_decode(s, d); break;
         case FMT_LEVEL5_LZSS: sszl_decode(s, d, o); break;
         case FMT_SDPC: sdpc_decode(s, d); break;
+        case FMT_ECD: ecd_decode(s, d); break;
+        case FMT_LZ00: lz00_decode(s, d, o); break;
         default:
             if (fmt < FMT_AKLZ || fmt > FMT_GCZ) fail(INVALID_ARGUMENT);
             lzss_family_decode(fmt, s, d, o);
@@ -211,6 +327,8 @@ static void strip_lz1x_header(const OutBuf& core, OutBuf& out) {   // CompressHe
 
 void wrapper_encode(int fmt, const uint8_t* src, int n, OutBuf& out, const CodecOpts& o, int lz77_type, int chunk_size, int level5_type) {
     if (fmt >= FMT_AKLZ && fmt <= FMT_GCZ) return lzss_family_encode(fmt, src, n, out, o);
+    if (fmt == FMT_ECD) return ecd_encode(src, n, out, o);
+    if (fmt == FMT_LZ00) return lz00_encode(src, n, out, o);
     switch (fmt) {
         case FMT_GCLZ: out.Write(reinterpret_cast<const uint8_t*>("GCLZ"), 4); lz10_encode(src, n, out, o); break;
         case FMT_CXLZ: out.Write(reinterpret_cast<const uint8_t*>("CXLZ"), 4); lz10_encode(src, n, out, o); break;
@@ -305,6 +423,13 @@ uint32_t wrapper_decoded_size(int fmt, Src& s) {
         case FMT_LZSEGA: s.pos = 4; return s.ReadUInt32();                                     // LZSega.cs:41-46 (Position = +4)
         case FMT_GCZ: return s.ReadUInt32();                                                   // GCZ.cs:37
         case FMT_SDPC: s.MatchThrow("SDPC", 4); return s.ReadUInt32();                         // SDPC.cs:35-40
+        case FMT_ECD: {                                                                        // ECD.cs:43-51
+            s.MatchThrow("ECD", 3);
+            s.pos += 5;
+            if (uint64_t(s.ReadUInt32(Endian::Big)) + 0x10 > uint64_t(s.len)) return 0;
+            return s.ReadUInt32(Endian::Big);
+        }
+        case FMT_LZ00: s.MatchThrow("LZ00", 4); s.pos += 4 + 8 + 32; return s.ReadUInt32();     // LZ00.cs:41-47
         default: fail(INVALID_ARGUMENT);
     }
     // the prefixed LZ10 / LZ11 streams: type byte + u24 (LZ10.cs:47-57)

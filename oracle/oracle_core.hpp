@@ -35,7 +35,8 @@ enum Format : int {
     FMT_LZ4 = 8, FMT_LZ4_BLOCK = 9, FMT_LZ4_LEGACY = 10, FMT_LZO = 11, FMT_SNAPPY = 12,
     FMT_SNAPPY_BLOCK = 13, FMT_PRS = 14,
     FMT_GCLZ = 15, FMT_CXLZ = 16, FMT_COMP = 17, FMT_LZ_3DS = 18, FMT_LZ77 = 19, FMT_LEVEL5 = 20, FMT_LZON = 21, FMT_LEVEL5_LZSS = 22,
-    FMT_AKLZ = 23, FMT_LZ01 = 24, FMT_FCMP = 25, FMT_IECP = 26, FMT_MDB4 = 27, FMT_LZSEGA = 28, FMT_GCZ = 29, FMT_SDPC = 30
+    FMT_AKLZ = 23, FMT_LZ01 = 24, FMT_FCMP = 25, FMT_IECP = 26, FMT_MDB4 = 27, FMT_LZSEGA = 28, FMT_GCZ = 29, FMT_SDPC = 30,
+    FMT_ECD = 31, FMT_LZ00 = 32
 };
 
 struct Error {
@@ -427,6 +428,8 @@ struct CodecOpts {
     bool lz4Verify = false;
     uint32_t yaz0Alignment = 0;
     int lz77Type = 0x10, lz77ChunkSize = 0x1000, level5Type = 1;   // LZ77.Type / LZ77.ChunkSize / Level5.Type
+    uint32_t lz00Key = 0;       // LZ00.Compress(source, destination, key, settings)
+    int ecdPlainSize = 4;       // ECD.PlainSize
 };
 
 struct DecodeResult {

@@ -69,6 +69,13 @@ int main(int argc, char** argv) {
         bad += round_trip(LZSega(), raw, CompressionSettings::Balanced(), true, false);
         bad += round_trip(GCZ(), raw, CompressionSettings::Balanced(), true, false);
         bad += round_trip(SDPC(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(ECD(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(ECD(), raw, CompressionSettings::Fastest(), true);   // quality 0: stored
+        {
+            LZ00 keyed;
+            keyed.Key = 0x5EEDC0DEu;
+            bad += round_trip(keyed, raw, CompressionSettings::Balanced(), true);
+        }
         // GetDecompressedSize (DataRecognitionTest: 256 zero bytes)
         {
             std::string zeros(0x100, '\0');

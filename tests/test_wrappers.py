@@ -22,6 +22,10 @@ def _opt_sets(fmt):
         return [dict(), dict(lz77_type=0x11), dict(lz77_type=0xF7), dict(lz77_type=0xF7, lz77_chunk_size=0x400)]
     if fmt == A.FMT_LEVEL5:
         return [dict(), dict(quality=0)]
+    if fmt == A.FMT_ECD:
+        return [dict(), dict(quality=0), dict(ecd_plain_size=9)]
+    if fmt == A.FMT_LZ00:
+        return [dict(), dict(lz00_key=0xDEADBEEF)]
     return [dict()]
 
 
@@ -59,6 +63,31 @@ def test_oracle_wrapper_layouts(oracle, bmp):
     assert enc(A.FMT_LZSEGA) == le(len(bd)) + le(n) + bd                                                     # LZSega.cs:57-67
     assert enc(A.FMT_GCZ) == le(n) + b0                                                                      # GCZ.cs:47-51
     assert enc(A.FMT_SDPC) == b"SDPC" + le(n) + lzo                                                          # SDPC.cs:59-64
+    # ECD.cs:88-121: "ECD", flag, BE plain size / compressed size (plain bytes + body) / size, 4 plain bytes, LZSS body of
+    # the rest with LzProperties(0x400, 0x42, 3, 0x3BE); quality 0 and incompressible inputs are stored
+    ecd_body = oracle.encode(A.FMT_LZSS, raw[4:], A.make_opts(quality=8, lzss=A.lz_props_window(0x400, 0x42, 3, 0x3BE)))[0][16:]
+    be = lambda v: v.to_bytes(4, "big")
+    assert enc(A.FMT_ECD) == b"ECD\x01" + be(4) + be(4 + len(ecd_body)) + be(n) + raw[:4] + ecd_body
+    assert enc(A.FMT_ECD, quality=0) == b"ECD\x00" + be(0) + be(n) + be(n) + raw
+    noise = bytes(np.random.default_rng(5).integers(0, 256, 3000, dtype=np.uint8))
+    assert oracle.encode(A.FMT_ECD, noise, q8)[0] == b"ECD\x00" + be(0) + be(3000) + be(3000) + noise
+    assert oracle.encode(A.FMT_ECD, raw[:16], q8)[0] == b"ECD\x00" + be(0) + be(16) + be(16) + raw[:16]   # Length > 0x10 compresses
+    # LZ00.cs:83-139: 64-byte header, then the Lzss0 body XORed byte by byte; the key steps BEFORE every byte through the
+    # shift / subtract ladder of GenerateNextKey, restated here literally
+    def lz00_stream(key, count):
+        out, M = bytearray(), 0xFFFFFFFF
+        for _ in range(count):
+            x = ((((((((key << 1) + key) << 5) - key) << 5) + key) << 7) - key) & M
+            x = ((x << 6) - x) & M
+            x = ((x << 4) - x) & M
+            key = ((x << 2) - x + 12345) & M
+            t = (key >> 16) & 0x7FFF
+            out.append((((t << 8) - t) >> 15) & 0xFF)
+        return bytes(out)
+    key = 0x5EEDC0DE
+    z = enc(A.FMT_LZ00, lz00_key=key)
+    assert z[:64] == b"LZ00" + le(64 + len(b0)) + bytes(8) + b"Temp.dat" + bytes(24) + le(n) + le(key) + bytes(8)
+    assert z[64:] == bytes(a ^ b for a, b in zip(b0, lz00_stream(key, len(b0))))
     # ChunkLZ10 (LZ77.cs:75-100): 0xF7 | size << 8, u16 end offsets, independent LZ10 streams of ChunkSize bytes
     ch = enc(A.FMT_LZ77, lz77_type=0xF7)
     nseg = (len(raw) + 0xFFF) // 0x1000
@@ -145,6 +174,18 @@ def test_gpu_wrapper_decode_parity(codec, oracle, fmt):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fmt", [A.FMT_LEVEL5, A.FMT_ECD], ids=fmt_id)
+def test_gpu_wrapper_mixed_stored_and_compressed(codec, oracle, fmt):
+    """Stored payloads / ECD's plain prefix are written by the host; they must survive the core batch's device-to-host copy
+    of the destination span when stored and compressed streams alternate in ONE batch."""
+    rng = np.random.default_rng(8500 + fmt)
+    raws = [synth(rng, int(rng.choice([17, 100, 3000, 20000])), i % 5) for i in range(40)]
+    comps = [oracle.encode(fmt, r, A.make_opts(quality=0 if i % 2 else 8))[0] for i, r in enumerate(raws)]
+    outs, status = _compare(codec, oracle, fmt, comps, [len(r) for r in raws], what="mixed")
+    assert (status == 0).all() and all(o == r for o, r in zip(outs, raws))
+
+
+@pytest.mark.gpu
 def test_gpu_wrapper_unsupported_subtypes(codec, oracle):
     blobs = [b"LZ77" + bytes([0x28, 4, 0, 0]) + bytes(16), b"LZ77" + bytes([0x30, 4, 0, 0]) + bytes(16), b"LZ77" + bytes([0x42, 4, 0, 0]) + bytes(16)]
     _compare(codec, oracle, A.FMT_LZ77, blobs, [64] * 3, what="lz77 subtypes")
@@ -176,10 +217,10 @@ def test_gpu_wrapper_encode_parity(codec, oracle, fmt):
 @pytest.mark.gpu
 def test_gpu_wrapper_mirror_classes(bmp):
     """The reference-facing classes: Compress / Decompress / GetDecompressedSize / IsMatch over streams."""
-    from auroralib.compression_b200 import (AKLZ, COMP, CXLZ, FCMP, GCLZ, GCZ, IECP, LZ01, LZ77, LZ_3DS, MDB4, CompressionSettings,
+    from auroralib.compression_b200 import (AKLZ, COMP, CXLZ, ECD, FCMP, GCLZ, GCZ, IECP, LZ00, LZ01, LZ77, LZ_3DS, MDB4, CompressionSettings,
                                             InvalidIdentifierException, Level5, Level5LZSS, LZOn, LZSega, SDPC)
     raw = bmp[:30000]
-    for cls in (GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC):
+    for cls in (GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC, ECD, LZ00):
         alg = cls()
         blob = alg.Compress(raw, settings=CompressionSettings(8)).getvalue()
         src = io.BytesIO(b"pad" + blob + b"tail")
@@ -192,6 +233,14 @@ def test_gpu_wrapper_mirror_classes(bmp):
             assert alg.IsMatch(io.BytesIO(blob)) and not alg.IsMatch(io.BytesIO(b"nope" + blob[4:]))
             with pytest.raises(InvalidIdentifierException):
                 alg.Decompress(io.BytesIO(b"nope" + blob[4:]), io.BytesIO())
+    # LZ00.Compress(source, destination, key, settings) and ECD.PlainSize
+    z = LZ00().Compress(raw, key=0x1234, settings=CompressionSettings(8)).getvalue()
+    assert z[52:56] == (0x1234).to_bytes(4, "little") and LZ00().Decompress(io.BytesIO(z)).getvalue() == raw
+    e = ECD()
+    e.PlainSize = 11
+    z = e.Compress(raw, settings=CompressionSettings(8)).getvalue()
+    assert z[4:8] == (11).to_bytes(4, "big") and z[16:27] == raw[:11] and ECD().Decompress(io.BytesIO(z)).getvalue() == raw
+    assert ECD().Decompress(io.BytesIO(ECD().Compress(raw, settings=CompressionSettings(0)).getvalue())).getvalue() == raw
     chunked = LZ77()
     chunked.Type, chunked.ChunkSize = LZ77.CHUNK_LZ10_TYPE, 0x800
     blob = chunked.Compress(raw, settings=CompressionSettings(8)).getvalue()
