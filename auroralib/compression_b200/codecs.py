@@ -436,6 +436,13 @@ class SDPC(_SizedCodec):
     FORMAT, Name = _abi.FMT_SDPC, "SDPC"
 
 
+class LZHudson(_SizedCodec):
+    """HudsonSoft/LZHudson.cs: u32 BE size + Yay0 tokens under 4-byte big-endian flag words (a core format: the kernel decodes
+    it directly, 32 tokens = one flag word per warp iteration).  IsMatch is the stream part of LZHudson.cs:31-32 (more than 8
+    bytes, a non-zero first word); the reference also wants the ".lzHudson" extension when a file name is given."""
+    FORMAT, Name = _abi.FMT_LZHUDSON, "LZHudson"
+
+
 class _WholeHeaderPeek:
     # GetDecompressedSize looks past the first 16 bytes (LZ00: size at 48) or at the stream length (ECD)
     def GetDecompressedSize(self, source):
@@ -487,4 +494,4 @@ class LZ00(_WholeHeaderPeek, _SizedCodec):
 
 
 WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC, ECD, LZ00]
-ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS] + WRAPPERS
+ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS, LZHudson] + WRAPPERS

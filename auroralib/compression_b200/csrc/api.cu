@@ -97,7 +97,7 @@ thread_local std::string g_init_error;
 
 bool is_flaglz(int f) {
     return f == AURORA_FMT_YAZ0 || f == AURORA_FMT_YAZ1 || f == AURORA_FMT_YAY0 || f == AURORA_FMT_MIO0 ||
-           f == AURORA_FMT_LZ10 || f == AURORA_FMT_LZ11 || f == AURORA_FMT_LZSS;
+           f == AURORA_FMT_LZ10 || f == AURORA_FMT_LZ11 || f == AURORA_FMT_LZSS || f == AURORA_FMT_LZHUDSON;
 }
 bool is_bytelz(int f) {
     return f == AURORA_FMT_LZ4 || f == AURORA_FMT_LZ4_BLOCK || f == AURORA_FMT_LZ4_LEGACY || f == AURORA_FMT_LZO ||
@@ -144,8 +144,11 @@ struct Range {
     size_t begin, end;
 };
 
-// contiguous ranges of streams with balanced byte counts (streams are independent: SURVEY.md §8e)
-std::vector<Range> shard(size_t n, int g, const uint64_t* a, const uint64_t* b) {
+// contiguous ranges of streams with balanced byte counts (streams are independent: SURVEY.md §8e).
+// doff (optional): destination offsets — neighbours whose destination windows [doff, doff + b) overlap (the chunks of one
+// ChunkLZ10 file) are never cut apart: every device copies its own destination span back to the host, so overlapping
+// windows on two devices would let one device's copy overwrite bytes the other one decoded.
+std::vector<Range> shard(size_t n, int g, const uint64_t* a, const uint64_t* b, const uint64_t* doff = nullptr) {
     std::vector<Range> r;
     if (g <= 1 || n < size_t(g) * 2) {
         r.push_back(Range{0, n});
@@ -160,6 +163,10 @@ std::vector<Range> shard(size_t n, int g, const uint64_t* a, const uint64_t* b) 
         long double target = total * (k + 1) / g;
         while (i < n && (acc < target || k == g - 1)) {
             acc += (long double)(a[i] + (b ? b[i] : 0) + 64);
+            i++;
+        }
+        while (doff && b && i < n && i > start && doff[i] < doff[i - 1] + b[i - 1]) {
+            acc += (long double)(a[i] + b[i] + 64);
             i++;
         }
         r.push_back(Range{start, i});
@@ -448,6 +455,7 @@ int fill_encode_params(EncodeParams& p, int format, const aurora_codec_opts* o) 
         }
         case AURORA_FMT_YAZ0:
         case AURORA_FMT_YAZ1:
+        case AURORA_FMT_LZHUDSON:   // LZHudson.cs:24
         case AURORA_FMT_YAY0: aurora_lz_props_window(&lz, 0x1000, 0xff + 0x12, 3, 0, 1); break;
         case AURORA_FMT_MIO0: aurora_lz_props_window(&lz, 0x1000, 18, 3, 0, 1); break;
         case AURORA_FMT_LZSS:
@@ -733,7 +741,10 @@ int aurora_decoded_size_batch(aurora_ctx* ctx, int format, const aurora_codec_op
             const uint64_t len = src_len[i];
             int st = AURORA_OK;
             uint64_t sz = 0;
-            if (format == AURORA_FMT_LZ10 || format == AURORA_FMT_LZ11) {
+            if (format == AURORA_FMT_LZHUDSON) {   // LZHudson.cs:37-38
+                if (len < 4) st = AURORA_END_OF_STREAM;
+                else sz = be32(p);
+            } else if (format == AURORA_FMT_LZ10 || format == AURORA_FMT_LZ11) {
                 const uint8_t id = format == AURORA_FMT_LZ10 ? 0x10 : 0x11;
                 if (len < 1) st = AURORA_END_OF_STREAM;
                 else if (p[0] != id) st = AURORA_INVALID_IDENTIFIER;
@@ -894,6 +905,7 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
         switch (format) {
             case AURORA_FMT_YAZ0: m = magic16(i, "Yaz0", 4); break;
             case AURORA_FMT_YAZ1: m = magic16(i, "Yaz1", 4); break;
+            case AURORA_FMT_LZHUDSON: m = 0x8 < src_len[i] && (p[0] | p[1] | p[2] | p[3]) != 0; break;   // LZHudson.cs:31-32, no file name
             case AURORA_FMT_YAY0: m = magic16(i, "Yay0", 4); break;
             case AURORA_FMT_MIO0: m = magic16(i, "MIO0", 4); break;
             case AURORA_FMT_LZSS: m = magic16(i, "LZSS", 4); break;
@@ -1029,7 +1041,7 @@ int decode_core_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts
                       const uint64_t* dst_cap, const uint64_t* raw_size, uint64_t* out_len, uint64_t* consumed, int32_t* status,
                       const uint32_t* xor_key) {
     if (n == 0) return AURORA_OK;
-    const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, dst_cap);
+    const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, dst_cap, dst_off);
     return for_each_shard(ctx, ranges, [&](DeviceCtx* d, Range r) {
         return decode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
                             out_len, consumed, status, 0, raw_size, xor_key);

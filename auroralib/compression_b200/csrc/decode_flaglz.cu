@@ -43,14 +43,14 @@ constexpr int kSubMaxG = 2304;       // G32: output bytes per iteration (>= the 
 constexpr int kPairSpan = 4096;      // parser/replayer pipeline: two consecutive iterations in flight, window + both + drain slack <= ring
 
 
-enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5 };
+enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5, K_HUDSON = 6 };
 
 // Shared memory of one stream slot (the launcher adds 8 KiB of alignment slack for the rings):
 //   ring 8 KiB | staged sub-streams | match queue x2 (+ read slack) | group offsets | mailboxes x2 | stream descriptor | mbarriers
 template <int K>
 struct Traits {
     static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : 1;
-    static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0) ? 273 : (K == K_LZSS) ? 258 : 65808;
+    static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0 || K == K_HUDSON) ? 273 : (K == K_LZSS) ? 258 : 65808;
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
     static constexpr int kQueueLen = kStreams == 3 ? kQueueSplit : kQueue;
     static constexpr int kQueueBytes = 2 * kQueueLen * 8 + 32;
@@ -240,6 +240,39 @@ __device__ BodyResult decode_body(InStream* in, OutState& out, const uint32_t sl
                 tok_end = myoff + mysz;
                 bad = mypg >= slen || tok_end > slen;
             }
+        } else if constexpr (K == K_HUDSON) {
+            // LZHudson.cs:54-55: FlagReader(source, Endian.Big, 4, Endian.Big) — one 4-byte big-endian flag word governs exactly
+            // the 32 tokens of this iteration (bit 1 = literal, MSB first); tokens as Yaz0 (2 bytes, 3 when the high nibble
+            // of the first byte is 0).  A token's size depends on its own first byte, so the 32 token starts are one uniform
+            // walk over a ballot mask of "high nibble == 0" for the 96 bytes behind the flag word.
+            in[0].ensure(cur);
+            const uint32_t fw = (in[0].at(cur) << 24) | (in[0].at(cur + 1) << 16) | (in[0].at(cur + 2) << 8) | in[0].at(cur + 3);
+            const uint32_t t0 = cur + 4;
+            const uint64_t elo = uint64_t(__ballot_sync(kFull, (in[0].at(t0 + lane) >> 4) == 0)) |
+                                 (uint64_t(__ballot_sync(kFull, (in[0].at(t0 + 32 + lane) >> 4) == 0)) << 32);
+            const uint32_t ehi = __ballot_sync(kFull, (in[0].at(t0 + 64 + lane) >> 4) == 0);
+            uint32_t off = 0, myoff = 0, mysz = 1;
+#pragma unroll 4
+            for (int i = 0; i < 32; i++) {
+                const bool is_lit = ((fw >> (31 - i)) & 1u) != 0;
+                const uint32_t eb = off < 64 ? uint32_t(elo >> off) & 1u : (ehi >> (off - 64)) & 1u;
+                const uint32_t sz = is_lit ? 1u : 2u + eb;
+                if (lane == uint32_t(i)) {
+                    myoff = t0 + off;
+                    mysz = sz;
+                }
+                off += sz;
+            }
+            next_cur = t0 + off;
+            ism = mysz >= 2;
+            const uint32_t b1 = in[0].at(myoff), b2 = in[0].at(myoff + 1), b3 = in[0].at(myoff + 2);
+            lit = b1;
+            dist = (((b1 & 0xF) << 8) | b2) + 1;
+            const bool have_ext = myoff + 2 < slen;   // Stream.ReadByte() == -1 at EOF -> 0x11 (Yay0.cs:131)
+            len = !ism ? 1 : (mysz == 3 ? (have_ext ? b3 + 0x12 : 0x11) : (b1 >> 4) + 2);
+            tok_end = myoff + (ism ? 2 : 1);
+            bad = cur + 4 > slen || tok_end > slen;   // the flag word is a ReadInt32: all four bytes or EndOfStream
+            if (mysz == 3 && have_ext) tok_end = myoff + 3;
         } else {   // K_MIO0 / K_YAY0
             in[0].ensure(cur, 8);
             in[1].ensure(ccur, 72);
@@ -1263,6 +1296,9 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                 else { size = le32(4); body_off = 8; }
             }
         }
+    } else if (K == K_HUDSON) {   // LZHudson.cs:41-45: u32 big-endian size, no identifier
+        if (slen < 4) { status = AURORA_END_OF_STREAM; consumed = slen; }
+        else { size = be32(0); body_off = 4; }
     } else if (K == K_YAZ0 || K == K_LZSS || K == K_MIO0 || K == K_YAY0) {
         uint32_t magic;
         if (K == K_YAZ0) magic = P.format == AURORA_FMT_YAZ1 ? 0x59617A31u : 0x59617A30u;   // "Yaz1" / "Yaz0"
@@ -1321,15 +1357,18 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                     in[0].begin(P.src_base, P.src_limit, src);
                 }
                 BodyResult r;
-                bool g32 = true;
+                bool g32 = K != K_HUDSON;
                 if (K == K_LZSS) g32 = 8u * (((1u << P.lzss.length_bits) - 1u) + uint32_t(P.lzss.min_length)) <= uint32_t(kSubMaxG);
                 if (g32) {
+                    if constexpr (K != K_HUDSON) {
                     sink.begin(ring, fill, dst, limit);
                     if constexpr (K == K_MIO0 || K == K_YAY0) r = decode_body_g32_split<K>(in, sink, slen, size, comp_off, lit_off);
                     else if constexpr (K == K_YAZ0 || K == K_LZ11) r = decode_body_g32_var<K>(in, sink, gaddr, slen, size, body_off);
                     else r = decode_body_g32<K>(in, sink, gaddr, slen, size, body_off, P.lzss);
-                } else if constexpr (K == K_LZSS) {
-                    // LzProperties whose largest group exceeds an iteration: the token-per-lane core, run by this warp alone
+                    }
+                } else if constexpr (K == K_LZSS || K == K_HUDSON) {
+                    // LzProperties whose largest group exceeds an iteration, and LZHudson (a 32-bit flag word is exactly one
+                    // 32-token iteration): the token-per-lane core, run by this warp alone
                     sink.wait_idle();
                     ring_prefill(ring, fill);
                     OutState out;
@@ -1452,6 +1491,7 @@ cudaError_t launch_decode_flaglz(const DecodeParams& p, int sm_count, cudaStream
         case AURORA_FMT_LZSS: return launch<K_LZSS>(p, sm_count, st);
         case AURORA_FMT_MIO0: return launch<K_MIO0>(p, sm_count, st);
         case AURORA_FMT_YAY0: return launch<K_YAY0>(p, sm_count, st);
+        case AURORA_FMT_LZHUDSON: return launch<K_HUDSON>(p, sm_count, st);
         default: return cudaErrorInvalidValue;
     }
 }

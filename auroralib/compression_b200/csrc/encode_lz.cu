@@ -79,6 +79,10 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
                 put_u32(w, id, false);
                 put_u32(w, uint32_t(n), false);
             }
+        } else if (K == E_YAZ0 && P.format == AURORA_FMT_LZHUDSON) {
+            // LZHudson.cs:48-59: u32 BE size, then Yay0.CompressHeaderless under FlagWriter(destination, Endian.Big, 4, Endian.Big)
+            put_u32(w, uint32_t(n), true);
+            w.flag_bytes = 4;
         } else if (K == E_YAZ0) {
             const char* magic = P.format == AURORA_FMT_YAZ1 ? "Yaz1" : "Yaz0";
             for (int i = 0; i < 4; i++) w.raw_byte(uint8_t(magic[i]));
@@ -253,7 +257,8 @@ cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st) 
         case AURORA_FMT_LZ10: return launch<E_LZ10>(p, warps, st);
         case AURORA_FMT_LZ11: return launch<E_LZ11>(p, warps, st);
         case AURORA_FMT_YAZ0:
-        case AURORA_FMT_YAZ1: return launch<E_YAZ0>(p, warps, st);
+        case AURORA_FMT_YAZ1:
+        case AURORA_FMT_LZHUDSON: return launch<E_YAZ0>(p, warps, st);   // the same tokens under 4-byte flag words
         case AURORA_FMT_LZSS: return launch<E_LZSS>(p, warps, st);
         case AURORA_FMT_MIO0: return launch<E_MIO0>(p, warps, st);
         case AURORA_FMT_YAY0: return launch<E_YAY0>(p, warps, st);

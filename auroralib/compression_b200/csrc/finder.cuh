@@ -149,6 +149,7 @@ struct Writer {
     uint64_t pos;
     int64_t flag_pos;
     uint32_t flag_val, bits;
+    uint32_t flag_bytes = 1;   // FlagWriter flag size: 1, or 4 (big-endian word: LZHudson)
     bool msb_first, overflow;
     __device__ __forceinline__ void put(uint64_t at, uint32_t b) {
         if (at < cap) {
@@ -160,10 +161,19 @@ struct Writer {
     __device__ __forceinline__ void raw_byte(uint32_t b) { put(pos++, b); }
     __device__ __forceinline__ void group() {
         if (flag_pos < 0) {
-            flag_pos = int64_t(pos++);
+            flag_pos = int64_t(pos);
+            pos += flag_bytes;
             flag_val = 0;
             bits = 0;
         }
+    }
+    __device__ __forceinline__ void put_flag() {
+        if (flag_bytes == 1) {
+            put(uint64_t(flag_pos), flag_val);
+        } else {
+            for (uint32_t i = 0; i < flag_bytes; i++) put(uint64_t(flag_pos) + i, (flag_val >> (8 * (flag_bytes - 1 - i))) & 0xFF);
+        }
+        flag_pos = -1;
     }
     __device__ __forceinline__ void byte(uint32_t b) {
         group();
@@ -171,15 +181,11 @@ struct Writer {
     }
     __device__ __forceinline__ void bit(bool v) {
         group();
-        if (v) flag_val |= msb_first ? (0x80u >> bits) : (1u << bits);
-        if (++bits == 8) {
-            put(uint64_t(flag_pos), flag_val);
-            flag_pos = -1;
-        }
+        if (v) flag_val |= msb_first ? ((0x80u << (8 * (flag_bytes - 1))) >> bits) : (1u << bits);
+        if (++bits == 8 * flag_bytes) put_flag();
     }
     __device__ __forceinline__ void dispose() {
-        if (flag_pos >= 0) put(uint64_t(flag_pos), flag_val);
-        flag_pos = -1;
+        if (flag_pos >= 0) put_flag();
     }
 };
 

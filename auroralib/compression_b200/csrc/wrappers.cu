@@ -299,6 +299,8 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
             const uint64_t cap = dst_cap[s.stream];
             dof[j] = dst_off[s.stream] + std::min(s.doff, cap);
             dc[j] = s.doff < cap ? cap - s.doff : 0;
+            // (ChunkLZ10: the capacity windows of one file's chunks overlap — every chunk may write up to the end of the
+            //  file's slot, like the reference's single destination stream; decode_core_batch keeps such streams on one device)
             raw[j] = s.raw;
             if (!keys.empty()) keys[j] = s.key;
         }
@@ -310,6 +312,40 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
             r_out[idx[j]] = ol[j];
             r_cons[idx[j]] = cs[j];
             r_st[idx[j]] = st[j];
+        }
+    }
+
+    // ChunkLZ10 on corrupt input: the reference decodes the chunks one after the other and stops at the first failure, so
+    // the bytes a failing chunk writes past its own size (an overshooting last match: SIZE_MISMATCH) are the last thing
+    // its destination sees.  Here all chunks ran at once and the next chunk wrote the same bytes: decode the failing
+    // chunks once more, alone, so that their bytes win deterministically.
+    if (format == AURORA_FMT_LZ77) {
+        std::vector<size_t> redo;
+        for (size_t i = 0; i < n; i++) {
+            const Plan& pl = plans[i];
+            if (pl.status != AURORA_OK || !pl.end_consumed) continue;
+            for (size_t k = 0; k < pl.n_sub; k++) {
+                const size_t q = pl.first_sub + k;
+                if (r_st[q] == AURORA_OK) continue;
+                if (r_st[q] == AURORA_SIZE_MISMATCH && k + 1 < pl.n_sub) redo.push_back(q);
+                break;
+            }
+        }
+        if (!redo.empty()) {
+            const size_t m = redo.size();
+            std::vector<uint64_t> so(m), sl(m), dof(m), dc(m), ol(m), cs(m);
+            std::vector<int32_t> st(m);
+            for (size_t j = 0; j < m; j++) {
+                const Sub& s = subs[redo[j]];
+                const uint64_t cap = dst_cap[s.stream];
+                so[j] = src_off[s.stream] + s.off;
+                sl[j] = s.len;
+                dof[j] = dst_off[s.stream] + std::min(s.doff, cap);
+                dc[j] = s.doff < cap ? cap - s.doff : 0;
+            }
+            const int rc = decode_core_batch(ctx, AURORA_FMT_LZ10, &o, m, src_base, so.data(), sl.data(), dst_base, dof.data(), dc.data(),
+                                             nullptr, ol.data(), cs.data(), st.data());
+            if (rc != AURORA_OK) return rc;
         }
     }
 

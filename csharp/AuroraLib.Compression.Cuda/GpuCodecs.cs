@@ -269,6 +269,14 @@ namespace AuroraLib.Compression.Cuda
         public uint GetDecompressedSize(Stream source) => PeekSize(source);
     }
 
+    public sealed class GpuLZHudson : GpuCodec, IProvidesDecompressedSize   // u32 BE size + Yay0 tokens under 4-byte flag words
+    {
+        private readonly Formats.HudsonSoft.LZHudson _managed = new Formats.HudsonSoft.LZHudson();
+        protected override AuroraFormat Format => AuroraFormat.LZHudson;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
     public sealed class GpuECD : GpuCodec, IProvidesDecompressedSize   // plain bytes + LZSS(0x400, 0x42, 3, 0x3BE), or stored
     {
         private readonly Formats.Specialized.ECD _managed = new Formats.Specialized.ECD();

@@ -20,7 +20,9 @@ namespace AuroraLib.Compression.Cuda
         // the LZSS-property family (AuroraLib.Compression.Sega, AuroraLib.Compression-Extended)
         AKLZ = 23, LZ01 = 24, FCMP = 25, IECP = 26, MDB4 = 27, LZSega = 28, GCZ = 29, SDPC = 30,
         // LZSS wrappers with extra work around the core: stored prefix / stored fallback (ECD), LCG keystream on the device (LZ00)
-        ECD = 31, LZ00 = 32
+        ECD = 31, LZ00 = 32,
+        // a core format: Yay0 tokens under 32-bit big-endian flag words (HudsonSoft/LZHudson.cs)
+        LZHudson = 33
     }
 
     [StructLayout(LayoutKind.Sequential)]

@@ -351,6 +351,10 @@ class SDPC : public SizedAlgorithm {   // Extended/Specialized/SDPC.cs: "SDPC" +
   public:
     AURORA_FORMAT(SDPC, AURORA_FMT_SDPC, "SDPC")
 };
+class LZHudson : public SizedAlgorithm {   // HudsonSoft/LZHudson.cs: u32 BE size + Yay0 tokens under 4-byte big-endian flag words
+  public:
+    AURORA_FORMAT(LZHudson, AURORA_FMT_LZHUDSON, "LZHudson")
+};
 class ECD : public SizedAlgorithm {   // Extended/Specialized/ECD.cs: plain bytes + LZSS(0x400, 0x42, 3, 0x3BE), or stored
   public:
     AURORA_FORMAT(ECD, AURORA_FMT_ECD, "ECD lzss")

@@ -81,7 +81,9 @@ typedef enum aurora_format {
     AURORA_FMT_GCZ          = 29, /* Konami/GCZ.cs: size, Lzss0                              */
     AURORA_FMT_SDPC         = 30, /* -Extended/Specialized/SDPC.cs: "SDPC" + size + LZO      */
     AURORA_FMT_ECD          = 31, /* -Extended/Specialized/ECD.cs: "ECD" header + plain bytes + LZSS(0x400, 0x42, 3, 0x3BE) / stored */
-    AURORA_FMT_LZ00         = 32  /* Sega/LZ00.cs: 64-byte header + LZSS (Lzss0) under a per-byte LCG keystream (on the device) */
+    AURORA_FMT_LZ00         = 32, /* Sega/LZ00.cs: 64-byte header + LZSS (Lzss0) under a per-byte LCG keystream (on the device) */
+    /* a core format (kernel path, device entry points included): Yay0 tokens under 32-bit big-endian flag words */
+    AURORA_FMT_LZHUDSON     = 33  /* HudsonSoft/LZHudson.cs: u32 BE size + interleaved 4-byte flag words / tokens */
 } aurora_format;
 
 typedef enum aurora_endian {

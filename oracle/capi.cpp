@@ -69,6 +69,7 @@ DecodeResult decode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t
             case FMT_SNAPPY: snappy_decode(s, d); break;
             case FMT_SNAPPY_BLOCK: snappy_block_decode(s, d); break;
             case FMT_PRS: prs_decode(s, d); break;
+            case FMT_LZHUDSON: lzhudson_decode(s, d); break;
             default:
                 if (!is_wrapper_format(fmt)) fail(INVALID_ARGUMENT);
                 wrapper_decode(fmt, s, d, o);
@@ -102,6 +103,7 @@ int encode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t n64, std
             case FMT_SNAPPY: snappy_encode(src, n, b, o); break;
             case FMT_SNAPPY_BLOCK: snappy_block_encode(src, n, b, o); break;
             case FMT_PRS: prs_encode(src, n, b, o); break;
+            case FMT_LZHUDSON: lzhudson_encode(src, n, b, o); break;
             default:
                 if (!is_wrapper_format(fmt)) return INVALID_ARGUMENT;
                 wrapper_encode(fmt, src, n, b, o, o.lz77Type, o.lz77ChunkSize, o.level5Type);
@@ -123,6 +125,7 @@ uint32_t decoded_size(int fmt, Src& s, const CodecOpts& o) {
         case FMT_LZSS:   // LZSS.cs:45-50
             s.MatchThrow("LZSS", 4);
             return s.ReadUInt32(Endian::Big);
+        case FMT_LZHUDSON: return s.ReadUInt32(Endian::Big);   // LZHudson.cs:37-38
     }
     if (is_wrapper_format(fmt)) return wrapper_decoded_size(fmt, s);
     fail(NOT_SUPPORTED);
@@ -156,6 +159,7 @@ bool is_match(int fmt, Src& s, const CodecOpts&) {
             return (flag > 11 && flag < 0x20) || (flag != -1 && flag < 0x10);
         }
         case FMT_PRS: return s.pos + 0x4 < s.len && prs_get_byte_order(s) >= 0;   // PRS.cs:31-32
+        case FMT_LZHUDSON: return s.pos + 0x8 < s.len && s.ReadUInt32() != 0;     // LZHudson.cs:31-32 (no file name given)
         // wrapper formats (GCLZ.cs:30-31, CXLZ.cs:31-32, COMP.cs:30-31, 3DS-LZ.cs:29-30, LZ77.cs:46-47, LZOn.cs:29-30,
         // Level5LZSS.cs:29-30); Level5.IsMatch needs zlib and the file name: not restated
         case FMT_GCLZ: return s.pos + 0x8 < s.len && s.Match("GCLZ", 4) && s.pos + 0x8 < s.len && lz1x_validate(s, false);

@@ -229,6 +229,22 @@ void yaz0_encode(const uint8_t* source, int n, OutBuf& destination, const CodecO
     flag.Dispose();
 }
 
+// ------------------------------------------------------------------ LZHudson
+// AuroraLib.Compression.Nintendo/HudsonSoft/LZHudson.cs:41-59: u32 BE size, then the Yay0 token core with all three
+// sub-streams = the source and a FlagReader over 4-byte big-endian flag words, MSB first.
+void lzhudson_decode(Src& source, Sink& destination) {
+    uint32_t decompressedSize = source.ReadUInt32(Endian::Big);
+    FlagReader flag(&source, Endian::Big, 4, Endian::Big);
+    yay0_core(flag, source, source, destination, decompressedSize);
+}
+
+void lzhudson_encode(const uint8_t* source, int n, OutBuf& destination, const CodecOpts& o) {
+    destination.WriteU32(uint32_t(n), Endian::Big);
+    FlagWriter flag(&destination, Endian::Big, 4, Endian::Big);
+    yay0_core_encode(source, n, flag.Buffer, flag.Buffer, flag, o.settings);
+    flag.Dispose();
+}
+
 // ------------------------------------------------------------------ DetectByteOrder<uint>(3)
 // AuroraLib.Core 1.7.0 (not in the tree): "parity unpinned".  Restated as the plausibility rule of
 // an order is plausible when 0x10 <= compOff <= litOff <= total length.

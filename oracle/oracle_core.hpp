@@ -36,7 +36,8 @@ enum Format : int {
     FMT_SNAPPY_BLOCK = 13, FMT_PRS = 14,
     FMT_GCLZ = 15, FMT_CXLZ = 16, FMT_COMP = 17, FMT_LZ_3DS = 18, FMT_LZ77 = 19, FMT_LEVEL5 = 20, FMT_LZON = 21, FMT_LEVEL5_LZSS = 22,
     FMT_AKLZ = 23, FMT_LZ01 = 24, FMT_FCMP = 25, FMT_IECP = 26, FMT_MDB4 = 27, FMT_LZSEGA = 28, FMT_GCZ = 29, FMT_SDPC = 30,
-    FMT_ECD = 31, FMT_LZ00 = 32
+    FMT_ECD = 31, FMT_LZ00 = 32,
+    FMT_LZHUDSON = 33
 };
 
 struct Error {
@@ -447,6 +448,8 @@ void lz10_decode(Src& s, Sink& d);
 void lz11_decode(Src& s, Sink& d);
 void yaz0_decode(Src& s, Sink& d, const CodecOpts& o, const char* magic);
 void yay0_decode(Src& s, Sink& d, const CodecOpts& o);
+void lzhudson_decode(Src& s, Sink& d);
+void lzhudson_encode(const uint8_t* src, int n, OutBuf& out, const CodecOpts& o);
 void mio0_decode(Src& s, Sink& d, const CodecOpts& o);
 void lzss_decode(Src& s, Sink& d, const CodecOpts& o);
 void lz4_decode(Src& s, Sink& d, const CodecOpts& o);

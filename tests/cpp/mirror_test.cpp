@@ -69,6 +69,7 @@ int main(int argc, char** argv) {
         bad += round_trip(LZSega(), raw, CompressionSettings::Balanced(), true, false);
         bad += round_trip(GCZ(), raw, CompressionSettings::Balanced(), true, false);
         bad += round_trip(SDPC(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(LZHudson(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(ECD(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(ECD(), raw, CompressionSettings::Fastest(), true);   // quality 0: stored
         {
