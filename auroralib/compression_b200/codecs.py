@@ -443,6 +443,24 @@ class LZHudson(_SizedCodec):
     FORMAT, Name = _abi.FMT_LZHUDSON, "LZHudson"
 
 
+class LZ40(_SizedCodec):
+    """Nintendo/LZ40.cs: 0x40 + u24 size, negated flag bytes, little-endian 2 / 3 / 4-byte match tokens (a core format)"""
+    FORMAT, Name = _abi.FMT_LZ40, "Nintendo LZ40"
+
+    def __init__(self):
+        self.GbaVramCompatibilityMode = False   # LZ40.cs:35
+
+    def _opts(self, settings=None):
+        o = super()._opts(settings)
+        o.vram_mode = 1 if self.GbaVramCompatibilityMode else 0
+        return o
+
+
+class LZ60(LZ40):
+    """Nintendo/LZ60.cs: the LZ40 codec under identifier 0x60"""
+    FORMAT, Name = _abi.FMT_LZ60, "Nintendo LZ60"
+
+
 class _WholeHeaderPeek:
     # GetDecompressedSize looks past the first 16 bytes (LZ00: size at 48) or at the stream length (ECD)
     def GetDecompressedSize(self, source):
@@ -494,4 +512,4 @@ class LZ00(_WholeHeaderPeek, _SizedCodec):
 
 
 WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC, ECD, LZ00]
-ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS, LZHudson] + WRAPPERS
+ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS, LZHudson, LZ40, LZ60] + WRAPPERS

@@ -97,7 +97,8 @@ thread_local std::string g_init_error;
 
 bool is_flaglz(int f) {
     return f == AURORA_FMT_YAZ0 || f == AURORA_FMT_YAZ1 || f == AURORA_FMT_YAY0 || f == AURORA_FMT_MIO0 ||
-           f == AURORA_FMT_LZ10 || f == AURORA_FMT_LZ11 || f == AURORA_FMT_LZSS || f == AURORA_FMT_LZHUDSON;
+           f == AURORA_FMT_LZ10 || f == AURORA_FMT_LZ11 || f == AURORA_FMT_LZSS || f == AURORA_FMT_LZHUDSON ||
+           f == AURORA_FMT_LZ40 || f == AURORA_FMT_LZ60;
 }
 bool is_bytelz(int f) {
     return f == AURORA_FMT_LZ4 || f == AURORA_FMT_LZ4_BLOCK || f == AURORA_FMT_LZ4_LEGACY || f == AURORA_FMT_LZO ||
@@ -448,6 +449,8 @@ int fill_encode_params(EncodeParams& p, int format, const aurora_codec_opts* o) 
             aurora_lz_props_window(&lz, 0x1000, 18, 3, 0, vram ? 2 : 1);
             break;
         }
+        case AURORA_FMT_LZ40:   // LZ40.cs:29-30, :35: the LZ11 properties, GbaVramCompatibilityMode default false
+        case AURORA_FMT_LZ60:
         case AURORA_FMT_LZ11: {
             const bool vram = o && o->vram_mode > 0;     // LZ11.cs:29 default false
             aurora_lz_props_window(&lz, 0x1000, 0x4000, 3, 0, vram ? 2 : 1);
@@ -744,8 +747,8 @@ int aurora_decoded_size_batch(aurora_ctx* ctx, int format, const aurora_codec_op
             if (format == AURORA_FMT_LZHUDSON) {   // LZHudson.cs:37-38
                 if (len < 4) st = AURORA_END_OF_STREAM;
                 else sz = be32(p);
-            } else if (format == AURORA_FMT_LZ10 || format == AURORA_FMT_LZ11) {
-                const uint8_t id = format == AURORA_FMT_LZ10 ? 0x10 : 0x11;
+            } else if (format == AURORA_FMT_LZ10 || format == AURORA_FMT_LZ11 || format == AURORA_FMT_LZ40 || format == AURORA_FMT_LZ60) {
+                const uint8_t id = format == AURORA_FMT_LZ10 ? 0x10 : format == AURORA_FMT_LZ11 ? 0x11 : format == AURORA_FMT_LZ40 ? 0x40 : 0x60;
                 if (len < 1) st = AURORA_END_OF_STREAM;
                 else if (p[0] != id) st = AURORA_INVALID_IDENTIFIER;
                 else if (len < 4) st = AURORA_END_OF_STREAM;
@@ -906,6 +909,10 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
             case AURORA_FMT_YAZ0: m = magic16(i, "Yaz0", 4); break;
             case AURORA_FMT_YAZ1: m = magic16(i, "Yaz1", 4); break;
             case AURORA_FMT_LZHUDSON: m = 0x8 < src_len[i] && (p[0] | p[1] | p[2] | p[3]) != 0; break;   // LZHudson.cs:31-32, no file name
+            case AURORA_FMT_LZ40:   // LZ40.cs:41-43, LZ60.cs:31-33: identifier and a non-zero size ("recognition is inaccurate!")
+            case AURORA_FMT_LZ60:
+                m = 0x8 < src_len[i] && p[0] == (format == AURORA_FMT_LZ40 ? 0x40 : 0x60) && ((p[1] | p[2] | p[3]) != 0 || (p[4] | p[5] | p[6] | p[7]) != 0);
+                break;
             case AURORA_FMT_YAY0: m = magic16(i, "Yay0", 4); break;
             case AURORA_FMT_MIO0: m = magic16(i, "MIO0", 4); break;
             case AURORA_FMT_LZSS: m = magic16(i, "LZSS", 4); break;

@@ -43,14 +43,14 @@ constexpr int kSubMaxG = 2304;       // G32: output bytes per iteration (>= the 
 constexpr int kPairSpan = 4096;      // parser/replayer pipeline: two consecutive iterations in flight, window + both + drain slack <= ring
 
 
-enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5, K_HUDSON = 6 };
+enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5, K_HUDSON = 6, K_LZ40 = 7 };
 
 // Shared memory of one stream slot (the launcher adds 8 KiB of alignment slack for the rings):
 //   ring 8 KiB | staged sub-streams | match queue x2 (+ read slack) | group offsets | mailboxes x2 | stream descriptor | mbarriers
 template <int K>
 struct Traits {
     static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : 1;
-    static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0 || K == K_HUDSON) ? 273 : (K == K_LZSS) ? 258 : 65808;
+    static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0 || K == K_HUDSON) ? 273 : (K == K_LZSS) ? 258 : 65808;   // LZ11 65 808, LZ40 65 807
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
     static constexpr int kQueueLen = kStreams == 3 ? kQueueSplit : kQueue;
     static constexpr int kQueueBytes = 2 * kQueueLen * 8 + 32;
@@ -240,6 +240,43 @@ __device__ BodyResult decode_body(InStream* in, OutState& out, const uint32_t sl
                 tok_end = myoff + mysz;
                 bad = mypg >= slen || tok_end > slen;
             }
+        } else if constexpr (K == K_LZ40) {
+            // LZ40.cs:73-124: the flag byte is NEGATED ((byte)-ReadByte()), MSB first, bit 1 = match.  A match is a little-endian
+            // u16 DDDDDDDD DDDDLLLL; length nibble 0 -> one more byte (+16), 1 -> two more bytes LE (+272), else the length
+            // itself.  Distance 0 (the encoder's 0x1000 << 4 truncated to 16 bits) is BackCopy(0, n): one 4 KiB window back.
+            in[0].ensure(cur);
+            uint32_t pg = cur, myoff = 0, mysz = 1, mypg = 0;
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const uint32_t f = (0u - in[0].at(pg)) & 0xFFu;
+                const uint32_t lo = in[0].at(pg + 1 + lane) & 0xFu;
+                const uint32_t e0 = __ballot_sync(kFull, lo == 0);
+                const uint32_t e1 = __ballot_sync(kFull, lo == 1);
+                uint32_t off = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const bool is_lit = ((f >> (7 - i)) & 1u) == 0;
+                    const uint32_t sz = is_lit ? 1u : 2u + ((e0 >> off) & 1u) + 2u * ((e1 >> off) & 1u);
+                    if (lane == uint32_t(g * 8 + i)) {
+                        myoff = pg + 1 + off;
+                        mysz = sz;
+                        mypg = pg;
+                    }
+                    off += sz;
+                }
+                pg += 1 + off;
+            }
+            next_cur = pg;
+            ism = mysz >= 2;
+            const uint32_t b1 = in[0].at(myoff), b2 = in[0].at(myoff + 1), b3 = in[0].at(myoff + 2), b4 = in[0].at(myoff + 3);
+            lit = b1;
+            const uint32_t v = b1 | (b2 << 8);
+            dist = v >> 4;
+            if (dist == 0) dist = uint32_t(kWindow);
+            len = !ism ? 1 : (mysz == 3 ? b3 + 16 : mysz == 4 ? (b3 | (b4 << 8)) + 272 : (v & 0xFu));
+            tok_end = myoff + mysz;
+            // a flag byte past the end reads as -1 -> 0x01, and the token read that follows throws: EndOfStream either way
+            bad = mypg >= slen || tok_end > slen;
         } else if constexpr (K == K_HUDSON) {
             // LZHudson.cs:54-55: FlagReader(source, Endian.Big, 4, Endian.Big) — one 4-byte big-endian flag word governs exactly
             // the 32 tokens of this iteration (bit 1 = literal, MSB first); tokens as Yaz0 (2 bytes, 3 when the high nibble
@@ -1283,8 +1320,8 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
 
     if (headerless) {
         size = given_size;   // DecompressHeaderless(source, destination, decomLength): LZ10.cs:82, LZ11.cs:83, LZSS.cs:91
-    } else if (K == K_LZ10 || K == K_LZ11) {
-        const uint32_t id = (K == K_LZ10) ? 0x10 : 0x11;
+    } else if (K == K_LZ10 || K == K_LZ11 || K == K_LZ40) {
+        const uint32_t id = (K == K_LZ10) ? 0x10 : (K == K_LZ11) ? 0x11 : (P.format == AURORA_FMT_LZ60 ? 0x60 : 0x40);
         if (slen < 1) { status = AURORA_END_OF_STREAM; consumed = slen; }
         else if (H(0) != id) { status = AURORA_INVALID_IDENTIFIER; consumed = 1; }
         else if (slen < 4) { status = AURORA_END_OF_STREAM; consumed = slen; }
@@ -1357,18 +1394,18 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                     in[0].begin(P.src_base, P.src_limit, src);
                 }
                 BodyResult r;
-                bool g32 = K != K_HUDSON;
+                bool g32 = K != K_HUDSON && K != K_LZ40;
                 if (K == K_LZSS) g32 = 8u * (((1u << P.lzss.length_bits) - 1u) + uint32_t(P.lzss.min_length)) <= uint32_t(kSubMaxG);
                 if (g32) {
-                    if constexpr (K != K_HUDSON) {
+                    if constexpr (K != K_HUDSON && K != K_LZ40) {
                     sink.begin(ring, fill, dst, limit);
                     if constexpr (K == K_MIO0 || K == K_YAY0) r = decode_body_g32_split<K>(in, sink, slen, size, comp_off, lit_off);
                     else if constexpr (K == K_YAZ0 || K == K_LZ11) r = decode_body_g32_var<K>(in, sink, gaddr, slen, size, body_off);
                     else r = decode_body_g32<K>(in, sink, gaddr, slen, size, body_off, P.lzss);
                     }
-                } else if constexpr (K == K_LZSS || K == K_HUDSON) {
-                    // LzProperties whose largest group exceeds an iteration, and LZHudson (a 32-bit flag word is exactly one
-                    // 32-token iteration): the token-per-lane core, run by this warp alone
+                } else if constexpr (K == K_LZSS || K == K_HUDSON || K == K_LZ40) {
+                    // LzProperties whose largest group exceeds an iteration, LZHudson (a 32-bit flag word is exactly one
+                    // 32-token iteration) and LZ40 / LZ60: the token-per-lane core, run by this warp alone
                     sink.wait_idle();
                     ring_prefill(ring, fill);
                     OutState out;
@@ -1492,6 +1529,8 @@ cudaError_t launch_decode_flaglz(const DecodeParams& p, int sm_count, cudaStream
         case AURORA_FMT_MIO0: return launch<K_MIO0>(p, sm_count, st);
         case AURORA_FMT_YAY0: return launch<K_YAY0>(p, sm_count, st);
         case AURORA_FMT_LZHUDSON: return launch<K_HUDSON>(p, sm_count, st);
+        case AURORA_FMT_LZ40:
+        case AURORA_FMT_LZ60: return launch<K_LZ40>(p, sm_count, st);
         default: return cudaErrorInvalidValue;
     }
 }

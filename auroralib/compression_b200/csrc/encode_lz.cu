@@ -71,8 +71,10 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
         }
 
         // ---- headers
+        const bool lz40 = K == E_LZ11 && (P.format == AURORA_FMT_LZ40 || P.format == AURORA_FMT_LZ60);   // LZ40.cs:126-168
         if (K == E_LZ10 || K == E_LZ11) {
-            const uint32_t id = K == E_LZ10 ? 0x10 : 0x11;
+            const uint32_t id = K == E_LZ10 ? 0x10 : !lz40 ? 0x11 : P.format == AURORA_FMT_LZ40 ? 0x40 : 0x60;
+            w.negate = lz40;
             if (n <= 0xFFFFFF) {
                 put_u32(w, id | (uint32_t(n) << 8), false);
             } else {
@@ -127,6 +129,23 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
                 const uint32_t v = uint32_t(m.length - 3) << 12 | d1;
                 w.byte((v >> 8) & 0xFF);
                 w.byte(v & 0xFF);
+                w.bit(true);
+            } else if (K == E_LZ11 && lz40) {
+                // (ushort)(Distance << 4 | ...), little-endian: a distance of 0x1000 truncates to 0
+                const uint32_t dd = (uint32_t(m.distance) << 4) & 0xFFFF;
+                if (m.length < 16) {
+                    w.byte((dd | uint32_t(m.length)) & 0xFF);
+                    w.byte(dd >> 8);
+                } else if (m.length < 272) {
+                    w.byte(dd & 0xFF);
+                    w.byte(dd >> 8);
+                    w.byte(uint32_t(m.length - 16) & 0xFF);
+                } else {
+                    w.byte((dd | 1u) & 0xFF);
+                    w.byte(dd >> 8);
+                    w.byte(uint32_t(m.length - 272) & 0xFF);
+                    w.byte((uint32_t(m.length - 272) >> 8) & 0xFF);
+                }
                 w.bit(true);
             } else if (K == E_LZ11) {
                 if (m.length <= 16) {
@@ -255,7 +274,9 @@ size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64
 cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st) {
     switch (p.format) {
         case AURORA_FMT_LZ10: return launch<E_LZ10>(p, warps, st);
-        case AURORA_FMT_LZ11: return launch<E_LZ11>(p, warps, st);
+        case AURORA_FMT_LZ11:
+        case AURORA_FMT_LZ40:
+        case AURORA_FMT_LZ60: return launch<E_LZ11>(p, warps, st);   // LZ40 / LZ60: the LZ11 parse with LE tokens and negated flags
         case AURORA_FMT_YAZ0:
         case AURORA_FMT_YAZ1:
         case AURORA_FMT_LZHUDSON: return launch<E_YAZ0>(p, warps, st);   // the same tokens under 4-byte flag words

@@ -151,6 +151,7 @@ struct Writer {
     uint32_t flag_val, bits;
     uint32_t flag_bytes = 1;   // FlagWriter flag size: 1, or 4 (big-endian word: LZHudson)
     bool msb_first, overflow;
+    bool negate = false;       // the flag byte is written as (byte)-flag (LZ40.cs:137)
     __device__ __forceinline__ void put(uint64_t at, uint32_t b) {
         if (at < cap) {
             if (lane_id() == 0) out[at] = uint8_t(b);
@@ -169,7 +170,7 @@ struct Writer {
     }
     __device__ __forceinline__ void put_flag() {
         if (flag_bytes == 1) {
-            put(uint64_t(flag_pos), flag_val);
+            put(uint64_t(flag_pos), negate ? (0u - flag_val) & 0xFFu : flag_val);
         } else {
             for (uint32_t i = 0; i < flag_bytes; i++) put(uint64_t(flag_pos) + i, (flag_val >> (8 * (flag_bytes - 1 - i))) & 0xFF);
         }

@@ -277,6 +277,26 @@ namespace AuroraLib.Compression.Cuda
         public uint GetDecompressedSize(Stream source) => PeekSize(source);
     }
 
+    public sealed class GpuLZ40 : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Nintendo.LZ40 _managed = new Formats.Nintendo.LZ40();
+        protected override AuroraFormat Format => AuroraFormat.LZ40;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public bool GbaVramCompatibilityMode { get; set; } = false;
+        protected override void FillOptions(ref AuroraCodecOpts o, CompressionSettings s) { o.VramMode = GbaVramCompatibilityMode ? 1 : 0; }
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
+    public sealed class GpuLZ60 : GpuCodec, IProvidesDecompressedSize   // the LZ40 codec under identifier 0x60
+    {
+        private readonly Formats.Nintendo.LZ60 _managed = new Formats.Nintendo.LZ60();
+        protected override AuroraFormat Format => AuroraFormat.LZ60;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public bool GbaVramCompatibilityMode { get; set; } = false;
+        protected override void FillOptions(ref AuroraCodecOpts o, CompressionSettings s) { o.VramMode = GbaVramCompatibilityMode ? 1 : 0; }
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
     public sealed class GpuECD : GpuCodec, IProvidesDecompressedSize   // plain bytes + LZSS(0x400, 0x42, 3, 0x3BE), or stored
     {
         private readonly Formats.Specialized.ECD _managed = new Formats.Specialized.ECD();

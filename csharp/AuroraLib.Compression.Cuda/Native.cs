@@ -22,7 +22,9 @@ namespace AuroraLib.Compression.Cuda
         // LZSS wrappers with extra work around the core: stored prefix / stored fallback (ECD), LCG keystream on the device (LZ00)
         ECD = 31, LZ00 = 32,
         // a core format: Yay0 tokens under 32-bit big-endian flag words (HudsonSoft/LZHudson.cs)
-        LZHudson = 33
+        LZHudson = 33,
+        // core formats: LZ11-like tokens, little-endian with the length in the low nibble, negated flag bytes
+        LZ40 = 34, LZ60 = 35
     }
 
     [StructLayout(LayoutKind.Sequential)]

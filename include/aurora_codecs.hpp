@@ -355,6 +355,22 @@ class LZHudson : public SizedAlgorithm {   // HudsonSoft/LZHudson.cs: u32 BE siz
   public:
     AURORA_FORMAT(LZHudson, AURORA_FMT_LZHUDSON, "LZHudson")
 };
+class LZ40 : public SizedAlgorithm {   // Nintendo/LZ40.cs: negated flag bytes, little-endian 2 / 3 / 4-byte match tokens
+  public:
+    AURORA_FORMAT(LZ40, AURORA_FMT_LZ40, "Nintendo LZ40")
+    bool GbaVramCompatibilityMode = false;
+
+  protected:
+    void Fill(aurora_codec_opts& o, bool) const override { o.vram_mode = GbaVramCompatibilityMode ? 1 : 0; }
+};
+class LZ60 : public SizedAlgorithm {   // Nintendo/LZ60.cs: the LZ40 codec under identifier 0x60
+  public:
+    AURORA_FORMAT(LZ60, AURORA_FMT_LZ60, "Nintendo LZ60")
+    bool GbaVramCompatibilityMode = false;
+
+  protected:
+    void Fill(aurora_codec_opts& o, bool) const override { o.vram_mode = GbaVramCompatibilityMode ? 1 : 0; }
+};
 class ECD : public SizedAlgorithm {   // Extended/Specialized/ECD.cs: plain bytes + LZSS(0x400, 0x42, 3, 0x3BE), or stored
   public:
     AURORA_FORMAT(ECD, AURORA_FMT_ECD, "ECD lzss")

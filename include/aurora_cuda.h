@@ -83,7 +83,9 @@ typedef enum aurora_format {
     AURORA_FMT_ECD          = 31, /* -Extended/Specialized/ECD.cs: "ECD" header + plain bytes + LZSS(0x400, 0x42, 3, 0x3BE) / stored */
     AURORA_FMT_LZ00         = 32, /* Sega/LZ00.cs: 64-byte header + LZSS (Lzss0) under a per-byte LCG keystream (on the device) */
     /* a core format (kernel path, device entry points included): Yay0 tokens under 32-bit big-endian flag words */
-    AURORA_FMT_LZHUDSON     = 33  /* HudsonSoft/LZHudson.cs: u32 BE size + interleaved 4-byte flag words / tokens */
+    AURORA_FMT_LZHUDSON     = 33, /* HudsonSoft/LZHudson.cs: u32 BE size + interleaved 4-byte flag words / tokens */
+    AURORA_FMT_LZ40         = 34, /* Nintendo/LZ40.cs: 0x40 + u24 size; negated flag bytes, LE tokens of 2 / 3 / 4 bytes */
+    AURORA_FMT_LZ60         = 35  /* Nintendo/LZ60.cs: the LZ40 codec under identifier 0x60                   */
 } aurora_format;
 
 typedef enum aurora_endian {

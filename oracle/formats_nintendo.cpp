@@ -229,6 +229,73 @@ void yaz0_encode(const uint8_t* source, int n, OutBuf& destination, const CodecO
     flag.Dispose();
 }
 
+// ------------------------------------------------------------------ LZ40 / LZ60
+// AuroraLib.Compression.Nintendo/Nintendo/LZ40.cs:47-52 (header as LZ10 with identifier 0x40), :73-124 (body), :126-168
+// (encoder); LZ60.cs:53-71 is the same codec under identifier 0x60.
+static void lz40_headerless(Src& source, Sink& destination, uint32_t decomLength) {
+    int64_t endPosition = destination.pos + decomLength;
+    destination.SetLength(endPosition);
+    {
+        LzWindows buffer(&destination, kLz11.WindowsBits);   // LzProperties(0x1000, 0x4000, 3): 12 window bits
+        int flag = 0, flagbits = 0;
+        while (destination.pos + buffer.Position() < endPosition) {
+            if (flagbits == 0) {
+                flag = uint8_t(-source.ReadByte());   // BCL ReadByte: -1 at the end -> flag 0x01, the token read then throws
+                flagbits = 8;
+            }
+            if ((flag & 0x80) != 0) {
+                int distance = source.ReadUInt16(Endian::Little);
+                int length = distance & 0xF;
+                distance >>= 4;
+                if (length <= 1) {
+                    if (length == 0) length = source.ReadUInt8() + 16;
+                    else length = source.ReadUInt16(Endian::Little) + 272;
+                }
+                buffer.BackCopy(distance, length);
+            } else {
+                buffer.WriteByte(source.ReadUInt8());
+            }
+            flag <<= 1;
+            flagbits--;
+        }
+    }
+    if (destination.pos > endPosition) fail(SIZE_MISMATCH, decomLength, destination.pos - (endPosition - decomLength));
+}
+
+void lz40_decode(Src& s, Sink& d, uint8_t id) { lz40_headerless(s, d, lz1x_size(s, id)); }
+
+void lz40_encode(const uint8_t* source, int n, OutBuf& destination, const CodecOpts& o, uint8_t id) {
+    lz1x_header(destination, id, n);
+    bool vram = o.vramMode < 0 ? false : o.vramMode != 0;   // LZ40.cs:35 default false
+    int sourcePointer = 0;
+    MatchFinder mf(vram ? kLz11Vram : kLz11, o.settings);
+    FlagWriter flag(&destination, Endian::Big);
+    flag.negate8 = true;
+    while (true) {
+        LzMatch match = mf.FindNextBestMatch(source, n);
+        int plain = match.Offset - sourcePointer;
+        while (plain != 0) {
+            plain--;
+            flag.Buffer.WriteByte(source[sourcePointer++]);
+            flag.WriteBit(false);
+        }
+        if (match.Length == 0) break;
+        // (ushort)(match.Distance << 4 | ...): a distance of 0x1000 wraps to 0, which BackCopy resolves one window back
+        if (match.Length < 16) {
+            flag.Buffer.WriteU16(uint16_t(match.Distance << 4 | match.Length), Endian::Little);
+        } else if (match.Length < 272) {
+            flag.Buffer.WriteU16(uint16_t(match.Distance << 4), Endian::Little);
+            flag.Buffer.WriteByte(uint8_t(match.Length - 16));
+        } else {
+            flag.Buffer.WriteU16(uint16_t(match.Distance << 4 | 1), Endian::Little);
+            flag.Buffer.WriteU16(uint16_t(match.Length - 272), Endian::Little);
+        }
+        sourcePointer += match.Length;
+        flag.WriteBit(true);
+    }
+    flag.Dispose();
+}
+
 // ------------------------------------------------------------------ LZHudson
 // AuroraLib.Compression.Nintendo/HudsonSoft/LZHudson.cs:41-59: u32 BE size, then the Yay0 token core with all three
 // sub-streams = the source and a FlagReader over 4-byte big-endian flag words, MSB first.
@@ -410,6 +477,8 @@ uint32_t nintendo_decoded_size(int fmt, Src& s, const CodecOpts& o) {
     switch (fmt) {
         case FMT_LZ10: return lz1x_size(s, 0x10);
         case FMT_LZ11: return lz1x_size(s, 0x11);
+        case FMT_LZ40: return lz1x_size(s, 0x40);   // LZ40.cs:47-52
+        case FMT_LZ60: return lz1x_size(s, 0x60);   // LZ60.cs:37-47
         case FMT_YAZ0:
         case FMT_YAZ1: {   // Yaz0.cs:50-55
             s.MatchThrow(fmt == FMT_YAZ0 ? "Yaz0" : "Yaz1", 4);

@@ -37,7 +37,7 @@ enum Format : int {
     FMT_GCLZ = 15, FMT_CXLZ = 16, FMT_COMP = 17, FMT_LZ_3DS = 18, FMT_LZ77 = 19, FMT_LEVEL5 = 20, FMT_LZON = 21, FMT_LEVEL5_LZSS = 22,
     FMT_AKLZ = 23, FMT_LZ01 = 24, FMT_FCMP = 25, FMT_IECP = 26, FMT_MDB4 = 27, FMT_LZSEGA = 28, FMT_GCZ = 29, FMT_SDPC = 30,
     FMT_ECD = 31, FMT_LZ00 = 32,
-    FMT_LZHUDSON = 33
+    FMT_LZHUDSON = 33, FMT_LZ40 = 34, FMT_LZ60 = 35
 };
 
 struct Error {
@@ -335,6 +335,7 @@ class FlagWriter {
   public:
     int BitsLeft;
     OutBuf Buffer;
+    bool negate8 = false;   // WriteFlagDelegate = i => destination.WriteByte((byte)-i)  (LZ40.cs:137)
     FlagWriter(OutBuf* destination, Endian bitOrder, int flagSizeBytes = 1, Endian byteOrder = Endian::Little)
         : base_(destination), flagSize_(8 * flagSizeBytes), bitOrderBe_(bitOrder == Endian::Big), byteOrder_(byteOrder), BitsLeft(8 * flagSizeBytes) {}
     void WriteBit(bool bit) {
@@ -352,7 +353,7 @@ class FlagWriter {
     void Flush() {
         if (BitsLeft != flagSize_) {
             switch (flagSize_) {
-                case 8: base_->WriteByte(uint8_t(current_)); break;
+                case 8: base_->WriteByte(negate8 ? uint8_t(-current_) : uint8_t(current_)); break;
                 case 16: base_->WriteU16(uint16_t(current_), byteOrder_); break;
                 case 24: base_->WriteU24(uint32_t(current_), byteOrder_); break;
                 default: base_->WriteU32(uint32_t(current_), byteOrder_); break;
@@ -448,6 +449,8 @@ void lz10_decode(Src& s, Sink& d);
 void lz11_decode(Src& s, Sink& d);
 void yaz0_decode(Src& s, Sink& d, const CodecOpts& o, const char* magic);
 void yay0_decode(Src& s, Sink& d, const CodecOpts& o);
+void lz40_decode(Src& s, Sink& d, uint8_t id);
+void lz40_encode(const uint8_t* src, int n, OutBuf& out, const CodecOpts& o, uint8_t id);
 void lzhudson_decode(Src& s, Sink& d);
 void lzhudson_encode(const uint8_t* src, int n, OutBuf& out, const CodecOpts& o);
 void mio0_decode(Src& s, Sink& d, const CodecOpts& o);

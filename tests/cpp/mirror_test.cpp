@@ -70,6 +70,8 @@ int main(int argc, char** argv) {
         bad += round_trip(GCZ(), raw, CompressionSettings::Balanced(), true, false);
         bad += round_trip(SDPC(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(LZHudson(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(LZ40(), raw, CompressionSettings::Maximum(), true);
+        bad += round_trip(LZ60(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(ECD(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(ECD(), raw, CompressionSettings::Fastest(), true);   // quality 0: stored
         {

@@ -10,7 +10,7 @@ from tests.util import fmt_id, synth
 pytestmark = pytest.mark.gpu
 
 ENC_FORMATS = [A.FMT_LZ10, A.FMT_LZ11, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS, A.FMT_MIO0, A.FMT_YAY0, A.FMT_LZ4, A.FMT_LZ4_LEGACY,
-               A.FMT_LZ4_BLOCK, A.FMT_LZO, A.FMT_SNAPPY, A.FMT_SNAPPY_BLOCK, A.FMT_PRS, A.FMT_LZHUDSON]
+               A.FMT_LZ4_BLOCK, A.FMT_LZO, A.FMT_SNAPPY, A.FMT_SNAPPY_BLOCK, A.FMT_PRS, A.FMT_LZHUDSON, A.FMT_LZ40, A.FMT_LZ60]
 
 
 def _check(codec, oracle, fmt, raws, opts):
@@ -25,7 +25,7 @@ def _check(codec, oracle, fmt, raws, opts):
         if st[i] != 0:
             assert len(r) < 5 and fmt in (A.FMT_LZ4, A.FMT_LZ4_LEGACY, A.FMT_LZ4_BLOCK)   # LZ4 encoders reject inputs shorter than 5 bytes
             continue
-        if len(r) == 0 and fmt in (A.FMT_LZ10, A.FMT_LZ11, A.FMT_LZ4_LEGACY, A.FMT_LZO):
+        if len(r) == 0 and fmt in (A.FMT_LZ10, A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60, A.FMT_LZ4_LEGACY, A.FMT_LZO):
             continue   # the reference cannot decode its own empty stream for these formats
         if fmt in (A.FMT_LZO, A.FMT_PRS) and not (dst[i] == 0 and outs[i] == r):
             continue   # known self-inconsistencies of the reference (LZO double literal run, PRS order heuristic); bytes equal the oracle's

@@ -33,7 +33,8 @@ def test_lzss_static_decoding(oracle, bmp, test_lz):
 
 
 Q0_SIZES = {A.FMT_YAZ0: 183160, A.FMT_YAY0: 183160, A.FMT_LZ10: 261953, A.FMT_MIO0: 261898, A.FMT_LZSS: 261898,
-            A.FMT_LZ11: 179455, A.FMT_LZ4_LEGACY: 175023, A.FMT_LZO: 161204, A.FMT_SNAPPY: 209184, A.FMT_PRS: 165729}
+            A.FMT_LZ11: 179455, A.FMT_LZ4_LEGACY: 175023, A.FMT_LZO: 161204, A.FMT_SNAPPY: 209184, A.FMT_PRS: 165729,
+            A.FMT_LZ40: 179488, A.FMT_LZ60: 179488, A.FMT_LZ00: 261946}
 
 
 @pytest.mark.parametrize("fmt", sorted(Q0_SIZES), ids=fmt_id)
@@ -43,7 +44,8 @@ def test_published_q0_ratios(oracle, bmp, fmt):
     comp, st = oracle.encode(fmt, raw, A.make_opts(quality=0))
     assert st == 0 and len(comp) == Q0_SIZES[fmt]
     published = {A.FMT_YAZ0: 17.89, A.FMT_YAY0: 17.89, A.FMT_LZ10: 25.58, A.FMT_MIO0: 25.58, A.FMT_LZSS: 25.58, A.FMT_LZ11: 17.52,
-                 A.FMT_LZ4_LEGACY: 17.09, A.FMT_LZO: 15.74, A.FMT_SNAPPY: 20.43, A.FMT_PRS: 16.18}[fmt]
+                 A.FMT_LZ4_LEGACY: 17.09, A.FMT_LZO: 15.74, A.FMT_SNAPPY: 20.43, A.FMT_PRS: 16.18,
+                 A.FMT_LZ40: 17.53, A.FMT_LZ60: 17.53, A.FMT_LZ00: 25.58}[fmt]   # (LZ60 is LZ40 under another identifier)
     assert round(100 * len(comp) / len(raw), 2) == published
     out, out_len, consumed, status = oracle.decode(fmt, comp, len(raw))
     assert status == 0 and out == raw and consumed == len(comp)
