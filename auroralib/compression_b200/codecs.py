@@ -443,6 +443,12 @@ class LZHudson(_SizedCodec):
     FORMAT, Name = _abi.FMT_LZHUDSON, "LZHudson"
 
 
+class SMSR00(_SizedCodec):
+    """Nintendo/SMSR00.cs: "SMSR00" header, MIO0 tokens with 16-bit big-endian mask words interleaved with the codes and the
+    literals in their own section (a core format)"""
+    FORMAT, Name = _abi.FMT_SMSR00, "Nintendo SMSR00"
+
+
 class LZ40(_SizedCodec):
     """Nintendo/LZ40.cs: 0x40 + u24 size, negated flag bytes, little-endian 2 / 3 / 4-byte match tokens (a core format)"""
     FORMAT, Name = _abi.FMT_LZ40, "Nintendo LZ40"
@@ -512,4 +518,4 @@ class LZ00(_WholeHeaderPeek, _SizedCodec):
 
 
 WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC, ECD, LZ00]
-ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS, LZHudson, LZ40, LZ60] + WRAPPERS
+ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS, LZHudson, LZ40, LZ60, SMSR00] + WRAPPERS

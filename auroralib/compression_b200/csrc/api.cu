@@ -98,7 +98,7 @@ thread_local std::string g_init_error;
 bool is_flaglz(int f) {
     return f == AURORA_FMT_YAZ0 || f == AURORA_FMT_YAZ1 || f == AURORA_FMT_YAY0 || f == AURORA_FMT_MIO0 ||
            f == AURORA_FMT_LZ10 || f == AURORA_FMT_LZ11 || f == AURORA_FMT_LZSS || f == AURORA_FMT_LZHUDSON ||
-           f == AURORA_FMT_LZ40 || f == AURORA_FMT_LZ60;
+           f == AURORA_FMT_LZ40 || f == AURORA_FMT_LZ60 || f == AURORA_FMT_SMSR00;
 }
 bool is_bytelz(int f) {
     return f == AURORA_FMT_LZ4 || f == AURORA_FMT_LZ4_BLOCK || f == AURORA_FMT_LZ4_LEGACY || f == AURORA_FMT_LZO ||
@@ -460,6 +460,7 @@ int fill_encode_params(EncodeParams& p, int format, const aurora_codec_opts* o) 
         case AURORA_FMT_YAZ1:
         case AURORA_FMT_LZHUDSON:   // LZHudson.cs:24
         case AURORA_FMT_YAY0: aurora_lz_props_window(&lz, 0x1000, 0xff + 0x12, 3, 0, 1); break;
+        case AURORA_FMT_SMSR00:   // SMSR00.cs:30 (and MIO0.CompressHeaderless with MIO0's own properties: the same)
         case AURORA_FMT_MIO0: aurora_lz_props_window(&lz, 0x1000, 18, 3, 0, 1); break;
         case AURORA_FMT_LZSS:
             if (o && o->lzss.windows_bits != 0) lz = o->lzss;
@@ -747,6 +748,11 @@ int aurora_decoded_size_batch(aurora_ctx* ctx, int format, const aurora_codec_op
             if (format == AURORA_FMT_LZHUDSON) {   // LZHudson.cs:37-38
                 if (len < 4) st = AURORA_END_OF_STREAM;
                 else sz = be32(p);
+            } else if (format == AURORA_FMT_SMSR00) {   // SMSR00.cs:40-46
+                if (len < 6) st = AURORA_END_OF_STREAM;
+                else if (std::memcmp(p, "SMSR00", 6) != 0) st = AURORA_INVALID_IDENTIFIER;
+                else if (len < 12) st = AURORA_END_OF_STREAM;
+                else sz = be32(p + 8);
             } else if (format == AURORA_FMT_LZ10 || format == AURORA_FMT_LZ11 || format == AURORA_FMT_LZ40 || format == AURORA_FMT_LZ60) {
                 const uint8_t id = format == AURORA_FMT_LZ10 ? 0x10 : format == AURORA_FMT_LZ11 ? 0x11 : format == AURORA_FMT_LZ40 ? 0x40 : 0x60;
                 if (len < 1) st = AURORA_END_OF_STREAM;
@@ -909,6 +915,7 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
             case AURORA_FMT_YAZ0: m = magic16(i, "Yaz0", 4); break;
             case AURORA_FMT_YAZ1: m = magic16(i, "Yaz1", 4); break;
             case AURORA_FMT_LZHUDSON: m = 0x8 < src_len[i] && (p[0] | p[1] | p[2] | p[3]) != 0; break;   // LZHudson.cs:31-32, no file name
+            case AURORA_FMT_SMSR00: m = magic16(i, "SMSR00", 6); break;   // SMSR00.cs:36-37
             case AURORA_FMT_LZ40:   // LZ40.cs:41-43, LZ60.cs:31-33: identifier and a non-zero size ("recognition is inaccurate!")
             case AURORA_FMT_LZ60:
                 m = 0x8 < src_len[i] && p[0] == (format == AURORA_FMT_LZ40 ? 0x40 : 0x60) && ((p[1] | p[2] | p[3]) != 0 || (p[4] | p[5] | p[6] | p[7]) != 0);
@@ -1095,7 +1102,7 @@ int aurora_encode_batch_device(aurora_ctx* ctx, int device, int format, const au
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
     // MIO0/Yay0 stage their code and literal sections per warp, sized by the largest stream of the batch
     uint64_t max_len = 0;
-    if (format == AURORA_FMT_MIO0 || format == AURORA_FMT_YAY0) {
+    if (format == AURORA_FMT_MIO0 || format == AURORA_FMT_YAY0 || format == AURORA_FMT_SMSR00) {
         CU_TRY(ctx, d->hdesc.reserve(n * sizeof(uint64_t)));
         CU_TRY(ctx, cudaMemcpyAsync(d->hdesc.p, d_src_len, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaStreamSynchronize(st));

@@ -43,14 +43,14 @@ constexpr int kSubMaxG = 2304;       // G32: output bytes per iteration (>= the 
 constexpr int kPairSpan = 4096;      // parser/replayer pipeline: two consecutive iterations in flight, window + both + drain slack <= ring
 
 
-enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5, K_HUDSON = 6, K_LZ40 = 7 };
+enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5, K_HUDSON = 6, K_LZ40 = 7, K_SMSR = 8 };
 
 // Shared memory of one stream slot (the launcher adds 8 KiB of alignment slack for the rings):
 //   ring 8 KiB | staged sub-streams | match queue x2 (+ read slack) | group offsets | mailboxes x2 | stream descriptor | mbarriers
 template <int K>
 struct Traits {
-    static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : 1;
-    static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0) ? 18 : (K == K_YAZ0 || K == K_YAY0 || K == K_HUDSON) ? 273 : (K == K_LZSS) ? 258 : 65808;   // LZ11 65 808, LZ40 65 807
+    static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : (K == K_SMSR) ? 2 : 1;
+    static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0 || K == K_SMSR) ? 18 : (K == K_YAZ0 || K == K_YAY0 || K == K_HUDSON) ? 273 : (K == K_LZSS) ? 258 : 65808;   // LZ11 65 808, LZ40 65 807
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
     static constexpr int kQueueLen = kStreams == 3 ? kQueueSplit : kQueue;
     static constexpr int kQueueBytes = 2 * kQueueLen * 8 + 32;
@@ -138,9 +138,9 @@ __device__ BodyResult decode_body(InStream* in, OutState& out, const uint32_t sl
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint8_t* ring = out.ring;
     uint32_t written = 0;
-    uint32_t cur = (K == K_MIO0 || K == K_YAY0) ? 0u : body_off;
+    uint32_t cur = (K == K_MIO0 || K == K_YAY0 || K == K_SMSR) ? 0u : body_off;
     uint32_t ccur = 0, lcur = 0;   // split formats: relative cursors
-    uint32_t consumed = (K == K_MIO0 || K == K_YAY0) ? max(comp_off, lit_off) : body_off;
+    uint32_t consumed = (K == K_MIO0 || K == K_YAY0) ? max(comp_off, lit_off) : (K == K_SMSR) ? lit_off : body_off;
     int status = AURORA_OK;
 
     while (written < size) {
@@ -240,6 +240,29 @@ __device__ BodyResult decode_body(InStream* in, OutState& out, const uint32_t sl
                 tok_end = myoff + mysz;
                 bad = mypg >= slen || tok_end > slen;
             }
+        } else if constexpr (K == K_SMSR) {
+            // SMSR00.cs:91-134.  in[0] = the code section (relative to blob offset 0x10, comp_off = its addressable bytes), in[1] =
+            // the literals (relative to lit_off).  A 16-bit big-endian mask word (MSB first, 1 = literal) is followed by the
+            // 16-bit codes of its 0 bits, so the next mask sits 2 + 2 * zeros bytes further: two masks = the 32 tokens of
+            // this iteration.  Code index -> popcount of 0 bits before, literal index -> popcount of 1 bits before.
+            in[0].ensure(cur, 72);
+            in[1].ensure(lcur, 40);
+            const uint32_t m0 = (in[0].at(cur) << 8) | in[0].at(cur + 1);
+            const uint32_t p1 = cur + 2 + 2 * (16 - __popc(m0));
+            const uint32_t m1 = (in[0].at(p1) << 8) | in[0].at(p1 + 1);
+            next_cur = p1 + 2 + 2 * (16 - __popc(m1));
+            const uint32_t j = lane & 15;
+            const uint32_t mk = lane < 16 ? m0 : m1, mpos = lane < 16 ? cur : p1;
+            ism = ((mk >> (15 - j)) & 1u) == 0;
+            const uint32_t lits_in = j ? __popc(mk >> (16 - j)) : 0;
+            const uint32_t crel = mpos + 2 + 2 * (j - lits_in);
+            const uint32_t lrel = lcur + lits_in + (lane < 16 ? 0u : uint32_t(__popc(m0)));
+            const uint32_t b1 = in[0].at(crel), b2 = in[0].at(crel + 1);
+            dist = (((b1 & 0xF) << 8) | b2) + 1;
+            len = ism ? (b1 >> 4) + 3 : 1;
+            lit = in[1].at(lrel);
+            // the mask word and a code are span elements (IndexOutOfRange past the section), a literal is a ReadUInt8 of the stream
+            bad = mpos + 2 > comp_off || (ism ? crel + 2 > comp_off : lit_off + lrel + 1 > slen);
         } else if constexpr (K == K_LZ40) {
             // LZ40.cs:73-124: the flag byte is NEGATED ((byte)-ReadByte()), MSB first, bit 1 = match.  A match is a little-endian
             // u16 DDDDDDDD DDDDLLLL; length nibble 0 -> one more byte (+16), 1 -> two more bytes LE (+272), else the length
@@ -373,6 +396,9 @@ __device__ BodyResult decode_body(InStream* in, OutState& out, const uint32_t sl
             ccur += 2 * __popc(__ballot_sync(kFull, active && ism));
             lcur += __popc(__ballot_sync(kFull, active && !ism)) + __popc(__ballot_sync(kFull, active && ext_used));
             consumed = max(comp_off + ccur, lit_off + lcur);
+        } else if constexpr (K == K_SMSR) {
+            lcur += __popc(__ballot_sync(kFull, active && !ism));
+            consumed = lit_off + lcur;   // source.Position: behind the last literal read
         } else {
             consumed = __shfl_sync(kFull, tok_end, nact - 1);
         }
@@ -1333,6 +1359,18 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                 else { size = le32(4); body_off = 8; }
             }
         }
+    } else if (K == K_SMSR) {   // SMSR00.cs:49-57
+        if (slen < 6) { status = AURORA_END_OF_STREAM; consumed = slen; }
+        else if (H(0) != 'S' || H(1) != 'M' || H(2) != 'S' || H(3) != 'R' || H(4) != '0' || H(5) != '0') { status = AURORA_INVALID_IDENTIFIER; consumed = 6; }
+        else if (slen < 16) { status = AURORA_END_OF_STREAM; consumed = slen; }
+        else {
+            size = be32(8);
+            lit_off = be32(12);
+            body_off = 16;
+            if (lit_off < 16 || lit_off > 0x7FFFFFFFu) { status = AURORA_INVALID_DATA; consumed = 16; }   // ArrayPool.Rent(negative)
+            else if (lit_off > slen) { status = AURORA_END_OF_STREAM; consumed = slen; }                  // ReadExactly
+            else comp_off = (lit_off - 16) & ~1u;   // the ushort span: an odd trailing byte is not addressable
+        }
     } else if (K == K_HUDSON) {   // LZHudson.cs:41-45: u32 big-endian size, no identifier
         if (slen < 4) { status = AURORA_END_OF_STREAM; consumed = slen; }
         else { size = be32(0); body_off = 4; }
@@ -1382,7 +1420,7 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
             if (uint64_t(size) > cap) {   // destination.SetLength on a non-expandable stream
                 status = AURORA_DST_TOO_SMALL;
                 written = 0;
-                consumed = (K == K_MIO0 || K == K_YAY0) ? slen : body_off;
+                consumed = (K == K_MIO0 || K == K_YAY0) ? slen : (K == K_SMSR) ? lit_off : body_off;   // SMSR00: SetLength follows ReadExactly
             } else {
                 const uint32_t fill = K == K_LZSS ? uint32_t(P.lzss.initial_fill) & 0xFFu : 0u;
                 const uint32_t limit = uint32_t(min(uint64_t(0xFFFFFFFFu), cap));
@@ -1390,20 +1428,23 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                     in[0].begin(P.src_base, P.src_limit, src + 0x10);
                     in[1].begin(P.src_base, P.src_limit, src + comp_off);
                     in[2].begin(P.src_base, P.src_limit, src + lit_off);
+                } else if constexpr (K == K_SMSR) {
+                    in[0].begin(P.src_base, P.src_limit, src + 0x10);
+                    in[1].begin(P.src_base, P.src_limit, src + lit_off);
                 } else {
                     in[0].begin(P.src_base, P.src_limit, src);
                 }
                 BodyResult r;
-                bool g32 = K != K_HUDSON && K != K_LZ40;
+                bool g32 = K != K_HUDSON && K != K_LZ40 && K != K_SMSR;
                 if (K == K_LZSS) g32 = 8u * (((1u << P.lzss.length_bits) - 1u) + uint32_t(P.lzss.min_length)) <= uint32_t(kSubMaxG);
                 if (g32) {
-                    if constexpr (K != K_HUDSON && K != K_LZ40) {
+                    if constexpr (K != K_HUDSON && K != K_LZ40 && K != K_SMSR) {
                     sink.begin(ring, fill, dst, limit);
                     if constexpr (K == K_MIO0 || K == K_YAY0) r = decode_body_g32_split<K>(in, sink, slen, size, comp_off, lit_off);
                     else if constexpr (K == K_YAZ0 || K == K_LZ11) r = decode_body_g32_var<K>(in, sink, gaddr, slen, size, body_off);
                     else r = decode_body_g32<K>(in, sink, gaddr, slen, size, body_off, P.lzss);
                     }
-                } else if constexpr (K == K_LZSS || K == K_HUDSON || K == K_LZ40) {
+                } else if constexpr (K == K_LZSS || K == K_HUDSON || K == K_LZ40 || K == K_SMSR) {
                     // LzProperties whose largest group exceeds an iteration, LZHudson (a 32-bit flag word is exactly one
                     // 32-token iteration) and LZ40 / LZ60: the token-per-lane core, run by this warp alone
                     sink.wait_idle();
@@ -1531,6 +1572,7 @@ cudaError_t launch_decode_flaglz(const DecodeParams& p, int sm_count, cudaStream
         case AURORA_FMT_LZHUDSON: return launch<K_HUDSON>(p, sm_count, st);
         case AURORA_FMT_LZ40:
         case AURORA_FMT_LZ60: return launch<K_LZ40>(p, sm_count, st);
+        case AURORA_FMT_SMSR00: return launch<K_SMSR>(p, sm_count, st);
         default: return cudaErrorInvalidValue;
     }
 }

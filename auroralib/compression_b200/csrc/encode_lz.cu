@@ -96,6 +96,16 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
             put_u32(w, uint32_t(n), true);
             put_u32(w, 0, false);   // compressed size, patched below
             put_u32(w, 0, false);
+        } else if (K == E_MIO0 && P.format == AURORA_FMT_SMSR00) {
+            // SMSR00.cs:60-75: "SMSR00", u16 0, BE size, BE pointer to the literal section (patched below); the code section is
+            // MIO0.CompressHeaderless under FlagWriter(codeData, Endian.Big, 2, Endian.Big) with the codes in its buffer
+            const char* magic = "SMSR00";
+            for (int i = 0; i < 6; i++) w.raw_byte(uint8_t(magic[i]));
+            w.raw_byte(0);
+            w.raw_byte(0);
+            put_u32(w, uint32_t(n), true);
+            put_u32(w, 0, true);
+            w.flag_bytes = 2;
         } else {
             const char* magic = K == E_MIO0 ? "MIO0" : "Yay0";
             for (int i = 0; i < 4; i++) w.raw_byte(uint8_t(magic[i]));
@@ -188,11 +198,16 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
                 if (K == E_MIO0) v = (uint32_t(m.distance - 1) | uint32_t(m.length - 3) << 12) & 0xFFFF;
                 else if (m.length < 18) v = (uint32_t(m.distance - 1) | uint32_t(m.length - 2) << 12) & 0xFFFF;
                 else v = d1;
-                if (lane == 0) {
-                    codes[ncodes] = uint8_t(v >> 8);
-                    codes[ncodes + 1] = uint8_t(v & 0xFF);
+                if (K == E_MIO0 && P.format == AURORA_FMT_SMSR00) {   // the codes share the section of their mask words
+                    w.byte(v >> 8);
+                    w.byte(v & 0xFF);
+                } else {
+                    if (lane == 0) {
+                        codes[ncodes] = uint8_t(v >> 8);
+                        codes[ncodes + 1] = uint8_t(v & 0xFF);
+                    }
+                    ncodes += 2;
                 }
-                ncodes += 2;
                 if (K == E_YAY0 && m.length >= 18) {
                     if (lane == 0) lits[nlits] = uint8_t(m.length - 0x12);
                     nlits++;
@@ -213,9 +228,14 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
             w.pos = lit_off + nlits;
             if (w.pos > w.cap) w.overflow = true;
             const uint64_t save = w.pos;
-            w.pos = 8;
-            put_u32(w, uint32_t(comp_off), big);
-            put_u32(w, uint32_t(lit_off), big);
+            if (K == E_MIO0 && P.format == AURORA_FMT_SMSR00) {
+                w.pos = 12;
+                put_u32(w, uint32_t(lit_off), true);   // ncodes == 0: the literal section starts where the code section ends
+            } else {
+                w.pos = 8;
+                put_u32(w, uint32_t(comp_off), big);
+                put_u32(w, uint32_t(lit_off), big);
+            }
             w.pos = save;
         } else {
             w.dispose();
@@ -267,7 +287,7 @@ int encode_resident_warps(int sm_count) { return sm_count * 48; }
 // head + chain + min tables, plus (MIO0/Yay0) staging for the code and literal sections
 size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64_t max_src_len) {
     size_t bytes = (size_t(1) << hash_bits) * 4 + (size_t(1) << chain_bits) * 4 + 65536 * 4;
-    if (format == AURORA_FMT_MIO0 || format == AURORA_FMT_YAY0) bytes += 2 * (size_t(max_src_len) + 64);
+    if (format == AURORA_FMT_MIO0 || format == AURORA_FMT_YAY0 || format == AURORA_FMT_SMSR00) bytes += 2 * (size_t(max_src_len) + 64);
     return (bytes + 255) & ~size_t(255);
 }
 
@@ -281,7 +301,8 @@ cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st) 
         case AURORA_FMT_YAZ1:
         case AURORA_FMT_LZHUDSON: return launch<E_YAZ0>(p, warps, st);   // the same tokens under 4-byte flag words
         case AURORA_FMT_LZSS: return launch<E_LZSS>(p, warps, st);
-        case AURORA_FMT_MIO0: return launch<E_MIO0>(p, warps, st);
+        case AURORA_FMT_MIO0:
+        case AURORA_FMT_SMSR00: return launch<E_MIO0>(p, warps, st);   // SMSR00: MIO0 tokens, 16-bit masks interleaved with the codes
         case AURORA_FMT_YAY0: return launch<E_YAY0>(p, warps, st);
         default: return cudaErrorNotSupported;
     }

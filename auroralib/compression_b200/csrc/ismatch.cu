@@ -128,6 +128,8 @@ __device__ bool is_match_one(const uint8_t* p, uint64_t len, int format) {
         case AURORA_FMT_YAZ0: return magic(0x59617A30u);
         case AURORA_FMT_YAZ1: return magic(0x59617A31u);
         case AURORA_FMT_LZHUDSON: return 0x8 < len && (p[0] | p[1] | p[2] | p[3]) != 0;   // LZHudson.cs:31-32
+        case AURORA_FMT_SMSR00:   // SMSR00.cs:36-37
+            return 0x10 < len && p[0] == 'S' && p[1] == 'M' && p[2] == 'S' && p[3] == 'R' && p[4] == '0' && p[5] == '0';
         case AURORA_FMT_LZ40:   // LZ40.cs:41-43, LZ60.cs:31-33
         case AURORA_FMT_LZ60:
             return 0x8 < len && p[0] == (format == AURORA_FMT_LZ40 ? 0x40 : 0x60) && ((p[1] | p[2] | p[3]) != 0 || (p[4] | p[5] | p[6] | p[7]) != 0);

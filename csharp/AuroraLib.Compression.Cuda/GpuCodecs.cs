@@ -277,6 +277,14 @@ namespace AuroraLib.Compression.Cuda
         public uint GetDecompressedSize(Stream source) => PeekSize(source);
     }
 
+    public sealed class GpuSMSR00 : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Nintendo.SMSR00 _managed = new Formats.Nintendo.SMSR00();
+        protected override AuroraFormat Format => AuroraFormat.SMSR00;
+        protected override ICompressionAlgorithm Managed => _managed;
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
     public sealed class GpuLZ40 : GpuCodec, IProvidesDecompressedSize
     {
         private readonly Formats.Nintendo.LZ40 _managed = new Formats.Nintendo.LZ40();

@@ -24,7 +24,9 @@ namespace AuroraLib.Compression.Cuda
         // a core format: Yay0 tokens under 32-bit big-endian flag words (HudsonSoft/LZHudson.cs)
         LZHudson = 33,
         // core formats: LZ11-like tokens, little-endian with the length in the low nibble, negated flag bytes
-        LZ40 = 34, LZ60 = 35
+        LZ40 = 34, LZ60 = 35,
+        // core format: MIO0 tokens, 16-bit big-endian mask words interleaved with the codes, literals in their own section
+        SMSR00 = 36
     }
 
     [StructLayout(LayoutKind.Sequential)]

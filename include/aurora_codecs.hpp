@@ -355,6 +355,10 @@ class LZHudson : public SizedAlgorithm {   // HudsonSoft/LZHudson.cs: u32 BE siz
   public:
     AURORA_FORMAT(LZHudson, AURORA_FMT_LZHUDSON, "LZHudson")
 };
+class SMSR00 : public SizedAlgorithm {   // Nintendo/SMSR00.cs: MIO0 tokens, 16-bit masks interleaved with the codes
+  public:
+    AURORA_FORMAT(SMSR00, AURORA_FMT_SMSR00, "Nintendo SMSR00")
+};
 class LZ40 : public SizedAlgorithm {   // Nintendo/LZ40.cs: negated flag bytes, little-endian 2 / 3 / 4-byte match tokens
   public:
     AURORA_FORMAT(LZ40, AURORA_FMT_LZ40, "Nintendo LZ40")

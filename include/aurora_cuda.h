@@ -85,7 +85,8 @@ typedef enum aurora_format {
     /* a core format (kernel path, device entry points included): Yay0 tokens under 32-bit big-endian flag words */
     AURORA_FMT_LZHUDSON     = 33, /* HudsonSoft/LZHudson.cs: u32 BE size + interleaved 4-byte flag words / tokens */
     AURORA_FMT_LZ40         = 34, /* Nintendo/LZ40.cs: 0x40 + u24 size; negated flag bytes, LE tokens of 2 / 3 / 4 bytes */
-    AURORA_FMT_LZ60         = 35  /* Nintendo/LZ60.cs: the LZ40 codec under identifier 0x60                   */
+    AURORA_FMT_LZ60         = 35, /* Nintendo/LZ60.cs: the LZ40 codec under identifier 0x60                   */
+    AURORA_FMT_SMSR00       = 36  /* Nintendo/SMSR00.cs: MIO0 tokens, 16-bit BE masks interleaved with the codes, literals in their own section */
 } aurora_format;
 
 typedef enum aurora_endian {

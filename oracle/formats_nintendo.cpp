@@ -472,6 +472,79 @@ void mio0_encode(const uint8_t* source, int n, OutBuf& destination, const CodecO
     destination.Write(uncompressedData.v.data(), uncompressedData.size());
 }
 
+// ------------------------------------------------------------------ SMSR00
+// AuroraLib.Compression.Nintendo/Nintendo/SMSR00.cs:49-57 (header), :77-141 (body), :60-75 + :143-147 (encoder).
+// Header 0x10 bytes: "SMSR00", 2 skipped, u32 BE size, u32 BE pointer to the literal section.  The code section between
+// the header and that pointer interleaves 16-bit big-endian mask words (MSB first, 1 = literal) with the 16-bit big-endian
+// match codes of their 0 bits (MIO0's code layout); literals are read from the stream behind the code section.
+void smsr00_decode(Src& source, Sink& destination) {
+    source.MatchThrow("SMSR00", 6);
+    source.pos += 2;   // Skip(2): a seek
+    uint32_t decomLength = source.ReadUInt32(Endian::Big);
+    uint32_t uncompressedDataPointer = source.ReadUInt32(Endian::Big);
+    int codesLength = int(int64_t(uncompressedDataPointer) - source.pos);
+    if (codesLength < 0) fail(INVALID_DATA);   // ArrayPool.Rent(negative): ArgumentOutOfRangeException
+    source.need(codesLength);                  // ReadExactly
+    const uint8_t* codes = source.p + source.pos;
+    source.pos += codesLength;
+    const int ncodes = codesLength / 2;        // MemoryMarshal.Cast<byte, ushort>: an odd trailing byte is not addressable
+    auto code = [&](int i) -> uint16_t {
+        if (i >= ncodes) { source.pos = source.len; fail(END_OF_STREAM); }   // IndexOutOfRangeException on the span: input exhausted
+        return uint16_t(codes[2 * i] << 8 | codes[2 * i + 1]);               // ReverseEndianness of the little-endian cast
+    };
+    int64_t endPosition = destination.pos + decomLength;
+    destination.SetLength(endPosition);
+    {
+        LzWindows buffer(&destination, kLz10.WindowsBits);   // LzProperties(0x1000, 18, 3)
+        int codePointer = 0, maskBitCounter = 0;
+        uint16_t currentMask = 0;
+        while (destination.pos + buffer.Position() < endPosition) {
+            if (maskBitCounter == 0) {
+                currentMask = code(codePointer++);
+                maskBitCounter = 16;
+            }
+            if ((currentMask & 0x8000) == 0x8000) {
+                buffer.WriteByte(source.ReadUInt8());
+            } else {
+                uint16_t data = code(codePointer++);
+                buffer.BackCopy((data & 0x0FFF) + 1, (data >> 12) + 3);
+            }
+            currentMask = uint16_t(currentMask << 1);
+            maskBitCounter--;
+        }
+    }
+    if (destination.pos > endPosition) fail(SIZE_MISMATCH, decomLength, destination.pos - (endPosition - decomLength));
+}
+
+void smsr00_encode(const uint8_t* source, int n, OutBuf& destination, const CodecOpts& o) {
+    OutBuf uncompressedData, codeData;
+    {
+        FlagWriter flag(&codeData, Endian::Big, 2, Endian::Big);
+        int sourcePointer = 0;
+        MatchFinder mf(kLz10, o.settings);   // MIO0.CompressHeaderless with MIO0's LzProperties(0x1000, 18, 3)
+        while (true) {
+            LzMatch match = mf.FindNextBestMatch(source, n);
+            int plain = match.Offset - sourcePointer;
+            while (plain != 0) {
+                plain--;
+                uncompressedData.WriteByte(source[sourcePointer++]);
+                flag.WriteBit(true);
+            }
+            if (match.Length == 0) break;
+            flag.Buffer.WriteU16(uint16_t((match.Distance - 0x1) | ((match.Length - 0x3) << 12)), Endian::Big);
+            sourcePointer += match.Length;
+            flag.WriteBit(false);
+        }
+        flag.Dispose();
+    }
+    destination.Write(reinterpret_cast<const uint8_t*>("SMSR00"), 6);
+    destination.WriteU16(0, Endian::Little);
+    destination.WriteU32(uint32_t(n), Endian::Big);
+    destination.WriteU32(uint32_t(0x10 + codeData.size()), Endian::Big);
+    destination.Write(codeData.v.data(), codeData.size());
+    destination.Write(uncompressedData.v.data(), uncompressedData.size());
+}
+
 // ------------------------------------------------------------------ sizes / IsMatch helpers
 uint32_t nintendo_decoded_size(int fmt, Src& s, const CodecOpts& o) {
     switch (fmt) {
@@ -479,6 +552,7 @@ uint32_t nintendo_decoded_size(int fmt, Src& s, const CodecOpts& o) {
         case FMT_LZ11: return lz1x_size(s, 0x11);
         case FMT_LZ40: return lz1x_size(s, 0x40);   // LZ40.cs:47-52
         case FMT_LZ60: return lz1x_size(s, 0x60);   // LZ60.cs:37-47
+        case FMT_SMSR00: s.MatchThrow("SMSR00", 6); s.pos += 2; return s.ReadUInt32(Endian::Big);   // SMSR00.cs:40-46
         case FMT_YAZ0:
         case FMT_YAZ1: {   // Yaz0.cs:50-55
             s.MatchThrow(fmt == FMT_YAZ0 ? "Yaz0" : "Yaz1", 4);

@@ -70,6 +70,7 @@ int main(int argc, char** argv) {
         bad += round_trip(GCZ(), raw, CompressionSettings::Balanced(), true, false);
         bad += round_trip(SDPC(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(LZHudson(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(SMSR00(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(LZ40(), raw, CompressionSettings::Maximum(), true);
         bad += round_trip(LZ60(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(ECD(), raw, CompressionSettings::Balanced(), true);
