@@ -263,43 +263,6 @@ __device__ BodyResult decode_body(InStream* in, OutState& out, const uint32_t sl
             lit = in[1].at(lrel);
             // the mask word and a code are span elements (IndexOutOfRange past the section), a literal is a ReadUInt8 of the stream
             bad = mpos + 2 > comp_off || (ism ? crel + 2 > comp_off : lit_off + lrel + 1 > slen);
-        } else if constexpr (K == K_LZ40) {
-            // LZ40.cs:73-124: the flag byte is NEGATED ((byte)-ReadByte()), MSB first, bit 1 = match.  A match is a little-endian
-            // u16 DDDDDDDD DDDDLLLL; length nibble 0 -> one more byte (+16), 1 -> two more bytes LE (+272), else the length
-            // itself.  Distance 0 (the encoder's 0x1000 << 4 truncated to 16 bits) is BackCopy(0, n): one 4 KiB window back.
-            in[0].ensure(cur);
-            uint32_t pg = cur, myoff = 0, mysz = 1, mypg = 0;
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const uint32_t f = (0u - in[0].at(pg)) & 0xFFu;
-                const uint32_t lo = in[0].at(pg + 1 + lane) & 0xFu;
-                const uint32_t e0 = __ballot_sync(kFull, lo == 0);
-                const uint32_t e1 = __ballot_sync(kFull, lo == 1);
-                uint32_t off = 0;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const bool is_lit = ((f >> (7 - i)) & 1u) == 0;
-                    const uint32_t sz = is_lit ? 1u : 2u + ((e0 >> off) & 1u) + 2u * ((e1 >> off) & 1u);
-                    if (lane == uint32_t(g * 8 + i)) {
-                        myoff = pg + 1 + off;
-                        mysz = sz;
-                        mypg = pg;
-                    }
-                    off += sz;
-                }
-                pg += 1 + off;
-            }
-            next_cur = pg;
-            ism = mysz >= 2;
-            const uint32_t b1 = in[0].at(myoff), b2 = in[0].at(myoff + 1), b3 = in[0].at(myoff + 2), b4 = in[0].at(myoff + 3);
-            lit = b1;
-            const uint32_t v = b1 | (b2 << 8);
-            dist = v >> 4;
-            if (dist == 0) dist = uint32_t(kWindow);
-            len = !ism ? 1 : (mysz == 3 ? b3 + 16 : mysz == 4 ? (b3 | (b4 << 8)) + 272 : (v & 0xFu));
-            tok_end = myoff + mysz;
-            // a flag byte past the end reads as -1 -> 0x01, and the token read that follows throws: EndOfStream either way
-            bad = mypg >= slen || tok_end > slen;
         } else if constexpr (K == K_HUDSON) {
             // LZHudson.cs:54-55: FlagReader(source, Endian.Big, 4, Endian.Big) — one 4-byte big-endian flag word governs exactly
             // the 32 tokens of this iteration (bit 1 = literal, MSB first); tokens as Yaz0 (2 bytes, 3 when the high nibble
@@ -910,8 +873,10 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
 }
 
 // ---------------------------------------------------------------------------------------------
-// G32 core for Yaz0/Yaz1 (Yay0.cs:110-144 through Yaz0.cs:91-92) and LZ11 (LZ11.cs:83-133).  A match token is 2 bytes, or 3
-// when the high nibble of its first byte is 0 (LZ11: also 4 when it is 1), so a group's size depends on its own data and the chain of group starts cannot be a pure
+// G32 core for Yaz0/Yaz1 (Yay0.cs:110-144 through Yaz0.cs:91-92), LZ11 (LZ11.cs:83-133) and LZ40 / LZ60 (LZ40.cs:73-124: the flag
+// byte is negated, a match is a little-endian u16 DDDDDDDD DDDDLLLL whose LOW nibble selects the size, distance 0 is one
+// window back).  A match token is 2 bytes, or 3
+// when the selector nibble of its first byte is 0 (LZ11 / LZ40: also 4 when it is 1), so a group's size depends on its own data and the chain of group starts cannot be a pure
 // popcount chain.  The chain is still the only serial part: per group the warp loads the flag byte, builds a ballot mask
 // E of "high nibble == 0" over the group's next 32 bytes, and walks only the MATCH tokens of the group (highest flag bit
 // first) accumulating the number of 3-byte tokens: token i starts at 1 + i + matches_before + ext_before, and its
@@ -919,13 +884,19 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
 // (A fixed-point iteration over guessed group starts was tried first; on data with many long matches it needs one
 // round per group and was slower.)
 // ---------------------------------------------------------------------------------------------
-template <int K, class Sink>   // K_YAZ0 or K_LZ11
+template <int K, class Sink>   // K_YAZ0, K_LZ11 or K_LZ40
 __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32_t gaddr, const uint32_t slen,
                                            const uint32_t size, const uint32_t body_off) {
     const uint32_t lane = lane_id();
     const uint32_t rb = sink.rbase;
     uint32_t written = 0, cur = body_off, consumed = body_off;
     int status = AURORA_OK;
+    constexpr bool kFour = K == K_LZ11 || K == K_LZ40;                 // 2/3/4-byte match tokens (Yaz0: 2/3)
+    // the nibble of a match token's first byte that selects its size (0 -> 3 bytes, 1 -> 4 bytes): LZ40 keeps the length in
+    // the LOW nibble of a little-endian u16 (LZ40.cs:98-113), the others in the high nibble of the first byte
+    auto sel = [](uint32_t b1) { return K == K_LZ40 ? (b1 & 0xFu) : (b1 >> 4); };
+    // flag byte -> "bit set = match" (MSB first): Yaz0 inverts, LZ40 negates ((byte)-ReadByte(), LZ40.cs:88)
+    auto mbits = [](uint32_t fb) { return K == K_YAZ0 ? (fb ^ 0xFFu) : K == K_LZ40 ? ((0u - fb) & 0xFFu) : fb; };
     // Chain reuse: an iteration cut by the byte budget executes only its first groups; the starts of the others stay
     // exact, so they are carried (as offsets relative to the next window) instead of being walked again.
     uint32_t nkeep = 0, chain_rel = 0;   // carried groups; offset at which the walk continues
@@ -947,11 +918,11 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
             if (ca - wa > wlimit) break;
             sts_u32(gaddr + 4 * g, ca - wa);
             const uint32_t fb = lds_u8(ca);
-            const uint32_t hi4 = lds_u8(ca + 1 + lane) >> 4;
-            uint32_t mm = (K == K_YAZ0) ? (fb ^ 0xFFu) : fb, x = 0, cnt = 0;               // match bits, MSB first
+            const uint32_t hi4 = sel(lds_u8(ca + 1 + lane));
+            uint32_t mm = mbits(fb), x = 0, cnt = 0;                                       // match bits, MSB first
             if (mm) {   // an all-literal group is 9 bytes: no extension masks, no walk
                 const uint32_t E = __ballot_sync(kFull, hi4 == 0);                         // +1 byte
-                const uint32_t E2 = (K == K_LZ11) ? __ballot_sync(kFull, hi4 == 1) : 0u;   // +2 bytes (LZ11 4-byte tokens)
+                const uint32_t E2 = kFour ? __ballot_sync(kFull, hi4 == 1) : 0u;           // +2 bytes (LZ11 / LZ40 4-byte tokens)
                 do {   // visit only the match tokens (a branch-free walk over all eight tokens was measured: no gain)
                     const uint32_t hb = 31 - __clz(mm);
                     const uint32_t at = 7 - hb + cnt + x;
@@ -971,14 +942,14 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
         // ---- pass 1: my 8 tokens
         uint32_t b1v[8], lenv[8], orel[8];
         uint32_t gsize = 0, gin;
-        const uint32_t f = lds_u8(mya);
+        const uint32_t f = mbits(lds_u8(mya));   // bit set = match
         {
             uint32_t a = mya + 1;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const bool lit = ((f >> (7 - j)) & 1) == (K == K_YAZ0 ? 1u : 0u);
+                const bool lit = ((f >> (7 - j)) & 1) == 0;
                 const uint32_t b1 = lds_u8(a);
-                const uint32_t n = b1 >> 4;
+                const uint32_t n = sel(b1);
                 b1v[j] = b1;
                 orel[j] = gsize;
                 if (K == K_YAZ0) {
@@ -986,6 +957,13 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
                     const uint32_t b3 = lds_u8(a + 2);
                     lenv[j] = lit ? 1u : (ext ? b3 + 0x12u : n + 2u);
                     a += lit ? 1u : (ext ? 3u : 2u);
+                } else if (K == K_LZ40) {
+                    const uint32_t b3 = lds_u8(a + 2), b4 = lds_u8(a + 3);
+                    uint32_t l = n, sz = 2;   // DDDDDDDD DDDDLLLL little-endian: lengths 2..15 in the nibble itself
+                    if (n == 0) { l = b3 + 16; sz = 3; }
+                    if (n == 1) { l = (b3 | (b4 << 8)) + 272; sz = 4; }
+                    lenv[j] = lit ? 1u : l;
+                    a += lit ? 1u : sz;
                 } else {
                     const uint32_t b2 = lds_u8(a + 1), b3 = lds_u8(a + 2);
                     uint32_t l = n + 1, sz = 2;
@@ -998,7 +976,7 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
             }
             gin = a - mya;
         }
-        const uint32_t nm = __popc((K == K_YAZ0) ? (f ^ 0xFFu) : f);
+        const uint32_t nm = __popc(f);
         const uint32_t gclamp = min(gsize, 4095u);   // LZ11 groups can be huge; anything above kSubMaxG takes the long-group path
         const uint32_t incl = warp_incl_scan(valid ? (gclamp | (nm << 20)) : 0u);
         const uint32_t gincl = incl & 0xFFFFFu, gexcl = gincl - (valid ? gclamp : 0u);
@@ -1023,8 +1001,8 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
             bool stop = false;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const bool lit = ((f >> (7 - j)) & 1) == (K == K_YAZ0 ? 1u : 0u);
-                const uint32_t n = b1v[j] >> 4;
+                const bool lit = ((f >> (7 - j)) & 1) == 0;
+                const uint32_t n = sel(b1v[j]);
                 uint32_t need, next_a;
                 if (K == K_YAZ0) {
                     need = a + (lit ? 1u : 2u);   // the extended-length byte is optional (ReadByte)
@@ -1056,7 +1034,7 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
         break;
       }
         if (nlan == 0) {
-            if (K == K_LZ11 && status == AURORA_OK && __shfl_sync(kFull, gsize, 0) > uint32_t(kSubMaxG)) {
+            if (kFour && status == AURORA_OK && __shfl_sync(kFull, gsize, 0) > uint32_t(kSubMaxG)) {
                 // long-group path: the first group alone exceeds the iteration budget (matches of up to 65 808 bytes):
                 // its 8 tokens run one at a time, long matches as periodic 2 KiB segments with a drain in between
                 const uint32_t rel0 = __shfl_sync(kFull, myrel, 0), f0 = __shfl_sync(kFull, f, 0);
@@ -1066,7 +1044,7 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
                 for (int j = 0; j < 8; j++) {
                     const uint32_t b1 = __shfl_sync(kFull, b1v[j], 0), l = __shfl_sync(kFull, lenv[j], 0);
                     const bool lit = ((f0 >> (7 - j)) & 1) == 0;
-                    const uint32_t n = b1 >> 4, sz = lit ? 1u : (n == 0 ? 3u : n == 1 ? 4u : 2u);
+                    const uint32_t n = sel(b1), sz = lit ? 1u : (n == 0 ? 3u : n == 1 ? 4u : 2u);
                     if (!done && written < size) {
                         if (cur + rel0 >= slen || cur + a + sz > slen) {
                             status = AURORA_END_OF_STREAM;
@@ -1078,7 +1056,11 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
                             } else {
                                 const uint32_t ta = wa + a;
                                 const uint32_t c2 = lds_u8(ta + 1), c3 = lds_u8(ta + 2), c4 = lds_u8(ta + 3);
-                                const uint32_t d = n == 0 ? (((c2 & 0xF) << 8) | c3) + 1 : n == 1 ? (((c3 & 0xF) << 8) | c4) + 1 : (((b1 & 0xF) << 8) | c2) + 1;
+                                uint32_t d = n == 0 ? (((c2 & 0xF) << 8) | c3) + 1 : n == 1 ? (((c3 & 0xF) << 8) | c4) + 1 : (((b1 & 0xF) << 8) | c2) + 1;
+                                if (K == K_LZ40) {
+                                    d = (b1 | (c2 << 8)) >> 4;
+                                    if (d == 0) d = uint32_t(kWindow);   // BackCopy(0, n): one window back
+                                }
                                 sink.long_match(written, d, l);
                                 written += l;
                             }
@@ -1105,9 +1087,9 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
             const uint32_t gabs1 = cur + myrel + 1;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const bool lit = ((f >> (7 - j)) & 1) == (K == K_YAZ0 ? 1u : 0u);
+                const bool lit = ((f >> (7 - j)) & 1) == 0;
                 const bool e = uint32_t(j) < jexec;
-                const uint32_t b1 = b1v[j], n = b1 >> 4;
+                const uint32_t b1 = b1v[j], n = sel(b1);
                 const uint32_t pos = gbase + orel[j];
                 uint32_t len = lenv[j], sz;
                 if (K == K_YAZ0) {
@@ -1125,6 +1107,10 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
                     uint32_t dist = (((b1 & 0xF) << 8) | b2) + 1;
                     if (K == K_LZ11 && n == 0) dist = (((b2 & 0xF) << 8) | lds_u8(a + 2)) + 1;
                     if (K == K_LZ11 && n == 1) dist = (((lds_u8(a + 2) & 0xF) << 8) | lds_u8(a + 3)) + 1;
+                    if (K == K_LZ40) {
+                        dist = (b1 | (b2 << 8)) >> 4;
+                        if (dist == 0) dist = uint32_t(kWindow);   // BackCopy(0, n): one window back
+                    }
                     sts_u64(qaddr + 8 * qi, pos, len | (dist << 17));
                     qi++;
                 }
@@ -1435,18 +1421,18 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
                     in[0].begin(P.src_base, P.src_limit, src);
                 }
                 BodyResult r;
-                bool g32 = K != K_HUDSON && K != K_LZ40 && K != K_SMSR;
+                bool g32 = K != K_HUDSON && K != K_SMSR;
                 if (K == K_LZSS) g32 = 8u * (((1u << P.lzss.length_bits) - 1u) + uint32_t(P.lzss.min_length)) <= uint32_t(kSubMaxG);
                 if (g32) {
-                    if constexpr (K != K_HUDSON && K != K_LZ40 && K != K_SMSR) {
+                    if constexpr (K != K_HUDSON && K != K_SMSR) {
                     sink.begin(ring, fill, dst, limit);
                     if constexpr (K == K_MIO0 || K == K_YAY0) r = decode_body_g32_split<K>(in, sink, slen, size, comp_off, lit_off);
-                    else if constexpr (K == K_YAZ0 || K == K_LZ11) r = decode_body_g32_var<K>(in, sink, gaddr, slen, size, body_off);
+                    else if constexpr (K == K_YAZ0 || K == K_LZ11 || K == K_LZ40) r = decode_body_g32_var<K>(in, sink, gaddr, slen, size, body_off);
                     else r = decode_body_g32<K>(in, sink, gaddr, slen, size, body_off, P.lzss);
                     }
-                } else if constexpr (K == K_LZSS || K == K_HUDSON || K == K_LZ40 || K == K_SMSR) {
+                } else if constexpr (K == K_LZSS || K == K_HUDSON || K == K_SMSR) {
                     // LzProperties whose largest group exceeds an iteration, LZHudson (a 32-bit flag word is exactly one
-                    // 32-token iteration) and LZ40 / LZ60: the token-per-lane core, run by this warp alone
+                    // 32-token iteration) and SMSR00: the token-per-lane core, run by this warp alone
                     sink.wait_idle();
                     ring_prefill(ring, fill);
                     OutState out;
