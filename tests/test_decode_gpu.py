@@ -133,10 +133,12 @@ def test_lzss_properties(codec, oracle, props):
         assert (status == 0).all() and all(o == r for o, r in zip(outs, raws))
 
 
-def test_lz11_long_matches(codec, oracle):
-    """LZ11 matches of up to 65 808 bytes (LZ11.cs:106-112, 4-byte tokens): long constant / periodic runs between
-    literal-heavy stretches, valid, truncated and with short destinations — the group-per-lane core's long-group path."""
-    rng = np.random.default_rng(4111)
+@pytest.mark.parametrize("fmt", [A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60], ids=fmt_id)
+def test_lz11_long_matches(codec, oracle, fmt):
+    """LZ11 matches of up to 65 808 bytes (LZ11.cs:106-112, 4-byte tokens; LZ40 / LZ60: up to 65 807, LZ40.cs:103-113, and
+    a period of 4096 is encoded as distance 0): long constant / periodic runs between literal-heavy stretches, valid,
+    truncated and with short destinations — the group-per-lane core's long-group path."""
+    rng = np.random.default_rng(4111 + fmt)
     raws = []
     for i in range(48):
         parts = []
@@ -146,13 +148,43 @@ def test_lz11_long_matches(codec, oracle):
             n = int(rng.choice([272, 273, 274, 2303, 2304, 2305, 4000, 20000, 65807, 65808, 65809, 70000, 150000]))
             parts.append((period * (n // len(period) + 1))[:n])
         raws.append(b"".join(parts))
-    comps, st = oracle.encode_batch(A.FMT_LZ11, raws, A.make_opts(quality=8))
+    comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=8))
     assert (st == 0).all()
-    outs, status = _compare(codec, oracle, A.FMT_LZ11, comps, [len(r) for r in raws], what="lz11 long")
+    outs, status = _compare(codec, oracle, fmt, comps, [len(r) for r in raws], what="lz11 long")
     assert (status == 0).all() and all(o == r for o, r in zip(outs, raws))
     cut = [c[:int(rng.integers(5, len(c)))] for c in comps]
-    _compare(codec, oracle, A.FMT_LZ11, cut, [len(r) for r in raws], what="lz11 long truncated")
-    _compare(codec, oracle, A.FMT_LZ11, comps, [max(0, len(r) - int(rng.integers(1, 3000))) for r in raws], what="lz11 long short dst")
+    _compare(codec, oracle, fmt, cut, [len(r) for r in raws], what="lz11 long truncated")
+    _compare(codec, oracle, fmt, comps, [max(0, len(r) - int(rng.integers(1, 3000))) for r in raws], what="lz11 long short dst")
+
+
+@pytest.mark.parametrize("order", [A.ENDIAN_BIG, A.ENDIAN_LITTLE], ids=["big", "little"])
+def test_prs_batch_boundaries(codec, oracle, order):
+    """PRS element-per-lane batches (prs_batch32): literal runs that straddle flag bytes, short matches (2..5 bytes, distance
+    <= 256), long matches with and without the length byte (3..9 / 10..256 bytes, distances up to 8192), stretches of tiny
+    tokens, the end token and truncations inside a batch, in both byte orders."""
+    rng = np.random.default_rng(5300 + order)
+    opts = A.make_opts(quality=8, byte_order=order)
+    raws = []
+    for i in range(64):
+        out = bytearray(rng.integers(0, 256, size=int(rng.integers(8, 3000)), dtype=np.uint8).tobytes())
+        for _ in range(int(rng.integers(20, 400))):
+            lit = int(rng.choice([0, 0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 40]))
+            out += rng.integers(0, 256, size=lit, dtype=np.uint8).tobytes()
+            mlen = int(rng.choice([2, 3, 4, 5, 6, 9, 10, 11, 32, 33, 255, 256, 257, 600]))
+            dist = int(rng.choice([1, 2, 3, 7, 255, 256, 257, 1023, 1024, 1025, 2048, 8191, 8192, 8193]))
+            dist = min(dist, len(out))
+            for k in range(mlen):
+                out.append(out[len(out) - dist])
+        raws.append(bytes(out))
+    comps, st = oracle.encode_batch(A.FMT_PRS, raws, opts)
+    assert (st == 0).all()
+    outs, status = _compare(codec, oracle, A.FMT_PRS, comps, [len(r) for r in raws], opts, what="prs batch boundaries")
+    ok = sum(1 for o, r, s_ in zip(outs, raws, status) if s_ == 0 and o == r)
+    assert ok >= len(raws) - 12   # the reference's byte-order heuristic may pick the other order (DESIGN.md section 2)
+    cut = [c[:int(rng.integers(1, len(c)))] for c in comps]
+    _compare(codec, oracle, A.FMT_PRS, cut, [len(r) for r in raws], opts, what="prs batch boundaries truncated")
+    _compare(codec, oracle, A.FMT_PRS, comps, [max(0, len(r) - int(rng.integers(1, 2000))) for r in raws], opts, what="prs batch boundaries short dst")
+    _compare(codec, oracle, A.FMT_PRS, [c + bytes(rng.integers(0, 256, size=40, dtype=np.uint8)) for c in comps], [len(r) + 64 for r in raws], opts, what="prs trailing bytes")
 
 
 @pytest.mark.parametrize("fmt", [A.FMT_LZ4_BLOCK, A.FMT_LZ4, A.FMT_SNAPPY_BLOCK, A.FMT_SNAPPY, A.FMT_LZO], ids=fmt_id)

@@ -11,7 +11,7 @@ codec = BatchCodec(1)
 rng = np.random.default_rng(3)
 raws = [synth(rng, int(n), i % 5) for i, n in enumerate([0, 1, 5, 17, 300, 4097, 9000, 20000, 70000, 33, 1000, 2500])]
 bad = 0
-for fmt in ALL_FORMATS:
+for fmt in ALL_FORMATS + [A.FMT_ECD, A.FMT_LZ00, A.FMT_LZ77]:   # + the keystream pass, host-written prefixes, chunked sub-streams
     comps, st = O.encode_batch(fmt, raws, A.make_opts(quality=8))
     blobs, caps = [], []
     for r, c, s in zip(raws, comps, st):
@@ -21,7 +21,7 @@ for fmt in ALL_FORMATS:
     outs, ol, co, gs = codec.decode_batch(fmt, blobs, caps)
     ref, rl, rc, rs = O.decode_batch(fmt, blobs, caps)
     bad += sum(1 for i in range(len(blobs)) if outs[i] != ref[i] or gs[i] != rs[i])
-for fmt in (A.FMT_LZ10, A.FMT_YAZ0, A.FMT_MIO0, A.FMT_LZSS):
+for fmt in (A.FMT_LZ10, A.FMT_YAZ0, A.FMT_MIO0, A.FMT_LZSS, A.FMT_LZHUDSON, A.FMT_LZ40, A.FMT_SMSR00, A.FMT_LZ00, A.FMT_ECD, A.FMT_PRS):
     got, st = codec.encode_batch(fmt, raws[:9], A.make_opts(quality=8))
     ref, rst = O.encode_batch(fmt, raws[:9], A.make_opts(quality=8))
     bad += sum(1 for a, b in zip(got, ref) if a != b)
