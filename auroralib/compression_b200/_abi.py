@@ -21,6 +21,7 @@ FMT_LZ00 = 32   # 64-byte header + LZSS (Lzss0) under a per-byte LCG keystream
 WRAPPER_FORMATS = list(range(15, 33))
 FMT_LZHUDSON = 33   # a core format: Yay0 tokens under 32-bit big-endian flag words
 FMT_LZ40, FMT_LZ60 = 34, 35   # core formats: LZ11-like 2/3/4-byte tokens (LE, length in the low nibble), negated flag bytes
+FMT_BLZ = 37                  # core format (own kernel): Nintendo BLZ, parsed and written backwards from the end of the stream
 FMT_SMSR00 = 36               # core format: MIO0 tokens, 16-bit BE mask words interleaved with the codes, literals in their own section
 FORMAT_NAMES = {FMT_YAZ0: "Yaz0", FMT_YAZ1: "Yaz1", FMT_YAY0: "Yay0", FMT_MIO0: "MIO0", FMT_LZ10: "LZ10",
                 FMT_LZ11: "LZ11", FMT_LZSS: "LZSS", FMT_LZ4: "LZ4", FMT_LZ4_BLOCK: "LZ4Block",
@@ -28,7 +29,7 @@ FORMAT_NAMES = {FMT_YAZ0: "Yaz0", FMT_YAZ1: "Yaz1", FMT_YAY0: "Yay0", FMT_MIO0: 
                 FMT_SNAPPY_BLOCK: "SnappyBlock", FMT_PRS: "PRS", FMT_GCLZ: "GCLZ", FMT_CXLZ: "CXLZ", FMT_COMP: "COMP",
                 FMT_LZ_3DS: "3DS-LZ", FMT_LZ77: "LZ77", FMT_LEVEL5: "Level5", FMT_LZON: "LZOn", FMT_LEVEL5_LZSS: "Level5LZSS",
                 FMT_AKLZ: "AKLZ", FMT_LZ01: "LZ01", FMT_FCMP: "FCMP", FMT_IECP: "IECP", FMT_MDB4: "MDB4", FMT_LZSEGA: "LZSega",
-                FMT_GCZ: "GCZ", FMT_SDPC: "SDPC", FMT_ECD: "ECD", FMT_LZ00: "LZ00", FMT_LZHUDSON: "LZHudson", FMT_LZ40: "LZ40", FMT_LZ60: "LZ60", FMT_SMSR00: "SMSR00"}
+                FMT_GCZ: "GCZ", FMT_SDPC: "SDPC", FMT_ECD: "ECD", FMT_LZ00: "LZ00", FMT_LZHUDSON: "LZHudson", FMT_LZ40: "LZ40", FMT_LZ60: "LZ60", FMT_SMSR00: "SMSR00", FMT_BLZ: "BLZ"}
 
 ENDIAN_LITTLE, ENDIAN_BIG, ENDIAN_DEFAULT = 0, 1, 2
 

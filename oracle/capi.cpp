@@ -73,6 +73,7 @@ DecodeResult decode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t
             case FMT_LZ40: lz40_decode(s, d, 0x40); break;
             case FMT_LZ60: lz40_decode(s, d, 0x60); break;
             case FMT_SMSR00: smsr00_decode(s, d); break;
+            case FMT_BLZ: blz_decode(s, d); break;
             default:
                 if (!is_wrapper_format(fmt)) fail(INVALID_ARGUMENT);
                 wrapper_decode(fmt, s, d, o);
@@ -110,6 +111,7 @@ int encode_one(int fmt, const CodecOpts& o, const uint8_t* src, int64_t n64, std
             case FMT_LZ40: lz40_encode(src, n, b, o, 0x40); break;
             case FMT_LZ60: lz40_encode(src, n, b, o, 0x60); break;
             case FMT_SMSR00: smsr00_encode(src, n, b, o); break;
+            case FMT_BLZ: blz_encode(src, n, b, o); break;
             default:
                 if (!is_wrapper_format(fmt)) return INVALID_ARGUMENT;
                 wrapper_encode(fmt, src, n, b, o, o.lz77Type, o.lz77ChunkSize, o.level5Type);
@@ -127,7 +129,7 @@ uint32_t decoded_size(int fmt, Src& s, const CodecOpts& o) {
     struct R { Src& s; int64_t p; ~R() { s.pos = p; } } r{s, p0};
     switch (fmt) {
         case FMT_YAZ0: case FMT_YAZ1: case FMT_YAY0: case FMT_MIO0: case FMT_LZ10: case FMT_LZ11: case FMT_LZ40: case FMT_LZ60:
-        case FMT_SMSR00:
+        case FMT_SMSR00: case FMT_BLZ:
             return nintendo_decoded_size(fmt, s, o);
         case FMT_LZSS:   // LZSS.cs:45-50
             s.MatchThrow("LZSS", 4);
@@ -168,6 +170,11 @@ bool is_match(int fmt, Src& s, const CodecOpts&) {
         case FMT_PRS: return s.pos + 0x4 < s.len && prs_get_byte_order(s) >= 0;   // PRS.cs:31-32
         case FMT_LZHUDSON: return s.pos + 0x8 < s.len && s.ReadUInt32() != 0;     // LZHudson.cs:31-32 (no file name given)
         case FMT_SMSR00: return s.pos + 0x10 < s.len && s.Match("SMSR00", 6);   // SMSR00.cs:36-37
+        case FMT_BLZ: {   // BLZ.cs:31-32: the footer's compressed size is the whole stream, footer size >= 8
+            if (s.len < 8) return false;
+            s.pos = s.len - 8;
+            return int64_t(s.ReadUInt24()) == s.len && s.ReadByte() >= 8;
+        }
         case FMT_LZ40: case FMT_LZ60:   // LZ40.cs:41-43, LZ60.cs:31-33: identifier and a non-zero size ("recognition is inaccurate!")
             return s.pos + 0x8 < s.len && s.ReadByte() == (fmt == FMT_LZ40 ? 0x40 : 0x60) && (s.ReadUInt24() != 0 || s.ReadUInt32() != 0);
         // wrapper formats (GCLZ.cs:30-31, CXLZ.cs:31-32, COMP.cs:30-31, 3DS-LZ.cs:29-30, LZ77.cs:46-47, LZOn.cs:29-30,

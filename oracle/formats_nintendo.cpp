@@ -545,6 +545,113 @@ void smsr00_encode(const uint8_t* source, int n, OutBuf& destination, const Code
     destination.Write(uncompressedData.v.data(), uncompressedData.size());
 }
 
+// ------------------------------------------------------------------ BLZ
+// AuroraLib.Compression.Nintendo/Nintendo/BLZ.cs: the stream is parsed from its END.  Footer (last 8 bytes): u24 LE compressed
+// size (codes + padding + footer), u8 footer-and-padding size (>= 8), i32 LE (decoded size - compressed size).  The codes are
+// read backwards (:104-141): flag byte (MSB first, 0 = literal), literals and big-endian-when-reversed u16 codes
+// (length - 3) << 12 | (distance - 3), and the output is written backwards.  Decompress (:45-69) decodes into a rented
+// buffer and writes it to the destination only when the decode succeeded.
+static const LzProps kBlz = LzProps::Window(0x1000, 18, 3, 0, 3);   // BLZ.cs:24
+
+void blz_decode(Src& source, Sink& destination) {
+    const int64_t length = source.len;
+    if (length < 8) { source.pos = length; fail(END_OF_STREAM); }   // Position = Length - 8 is negative / the footer reads run out
+    source.pos = length - 8;
+    const uint32_t compressedSize = source.ReadUInt24();
+    const uint8_t headerAndPaddingSize = source.ReadUInt8();
+    const int32_t decompressedSize = int32_t(uint32_t(source.ReadUInt32()) + compressedSize);
+    const int32_t codeSize = int32_t(compressedSize) - headerAndPaddingSize;
+    if (headerAndPaddingSize < 8) fail(INVALID_DATA);                // "Invalid BLZ header."
+    if (int64_t(compressedSize) > length) fail(INVALID_DATA);        // Position = negative: ArgumentOutOfRangeException
+    if (codeSize < 0 || decompressedSize < 0) fail(INVALID_DATA);    // ArrayPool.Rent(negative)
+    source.pos = length - compressedSize;
+    const uint8_t* in = source.p + source.pos;
+    source.pos += codeSize;                                          // source.Read(inBuffer, 0, codeSize)
+    std::vector<uint8_t> out(size_t(decompressedSize) + 1);
+    {
+        int src = codeSize, dst = decompressedSize;
+        int flags = 0, mask = 0;
+        while (src > 0) {
+            if ((mask >>= 1) == 0) {
+                flags = in[--src];
+                mask = 0x80;
+            }
+            if ((flags & mask) == 0) {
+                if (dst == 0) fail(INVALID_DATA);     // destination[--dst]: IndexOutOfRangeException (evaluated before the source read)
+                if (src == 0) fail(END_OF_STREAM);    // source[--src]
+                out[size_t(--dst)] = in[--src];
+            } else {
+                if (src < 2) fail(END_OF_STREAM);
+                int info = (in[src - 1] << 8) | in[src - 2];
+                src -= 2;
+                int distance = (info & 0x0FFF) + 3;
+                int len = ((info >> 12) & 0xF) + 3;
+                for (int i = 0; i < len && dst > 0; i++) {
+                    if (dst - 1 + distance >= decompressedSize) fail(INVALID_DATA);   // reads past the end of the buffer
+                    out[size_t(dst - 1)] = out[size_t(dst - 1 + distance)];
+                    dst--;
+                }
+            }
+        }
+        if (dst != 0) fail(SIZE_MISMATCH, uint32_t(decompressedSize), int64_t(decompressedSize) - dst);
+    }
+    // destination.Write(outBuffer, 0, decompressedSize): a fixed-size destination refuses the whole write
+    if (destination.pos + decompressedSize > destination.cap && !destination.size_only) fail(DST_TOO_SMALL);
+    destination.Write(out.data(), decompressedSize);
+}
+
+void blz_encode(const uint8_t* sourceIn, int n, OutBuf& destinationStream, const CodecOpts& o) {
+    // CompressHeaderless (:143-215): the match finder runs over the REVERSED source, tokens are written from the end of a buffer
+    std::vector<uint8_t> destination(size_t(n) + size_t(n) / 5 + 64);
+    std::vector<uint8_t> source(sourceIn, sourceIn + n);
+    std::reverse(source.begin(), source.end());
+    int src = 0, dst = int(destination.size()) - 2, flag = 1, flagPos = int(destination.size()) - 1;
+    MatchFinder mf(kBlz, o.settings);
+    auto WriteFlag = [&]() {
+        if ((flag & 0x100) != 0) {
+            destination[size_t(flagPos)] = uint8_t(flag);
+            flag = 1;
+            flagPos = dst--;
+        }
+    };
+    while (src < n) {
+        LzMatch match = mf.FindNextBestMatch(source.data(), n);
+        int plain = match.Offset - src;
+        while (plain != 0) {
+            flag <<= 1;
+            destination[size_t(dst--)] = source[size_t(src++)];
+            WriteFlag();
+            plain--;
+        }
+        if (match.Length == 0) break;
+        flag <<= 1;
+        int lzCode = uint16_t((match.Length - 3) << 12 | ((match.Distance - 3) & 0xFFF));
+        destination[size_t(dst--)] = uint8_t(lzCode >> 8);
+        destination[size_t(dst--)] = uint8_t(lzCode);
+        src += match.Length;
+        flag |= 1;
+        WriteFlag();
+    }
+    if (flag != 1) {
+        while ((flag & 0x100) == 0) flag <<= 1;   // == flag << (8 - Log2(flag)): left-align the partial flag byte
+        destination[size_t(flagPos)] = uint8_t(flag);
+    } else {
+        dst++;   // no flag written, one step back
+    }
+    const int compressedSize = int(destination.size()) - dst - 1;
+    // Compress (:71-99): the codes, 0xFF padding to 16 bytes, then the footer
+    destinationStream.Write(destination.data() + destination.size() - size_t(compressedSize), size_t(compressedSize));
+    int headerSize = 8;
+    int totalSize = compressedSize + headerSize;
+    const int padding = (16 - (totalSize % 16)) % 16;
+    totalSize += padding;
+    headerSize += padding;
+    for (int i = 0; i < padding; i++) destinationStream.WriteByte(0xFF);
+    destinationStream.WriteU24(uint32_t(totalSize), Endian::Little);
+    destinationStream.WriteByte(uint8_t(headerSize));
+    destinationStream.WriteU32(uint32_t(n - totalSize), Endian::Little);
+}
+
 // ------------------------------------------------------------------ sizes / IsMatch helpers
 uint32_t nintendo_decoded_size(int fmt, Src& s, const CodecOpts& o) {
     switch (fmt) {
@@ -553,6 +660,13 @@ uint32_t nintendo_decoded_size(int fmt, Src& s, const CodecOpts& o) {
         case FMT_LZ40: return lz1x_size(s, 0x40);   // LZ40.cs:47-52
         case FMT_LZ60: return lz1x_size(s, 0x60);   // LZ60.cs:37-47
         case FMT_SMSR00: s.MatchThrow("SMSR00", 6); s.pos += 2; return s.ReadUInt32(Endian::Big);   // SMSR00.cs:40-46
+        case FMT_BLZ: {   // BLZ.cs:35-43
+            if (s.len < 8) { s.pos = s.len; fail(END_OF_STREAM); }
+            s.pos = s.len - 8;
+            uint32_t compressedSize = s.ReadUInt24();
+            if (s.ReadUInt8() < 8) fail(INVALID_DATA);
+            return s.ReadUInt32() + compressedSize;
+        }
         case FMT_YAZ0:
         case FMT_YAZ1: {   // Yaz0.cs:50-55
             s.MatchThrow(fmt == FMT_YAZ0 ? "Yaz0" : "Yaz1", 4);

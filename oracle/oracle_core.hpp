@@ -37,7 +37,7 @@ enum Format : int {
     FMT_GCLZ = 15, FMT_CXLZ = 16, FMT_COMP = 17, FMT_LZ_3DS = 18, FMT_LZ77 = 19, FMT_LEVEL5 = 20, FMT_LZON = 21, FMT_LEVEL5_LZSS = 22,
     FMT_AKLZ = 23, FMT_LZ01 = 24, FMT_FCMP = 25, FMT_IECP = 26, FMT_MDB4 = 27, FMT_LZSEGA = 28, FMT_GCZ = 29, FMT_SDPC = 30,
     FMT_ECD = 31, FMT_LZ00 = 32,
-    FMT_LZHUDSON = 33, FMT_LZ40 = 34, FMT_LZ60 = 35, FMT_SMSR00 = 36
+    FMT_LZHUDSON = 33, FMT_LZ40 = 34, FMT_LZ60 = 35, FMT_SMSR00 = 36, FMT_BLZ = 37
 };
 
 struct Error {
@@ -451,6 +451,8 @@ void yaz0_decode(Src& s, Sink& d, const CodecOpts& o, const char* magic);
 void yay0_decode(Src& s, Sink& d, const CodecOpts& o);
 void lz40_decode(Src& s, Sink& d, uint8_t id);
 void lz40_encode(const uint8_t* src, int n, OutBuf& out, const CodecOpts& o, uint8_t id);
+void blz_decode(Src& s, Sink& d);
+void blz_encode(const uint8_t* src, int n, OutBuf& out, const CodecOpts& o);
 void smsr00_decode(Src& s, Sink& d);
 void smsr00_encode(const uint8_t* src, int n, OutBuf& out, const CodecOpts& o);
 void lzhudson_decode(Src& s, Sink& d);
