@@ -443,6 +443,17 @@ class LZHudson(_SizedCodec):
     FORMAT, Name = _abi.FMT_LZHUDSON, "LZHudson"
 
 
+class BLZ(_SizedCodec):
+    """Nintendo/BLZ.cs: parsed and written backwards from the footer at the end of the stream (its own kernel, decode_blz.cu)."""
+    FORMAT, Name = _abi.FMT_BLZ, "Nintendo BLZ"
+
+    def GetDecompressedSize(self, source):   # the footer sits at Length - 8: the whole stream is needed
+        _, data = _remaining(source)
+        size, st = default_codec().decoded_size_batch(self.FORMAT, [data], self._opts())
+        _raise_for(int(st[0]))
+        return int(size[0])
+
+
 class SMSR00(_SizedCodec):
     """Nintendo/SMSR00.cs: "SMSR00" header, MIO0 tokens with 16-bit big-endian mask words interleaved with the codes and the
     literals in their own section (a core format)"""
@@ -518,4 +529,4 @@ class LZ00(_WholeHeaderPeek, _SizedCodec):
 
 
 WRAPPERS = [GCLZ, CXLZ, COMP, LZ_3DS, LZ77, Level5, LZOn, Level5LZSS, AKLZ, LZ01, FCMP, IECP, MDB4, LZSega, GCZ, SDPC, ECD, LZ00]
-ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS, LZHudson, LZ40, LZ60, SMSR00] + WRAPPERS
+ALGORITHMS = [Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZ4, LZ4Legacy, LZO, Snappy, PRS, LZHudson, LZ40, LZ60, SMSR00, BLZ] + WRAPPERS

@@ -137,6 +137,7 @@ cudaError_t launch_encode(const EncodeParams& p, int warps, cudaStream_t st) {
 }
 
 cudaError_t launch_decode(const DecodeParams& p, int sm_count, cudaStream_t st) {
+    if (p.format == AURORA_FMT_BLZ) return launch_decode_blz(p, sm_count, st);
     if (is_flaglz(p.format)) return launch_decode_flaglz(p, sm_count, st);
     return launch_decode_bytelz(p, sm_count, st);
 }
@@ -715,7 +716,7 @@ int aurora_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* op
     if (!ctx) return AURORA_INVALID_ARGUMENT;
     if (n == 0) return AURORA_OK;
     if (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_cap || !status ||
-        !(is_flaglz(format) || is_bytelz(format) || aurora::is_wrapper_format(format))) {
+        !(is_flaglz(format) || is_bytelz(format) || format == AURORA_FMT_BLZ || aurora::is_wrapper_format(format))) {
         ctx->set_error("aurora_decode_batch: null argument or unknown format");
         return AURORA_INVALID_ARGUMENT;
     }
@@ -738,6 +739,20 @@ int aurora_decoded_size_batch(aurora_ctx* ctx, int format, const aurora_codec_op
     const int bo = opts ? opts->byte_order : AURORA_ENDIAN_DEFAULT;
     auto be32 = [](const uint8_t* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; };
     auto le32 = [](const uint8_t* p) { return uint32_t(p[0]) | (uint32_t(p[1]) << 8) | (uint32_t(p[2]) << 16) | (uint32_t(p[3]) << 24); };
+    if (format == AURORA_FMT_BLZ) {   // BLZ.cs:35-43: the footer at Length - 8
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t len = src_len[i];
+            const uint8_t* f = src_base + src_off[i] + (len >= 8 ? len - 8 : 0);
+            out_size[i] = 0;
+            if (len < 8) status[i] = AURORA_END_OF_STREAM;
+            else if (f[3] < 8) status[i] = AURORA_INVALID_DATA;   // "Invalid BLZ header."
+            else {
+                out_size[i] = uint32_t(le32(f + 4) + (uint32_t(f[0]) | (uint32_t(f[1]) << 8) | (uint32_t(f[2]) << 16)));
+                status[i] = AURORA_OK;
+            }
+        }
+        return AURORA_OK;
+    }
     if (is_flaglz(format)) {
         // GetDecompressedSize is a header peek (e.g. Yaz0.cs:50-55, LZ10.cs:47-57): a few bytes of host memory
         for (size_t i = 0; i < n; i++) {
@@ -916,6 +931,11 @@ int aurora_is_match_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* 
             case AURORA_FMT_YAZ1: m = magic16(i, "Yaz1", 4); break;
             case AURORA_FMT_LZHUDSON: m = 0x8 < src_len[i] && (p[0] | p[1] | p[2] | p[3]) != 0; break;   // LZHudson.cs:31-32, no file name
             case AURORA_FMT_SMSR00: m = magic16(i, "SMSR00", 6); break;   // SMSR00.cs:36-37
+            case AURORA_FMT_BLZ: {   // BLZ.cs:31-32: the footer's compressed size is the whole stream, footer size >= 8
+                const uint64_t len = src_len[i];
+                m = len >= 8 && (uint64_t(p[len - 8]) | (uint64_t(p[len - 7]) << 8) | (uint64_t(p[len - 6]) << 16)) == len && p[len - 5] >= 8;
+                break;
+            }
             case AURORA_FMT_LZ40:   // LZ40.cs:41-43, LZ60.cs:31-33: identifier and a non-zero size ("recognition is inaccurate!")
             case AURORA_FMT_LZ60:
                 m = 0x8 < src_len[i] && p[0] == (format == AURORA_FMT_LZ40 ? 0x40 : 0x60) && ((p[1] | p[2] | p[3]) != 0 || (p[4] | p[5] | p[6] | p[7]) != 0);
@@ -971,7 +991,7 @@ int aurora_decode_batch_device(aurora_ctx* ctx, int device, int format, const au
                                void* stream) {
     if (!ctx || device < 0 || device >= int(ctx->devs.size())) return AURORA_INVALID_ARGUMENT;
     if (n == 0) return AURORA_OK;
-    if (!(is_flaglz(format) || is_bytelz(format)) || n > 0xFFFFFFF0ull) return AURORA_INVALID_ARGUMENT;
+    if (!(is_flaglz(format) || is_bytelz(format) || format == AURORA_FMT_BLZ) || n > 0xFFFFFFF0ull) return AURORA_INVALID_ARGUMENT;
     if ((reinterpret_cast<uintptr_t>(d_src_base) & 15) != 0) {
         ctx->set_error("aurora_decode_batch_device: d_src_base must be 16-byte aligned");
         return AURORA_INVALID_ARGUMENT;

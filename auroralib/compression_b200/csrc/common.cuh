@@ -66,6 +66,7 @@ struct EncodeParams {
 // kernel launchers (one translation unit per kernel family); all return cudaGetLastError()
 cudaError_t launch_decode_flaglz(const DecodeParams& p, int sm_count, cudaStream_t st);
 cudaError_t launch_decode_bytelz(const DecodeParams& p, int sm_count, cudaStream_t st);
+cudaError_t launch_decode_blz(const DecodeParams& p, int sm_count, cudaStream_t st);
 cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st);
 cudaError_t launch_encode_bytelz(const EncodeParams& p, int warps, cudaStream_t st);
 size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64_t max_src_len);

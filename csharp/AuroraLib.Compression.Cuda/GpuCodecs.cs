@@ -277,6 +277,15 @@ namespace AuroraLib.Compression.Cuda
         public uint GetDecompressedSize(Stream source) => PeekSize(source);
     }
 
+    public sealed class GpuBLZ : GpuCodec, IProvidesDecompressedSize
+    {
+        private readonly Formats.Nintendo.BLZ _managed = new Formats.Nintendo.BLZ();
+        protected override AuroraFormat Format => AuroraFormat.BLZ;
+        protected override ICompressionAlgorithm Managed => _managed;
+        protected override long PeekBytes => long.MaxValue;   // the footer sits at Length - 8
+        public uint GetDecompressedSize(Stream source) => PeekSize(source);
+    }
+
     public sealed class GpuSMSR00 : GpuCodec, IProvidesDecompressedSize
     {
         private readonly Formats.Nintendo.SMSR00 _managed = new Formats.Nintendo.SMSR00();

@@ -26,7 +26,9 @@ namespace AuroraLib.Compression.Cuda
         // core formats: LZ11-like tokens, little-endian with the length in the low nibble, negated flag bytes
         LZ40 = 34, LZ60 = 35,
         // core format: MIO0 tokens, 16-bit big-endian mask words interleaved with the codes, literals in their own section
-        SMSR00 = 36
+        SMSR00 = 36,
+        // core format with its own kernel: parsed and written backwards from the footer at the end of the stream
+        BLZ = 37
     }
 
     [StructLayout(LayoutKind.Sequential)]

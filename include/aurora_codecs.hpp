@@ -355,6 +355,13 @@ class LZHudson : public SizedAlgorithm {   // HudsonSoft/LZHudson.cs: u32 BE siz
   public:
     AURORA_FORMAT(LZHudson, AURORA_FMT_LZHUDSON, "LZHudson")
 };
+class BLZ : public SizedAlgorithm {   // Nintendo/BLZ.cs: backwards from the footer at the end of the stream
+  public:
+    AURORA_FORMAT(BLZ, AURORA_FMT_BLZ, "Nintendo BLZ")
+
+  protected:
+    size_t PeekBytes() const override { return SIZE_MAX; }   // the footer sits at Length - 8
+};
 class SMSR00 : public SizedAlgorithm {   // Nintendo/SMSR00.cs: MIO0 tokens, 16-bit masks interleaved with the codes
   public:
     AURORA_FORMAT(SMSR00, AURORA_FMT_SMSR00, "Nintendo SMSR00")

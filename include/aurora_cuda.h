@@ -86,7 +86,9 @@ typedef enum aurora_format {
     AURORA_FMT_LZHUDSON     = 33, /* HudsonSoft/LZHudson.cs: u32 BE size + interleaved 4-byte flag words / tokens */
     AURORA_FMT_LZ40         = 34, /* Nintendo/LZ40.cs: 0x40 + u24 size; negated flag bytes, LE tokens of 2 / 3 / 4 bytes */
     AURORA_FMT_LZ60         = 35, /* Nintendo/LZ60.cs: the LZ40 codec under identifier 0x60                   */
-    AURORA_FMT_SMSR00       = 36  /* Nintendo/SMSR00.cs: MIO0 tokens, 16-bit BE masks interleaved with the codes, literals in their own section */
+    AURORA_FMT_SMSR00       = 36, /* Nintendo/SMSR00.cs: MIO0 tokens, 16-bit BE masks interleaved with the codes, literals in their own section */
+    AURORA_FMT_BLZ          = 37  /* Nintendo/BLZ.cs: parsed and written backwards from the footer at the end of the stream (decode: own kernel;
+                                     encode: not built yet, AURORA_NOT_SUPPORTED)                          */
 } aurora_format;
 
 typedef enum aurora_endian {

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from auroralib.compression_b200 import _abi as A
-from tests.util import ALL_FORMATS, SIZED_FORMATS, fmt_id, synth
+from tests.util import ALL_FORMATS, SIZED_FORMATS, end_position, fmt_id, synth
 
 
 def test_fixture_integrity(bmp, test_lz):
@@ -34,7 +34,7 @@ def test_lzss_static_decoding(oracle, bmp, test_lz):
 
 Q0_SIZES = {A.FMT_YAZ0: 183160, A.FMT_YAY0: 183160, A.FMT_LZ10: 261953, A.FMT_MIO0: 261898, A.FMT_LZSS: 261898,
             A.FMT_LZ11: 179455, A.FMT_LZ4_LEGACY: 175023, A.FMT_LZO: 161204, A.FMT_SNAPPY: 209184, A.FMT_PRS: 165729,
-            A.FMT_LZ40: 179488, A.FMT_LZ60: 179488, A.FMT_LZ00: 261946}
+            A.FMT_LZ40: 179488, A.FMT_LZ60: 179488, A.FMT_LZ00: 261946, A.FMT_BLZ: 345456}
 
 
 @pytest.mark.parametrize("fmt", sorted(Q0_SIZES), ids=fmt_id)
@@ -45,10 +45,10 @@ def test_published_q0_ratios(oracle, bmp, fmt):
     assert st == 0 and len(comp) == Q0_SIZES[fmt]
     published = {A.FMT_YAZ0: 17.89, A.FMT_YAY0: 17.89, A.FMT_LZ10: 25.58, A.FMT_MIO0: 25.58, A.FMT_LZSS: 25.58, A.FMT_LZ11: 17.52,
                  A.FMT_LZ4_LEGACY: 17.09, A.FMT_LZO: 15.74, A.FMT_SNAPPY: 20.43, A.FMT_PRS: 16.18,
-                 A.FMT_LZ40: 17.53, A.FMT_LZ60: 17.53, A.FMT_LZ00: 25.58}[fmt]   # (LZ60 is LZ40 under another identifier)
+                 A.FMT_LZ40: 17.53, A.FMT_LZ60: 17.53, A.FMT_LZ00: 25.58, A.FMT_BLZ: 33.74}[fmt]   # (LZ60 is LZ40 under another identifier)
     assert round(100 * len(comp) / len(raw), 2) == published
     out, out_len, consumed, status = oracle.decode(fmt, comp, len(raw))
-    assert status == 0 and out == raw and consumed == len(comp)
+    assert status == 0 and out == raw and consumed == end_position(fmt, comp)
 
 
 def test_q15_and_whole_file_sizes(oracle, bmp):
@@ -68,7 +68,7 @@ def test_reference_round_trips(oracle, bmp, fmt):
         comp, st = oracle.encode(fmt, bmp[:n], A.make_opts(quality=q))
         assert st == 0
         out, out_len, consumed, status = oracle.decode(fmt, comp, n)
-        assert status == 0 and out == bmp[:n] and consumed == len(comp)
+        assert status == 0 and out == bmp[:n] and consumed == end_position(fmt, comp)
 
 
 def test_lz4_frame_whole_file(oracle, bmp):

@@ -4,12 +4,18 @@ import numpy as np
 from auroralib.compression_b200 import _abi as A
 
 ALL_FORMATS = [A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_YAY0, A.FMT_MIO0, A.FMT_LZ10, A.FMT_LZ11, A.FMT_LZSS, A.FMT_LZ4,
-               A.FMT_LZ4_LEGACY, A.FMT_LZ4_BLOCK, A.FMT_LZO, A.FMT_SNAPPY, A.FMT_SNAPPY_BLOCK, A.FMT_PRS, A.FMT_LZHUDSON, A.FMT_LZ40, A.FMT_LZ60, A.FMT_SMSR00]
-SIZED_FORMATS = [A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_YAY0, A.FMT_MIO0, A.FMT_LZ10, A.FMT_LZ11, A.FMT_LZSS, A.FMT_LZHUDSON, A.FMT_LZ40, A.FMT_LZ60, A.FMT_SMSR00]
+               A.FMT_LZ4_LEGACY, A.FMT_LZ4_BLOCK, A.FMT_LZO, A.FMT_SNAPPY, A.FMT_SNAPPY_BLOCK, A.FMT_PRS, A.FMT_LZHUDSON, A.FMT_LZ40, A.FMT_LZ60, A.FMT_SMSR00, A.FMT_BLZ]
+SIZED_FORMATS = [A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_YAY0, A.FMT_MIO0, A.FMT_LZ10, A.FMT_LZ11, A.FMT_LZSS, A.FMT_LZHUDSON, A.FMT_LZ40, A.FMT_LZ60, A.FMT_SMSR00, A.FMT_BLZ]
 
 
 def fmt_id(f):
     return A.FORMAT_NAMES[f]
+
+
+def end_position(fmt, comp):
+    """source.Position after a successful Decompress: the end of the stream, except BLZ, which reads its codes from the middle
+    of the stream and leaves the position in front of the padding and the footer (BLZ.cs:56-62)."""
+    return len(comp) - comp[-5] if fmt == A.FMT_BLZ else len(comp)
 
 
 def synth(rng, n, kind):

@@ -17,7 +17,7 @@ from oracle import oracle as O  # noqa: E402
 
 FMT = {"lz10": A.FMT_LZ10, "yaz0": A.FMT_YAZ0, "lz4b": A.FMT_LZ4_BLOCK, "mio0": A.FMT_MIO0, "yay0": A.FMT_YAY0,
        "lz11": A.FMT_LZ11, "lzss": A.FMT_LZSS, "lzo": A.FMT_LZO, "snappyb": A.FMT_SNAPPY_BLOCK, "prs": A.FMT_PRS,
-       "lz4": A.FMT_LZ4, "snappy": A.FMT_SNAPPY, "lzhudson": A.FMT_LZHUDSON, "lz40": A.FMT_LZ40, "lz60": A.FMT_LZ60, "smsr00": A.FMT_SMSR00}
+       "lz4": A.FMT_LZ4, "snappy": A.FMT_SNAPPY, "lzhudson": A.FMT_LZHUDSON, "lz40": A.FMT_LZ40, "lz60": A.FMT_LZ60, "smsr00": A.FMT_SMSR00, "blz": A.FMT_BLZ}
 
 
 def main():
