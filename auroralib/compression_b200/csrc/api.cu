@@ -132,7 +132,7 @@ int fill_decode_params(DecodeParams& p, int format, const aurora_codec_opts* o) 
 }
 
 cudaError_t launch_encode(const EncodeParams& p, int warps, cudaStream_t st) {
-    if (is_flaglz(p.format)) return launch_encode_lz(p, warps, st);
+    if (is_flaglz(p.format) || p.format == AURORA_FMT_BLZ) return launch_encode_lz(p, warps, st);   // BLZ: LZ10's layout
     return launch_encode_bytelz(p, warps, st);
 }
 
@@ -450,6 +450,7 @@ int fill_encode_params(EncodeParams& p, int format, const aurora_codec_opts* o) 
             aurora_lz_props_window(&lz, 0x1000, 18, 3, 0, vram ? 2 : 1);
             break;
         }
+        case AURORA_FMT_BLZ: aurora_lz_props_window(&lz, 0x1000, 18, 3, 0, 3); break;   // BLZ.cs:24: minimum distance 3
         case AURORA_FMT_LZ40:   // LZ40.cs:29-30, :35: the LZ11 properties, GbaVramCompatibilityMode default false
         case AURORA_FMT_LZ60:
         case AURORA_FMT_LZ11: {
@@ -547,6 +548,10 @@ int encode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
             if (src_len[i]) CU_TRY(ctx, cudaMemcpyAsync(dsrc + S.dev_off[i - b], src_base + src_off[i], src_len[i], cudaMemcpyHostToDevice, st));
     }
     CU_TRY(ctx, cudaMemsetAsync(d->ticket.p, 0, 64, st));
+    if (format == AURORA_FMT_BLZ) {   // the match finder runs over the reversed source (the device copy, in place)
+        CU_TRY(ctx, launch_reverse_bytes(dsrc, dv, dv + n, nullptr, uint32_t(n), st));
+        ctx->launches++;
+    }
     P.scratch = static_cast<uint8_t*>(d->scratch.p);
     P.src_base = dsrc;
     P.src_limit = S.bytes;
@@ -561,6 +566,10 @@ int encode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     P.n = uint32_t(n);
     CU_TRY(ctx, launch_encode(P, warps, st));
     ctx->launches++;
+    if (format == AURORA_FMT_BLZ) {   // the codes are stored in the order the backwards decoder reads them
+        CU_TRY(ctx, launch_reverse_bytes(ddst, P.dst_off, P.out_len, P.dst_cap, P.n, st));
+        ctx->launches++;
+    }
     if (xor_key) {   // LZ00: the body the encoder just wrote goes under the keystream (bytes [skip, out_len) of every stream)
         uint32_t* hkey = reinterpret_cast<uint32_t*>(h + 5 * n) + n;
         uint32_t* dkey = reinterpret_cast<uint32_t*>(dv + 5 * n) + n;
@@ -1063,7 +1072,25 @@ int aurora_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* op
     }
     if (aurora::is_wrapper_format(format))
         return aurora::wrapped_encode_batch(ctx, format, opts, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status);
-    return aurora::encode_core_batch(ctx, format, opts, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status);
+    const int rc = aurora::encode_core_batch(ctx, format, opts, n, src_base, src_off, src_len, dst_base, dst_off, dst_cap, out_len, status);
+    if (rc == AURORA_OK && format == AURORA_FMT_BLZ) {
+        // BLZ.Compress (BLZ.cs:78-92): behind the codes 0xFF padding to a multiple of 16, then the footer — u24 LE total size,
+        // u8 footer-and-padding size, i32 LE (decoded size - total size)
+        for (size_t i = 0; i < n; i++) {
+            if (status[i] != AURORA_OK) continue;
+            const uint64_t total0 = out_len[i] + 8, padding = (16 - total0 % 16) % 16, total = total0 + padding;
+            if (total > dst_cap[i]) { status[i] = AURORA_DST_TOO_SMALL; continue; }
+            uint8_t* d = dst_base + dst_off[i] + out_len[i];
+            std::memset(d, 0xFF, size_t(padding));
+            d += padding;
+            d[0] = uint8_t(total); d[1] = uint8_t(total >> 8); d[2] = uint8_t(total >> 16);
+            d[3] = uint8_t(8 + padding);
+            const uint32_t delta = uint32_t(src_len[i]) - uint32_t(total);
+            d[4] = uint8_t(delta); d[5] = uint8_t(delta >> 8); d[6] = uint8_t(delta >> 16); d[7] = uint8_t(delta >> 24);
+            out_len[i] = total;
+        }
+    }
+    return rc;
 }
 
 }  // extern "C"
@@ -1114,7 +1141,8 @@ int aurora_encode_batch_device(aurora_ctx* ctx, int device, int format, const au
     std::lock_guard<std::mutex> guard(d->mu);
     CU_TRY(ctx, cudaSetDevice(d->dev));
     EncodeParams P{};
-    const int rc = fill_encode_params(P, format, opts);
+    const int rc = format == AURORA_FMT_BLZ ? AURORA_NOT_SUPPORTED   // needs the reversal passes and the host-written footer
+                                             : fill_encode_params(P, format, opts);
     if (rc != AURORA_OK) {
         ctx->set_error("aurora_encode_batch_device: unknown format or invalid settings");
         return rc;

@@ -67,6 +67,9 @@ struct EncodeParams {
 cudaError_t launch_decode_flaglz(const DecodeParams& p, int sm_count, cudaStream_t st);
 cudaError_t launch_decode_bytelz(const DecodeParams& p, int sm_count, cudaStream_t st);
 cudaError_t launch_decode_blz(const DecodeParams& p, int sm_count, cudaStream_t st);
+// in-place byte reversal of bytes [0, min(len[i], cap[i])) of every stream (BLZ encode; decode_blz.cu); cap may be null
+cudaError_t launch_reverse_bytes(uint8_t* base, const uint64_t* d_off, const uint64_t* d_len, const uint64_t* d_cap, uint32_t n,
+                                 cudaStream_t st);
 cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st);
 cudaError_t launch_encode_bytelz(const EncodeParams& p, int warps, cudaStream_t st);
 size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64_t max_src_len);

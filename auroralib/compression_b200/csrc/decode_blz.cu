@@ -110,7 +110,31 @@ __global__ void __launch_bounds__(kBlzWarpsPerBlock * 32) decode_blz_kernel(cons
     }
 }
 
+// in-place byte reversal of bytes [0, min(len[i], cap[i])) of every stream (the encoder's match finder "only works in one
+// direction", BLZ.cs:152-156: the source is reversed, encoded forwards, and the code stream reversed again)
+__global__ void __launch_bounds__(256) reverse_bytes_kernel(uint8_t* base, const uint64_t* off, const uint64_t* len, const uint64_t* cap,
+                                                           uint32_t n) {
+    for (uint32_t s = blockIdx.x; s < n; s += gridDim.x) {
+        uint64_t m = len[s];
+        if (cap && cap[s] < m) m = cap[s];
+        uint8_t* p = base + off[s];
+        for (uint64_t i = uint64_t(blockIdx.y) * blockDim.x + threadIdx.x; i < m / 2; i += uint64_t(gridDim.y) * blockDim.x) {
+            const uint8_t a = p[i], b = p[m - 1 - i];
+            p[i] = b;
+            p[m - 1 - i] = a;
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_reverse_bytes(uint8_t* base, const uint64_t* d_off, const uint64_t* d_len, const uint64_t* d_cap, uint32_t n,
+                                 cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const dim3 grid(n < 4736u ? n : 4736u, n >= 1184u ? 1u : n >= 148u ? 8u : 32u);
+    reverse_bytes_kernel<<<grid, 256, 0, st>>>(base, d_off, d_len, d_cap, n);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_decode_blz(const DecodeParams& p, int sm_count, cudaStream_t st) {
     int blocks = sm_count * 4;   // 64 resident warps per SM

@@ -71,8 +71,13 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
         }
 
         // ---- headers
+        // BLZ.cs:143-215: CompressHeaderless over the (already reversed) source — LZ10's flag / token layout without a header,
+        // distance - 3 in the code; the host side reverses the code stream and appends padding + footer
+        const bool blz = K == E_LZ10 && P.format == AURORA_FMT_BLZ;
         const bool lz40 = K == E_LZ11 && (P.format == AURORA_FMT_LZ40 || P.format == AURORA_FMT_LZ60);   // LZ40.cs:126-168
-        if (K == E_LZ10 || K == E_LZ11) {
+        if (blz) {
+            // no header
+        } else if (K == E_LZ10 || K == E_LZ11) {
             const uint32_t id = K == E_LZ10 ? 0x10 : !lz40 ? 0x11 : P.format == AURORA_FMT_LZ40 ? 0x40 : 0x60;
             w.negate = lz40;
             if (n <= 0xFFFFFF) {
@@ -136,7 +141,7 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
             if (m.length == 0) break;
             const uint32_t d1 = uint32_t(m.distance - 1) & 0xFFF;
             if (K == E_LZ10) {
-                const uint32_t v = uint32_t(m.length - 3) << 12 | d1;
+                const uint32_t v = uint32_t(m.length - 3) << 12 | (blz ? uint32_t(m.distance - 3) & 0xFFF : d1);
                 w.byte((v >> 8) & 0xFF);
                 w.byte(v & 0xFF);
                 w.bit(true);
@@ -293,7 +298,8 @@ size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64
 
 cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st) {
     switch (p.format) {
-        case AURORA_FMT_LZ10: return launch<E_LZ10>(p, warps, st);
+        case AURORA_FMT_LZ10:
+        case AURORA_FMT_BLZ: return launch<E_LZ10>(p, warps, st);   // BLZ: LZ10's layout over the reversed source, distance - 3
         case AURORA_FMT_LZ11:
         case AURORA_FMT_LZ40:
         case AURORA_FMT_LZ60: return launch<E_LZ11>(p, warps, st);   // LZ40 / LZ60: the LZ11 parse with LE tokens and negated flags

@@ -87,7 +87,9 @@ static __device__ __forceinline__ void match_search(Finder& f, const uint8_t* da
         if (cur != -1) {
             int distance = pos - cur;
             if (distance < f.min_dist) distance = f.min_dist;
-            if (distance <= f.max_dist) {
+            // (a raised distance that points in front of the buffer is no match: the reference compares through an unsafe
+            //  pointer against whatever memory precedes the source there — undefined; DESIGN.md section 2, deviation 6)
+            if (distance <= f.max_dist && pos - distance >= 0) {
                 best_len = match_length(data, pos, pos - distance, best_possible);
                 if (f.no_self_overlap && best_len > distance) best_len = distance;
                 best_dist = distance;

@@ -88,7 +88,7 @@ typedef enum aurora_format {
     AURORA_FMT_LZ60         = 35, /* Nintendo/LZ60.cs: the LZ40 codec under identifier 0x60                   */
     AURORA_FMT_SMSR00       = 36, /* Nintendo/SMSR00.cs: MIO0 tokens, 16-bit BE masks interleaved with the codes, literals in their own section */
     AURORA_FMT_BLZ          = 37  /* Nintendo/BLZ.cs: parsed and written backwards from the footer at the end of the stream (decode: own kernel;
-                                     encode: not built yet, AURORA_NOT_SUPPORTED)                          */
+                                     encode: reversal passes around the LZ10-layout encoder, host entry point only) */
 } aurora_format;
 
 typedef enum aurora_endian {

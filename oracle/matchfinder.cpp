@@ -149,7 +149,10 @@ void MatchFinder::MatchSearch(const uint8_t* data, int dataLength, int pos, int 
         if (cur != -1) {
             int distance = pos - cur;
             if (distance < minDistance_) distance = minDistance_;
-            if (distance <= maxDistance_) {
+            // Raising the distance to MinDistance can point in front of the buffer (pos < MinDistance: LZ10 / LZ11 VRAM mode,
+            // BLZ): the reference compares through an unsafe pointer there, i.e. against whatever memory precedes the source
+            // (undefined, nondeterministic).  Here — and in the GPU finder — such a candidate is no match.
+            if (distance <= maxDistance_ && pos - distance >= 0) {
                 bestLength = GetMatchLength(dataPos, data + pos - distance, bestPossible);
                 (void)ScoreMatch(bestLength, distance);
                 bestDistance = distance;

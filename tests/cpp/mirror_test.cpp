@@ -20,7 +20,9 @@ static int round_trip(T&& algo, const std::string& raw, const CompressionSetting
     if (comp.tellg() != std::streampos(0)) { std::printf("%s: IsMatch moved the stream\n", algo.Name()); return 1; }
     algo.Decompress(comp, out);
     if (out.str() != raw) { std::printf("%s: round trip differs\n", algo.Name()); return 1; }
-    if (size_t(comp.tellg()) != comp.str().size()) { std::printf("%s: source not left at the end of the compressed bytes\n", algo.Name()); return 1; }
+    size_t end = comp.str().size();
+    if (std::string(algo.Name()) == "Nintendo BLZ") end -= uint8_t(comp.str()[end - 5]);   // BLZ leaves the source in front of its padding + footer
+    if (size_t(comp.tellg()) != end) { std::printf("%s: source not left at the end of the compressed bytes\n", algo.Name()); return 1; }
     (void)sized;
     std::printf("%s: %zu -> %zu bytes ok\n", algo.Name(), raw.size(), comp.str().size());
     return 0;
@@ -71,6 +73,7 @@ int main(int argc, char** argv) {
         bad += round_trip(SDPC(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(LZHudson(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(SMSR00(), raw, CompressionSettings::Balanced(), true);
+        bad += round_trip(BLZ(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(LZ40(), raw, CompressionSettings::Maximum(), true);
         bad += round_trip(LZ60(), raw, CompressionSettings::Balanced(), true);
         bad += round_trip(ECD(), raw, CompressionSettings::Balanced(), true);
