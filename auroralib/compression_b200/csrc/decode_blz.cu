@@ -57,11 +57,30 @@ __device__ void blz_decode_stream(const DecodeParams& P, uint32_t idx) {
                     mask = 0x80;
                 }
                 if ((flags & mask) == 0) {
+#ifdef AURORA_BLZ_LITRUN
+                    // the literal bits that follow in the SAME flag byte govern the next code bytes: one warp step for the run.
+                    // The first literal fails on dst == 0 (checked first) or src == 0; before every further one the loop
+                    // condition ends the walk cleanly when the codes are used up, and dst == 0 is the error that remains.
+                    if (d == 0) { status = AURORA_INVALID_DATA; break; }
+                    if (src == 0) { status = AURORA_END_OF_STREAM; break; }
+                    const uint32_t below = flags & ((mask << 1) - 1u);            // the flag bits from `mask` downwards
+                    const int32_t run = below ? int32_t(__clz(below)) - int32_t(__clz(mask)) : 32 - int32_t(__clz(mask));
+                    const int32_t k = min(run, min(d, src));
+                    if (store && int32_t(lane) < k) out[d - 1 - int32_t(lane)] = in[src - 1 - int32_t(lane)];
+                    d -= k;
+                    src -= k;
+                    if (k < run) {
+                        if (src != 0) status = AURORA_INVALID_DATA;   // dst == 0 with codes left
+                        break;
+                    }
+                    mask >>= (k - 1);
+#else
                     if (d == 0) { status = AURORA_INVALID_DATA; break; }    // destination[--dst] is evaluated first
                     if (src == 0) { status = AURORA_END_OF_STREAM; break; }
                     --d;
                     --src;
                     if (store && lane == 0) out[d] = in[src];
+#endif
                 } else {
                     if (src < 2) { status = AURORA_END_OF_STREAM; break; }
                     const uint32_t info = (uint32_t(in[src - 1]) << 8) | in[src - 2];

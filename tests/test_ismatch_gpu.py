@@ -53,9 +53,10 @@ def test_decoded_size_parity(codec, oracle, fmt):
 def test_data_recognition_through_the_mirror(codec, oracle):
     """256 zero bytes at CompressionSettings.Fastest: Compress on the GPU, IsMatch true, GetDecompressedSize 0x100,
     Decompress round trip — the reference's DataRecognitionTest + EncodingAndDecodingMatchTest shape."""
-    from auroralib.compression_b200 import LZ10, LZ11, LZSS, MIO0, CompressionSettings, Yay0, Yaz0, Yaz1
+    from auroralib.compression_b200 import BLZ, LZ10, LZ11, LZ40, LZ60, LZSS, MIO0, SMSR00, CompressionSettings, LZHudson, Yay0, Yaz0, Yaz1
+    from tests.util import end_position
     data = bytes(0x100)
-    for cls in (Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS):
+    for cls in (Yaz0, Yaz1, Yay0, MIO0, LZ10, LZ11, LZSS, LZHudson, LZ40, LZ60, SMSR00, BLZ):
         algo = cls()
         comp = algo.Compress(data, None, CompressionSettings.Fastest)
         ref, st = oracle.encode(algo.FORMAT, data, A.make_opts(quality=0))
@@ -64,7 +65,7 @@ def test_data_recognition_through_the_mirror(codec, oracle):
         assert algo.GetDecompressedSize(comp) == 0x100
         assert comp.tell() == 0
         out = algo.Decompress(comp)
-        assert out.getvalue() == data and comp.tell() == len(ref)
+        assert out.getvalue() == data and comp.tell() == end_position(algo.FORMAT, ref)
 
 
 def test_mirror_streams_and_exceptions(codec, oracle, bmp):
