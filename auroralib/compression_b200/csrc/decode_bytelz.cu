@@ -763,7 +763,9 @@ __device__ __forceinline__ bool lzo_ext(InStream& in, uint32_t& sp, uint32_t sle
 // marker and instructions that leave the staged window end the batch.  `at` = position of the first flag byte.
 // Measured (round 1), batch + 20 warps vs element-at-a-time + 23 warps: C2 corpus 284 vs 266 GB/s, but C4-like (131 072 streams
 // of 4-64 KiB, the BASELINE config of LZO) 301 vs 351 GB/s — LZO's chain is twice as heavy as LZ4's and short literal-heavy
-// streams rarely batch.  Compiled only with -DAURORA_LZO_BATCH until the chain is cheaper.
+// streams rarely batch.  Re-measured at 16 warps (64 registers, no spills; the 20 / 23-warp builds spill): C2 corpus 313 vs 266
+// (class T 371 vs 247), C4-like 328 vs 351 GB/s: the batches win on long streams, the resident warps win on the short streams of
+// LZO's BASELINE config.  Compiled only with -DAURORA_LZO_BATCH (-DAURORA_LZO_WARPS=16) until one build wins both.
 __device__ __forceinline__ uint32_t lzo_batch32(InStream& in, GOut& out, uint32_t& at, uint32_t& plain_io, const uint32_t slen) {
     const uint32_t lane = lane_id();
     in.ensure(at, kInMirror - 16);
