@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -289,7 +290,15 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     size_t pieces = 1;
     // (not with a keystream pass: piece k+1's upload starts at a 16-byte boundary and may rewrite the tail of piece k's
     //  last stream, harmless only as long as the device copy still equals the host bytes)
-    if (S.span && (size_only || D.span) && total_bytes > (64ull << 20) && n >= 64 && !xor_key) pieces = std::min<size_t>(16, std::max<size_t>(2, total_bytes >> 28));
+    if (S.span && (size_only || D.span) && total_bytes > (64ull << 20) && n >= 64 && !xor_key) {
+        size_t max_pieces = 16;
+        int shift = 28;
+        if (const char* e = std::getenv("AURORA_MAX_PIECES")) {   // developer knob: finer pieces
+            max_pieces = std::min<size_t>(48, std::max<size_t>(2, size_t(std::atoi(e))));
+            shift = 27;
+        }
+        pieces = std::min<size_t>(max_pieces, std::max<size_t>(2, total_bytes >> shift));
+    }
     if (pieces > 1) {
         while (d->ev_in.size() < pieces) {
             cudaEvent_t e1, e2;
