@@ -61,6 +61,19 @@ def test_q15_and_whole_file_sizes(oracle, bmp):
             assert st == 0 and len(comp) == e
 
 
+def test_q15_ratios_within_a_tenth_of_a_point_of_the_published_ones(oracle, bmp):
+    """Benchmarks.md Q15 ratios on the first 1 024 000 bytes of Test.bmp.  LZO is exact (test above); the 4 KiB-window formats
+    come out 0.07-0.08 percentage points SMALLER than published (LZ10 22.76 vs 22.84 %, LZ11 14.20 vs 14.28 %, Yaz0 14.93 vs
+    15.01 %) — consistently, so either Benchmarks.md predates the mounted sources or the chain walk differs in a corner that
+    only deep chains reach ("parity unpinned" beyond this tolerance).  The Q0 ratios are exact."""
+    published = {A.FMT_LZ10: 22.84, A.FMT_LZ11: 14.28, A.FMT_YAZ0: 15.01, A.FMT_YAY0: 15.01, A.FMT_MIO0: 22.84, A.FMT_LZSS: 22.84,
+                 A.FMT_LZ40: 14.28, A.FMT_LZ00: 22.84, A.FMT_BLZ: 22.86, A.FMT_PRS: 13.83}
+    raw = bmp[:1024000]
+    for fmt, pct in published.items():
+        comp, st = oracle.encode(fmt, raw, A.make_opts(quality=15))
+        assert st == 0 and abs(100 * len(comp) / len(raw) - pct) <= 0.10, (fmt_id(fmt), 100 * len(comp) / len(raw), pct)
+
+
 @pytest.mark.parametrize("fmt", ALL_FORMATS, ids=fmt_id)
 def test_reference_round_trips(oracle, bmp, fmt):
     """EncodingAndDecodingMatchTest_{10b, 10kb_Balanced, 10kb_Maximum, 1MB_Fastest} (:81-130)."""
