@@ -217,12 +217,41 @@ Layout plan_layout(const uint64_t* off, const uint64_t* len, size_t b, size_t e)
     return L;
 }
 
+
+// Device -> host copy of the destination windows [off[i], off[i] + ext(i)) of streams [i0, i1) in span mode.  Windows that
+// follow each other in ascending order with a gap of at most `gap_tol` bytes (the alignment padding of a packed batch)
+// travel as one copy; anything else starts a new copy, and no copy starts before the first window of its run.  With
+// gap_tol = 0 only the windows themselves are written (the wrapper formats run several sub-batches over one destination).
+template <typename Ext>
+cudaError_t copy_back_windows(uint8_t* dst_base, const uint8_t* ddst, uint64_t dev_lo, const uint64_t* off, size_t i0, size_t i1, Ext ext,
+                              uint64_t gap_tol, cudaStream_t st) {
+    size_t i = i0;
+    while (i < i1) {
+        uint64_t lo = off[i], hi = off[i] + ext(i), prev = off[i];
+        size_t j = i + 1;
+        while (j < i1 && off[j] >= prev && off[j] <= hi + gap_tol) {
+            hi = std::max(hi, off[j] + ext(j));
+            prev = off[j];
+            j++;
+        }
+        if (hi > lo) {
+            cudaError_t e = cudaMemcpyAsync(dst_base + lo, ddst + (lo - dev_lo), hi - lo, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+        }
+        i = j;
+    }
+    return cudaSuccess;
+}
+
 int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_opts* opts, size_t b, size_t e,
                  const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
                  const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t* out_len, uint64_t* consumed, int32_t* status,
-                 int size_only, const uint64_t* raw_size = nullptr, const uint32_t* xor_key = nullptr) {
+                 int size_only, const uint64_t* raw_size = nullptr, const uint32_t* xor_key = nullptr, bool exact = false) {
     const size_t n = e - b;
     if (n == 0) return AURORA_OK;
+    // exact (the sub-batches of the wrapper formats): only the bytes a stream produced are written to the host.  Otherwise the
+    // whole capacity windows come back, and windows at most 15 bytes apart (alignment padding) travel as one copy.
+    const uint64_t gap_tol = exact ? 0 : 15;
     std::lock_guard<std::mutex> guard(d->mu);
     CU_TRY(ctx, cudaSetDevice(d->dev));
     DecodeParams P{};
@@ -290,7 +319,7 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     size_t pieces = 1;
     // (not with a keystream pass: piece k+1's upload starts at a 16-byte boundary and may rewrite the tail of piece k's
     //  last stream, harmless only as long as the device copy still equals the host bytes)
-    if (S.span && (size_only || D.span) && total_bytes > (64ull << 20) && n >= 64 && !xor_key) {
+    if (S.span && (size_only || D.span) && total_bytes > (64ull << 20) && n >= 64 && !xor_key && !exact) {
         size_t max_pieces = 16;
         int shift = 28;
         if (const char* e = std::getenv("AURORA_MAX_PIECES")) {   // developer knob: finer pieces
@@ -359,12 +388,7 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
             if (!size_only) {
                 CU_TRY(ctx, cudaEventRecord(d->ev_k[k], st));
                 CU_TRY(ctx, cudaStreamWaitEvent(d->s_out, d->ev_k[k], 0));
-                uint64_t dlo = ~0ull, dhi = 0;
-                for (size_t i = i0; i < i1; i++) {
-                    dlo = std::min(dlo, dst_off[b + i]);
-                    dhi = std::max(dhi, dst_off[b + i] + dst_cap[b + i]);
-                }
-                if (dhi > dlo) CU_TRY(ctx, cudaMemcpyAsync(dst_base + dlo, ddst + (dlo - D.lo), dhi - dlo, cudaMemcpyDeviceToHost, d->s_out));
+                CU_TRY(ctx, copy_back_windows(dst_base, ddst, D.lo, dst_off, b + i0, b + i1, [&](size_t i) { return dst_cap[i]; }, gap_tol, d->s_out));
             }
         }
         CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, 2 * n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -402,10 +426,13 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
         ctx->launches++;
         CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, 2 * n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         if (!size_only) {
-            if (D.span) {
-                uint64_t hi = 0;
-                for (size_t i = b; i < e; i++) hi = std::max(hi, dst_off[i] + dst_cap[i]);
-                if (hi > D.lo) CU_TRY(ctx, cudaMemcpyAsync(dst_base + D.lo, ddst, hi - D.lo, cudaMemcpyDeviceToHost, st));
+            if (D.span && exact) {
+                CU_TRY(ctx, cudaStreamSynchronize(st));   // out_len is on the host
+                CU_TRY(ctx, copy_back_windows(dst_base, ddst, D.lo, dst_off, b, e,
+                                              [&](size_t i) { return std::min<uint64_t>(h[4 * n + (i - b)], dst_cap[i]); }, 0, st));
+                CU_TRY(ctx, cudaStreamSynchronize(st));
+            } else if (D.span) {
+                CU_TRY(ctx, copy_back_windows(dst_base, ddst, D.lo, dst_off, b, e, [&](size_t i) { return dst_cap[i]; }, gap_tol, st));
                 CU_TRY(ctx, cudaStreamSynchronize(st));
             } else {
                 CU_TRY(ctx, cudaStreamSynchronize(st));
@@ -591,9 +618,9 @@ int encode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
     CU_TRY(ctx, cudaStreamSynchronize(st));
     const int32_t* hs = reinterpret_cast<const int32_t*>(h + 5 * n);
     if (D.span) {
-        uint64_t hi = 0;
-        for (size_t i = b; i < e; i++) hi = std::max(hi, dst_off[i] + std::min<uint64_t>(h[4 * n + (i - b)], dst_cap[i]));
-        if (hi > D.lo) CU_TRY(ctx, cudaMemcpyAsync(dst_base + D.lo, ddst, hi - D.lo, cudaMemcpyDeviceToHost, st));
+        // exactly the bytes every stream produced (the capacities of an encode batch are bounds, mostly unused)
+        CU_TRY(ctx, copy_back_windows(dst_base, ddst, D.lo, dst_off, b, e,
+                                      [&](size_t i) { return std::min<uint64_t>(h[4 * n + (i - b)], dst_cap[i]); }, 0, st));
     } else {
         for (size_t i = b; i < e; i++) {
             const uint64_t nbytes = std::min<uint64_t>(h[4 * n + (i - b)], dst_cap[i]);
@@ -1065,7 +1092,8 @@ uint64_t aurora_encode_bound(int format, uint64_t raw_len) {
         case AURORA_FMT_LZ4_BLOCK: return raw_len + raw_len / 255 + 64 + 8 * (raw_len / 0x400000 + 1);
         case AURORA_FMT_SNAPPY:
         case AURORA_FMT_SNAPPY_BLOCK: return raw_len + raw_len / 60 + 32 + 16 * (raw_len / 0x10000 + 1);
-        case AURORA_FMT_LZO: return raw_len + raw_len / 255 + 32;
+        // LZO: a far 3-byte match costs 3 bytes and splits the literal run around it (4 literals + 1 match = 7 bytes in, 8 out)
+        case AURORA_FMT_LZO: return raw_len + raw_len / 6 + 64;
         default: return raw_len + raw_len / 8 + 64;
     }
 }
@@ -1109,12 +1137,12 @@ namespace aurora {
 int decode_core_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
                       const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
                       const uint64_t* dst_cap, const uint64_t* raw_size, uint64_t* out_len, uint64_t* consumed, int32_t* status,
-                      const uint32_t* xor_key) {
+                      const uint32_t* xor_key, bool exact) {
     if (n == 0) return AURORA_OK;
     const std::vector<Range> ranges = shard(n, int(ctx->devs.size()), src_len, dst_cap, dst_off);
     return for_each_shard(ctx, ranges, [&](DeviceCtx* d, Range r) {
         return decode_shard(ctx, d, format, opts, r.begin, r.end, src_base, src_off, src_len, dst_base, dst_off, dst_cap,
-                            out_len, consumed, status, 0, raw_size, xor_key);
+                            out_len, consumed, status, 0, raw_size, xor_key, exact);
     });
 }
 

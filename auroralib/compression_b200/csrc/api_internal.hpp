@@ -11,10 +11,11 @@ namespace aurora {
 // raw_size: nullptr, or per-stream decoded sizes of headerless LZ10 / LZ11 / LZSS bodies (DecompressHeaderless).
 // xor_key: nullptr, or per-stream LZ00 keys: the keystream pass (keystream.cu) runs on the device copy of every source
 // stream before it is decoded, resp. over bytes [xor_skip, out_len) of every encoded stream.
+// exact: write only the bytes every stream produced to the host (several sub-batches share one destination).
 int decode_core_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
                       const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
                       const uint64_t* dst_cap, const uint64_t* raw_size, uint64_t* out_len, uint64_t* consumed, int32_t* status,
-                      const uint32_t* xor_key = nullptr);
+                      const uint32_t* xor_key = nullptr, bool exact = false);
 int encode_core_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* opts, size_t n, const uint8_t* src_base,
                       const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
                       const uint64_t* dst_cap, uint64_t* out_len, int32_t* status, const uint32_t* xor_key = nullptr,

@@ -11,17 +11,17 @@
 //   window AuroraLib.Compression/IO/LzWindows.cs:72-115 (BackCopy/OffsetCopy), FlagReader.cs:53-65
 //
 // Design (B200, sm_100a):
-//   * persistent grid, one warp per stream, streams handed out by a global ticket (largest first when
-//     the host supplies an order array);
-//   * the compressed bytes are staged into a per-warp shared-memory ring by 1-D TMA bulk copies
+//   * persistent grid, ONE WARP PER STREAM SLOT, streams handed out by a global ticket (largest first when the host
+//     supplies an order array); a block holds as many slots as its 227 KiB of shared memory allow;
+//   * the compressed bytes are staged into a per-slot shared-memory ring by 1-D TMA bulk copies
 //     (cp.async.bulk + mbarrier complete_tx), two 1 KiB chunks in flight per sub-stream;
-//   * 32 tokens are parsed per warp iteration: flag words give literal/match per lane, token offsets are
-//     popcount prefix sums (LZ10/LZSS/MIO0/Yay0) or a short uniform walk over an extended-token ballot
-//     mask (Yaz0/LZ11); output positions come from a shuffle prefix scan over the token lengths;
-//   * the decoded bytes live in a per-warp 8 KiB shared-memory ring that always holds the last 4 KiB
-//     window, so back-references never touch HBM: literals are scattered in one step, matches are
-//     warp-cooperative copies out[dst+i] = out[dst-d + (i mod d)] (the BackCopy chunk loop), and the ring
-//     is drained to HBM in 512-byte, 16-byte-per-lane vector stores.
+//   * one flag GROUP per lane (256 tokens per warp iteration): the serial part is only the chain of group starts,
+//     and runs of equally sized groups (all-literal, all-match) are resolved by one ballot instead of the walk;
+//   * the decoded bytes live in a per-slot 8 KiB shared-memory ring that always holds the last 4 KiB window, so
+//     back-references never touch HBM: literals are scattered lane-locally, the matches of an iteration are queued
+//     and then resolved ONE MATCH PER LANE in dependency rounds (a match is ready when the last unresolved match
+//     below it ends at or before its source), long matches warp-cooperatively, and the ring is drained to HBM in
+//     512-byte, 16-byte-per-lane vector stores.
 #include "common.cuh"
 #include "stage.cuh"
 
@@ -29,44 +29,59 @@ namespace aurora {
 
 namespace {
 
-constexpr int kRing = 8192;          // per-warp output ring (bytes)
+constexpr int kRing = 8192;          // per-slot output ring (bytes)
 constexpr int kRingMask = kRing - 1;
 constexpr int kWindow = 4096;        // largest back-reference distance of the family
-constexpr int kSubMax = 2048;        // output bytes resolved per sub-batch (ring keeps window + sub-batch + drain slack)
+constexpr int kSubMax = 2048;        // token-per-lane core: output bytes resolved per sub-batch
 constexpr int kFlush = 512;          // bytes per ring->HBM drain step (16 B per lane)
-constexpr int kQueueSplit = 168;     // same for the three-sub-stream formats (128 would give 12 slots per SM at 80 registers: measured slower, spills)
-constexpr int kQueue = 168;          // match descriptors per G32 iteration (an iteration is cut when its queue is full)
-constexpr int kSubMaxG = 2304;       // G32: output bytes per iteration (>= the largest single group)
+#ifndef AURORA_HANDOFF_AT
+#define AURORA_HANDOFF_AT 32
+#endif
+constexpr int kIterMatches = 144 - AURORA_HANDOFF_AT;    // match descriptors one iteration may queue (an iteration is cut at the group that would exceed it)
+constexpr int kHandoffAt = AURORA_HANDOFF_AT;       // queued matches at which a batch is handed to the resolver warp
+constexpr int kQueue = kIterMatches + kHandoffAt;   // entries of ONE queue buffer (a slot has two)
+constexpr int kHandoffSpan = 2048;   // ... or this many bytes of literals
+constexpr int kSubMaxG = 2304;       // smallest iteration budget the cores rely on (>= the largest single group: 8 x 273)
+constexpr int kIterCap = kRing - kWindow;   // output bytes of one iteration: window + iteration fit the ring, and the
+                                            // slots an iteration overwrites (positions 8192 lower) are below the window
+                                            // and below everything not yet drained (< 512 bytes behind the iteration)
 #ifndef AURORA_REG_DELTA
 #define AURORA_REG_DELTA 24
 #endif
-constexpr int kPairSpan = 4096;      // parser/replayer pipeline: two consecutive iterations in flight, window + both + drain slack <= ring
 
 
 enum Kind { K_LZ10 = 0, K_LZ11 = 1, K_YAZ0 = 2, K_LZSS = 3, K_MIO0 = 4, K_YAY0 = 5, K_HUDSON = 6, K_LZ40 = 7, K_SMSR = 8 };
 
 // Shared memory of one stream slot (the launcher adds 8 KiB of alignment slack for the rings):
-//   ring 8 KiB | staged sub-streams | match queue x2 (+ read slack) | group offsets | mailboxes x2 | stream descriptor | mbarriers
+//   ring 8 KiB | staged sub-streams | match queue x2 | group offsets | mailboxes x2 + stream descriptor | TMA mbarriers
+// A block holds kSlots slots served by 2 * kSlots warps (warpgroups alternate parser / resolver roles); a slot's parser and
+// resolver hand batches over through two hardware named barriers, so kSlots <= 8 (16 barriers per block) and an SM runs
+// as many blocks as its shared memory holds (two for the single-sub-stream formats).
 template <int K>
 struct Traits {
     static constexpr int kStreams = (K == K_MIO0 || K == K_YAY0) ? 3 : (K == K_SMSR) ? 2 : 1;
     static constexpr int kMaxTok = (K == K_LZ10 || K == K_MIO0 || K == K_SMSR) ? 18 : (K == K_YAZ0 || K == K_YAY0 || K == K_HUDSON) ? 273 : (K == K_LZSS) ? 258 : 65808;   // LZ11 65 808, LZ40 65 807
     static constexpr bool kNeedSub = kMaxTok * 32 > kSubMax;
-    static constexpr int kQueueLen = kStreams == 3 ? kQueueSplit : kQueue;
-    static constexpr int kQueueBytes = 2 * kQueueLen * 8 + 32;
-    static constexpr int kAuxBytes = kStreams * kInStage + kQueueBytes + 128 + 32 + 16 + (2 * kStreams + 4) * 8;
+    static constexpr int kQueueBytes = 2 * kQueue * 8;
+    static constexpr int kAuxBytes = kStreams * kInStage + kQueueBytes + 128 + 48 + 2 * kStreams * 8;
     static constexpr int kSmemPerSlot = kRing + kAuxBytes;
 #ifdef AURORA_FLAG_SLOTS
-    static constexpr int kSlots = AURORA_FLAG_SLOTS;                      // developer probe: stream slots per block
+    static constexpr int kSlots = AURORA_FLAG_SLOTS;                      // developer probe: stream slots per block (4 or 8)
 #else
-    // one block per SM; slots come in fours (a parser warpgroup + a replayer warpgroup)
-    static constexpr int kSlots = ((227 * 1024 - kRing) / kSmemPerSlot) / 4 * 4;
+    static constexpr int kSlots = 8 * kSmemPerSlot + kRing <= 115 * 1024 ? 8 : 4;
 #endif
-    // registers: the launch gives every thread kLaunchRegs (what ptxas derives from the launch bounds); the parser
-    // warpgroups then grow by kRegDelta and the replayer warpgroups shrink by it (setmaxnreg; the sum stays in the block's pool)
-    static constexpr int kLaunchRegs = (65536 / (kSlots * 64)) / 8 * 8 > 128 ? 128 : (65536 / (kSlots * 64)) / 8 * 8;
-    static constexpr bool kRegSplit = kLaunchRegs < 128;
-    static constexpr int kParserRegs = kLaunchRegs + AURORA_REG_DELTA, kReplayerRegs = kLaunchRegs - AURORA_REG_DELTA;
+    static constexpr int kSmemPerBlock = kSlots * kSmemPerSlot + kRing;   // + alignment slack for the rings
+    static constexpr int kBlocksPerSM = (228 * 1024) / (kSmemPerBlock + 1024) < 1 ? 1 : (228 * 1024) / (kSmemPerBlock + 1024);
+    // registers: the launch gives every thread kLaunchRegs; the parser warpgroups then grow by kRegDelta and the resolver
+    // warpgroups shrink by it (setmaxnreg; the sum stays in the block's pool)
+    static constexpr int kLaunchRegs0 = (65536 / (kBlocksPerSM * kSlots * 64)) / 8 * 8;
+    static constexpr int kLaunchRegs = kLaunchRegs0 > 128 ? 128 : kLaunchRegs0;
+#ifdef AURORA_AFFINE
+    static constexpr bool kRegSplit = false;
+#else
+    static constexpr bool kRegSplit = kLaunchRegs < 104;
+#endif
+    static constexpr int kParserRegs = kLaunchRegs + AURORA_REG_DELTA, kResolverRegs = kLaunchRegs - AURORA_REG_DELTA;
 };
 
 // out[dst+i] = out[dst-d + (i mod d)], i < len : LzWindows.BackCopy (IO/LzWindows.cs:72-100) on the flat ring.
@@ -416,48 +431,8 @@ __device__ BodyResult decode_body(InStream* in, OutState& out, const uint32_t sl
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// G32 token core for the fixed-token-size interleaved formats (LZ10, LZSS): one flag GROUP per lane, i.e. up to
-// 256 tokens per warp iteration.  The only serial part is the chain of 32 flag bytes (p += 9 + popc(matches));
-// every lane then sizes its own 8 tokens, one packed warp scan gives output bases and match-queue slots, literals
-// are scattered lane-locally and the matches of all groups are replayed in stream order from a shared-memory queue.
-// All shared-memory traffic uses 32-bit shared addresses; the output ring is 8 KiB aligned, so the wrapped
-// address (pos & mask) | base is a single LOP3.
-// ---------------------------------------------------------------------------------------------
-// one queued match: out[pos + i] = out[pos - d + (i mod d)], i < len, on the 8 KiB aligned ring at shared address rb
-template <bool kShort>   // kShort: len <= 32 guaranteed (LZ10: 18)
-__device__ __forceinline__ void ring_copy_queued(uint32_t rb, uint32_t pos, uint32_t d, uint32_t len) {
-    const uint32_t lane = lane_id();
-    const uint32_t srcp = pos - d;
-    if (d >= len) {
-        if (kShort) {
-            if (lane < len) sts_u8(((pos + lane) & kRingMask) | rb, lds_u8(((srcp + lane) & kRingMask) | rb));
-        } else {
-            for (uint32_t i = lane; i < len; i += 32) sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + i) & kRingMask) | rb));
-        }
-    } else {
-        const uint32_t r = c_rcp.v[d & 511];   // d < len <= 273: uniform constant-bank load
-        if (kShort) {
-            if (lane < len) {
-                const uint32_t off = lane - ((lane * r) >> 20) * d;
-                sts_u8(((pos + lane) & kRingMask) | rb, lds_u8(((srcp + off) & kRingMask) | rb));
-            }
-        } else {
-            for (uint32_t i = lane; i < len; i += 32) {
-                const uint32_t off = i - ((i * r) >> 20) * d;
-                sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + off) & kRingMask) | rb));
-            }
-        }
-    }
-}
-
-
-// Replays the queued matches of one iteration in stream order.  Entries are {pos, len | d << 17} (len up to 17 bits: LZ11).
-// Run merging: encoders split a long run (or a 32-byte tile) into maximum-length matches with the same distance that
-// follow each other without a gap; such a chain is exactly one longer periodic copy out[o] = out[o - d].  A parallel
-// post-pass (one entry per lane, chains cut at 32-entry blocks) compacts every chain into one entry in place, then the
-// replay is a plain loop with the next entry prefetched.
-// (A variant that ran hazard-free groups of four independent matches as one warp step was measured slower.)
+// one (long) match copied by the whole warp: out[pos + i] = out[pos - d + (i mod d)], i < len, on the 8 KiB aligned ring
+// at shared address rb (LzWindows.BackCopy's chunk loop, IO/LzWindows.cs:72-100)
 __device__ __forceinline__ void ring_copy_any(uint32_t rb, uint32_t pos, uint32_t d, uint32_t len) {
     const uint32_t lane = lane_id();
     const uint32_t srcp = pos - d;
@@ -469,7 +444,7 @@ __device__ __forceinline__ void ring_copy_any(uint32_t rb, uint32_t pos, uint32_
         }
     } else if (d >= len) {
         for (uint32_t i = lane; i < len; i += 32) sts_u8(((pos + i) & kRingMask) | rb, lds_u8(((srcp + i) & kRingMask) | rb));
-    } else if (len < 512) {
+    } else if (len < 512 && d < 512) {
         const uint32_t r = c_rcp.v[d];
         for (uint32_t i = lane; i < len; i += 32) {
             const uint32_t off = i - ((i * r) >> 20) * d;
@@ -487,80 +462,185 @@ __device__ __forceinline__ void ring_copy_any(uint32_t rb, uint32_t pos, uint32_
     }
 }
 
-// Replays the queued matches of one iteration in stream order (see the comment above ring_copy_any).
-// (Measured and rejected, round 1: groups of four independent short matches as one warp step, 8 lanes per match, with a
-// lane-parallel hazard classification; it removed ~30 % of the replayer's instructions but lost the entry prefetch and
-// was 10 % slower end to end: the replayer is bound by its dependent instruction chain, not by its instruction count.)
-__device__ __forceinline__ void replay_matches(uint32_t rb, uint32_t qaddr, uint32_t nq) {
+// ---------------------------------------------------------------------------------------------
+// Match resolution.  The queue holds {pos, len | d << 17} in stream order; all literals up to the last queued match are
+// already in the ring.
+//   A. run merging: encoders split a long run (or a 32-byte tile) into maximum-length matches with the same distance
+//      that follow each other without a gap; such a chain is exactly one longer copy out[o] = out[o - d].  A
+//      lane-parallel pass compacts every chain into one entry in place (chains are cut at 32-entry blocks).
+//   B. per block of 32 merged entries:
+//      fills   runs of a byte / u16 / u32 (d = 1, 2, 4, up to 128 bytes) whose d source bytes are not written by the entry
+//              before them depend on nothing unresolved: ALL of them go at once, one per lane — the d bytes become one
+//              pattern word (rotated to the destination's alignment), stored as head bytes, aligned words, tail bytes,
+//              no loads in the loop (tilemaps: most entries);
+//      steps   everything else runs in stream order: a long entry (> 32 bytes) is one warp-cooperative copy; short
+//              entries go up to FOUR PER STEP, eight lanes and four bytes per lane each, all loads of the step in flight
+//              before its stores.  The entries of a step must not read what the step writes: entry i + k joins only if
+//              its source ends below the destination of entry i (everything below that is final): one ballot.
+// (Measured first, profiles/r2_*: one match per lane in dependency rounds with per-class copy routines.  On tile sheets a
+//  round finds ~5 of 21 entries ready and an iteration of a tilemap holds ~8 entries, so the fixed cost per round
+//  dominated: ~200 instructions per round.)
+// ---------------------------------------------------------------------------------------------
+#ifndef AURORA_FILL_MAX
+#define AURORA_FILL_MAX 128
+#endif
+
+__device__ __forceinline__ void resolve_matches(uint32_t rb, uint32_t qaddr, uint32_t nq) {
     const uint32_t lane = lane_id();
-    if (nq == 0) return;
     const uint32_t lt = (1u << lane) - 1u;
+    // ---- A. merge + compact
     uint32_t nout = 0;
     for (uint32_t base = 0; base < nq; base += 32) {
         const uint32_t q = base + lane;
         const bool have = q < nq;
-        const uint2 e = lds_u64(qaddr + 8 * q);
+        uint2 e = make_uint2(0u, 0u);
+        if (have) e = lds_u64(qaddr + 8 * q);
         const uint32_t px = __shfl_up_sync(kFull, e.x, 1), py = __shfl_up_sync(kFull, e.y, 1);
         const bool cont = have && lane > 0 && e.x == px + (py & 0x1FFFFu) && (e.y >> 17) == (py >> 17);
         const uint32_t heads = __ballot_sync(kFull, have && !cont);
         const uint32_t valid = __ballot_sync(kFull, have);
-        // last entry of my chain: the lane before the next head (or the last valid lane of the block)
-        const uint32_t after = heads & ~lt & ~(1u << lane);
-        const uint32_t last = after ? uint32_t(__ffs(after) - 2) : uint32_t(31 - __clz(valid));
-        const uint32_t tx = __shfl_sync(kFull, e.x, last & 31), ty = __shfl_sync(kFull, e.y, last & 31);
-        __syncwarp();
-        if (have && !cont) sts_u64(qaddr + 8 * (nout + __popc(heads & lt)), e.x, (tx + (ty & 0x1FFFFu) - e.x) | (e.y & 0xFFFE0000u));
+        if (heads != valid) {
+            // last entry of my chain: the lane before the next head (or the last valid lane of the block)
+            const uint32_t after = heads & ~lt & ~(1u << lane);
+            const uint32_t last = after ? uint32_t(__ffs(after) - 2) : uint32_t(31 - __clz(valid));
+            const uint32_t tx = __shfl_sync(kFull, e.x, last & 31), ty = __shfl_sync(kFull, e.y, last & 31);
+            __syncwarp();
+            if (have && !cont) sts_u64(qaddr + 8 * (nout + __popc(heads & lt)), e.x, (tx + (ty & 0x1FFFFu) - e.x) | (e.y & 0xFFFE0000u));
+        } else if (nout != base) {
+            __syncwarp();
+            if (have) sts_u64(qaddr + 8 * (nout + lane), e.x, e.y);
+        }
         nout += __popc(heads);
     }
     __syncwarp();
-    // Two entries per step: when the second match's source ends at or before the first match's destination the two
-    // copies are independent, so both loads are issued before both stores (one barrier, twice the ILP); the slots
-    // past the end of the queue are readable (slack behind the queue).
-    uint2 e0 = lds_u64(qaddr), e1 = lds_u64(qaddr + 8);
-    uint32_t q = 0;
-    while (q + 1 < nout) {
-        const uint2 n0 = lds_u64(qaddr + 8 * (q + 2)), n1 = lds_u64(qaddr + 8 * (q + 3));
-        const uint32_t len0 = e0.y & 0x1FFFFu, d0 = e0.y >> 17, len1 = e1.y & 0x1FFFFu, d1 = e1.y >> 17;
-        if (max(len0, len1) < 512 && e1.x - d1 + min(len1, d1) <= e0.x) {
-            const uint32_t r0 = d0 < len0 ? c_rcp.v[d0] : 0u, r1 = d1 < len1 ? c_rcp.v[d1] : 0u;   // 0: no wrap, off = i
-            const uint32_t s0 = e0.x - d0, s1 = e1.x - d1, lmax = max(len0, len1);
-            for (uint32_t i = lane; i < lmax; i += 32) {
-                const uint32_t off0 = i - ((i * r0) >> 20) * d0, off1 = i - ((i * r1) >> 20) * d1;
+    // ---- B.
+    const uint32_t sub = lane >> 3, o0 = 4 * (lane & 7);   // steps: my entry of a step, my four bytes of it
+    for (uint32_t base = 0; base < nout; base += 32) {
+        const uint32_t q = base + lane;
+        const bool have = q < nout;
+        uint2 e = make_uint2(0u, 0u);
+        if (have) e = lds_u64(qaddr + 8 * q);
+        // ---- fills that depend on nothing unresolved: all at once
+        {
+            const uint32_t len = e.y & 0x1FFFFu, d = e.y >> 17;
+            const uint32_t pend = __shfl_up_sync(kFull, e.x + len, 1);   // end of the entry before mine
+            const bool act = have && len <= uint32_t(AURORA_FILL_MAX) && (d == 1 || d == 2 || d == 4) &&
+                             (lane == 0 || int32_t(e.x - d - pend) >= 0);
+            const uint32_t fmask = __ballot_sync(kFull, act);
+            if (__popc(fmask) >= 3) {   // (one or two: the steps below are cheaper)
+                const uint32_t t0 = e.x & kRingMask, s0 = (e.x - d) & kRingMask;
+                const uint32_t n = act ? min(len, uint32_t(kRing) - t0) : 0u;   // up to the end of the ring
+                uint32_t w0 = 0;   // the four bytes a destination word at pos would get
+                if (act) {
+                    const uint32_t q0 = lds_u8(s0 | rb);
+                    w0 = q0 * 0x01010101u;
+                    if (d >= 2) {
+                        const uint32_t q1 = lds_u8(((s0 + 1) & kRingMask) | rb);
+                        w0 = (q0 | (q1 << 8)) * 0x00010001u;
+                        if (d == 4) {
+                            const uint32_t q2 = lds_u8(((s0 + 2) & kRingMask) | rb), q3 = lds_u8(((s0 + 3) & kRingMask) | rb);
+                            w0 = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+                        }
+                    }
+                }
+                const uint32_t h = min((0u - e.x) & 3u, n);             // head bytes up to the first aligned word
+                const uint32_t w = __funnelshift_r(w0, w0, 8 * h);      // the pattern as every aligned word sees it
+                const uint32_t tp = t0 | rb;
+                if (h > 0) sts_u8(tp, w0);
+                if (h > 1) sts_u8(tp + 1, w0 >> 8);
+                if (h > 2) sts_u8(tp + 2, w0 >> 16);
+                const uint32_t nw = (n - h) >> 2, wp = tp + h;
+                const uint32_t wmax = __reduce_max_sync(kFull, nw);
+                for (uint32_t i = 0; i < wmax; i += 4) {
+                    if (i < nw) sts_u32(wp + 4 * i, w);
+                    if (i + 1 < nw) sts_u32(wp + 4 * i + 4, w);
+                    if (i + 2 < nw) sts_u32(wp + 4 * i + 8, w);
+                    if (i + 3 < nw) sts_u32(wp + 4 * i + 12, w);
+                }
+                const uint32_t tl = (n - h) & 3u, ep = wp + 4 * nw;
+                if (tl > 0) sts_u8(ep, w);
+                if (tl > 1) sts_u8(ep + 1, w >> 8);
+                if (tl > 2) sts_u8(ep + 2, w >> 16);
+                // done: a zero-length entry for the steps below (a fill cut at the end of the ring leaves them its rest)
+                e.x += n;
+                e.y -= n;
+                __syncwarp();
+            }
+        }
+        // ---- steps, in stream order.  How many entries a step that starts at entry i takes is known per lane up front:
+        //      entries i + 1 .. i + 3 join while they are short and their source ends below the destination of entry i
+        const uint32_t len = e.y & 0x1FFFFu, d = e.y >> 17;
+        const uint32_t ne = min(nout - base, 32u);
+        const uint32_t smask = __ballot_sync(kFull, have && len <= 32);
+        const uint32_t slast = e.x - d + min(len, d) - 1;   // my last source byte
+        uint32_t tk = 1;
+        {
+            const uint32_t s1 = __shfl_down_sync(kFull, slast, 1), s2 = __shfl_down_sync(kFull, slast, 2), s3 = __shfl_down_sync(kFull, slast, 3);
+            const uint32_t sm = smask >> lane;   // bit k: entry lane + k is short (0 beyond the block)
+            const bool ok1 = (sm & 2u) && int32_t(s1 - e.x) < 0;
+            const bool ok2 = ok1 && (sm & 4u) && int32_t(s2 - e.x) < 0;
+            const bool ok3 = ok2 && (sm & 8u) && int32_t(s3 - e.x) < 0;
+            tk = 1u + (ok1 ? 1u : 0u) + (ok2 ? 1u : 0u) + (ok3 ? 1u : 0u);
+        }
+        uint32_t i = 0;
+        while (i < ne) {
+            const uint32_t take = __shfl_sync(kFull, tk, i);
+            const uint32_t mx = __shfl_sync(kFull, e.x, (i + sub) & 31), my = __shfl_sync(kFull, e.y, (i + sub) & 31);
+            if (!((smask >> i) & 1u)) {   // long: the whole warp
+                const uint32_t px = __shfl_sync(kFull, mx, 0), py = __shfl_sync(kFull, my, 0);
+                ring_copy_any(rb, px, py >> 17, py & 0x1FFFFu);
+                __syncwarp();
+                i++;
+                continue;
+            }
+            const uint32_t mlen = my & 0x1FFFFu, md = my >> 17;
+            uint32_t nb = 0;   // my bytes: [o0, o0 + nb) of the entry
+            if (sub < take && o0 < mlen) nb = min(4u, mlen - o0);
+            const uint32_t t0 = (mx + o0) & kRingMask, s0 = (mx - md + o0) & kRingMask;
+            const uint32_t ta = t0 | rb, sa = s0 | rb;
+            const bool plain = md >= mlen && max(t0, s0) <= uint32_t(kRing - 4);   // no o mod d, not across the end of the ring
+            const uint32_t al = (t0 | s0 | nb) & 3u;                                  // 0: one word, 2: two halves
+            const uint32_t not_plain = __ballot_sync(kFull, nb && !plain), not_w = __ballot_sync(kFull, nb && al), not_h = __ballot_sync(kFull, nb && (al & 1u));
+            if (not_plain == 0 && not_w == 0) {
+                uint32_t v = 0;
+                if (nb) v = lds_u32(sa);
+                if (nb) sts_u32(ta, v);
+            } else if (not_plain == 0 && not_h == 0) {
                 uint32_t v0 = 0, v1 = 0;
-                if (i < len0) v0 = lds_u8(((s0 + off0) & kRingMask) | rb);
-                if (i < len1) v1 = lds_u8(((s1 + off1) & kRingMask) | rb);
-                if (i < len0) sts_u8(((e0.x + i) & kRingMask) | rb, v0);
-                if (i < len1) sts_u8(((e1.x + i) & kRingMask) | rb, v1);
+                if (nb > 0) v0 = lds_u16(sa);
+                if (nb > 2) v1 = lds_u16(sa + 2);
+                if (nb > 0) sts_u16(ta, v0);
+                if (nb > 2) sts_u16(ta + 2, v1);
+            } else if (not_plain == 0) {
+                uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                if (nb > 0) v0 = lds_u8(sa);
+                if (nb > 1) v1 = lds_u8(sa + 1);
+                if (nb > 2) v2 = lds_u8(sa + 2);
+                if (nb > 3) v3 = lds_u8(sa + 3);
+                if (nb > 0) sts_u8(ta, v0);
+                if (nb > 1) sts_u8(ta + 1, v1);
+                if (nb > 2) sts_u8(ta + 2, v2);
+                if (nb > 3) sts_u8(ta + 3, v3);
+            } else {
+                // periodic (d < len: the source offset is o mod d) or across the end of the ring
+                const uint32_t r = md < 32 ? c_rcp.v[md] : 0u;   // 0: d >= 32 >= len, o mod d = o
+                uint32_t v[4];
+#pragma unroll
+                for (uint32_t j = 0; j < 4; j++) {
+                    const uint32_t o = o0 + j;
+                    const uint32_t so = o - ((o * r) >> 20) * md;
+                    v[j] = 0;
+                    if (j < nb) v[j] = lds_u8(((mx - md + so) & kRingMask) | rb);
+                }
+#pragma unroll
+                for (uint32_t j = 0; j < 4; j++)
+                    if (j < nb) sts_u8(((mx + o0 + j) & kRingMask) | rb, v[j]);
             }
             __syncwarp();
-        } else {
-            ring_copy_any(rb, e0.x, d0, len0);
-            __syncwarp();
-            ring_copy_any(rb, e1.x, d1, len1);
-            __syncwarp();
+            i += take;
         }
-        e0 = n0;
-        e1 = n1;
-        q += 2;
-    }
-    if (q < nout) {
-        ring_copy_any(rb, e0.x, e0.y >> 17, e0.y & 0x1FFFFu);
-        __syncwarp();
     }
 }
-
-// ---------------------------------------------------------------------------------------------
-// Parser / replayer pipeline.  A stream slot is served by TWO warps: the parser walks the flag-byte chain, sizes the
-// tokens, scatters the literals into the ring and queues the matches of one iteration; the replayer merges and replays
-// the queued matches and drains the ring to HBM.  They overlap on consecutive iterations through two queue buffers, a
-// 16-byte mailbox per buffer and full/empty mbarriers (arrive = release.cta, try_wait = acquire.cta), so the slot keeps
-// two dependent instruction streams in flight instead of one (the kernel is latency bound, profiles/).
-//   ring safety: while the replayer works on iteration i (positions [w, w + t_i), sources >= w - 4096, undrained bytes
-//   >= w - 511) the parser may write iteration i+1 up to position w + t_i + t_{i+1}; the slots it overwrites hold
-//   positions 8192 lower, so t_i + t_{i+1} <= kPairSpan = 4096 keeps them below the window.  The parser acquires
-//   buffer (i+1) & 1 first, i.e. iteration i-1 is replayed and drained before anything of i+1 is written.
-// ---------------------------------------------------------------------------------------------
-enum : uint32_t { kMsgBegin = 1u, kMsgFinish = 2u, kMsgLong = 4u, kMsgExit = 8u };
 
 // one (possibly very long) match in segments of 2 KiB with a drain in between (LZ11: up to 65 808 bytes)
 __device__ __forceinline__ void long_match_copy(OutState& out, uint32_t pos, uint32_t d, uint32_t len) {
@@ -572,24 +652,65 @@ __device__ __forceinline__ void long_match_copy(OutState& out, uint32_t pos, uin
     }
 }
 
-// parser side of the pipeline (all members warp-uniform)
-struct PipeSink {
+// ---------------------------------------------------------------------------------------------
+// Parser / resolver pairs.  A stream slot is served by TWO warps.  The PARSER walks the token stream, scatters the literals
+// into the slot's ring and queues the matches; when a batch is worth it (kHandoffAt matches or kHandoffSpan bytes) it
+// hands the batch to the RESOLVER, which resolves the matches (resolve_matches) and drains the finished bytes to HBM while
+// the parser works on the next batch.  Why two warps: the slot's shared memory (8 KiB window ring) bounds the STREAMS per
+// SM to 16, and 16 warps leave the SM latency bound (measured: 50 % issue utilisation, stalls on fixed-latency
+// dependencies); a second warp per stream doubles the instruction streams in flight without a second window.
+//   hand-off: two queue buffers and two 16-byte mailboxes per slot, and two HARDWARE NAMED BARRIERS (bar.arrive / bar.sync
+//   over the 64 threads of the pair): F "batch is there" (parser arrives, resolver syncs) and E "batch is done" (resolver
+//   arrives, parser syncs).  The parser syncs on E before it hands the next batch over, so at most one batch is in
+//   flight and each barrier sees exactly one arrive and one sync per batch; a waiting warp sleeps in the barrier unit and
+//   issues nothing (round 1 polled mbarriers here: 30 % of all issued instructions).
+//   ring safety: while the resolver works on batch A (positions [a, a + sA), sources >= a - 4096, undrained bytes
+//   >= a - 511) the parser may write batch B up to position a + sA + sB; the slots it overwrites hold positions 8192
+//   lower, so sA + sB <= kIterCap = 4096 keeps them below the window.
+// (all members warp-uniform)
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { kMsgBegin = 1u, kMsgFinish = 2u, kMsgLong = 4u, kMsgExit = 8u };
+
+__device__ __forceinline__ void bar_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+struct SlotSink {
     uint32_t rbase;        // shared address of the slot's ring
-    uint32_t qbase;        // shared address of queue buffer 0 (buffer 1 follows qstride bytes later)
-    uint32_t qstride;
+    uint32_t qbase;        // shared address of queue buffer 0 (buffer 1 follows kQueue entries later)
     uint32_t mail;         // shared address of mailbox 0 (mailbox 1 follows), then the stream descriptor
-    uint64_t* full;        // [2]
-    uint64_t* empty;       // [2]
-    uint32_t it;           // messages sent over the lifetime of the warp
-    uint32_t prev_total;   // decoded bytes of the latest message, possibly still being replayed
+    uint32_t bar_f, bar_e; // named barriers of the slot
+    uint32_t it;           // batches handed over in the lifetime of the warp
+    uint32_t qn;           // matches queued in the current batch
+    uint32_t start;        // first position of the current batch
+    uint32_t produced;     // bytes scattered / queued so far
+    uint32_t span_a;       // bytes of the batch in flight (0: none outstanding)
+    bool outstanding;
     uint32_t flags_next;
 
-    __device__ __forceinline__ void wait_idle() {   // every message sent so far has been consumed
-        if (it >= 2) mbar_wait(&empty[it & 1], ((it - 2) >> 1) & 1);
-        if (it >= 1) mbar_wait(&empty[(it - 1) & 1], ((it - 1) >> 1) & 1);
-        prev_total = 0;
+    __device__ __forceinline__ void init() {
+        it = qn = start = produced = span_a = flags_next = 0;
+        outstanding = false;
     }
-    // new stream (or Yaz0's second attempt): the replayer is idle, so the ring and the descriptor are ours
+    // the batch in flight has been resolved and drained
+    __device__ __forceinline__ void wait_idle() {
+        if (outstanding) bar_sync(bar_e);
+        outstanding = false;
+        span_a = 0;
+    }
+    __device__ __forceinline__ void handoff(uint32_t flags, uint32_t x = 0) {
+        wait_idle();
+        __syncwarp();   // every lane's ring / queue stores are ordered before the arrive
+        if (lane_id() == 0) sts_u128(mail + 16 * (it & 1), (flags & kMsgLong) ? x : qn, produced, flags | flags_next, 0u);
+        __threadfence_block();
+        bar_arrive(bar_f);
+        it++;
+        outstanding = true;
+        span_a = produced - start;
+        start = produced;
+        qn = 0;
+        flags_next = 0;
+    }
+    // new stream (or Yaz0's second attempt): the resolver is idle, so the ring and the descriptor are ours
     __device__ __forceinline__ void begin(uint8_t* ring, uint32_t fill, uint8_t* dst, uint32_t limit) {
         wait_idle();
         const uint32_t w = fill * 0x01010101u;
@@ -600,53 +721,56 @@ struct PipeSink {
             const uint64_t a = reinterpret_cast<uint64_t>(dst);
             sts_u128(mail + 32, uint32_t(a), uint32_t(a >> 32), limit, (a & 15) == 0 ? 1u : 0u);
         }
+        qn = start = produced = 0;
         flags_next = kMsgBegin;
         __syncwarp();
     }
-    __device__ __forceinline__ uint32_t cap() const { return min(uint32_t(kSubMaxG), uint32_t(kPairSpan) - prev_total); }
-    // the budget was cut by the iteration still in flight: wait for it and offer the full budget once
-    __device__ __forceinline__ bool retry_full() {
-        if (prev_total == 0) return false;
-        wait_idle();
-        return true;
-    }
-    __device__ __forceinline__ uint32_t acquire() {
-        mbar_wait(&empty[it & 1], ((it >> 1) & 1) ^ 1);
-        return qbase + (it & 1) * qstride;
-    }
-    __device__ __forceinline__ void submit(uint32_t nq, uint32_t produced, uint32_t total, uint32_t flags = 0) {
-        __syncwarp();   // every lane's ring / queue stores are ordered before lane 0's releasing arrive
-        if (lane_id() == 0) {
-            sts_u128(mail + 16 * (it & 1), nq, produced, flags | flags_next, 0u);
-            mbar_arrive(&full[it & 1]);
+    // output bytes the next iteration may produce
+    __device__ __forceinline__ uint32_t cap() const { return uint32_t(kIterCap) - span_a - (produced - start); }
+    // room for an iteration of up to `need` bytes behind what is queued: wait for the batch in flight, or hand the
+    // current one over first; returns the shared address of the iteration's first queue entry
+    __device__ __forceinline__ uint32_t acquire_deferred(uint32_t need) {
+        need = min(need, uint32_t(kIterCap));
+        if (need > cap()) {
+            wait_idle();
+            if (need > cap()) {
+                handoff(0);
+                if (need > cap()) wait_idle();
+            }
         }
-        it++;
-        prev_total = total;
-        flags_next = 0;
+        return qbase + 8 * ((it & 1) * kQueue + qn);
     }
-    __device__ __forceinline__ void finish(uint32_t produced) {
-        acquire();
-        submit(0, produced, 0, kMsgFinish);
+    __device__ __forceinline__ void submit_deferred(uint32_t nq, uint32_t produced_now) {
+        qn += nq;
+        produced = produced_now;
+        if (qn >= uint32_t(kHandoffAt) || produced - start >= uint32_t(kHandoffSpan)) handoff(0);
     }
-    // LZ11 long-group path: tokens one at a time while the replayer is idle
+    // the cores that keep their own iteration budget: any cut they make must leave room for their largest group
+    __device__ __forceinline__ uint32_t acquire() { return acquire_deferred(uint32_t(kSubMaxG)); }
+    __device__ __forceinline__ void submit(uint32_t nq, uint32_t produced_now) { submit_deferred(nq, produced_now); }
+    __device__ __forceinline__ void finish(uint32_t produced_now) {
+        produced = produced_now;
+        handoff(kMsgFinish);
+    }
+    // LZ11 long-group path: tokens one at a time
     __device__ __forceinline__ void single_literal(uint32_t pos, uint32_t b) {
-        wait_idle();
+        acquire_deferred(1);
         if (lane_id() == 0) sts_u8((pos & kRingMask) | rbase, b);
+        produced = pos + 1;
     }
     __device__ __forceinline__ void long_match(uint32_t pos, uint32_t d, uint32_t len) {
-        const uint32_t q = acquire();
-        if (lane_id() == 0) sts_u64(q, pos, len | (d << 17));
-        submit(1, pos + len, 0, kMsgLong);
+        if (produced != start || qn) handoff(0);   // everything before the match
         wait_idle();
+        if (lane_id() == 0) sts_u64(qbase + 8 * ((it & 1) * kQueue), pos, len | (d << 17));
+        produced = pos + len;
+        handoff(kMsgLong, 1);
+        wait_idle();   // the match streams through the whole ring
     }
-    __device__ __forceinline__ void exit() {
-        acquire();
-        submit(0, 0, 0, kMsgExit);
-    }
+    __device__ __forceinline__ void exit() { handoff(kMsgExit); }
 };
 
-// replayer side of the pipeline: consumes messages until the parser says exit
-__device__ void replayer_role(uint8_t* ring, uint32_t qbase, uint32_t qstride, uint32_t mail, uint64_t* full, uint64_t* empty) {
+// resolver side: consumes batches until the parser says exit
+__device__ void resolver_role(uint8_t* ring, uint32_t qbase, uint32_t mail, uint32_t bar_f, uint32_t bar_e) {
     OutState out;
     out.ring = ring;
     out.rbase = smem_u32(ring);
@@ -656,7 +780,7 @@ __device__ void replayer_role(uint8_t* ring, uint32_t qbase, uint32_t qstride, u
     out.aligned = false;
     for (uint32_t m = 0;; m++) {
         const uint32_t b = m & 1;
-        mbar_wait(&full[b], (m >> 1) & 1);
+        bar_sync(bar_f);
         const uint4 msg = lds_u128(mail + 16 * b);   // {nq, produced, flags, -}
         if (msg.z & kMsgExit) break;
         if (msg.z & kMsgBegin) {
@@ -666,20 +790,129 @@ __device__ void replayer_role(uint8_t* ring, uint32_t qbase, uint32_t qstride, u
             out.aligned = d.w != 0;
             out.flushed = 0;
         }
-        const uint32_t q = qbase + b * qstride;
+        const uint32_t q = qbase + 8 * b * kQueue;
         if (msg.z & kMsgLong) {
             const uint2 e = lds_u64(q);
             long_match_copy(out, e.x, e.y >> 17, e.y & 0x1FFFFu);
         } else {
-#ifndef AURORA_EXP_NOREPLAY   // developer probe: parser-bound speed (output is wrong)
-            replay_matches(out.rbase, q, msg.x);
+#ifndef AURORA_EXP_NOREPLAY   // developer probe: parse-bound speed (output is wrong)
+            if (msg.x) resolve_matches(out.rbase, q, msg.x);
 #endif
         }
         if (msg.z & kMsgFinish) out.finish(msg.y);
         else out.drain(msg.y);
         __syncwarp();
-        if (lane_id() == 0) mbar_arrive(&empty[b]);
+        __threadfence_block();
+        bar_arrive(bar_e);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// G32 token core for the fixed-token-size interleaved formats (LZ10, LZSS): one flag GROUP per lane, i.e. up to
+// 256 tokens per warp iteration.  The only serial part is the chain of 32 group starts (p += 9 + popc(matches)); runs of
+// equally sized groups (random data: all literals; runs, tiles: all matches) are resolved by one ballot: every lane
+// looks at the flag byte its group would have if all groups before it had the size of the first one, and the walk starts
+// behind the leading lanes that agree.  Every lane then sizes its own 8 tokens, one packed warp scan gives output bases
+// and match-queue slots, literals are scattered lane-locally and the matches of all groups are queued for
+// resolve_matches().  All shared-memory traffic uses 32-bit shared addresses; the output ring is 8 KiB aligned, so the
+// wrapped address (pos & mask) | base is a single LOP3.
+// ---------------------------------------------------------------------------------------------
+struct CutResult {
+    uint32_t total, nq, nlan, consumed;
+    bool eos;
+};
+
+// End of the output, end of the input, or an iteration over the byte budget whose first group does not fit: the tokens
+// are cut one by one exactly where the reference stops (LZ10.cs:88-110 / LZSS.cs:100-126).  Out of line: it runs once or
+// twice per stream and would only dilute the instruction cache of the hot loop; it re-reads the tokens from the staged
+// window instead of taking the caller's register arrays.
+template <int K>
+__device__ __noinline__ CutResult g32_cut_tokens(uint32_t rb, uint32_t qaddr, uint32_t wa, uint32_t mya, uint32_t m, uint32_t written,
+                                                 uint32_t gexcl, uint32_t gincl, uint32_t qexcl, uint32_t qincl, uint32_t remaining, uint32_t cap,
+                                                 uint32_t cur, uint32_t slen, LzssParams lz) {
+    const uint32_t lane = lane_id();
+    const uint32_t lmask = (1u << lz.length_bits) - 1u;
+    const bool taken = gexcl < remaining && gincl <= cap && qincl <= uint32_t(kIterMatches);
+    const uint32_t lim = remaining - gexcl;   // only meaningful when taken
+    const uint32_t gabs = cur + (mya - wa);   // blob offset of my flag byte
+    uint32_t jexec = 0;
+    bool eos_here = false;
+    {
+        uint32_t a = gabs + 1, sa = mya + 1, o = 0;
+        bool stop = false;
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
+            uint32_t len = 1;
+            if (ism) len = (K == K_LZ10) ? (lds_u8(sa) >> 4) + 3 : (lds_u8(sa + 1) & lmask) + uint32_t(lz.min_length);
+            const uint32_t tend = a + (ism ? 2 : 1);
+            const bool want = o < lim;
+            const bool bad = gabs >= slen || tend > slen;
+            if (!stop && want && bad) eos_here = true;
+            stop = stop || !want || bad;
+            if (!stop) jexec = j + 1;
+            a = tend;
+            sa += ism ? 2 : 1;
+            o += len;
+        }
+    }
+    if (!taken) {
+        jexec = 0;
+        eos_here = false;
+    }
+    CutResult r{0u, 0u, 0u, 0u, false};
+    const uint32_t eosmask = __ballot_sync(kFull, eos_here);
+    if (eosmask) {
+        const uint32_t gb = __ffs(eosmask) - 1;
+        if (lane > gb) jexec = 0;
+        r.eos = true;
+    }
+    r.nlan = __popc(__ballot_sync(kFull, jexec > 0));   // a prefix of the lanes
+    if (r.nlan == 0) return r;
+    const uint32_t last = r.nlan - 1;
+    uint32_t oend = 0, qi = qexcl, aend = 0;
+    {
+        uint32_t sa = mya + 1, o = 0;
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
+            const bool e = uint32_t(j) < jexec;
+            const uint32_t pos = written + gexcl + o;
+            const uint32_t b1 = lds_u8(sa);
+            uint32_t len = 1;
+            if (e && !ism) sts_u8((pos & kRingMask) | rb, b1);
+            if (ism) {
+                const uint32_t b2 = lds_u8(sa + 1);
+                uint32_t dist;
+                if (K == K_LZ10) {
+                    len = (b1 >> 4) + 3;
+                    dist = (((b1 & 0xF) << 8) | b2) + 1;
+                } else {
+                    len = (b2 & lmask) + uint32_t(lz.min_length);
+                    const uint32_t raw = ((b2 >> lz.length_bits) << 8) | b1;
+                    const uint32_t ring_len = 1u << lz.windows_bits;
+                    const uint32_t offset = (uint32_t(lz.max_distance) + raw - uint32_t(lz.windows_start)) & uint32_t(lz.max_distance - 1);
+                    const uint32_t rp = pos & (ring_len - 1);
+                    dist = rp >= offset ? rp - offset : rp - offset + ring_len;
+                    if (dist == 0) dist = ring_len;
+                }
+                if (e) {
+                    sts_u64(qaddr + 8 * qi, pos, len | (dist << 17));
+                    qi++;
+                }
+            }
+            sa += ism ? 2 : 1;
+            o += len;
+            if (e) {
+                oend = o;
+                aend = sa - wa;
+            }
+        }
+    }
+    r.total = __shfl_sync(kFull, gexcl + oend, last);
+    r.nq = __shfl_sync(kFull, qi, last);
+    r.consumed = cur + __shfl_sync(kFull, aend, last);
+    return r;
 }
 
 template <int K, class Sink>
@@ -690,24 +923,64 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
     uint32_t written = 0, cur = body_off, consumed = body_off;
     int status = AURORA_OK;
     const uint32_t lmask = (1u << lz.length_bits) - 1u;
+    auto mbits = [](uint32_t fb) { return K == K_LZ10 ? fb : (fb ^ 0xFFu); };   // flag byte -> match bits in wire bit order
 
     while (written < size) {
         in[0].ensure(cur, kInMirror - 16);
         const uint32_t wa = smem_u32(in[0].window(cur));
+        const uint32_t remaining = size - written;
         // ---- chain of 32 group starts; bounded by 32 * 17 = 544 < kInMirror for any data
-        uint32_t ca = wa;
+        uint32_t mya, chain_end;
+        {
+            const uint32_t s = 9 + __popc(mbits(lds_u8(wa)));       // size of the first group
+            mya = wa + lane * s;                                       // my group's start if all groups before it have that size
+            const uint32_t nok = ~__ballot_sync(kFull, 9 + __popc(mbits(lds_u8(mya))) == s);
+            if (nok == 0) {
+                chain_end = 32 * s;
+                if (s == 9 && remaining >= 256 && cur + 288 <= slen) {
+                    // ---- 32 all-literal groups: 256 bytes, lane g copies in[9 g + 1 .. 9 g + 8] to out[8 g .. 8 g + 7]
+                    sink.acquire_deferred(256);
+                    const uint32_t t = written + 8 * lane;
+                    if ((written & kRingMask) <= uint32_t(kRing - 256)) {
+                        const uint32_t ta = (t & kRingMask) | rb;
 #pragma unroll
-        for (int g = 0; g < 32; g++) {
-            sts_u32(gaddr + 4 * g, ca);
-            const uint32_t f = lds_u8(ca);
-            ca = ca + 9 + __popc((K == K_LZ10) ? f : (f ^ 0xFFu));
+                        for (int j = 0; j < 8; j++) sts_u8(ta + j, lds_u8(mya + 1 + j));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sts_u8(((t + j) & kRingMask) | rb, lds_u8(mya + 1 + j));
+                    }
+                    written += 256;
+                    cur += 288;
+                    consumed = cur;
+                    sink.submit_deferred(0, written);
+                    continue;
+                }
+            } else {
+                const uint32_t k = __ffs(nok) - 1;   // >= 1: groups 0..k start where the guess says; walk from group k
+                uint32_t ca = wa + k * s;
+#define AURORA_CHAIN_STEP(g)                                   \
+    case g:                                                    \
+        sts_u32(gaddr + 4 * g, ca);                            \
+        ca += 9 + __popc(mbits(lds_u8(ca)));
+                switch (k) {
+                    AURORA_CHAIN_STEP(1) AURORA_CHAIN_STEP(2) AURORA_CHAIN_STEP(3) AURORA_CHAIN_STEP(4) AURORA_CHAIN_STEP(5)
+                    AURORA_CHAIN_STEP(6) AURORA_CHAIN_STEP(7) AURORA_CHAIN_STEP(8) AURORA_CHAIN_STEP(9) AURORA_CHAIN_STEP(10)
+                    AURORA_CHAIN_STEP(11) AURORA_CHAIN_STEP(12) AURORA_CHAIN_STEP(13) AURORA_CHAIN_STEP(14) AURORA_CHAIN_STEP(15)
+                    AURORA_CHAIN_STEP(16) AURORA_CHAIN_STEP(17) AURORA_CHAIN_STEP(18) AURORA_CHAIN_STEP(19) AURORA_CHAIN_STEP(20)
+                    AURORA_CHAIN_STEP(21) AURORA_CHAIN_STEP(22) AURORA_CHAIN_STEP(23) AURORA_CHAIN_STEP(24) AURORA_CHAIN_STEP(25)
+                    AURORA_CHAIN_STEP(26) AURORA_CHAIN_STEP(27) AURORA_CHAIN_STEP(28) AURORA_CHAIN_STEP(29) AURORA_CHAIN_STEP(30)
+                    AURORA_CHAIN_STEP(31)
+                    default: break;
+                }
+#undef AURORA_CHAIN_STEP
+                chain_end = ca - wa;
+                __syncwarp();
+                if (lane > k) mya = lds_u32(gaddr + 4 * lane);
+                __syncwarp();   // the table is rewritten by the next iteration's walk
+            }
         }
-        const uint32_t chain_end = ca - wa;
-        __syncwarp();
-        const uint32_t mya = lds_u32(gaddr + 4 * lane);
         const uint32_t myrel = mya - wa;
-        const uint32_t f = lds_u8(mya);
-        const uint32_t m = (K == K_LZ10) ? f : (f ^ 0xFFu);   // match bits in wire bit order
+        const uint32_t m = mbits(lds_u8(mya));   // match bits in wire bit order
 
         // ---- pass 1: sizes of my 8 tokens
         uint32_t b1v[8], orel[8];
@@ -731,17 +1004,14 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
         const uint32_t incl = warp_incl_scan(gsize | (nm << 20));
         const uint32_t gincl = incl & 0xFFFFFu, gexcl = gincl - gsize;
         const uint32_t qexcl = (incl >> 20) - nm;
-        const uint32_t remaining = size - written;
         const uint32_t gbase = written + gexcl;
         uint32_t total, nq, nlan;
-        const uint32_t qaddr = sink.acquire();   // the first ring / queue store of the iteration is below
-        bool stuck = false;
-
-      for (;;) {
+        // matches may stay queued across iterations (SlotSink): room for this iteration, or resolve first
+        const uint32_t qaddr = sink.acquire_deferred(__shfl_sync(kFull, incl, 31) & 0xFFFFFu);
         const uint32_t cap = sink.cap();
-        // groups that fit the byte budget and the queue (a prefix of the lanes): all of their tokens execute unless
-        // the output or the input ends inside them
-        const uint32_t nl = __popc(__ballot_sync(kFull, gincl <= cap && (incl >> 20) <= uint32_t(kQueue)));
+        // groups that fit the byte budget and the queue (a prefix of the lanes): all of their tokens execute unless the
+        // output or the input ends inside them
+        const uint32_t nl = __popc(__ballot_sync(kFull, gincl <= cap && (incl >> 20) <= uint32_t(kIterMatches)));
         const uint32_t cut = __shfl_sync(kFull, incl, (nl + 31) & 31);
         const uint32_t end_rel = nl == 32 ? chain_end : __shfl_sync(kFull, myrel, nl & 31);
         if (nl > 0 && (cut & 0xFFFFFu) <= remaining && cur + end_rel <= slen) {
@@ -749,86 +1019,12 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
             uint32_t a = mya + 1, qa = qaddr + 8 * qexcl;
             if (lane < nl) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
-                const uint32_t pos = gbase + orel[j];
-                if (!ism) {
-                    sts_u8((pos & kRingMask) | rb, b1v[j]);
-                } else {
-                    const uint32_t b1 = b1v[j], b2 = lds_u8(a + 1);
-                    uint32_t len, dist;
-                    if (K == K_LZ10) {
-                        len = (b1 >> 4) + 3;
-                        dist = (((b1 & 0xF) << 8) | b2) + 1;
-                    } else {
-                        len = (b2 & lmask) + uint32_t(lz.min_length);
-                        const uint32_t raw = ((b2 >> lz.length_bits) << 8) | b1;
-                        const uint32_t ring_len = 1u << lz.windows_bits;
-                        const uint32_t offset = (uint32_t(lz.max_distance) + raw - uint32_t(lz.windows_start)) & uint32_t(lz.max_distance - 1);
-                        const uint32_t rp = pos & (ring_len - 1);
-                        dist = rp >= offset ? rp - offset : rp - offset + ring_len;
-                        if (dist == 0) dist = ring_len;
-                    }
-                    sts_u64(qa, pos, len | (dist << 17));
-                    qa += 8;
-                }
-                a += ism ? 2 : 1;
-            }
-            }
-            total = cut & 0xFFFFFu;
-            nq = cut >> 20;
-            nlan = nl;
-            consumed = cur + end_rel;
-        } else {
-            // ---- slow path (end of the output, end of the input, or an oversized iteration): cut token by token
-            const bool taken = gexcl < remaining && gincl <= cap && (incl >> 20) <= uint32_t(kQueue);
-            const uint32_t lim = remaining - gexcl;   // only meaningful when taken
-            uint32_t jexec = 0;
-            bool eos_here = false;
-            {
-                const uint32_t gabs = cur + myrel;   // blob offset of my flag byte
-                uint32_t a = gabs + 1;
-                bool stop = false;
-#pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
-                    const uint32_t tend = a + (ism ? 2 : 1);
-                    const bool want = orel[j] < lim;
-                    const bool bad = gabs >= slen || tend > slen;
-                    if (!stop && want && bad) eos_here = true;
-                    stop = stop || !want || bad;
-                    if (!stop) jexec = j + 1;
-                    a = tend;
-                }
-            }
-            if (!taken) {
-                jexec = 0;
-                eos_here = false;
-            }
-            const uint32_t eosmask = __ballot_sync(kFull, eos_here);
-            if (eosmask) {
-                const uint32_t gb = __ffs(eosmask) - 1;
-                if (lane > gb) jexec = 0;
-                status = AURORA_END_OF_STREAM;
-            }
-            nlan = __popc(__ballot_sync(kFull, jexec > 0));   // a prefix of the lanes
-            if (nlan == 0) {
-                if (status == AURORA_OK && sink.retry_full()) continue;   // the budget was cut by the iteration in flight
-                stuck = true;
-                break;
-            }
-            const uint32_t last = nlan - 1;
-            uint32_t oend = 0, qi = qexcl, aend = 0;
-            {
-                uint32_t a = mya + 1;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const bool ism = (K == K_LZ10) ? (m >> (7 - j)) & 1 : (m >> j) & 1;
-                    const bool e = uint32_t(j) < jexec;
                     const uint32_t pos = gbase + orel[j];
-                    const uint32_t next_o = (j == 7) ? gsize : orel[(j + 1) & 7];
-                    if (e && !ism) sts_u8((pos & kRingMask) | rb, b1v[j]);
-                    if (e && ism) {
+                    if (!ism) {
+                        sts_u8((pos & kRingMask) | rb, b1v[j]);
+                    } else {
                         const uint32_t b1 = b1v[j], b2 = lds_u8(a + 1);
                         uint32_t len, dist;
                         if (K == K_LZ10) {
@@ -843,25 +1039,27 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
                             dist = rp >= offset ? rp - offset : rp - offset + ring_len;
                             if (dist == 0) dist = ring_len;
                         }
-                        sts_u64(qaddr + 8 * qi, pos, len | (dist << 17));
-                        qi++;
+                        sts_u64(qa, pos, len | (dist << 17));
+                        qa += 8;
                     }
                     a += ism ? 2 : 1;
-                    if (e) {
-                        oend = next_o;
-                        aend = a - wa;
-                    }
                 }
             }
-            total = __shfl_sync(kFull, gexcl + oend, last);
-            nq = __shfl_sync(kFull, qi, last);
-            consumed = cur + __shfl_sync(kFull, aend, last);
+            total = cut & 0xFFFFFu;
+            nq = cut >> 20;
+            nlan = nl;
+            consumed = cur + end_rel;
+        } else {
+            const CutResult r = g32_cut_tokens<K>(rb, qaddr, wa, mya, m, written, gexcl, gincl, qexcl, incl >> 20, remaining, cap, cur, slen, lz);
+            if (r.eos) status = AURORA_END_OF_STREAM;
+            if (r.nlan == 0) break;
+            total = r.total;
+            nq = r.nq;
+            nlan = r.nlan;
+            consumed = r.consumed;
         }
-        break;
-      }
-        if (stuck) break;
-        sink.submit(nq, written + total, total);
         written += total;
+        sink.submit_deferred(nq, written);
         if (status != AURORA_OK) break;
         cur += (nlan == 32) ? chain_end : __shfl_sync(kFull, myrel, nlan & 31);
     }
@@ -980,7 +1178,7 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
             gin = a - mya;
         }
         const uint32_t nm = __popc(f);
-        const uint32_t gclamp = min(gsize, 4095u);   // LZ11 groups can be huge; anything above kSubMaxG takes the long-group path
+        const uint32_t gclamp = min(gsize, 8191u);   // LZ11 groups can be huge; anything above the iteration budget takes the long-group path
         const uint32_t incl = warp_incl_scan(valid ? (gclamp | (nm << 20)) : 0u);
         const uint32_t gincl = incl & 0xFFFFFu, gexcl = gincl - (valid ? gclamp : 0u);
         const uint32_t qexcl = (incl >> 20) - (valid ? nm : 0u);
@@ -991,7 +1189,7 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
       for (;;) {
         // ---- which of my tokens execute (end of output, end of input, iteration byte budget, queue capacity)
         const uint32_t cap = sink.cap();
-        const bool taken = valid && gexcl < remaining && gincl <= cap && (incl >> 20) <= uint32_t(kQueue);
+        const bool taken = valid && gexcl < remaining && gincl <= cap && (incl >> 20) <= uint32_t(kIterMatches);
         const uint32_t lim = remaining - gexcl;
         jexec = 8;
         bool eos_here = false;
@@ -1033,11 +1231,10 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
             status = AURORA_END_OF_STREAM;
         }
         nlan = __popc(__ballot_sync(kFull, jexec > 0));
-        if (nlan == 0 && status == AURORA_OK && sink.retry_full()) continue;   // the budget was cut by the iteration in flight
         break;
       }
         if (nlan == 0) {
-            if (kFour && status == AURORA_OK && __shfl_sync(kFull, gsize, 0) > uint32_t(kSubMaxG)) {
+            if (kFour && status == AURORA_OK && __shfl_sync(kFull, gsize, 0) > sink.cap()) {
                 // long-group path: the first group alone exceeds the iteration budget (matches of up to 65 808 bytes):
                 // its 8 tokens run one at a time, long matches as periodic 2 KiB segments with a drain in between
                 const uint32_t rel0 = __shfl_sync(kFull, myrel, 0), f0 = __shfl_sync(kFull, f, 0);
@@ -1127,7 +1324,7 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
         const uint32_t total = __shfl_sync(kFull, gexcl + oend, last);
         const uint32_t nq = __shfl_sync(kFull, qi, last);
         consumed = cur + __shfl_sync(kFull, aend, last);
-        sink.submit(nq, written + total, total);
+        sink.submit(nq, written + total);
         written += total;
         if (status != AURORA_OK) break;
         // resume at the first group that was not executed (its start is exact: it follows exact groups)
@@ -1215,7 +1412,7 @@ __device__ BodyResult decode_body_g32_split(InStream* in, Sink& sink, const uint
         uint32_t jexec, nlan;
       for (;;) {
         const uint32_t cap = sink.cap();
-        const bool taken = gexcl < remaining && gincl <= cap && mincl <= uint32_t(kQueueSplit);
+        const bool taken = gexcl < remaining && gincl <= cap && mincl <= uint32_t(kIterMatches);
         const uint32_t lim = remaining - gexcl;
         // ---- which of my tokens execute
         jexec = 8;
@@ -1223,7 +1420,7 @@ __device__ BodyResult decode_body_g32_split(InStream* in, Sink& sink, const uint
         // fast path: all 256 tokens execute (not the end of the output, all three sub-streams have their bytes)
         const uint32_t all_out = __shfl_sync(kFull, gincl, 31), all_m = __shfl_sync(kFull, mincl, 31);
         const uint32_t all_l = 256 - all_m + ((K == K_YAY0) ? __shfl_sync(kFull, eb + next, 31) : 0u);
-        if (!(all_out <= min(remaining, cap) && all_m <= uint32_t(kQueueSplit) && 0x10 + cur + 32 <= slen && comp_off + ccur + 2 * all_m <= slen &&
+        if (!(all_out <= min(remaining, cap) && all_m <= uint32_t(kIterMatches) && 0x10 + cur + 32 <= slen && comp_off + ccur + 2 * all_m <= slen &&
               lit_off + lcur + all_l <= slen)) {
             jexec = 0;
             const bool fbad = 0x10 + cur + lane >= slen;
@@ -1253,7 +1450,6 @@ __device__ BodyResult decode_body_g32_split(InStream* in, Sink& sink, const uint
             status = AURORA_END_OF_STREAM;
         }
         nlan = __popc(__ballot_sync(kFull, jexec > 0));
-        if (nlan == 0 && status == AURORA_OK && sink.retry_full()) continue;   // the budget was cut by the iteration in flight
         break;
       }
         if (nlan == 0) break;
@@ -1287,7 +1483,7 @@ __device__ BodyResult decode_body_g32_split(InStream* in, Sink& sink, const uint
         const uint32_t total = __shfl_sync(kFull, gexcl + oend, last);
         const uint32_t nq = __shfl_sync(kFull, kend, last);
         const uint32_t nl = __shfl_sync(kFull, lend, last);
-        sink.submit(nq, written + total, total);
+        sink.submit(nq, written + total);
         written += total;
         ccur += 2 * nq;
         {
@@ -1467,13 +1663,19 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
 }
 
 template <int K>
-__global__ void __launch_bounds__(Traits<K>::kSlots * 64, 1) decode_flaglz_kernel(const DecodeParams P) {
+__global__ void __launch_bounds__(Traits<K>::kSlots * 64, Traits<K>::kBlocksPerSM) decode_flaglz_kernel(const DecodeParams P) {
     using T = Traits<K>;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
-    // warpgroups alternate parser / replayer; slot s is served by parser warp (s / 4) * 8 + s % 4 and the warp 4 above it
+#ifdef AURORA_AFFINE
+    // developer probe: roles by scheduler (warps 4k, 4k+1 parse, 4k+2, 4k+3 resolve; a warp runs on scheduler warp % 4), no register split
+    const int role = (warp >> 1) & 1;
+    const int slot = (warp >> 2) * 2 + (warp & 1);
+#else
+    // warpgroups alternate parser / resolver; slot s is served by parser warp (s / 4) * 8 + s % 4 and the warp 4 above it
     const int role = (warp >> 2) & 1;
     const int slot = (warp >> 3) * 4 + (warp & 3);
+#endif
     // rings first, 8 KiB aligned in the shared window (wrapped ring addresses become one LOP3); the launcher adds 8 KiB of slack
     const uint32_t s0 = smem_u32(smem);
     uint8_t* aligned = smem + (((s0 + kRing - 1) & ~uint32_t(kRing - 1)) - s0);
@@ -1481,35 +1683,23 @@ __global__ void __launch_bounds__(Traits<K>::kSlots * 64, 1) decode_flaglz_kerne
     uint8_t* aux = aligned + size_t(T::kSlots) * kRing + size_t(slot) * T::kAuxBytes;
     uint8_t* qptr = aux + T::kStreams * kInStage;
     const uint32_t qbase = smem_u32(qptr), gaddr = qbase + T::kQueueBytes, mail = gaddr + 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qptr + T::kQueueBytes + 128 + 32 + 16);
-    uint64_t* full = bars + 2 * T::kStreams;
-    uint64_t* empty = full + 2;
-    if (role == 0 && lane_id() == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&empty[0], 1);
-        mbar_init(&empty[1], 1);
-    }
-    InStream in[T::kStreams];
-    if (role == 0) {
-#pragma unroll
-        for (int s = 0; s < T::kStreams; s++) in[s].init(aux + s * kInStage, bars + 2 * s);
-        fence_proxy_async();
-    }
-    __syncthreads();   // the only block-wide barrier: the slots' mbarriers are initialised
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qptr + T::kQueueBytes + 128 + 48);
+    const uint32_t bar_f = 2 * slot, bar_e = 2 * slot + 1;   // the slot's two named barriers (no __syncthreads in this kernel)
 
     if (role == 0) {
         if constexpr (T::kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T::kParserRegs));
-        PipeSink sink;
+        InStream in[T::kStreams];
+#pragma unroll
+        for (int s = 0; s < T::kStreams; s++) in[s].init(aux + s * kInStage, bars + 2 * s);
+        fence_proxy_async();
+        __syncwarp();   // the slot's TMA mbarriers are initialised (only this warp uses them)
+        SlotSink sink;
         sink.rbase = smem_u32(ring);
         sink.qbase = qbase;
-        sink.qstride = T::kQueueLen * 8;
         sink.mail = mail;
-        sink.full = full;
-        sink.empty = empty;
-        sink.it = 0;
-        sink.prev_total = 0;
-        sink.flags_next = 0;
+        sink.bar_f = bar_f;
+        sink.bar_e = bar_e;
+        sink.init();
         for (;;) {
             uint32_t t = 0;
             if (lane_id() == 0) t = atomicAdd(P.ticket, 1u);
@@ -1522,16 +1712,17 @@ __global__ void __launch_bounds__(Traits<K>::kSlots * 64, 1) decode_flaglz_kerne
 #pragma unroll
         for (int s = 0; s < T::kStreams; s++) in[s].drain_inflight();
     } else {
-        if constexpr (T::kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T::kReplayerRegs));
-        replayer_role(ring, qbase, T::kQueueLen * 8, mail, full, empty);
+        if constexpr (T::kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T::kResolverRegs));
+        resolver_role(ring, qbase, mail, bar_f, bar_e);
     }
 }
 
 template <int K>
 cudaError_t launch(const DecodeParams& p, int sm_count, cudaStream_t st) {
     using T = Traits<K>;
+    static_assert(T::kSlots == 4 || T::kSlots == 8, "a block has 16 named barriers: at most 8 slots, in warpgroups of 4");
     const int threads = T::kSlots * 64;
-    const size_t smem = size_t(T::kSlots) * T::kSmemPerSlot + kRing;   // + alignment slack for the rings
+    const size_t smem = size_t(T::kSmemPerBlock);
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1540,7 +1731,7 @@ cudaError_t launch(const DecodeParams& p, int sm_count, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    int blocks = sm_count;
+    int blocks = sm_count * T::kBlocksPerSM;
     const int needed_blocks = int((p.n + T::kSlots - 1) / T::kSlots);
     if (needed_blocks < blocks) blocks = needed_blocks > 0 ? needed_blocks : 1;
     decode_flaglz_kernel<K><<<blocks, threads, smem, st>>>(p);

@@ -306,7 +306,7 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
         }
         const int rc = decode_core_batch(ctx, core, &o, m, src_base, so.data(), sl.data(), dst_base, dof.data(), dc.data(),
                                          want_raw ? raw.data() : nullptr, ol.data(), cs.data(), st.data(),
-                                         keys.empty() ? nullptr : keys.data());
+                                         keys.empty() ? nullptr : keys.data(), /*exact=*/true);
         if (rc != AURORA_OK) return rc;
         for (size_t j = 0; j < m; j++) {
             r_out[idx[j]] = ol[j];
@@ -344,7 +344,7 @@ int wrapped_decode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* o
                 dc[j] = s.doff < cap ? cap - s.doff : 0;
             }
             const int rc = decode_core_batch(ctx, AURORA_FMT_LZ10, &o, m, src_base, so.data(), sl.data(), dst_base, dof.data(), dc.data(),
-                                             nullptr, ol.data(), cs.data(), st.data());
+                                             nullptr, ol.data(), cs.data(), st.data(), nullptr, /*exact=*/true);
             if (rc != AURORA_OK) return rc;
         }
     }
