@@ -463,32 +463,25 @@ __device__ __forceinline__ void ring_copy_any(uint32_t rb, uint32_t pos, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Match resolution.  The queue holds {pos, len | d << 17} in stream order; all literals up to the last queued match are
-// already in the ring.
-//   A. run merging: encoders split a long run (or a 32-byte tile) into maximum-length matches with the same distance
-//      that follow each other without a gap; such a chain is exactly one longer copy out[o] = out[o - d].  A
-//      lane-parallel pass compacts every chain into one entry in place (chains are cut at 32-entry blocks).
-//   B. per block of 32 merged entries:
-//      fills   runs of a byte / u16 / u32 (d = 1, 2, 4, up to 128 bytes) whose d source bytes are not written by the entry
-//              before them depend on nothing unresolved: ALL of them go at once, one per lane — the d bytes become one
-//              pattern word (rotated to the destination's alignment), stored as head bytes, aligned words, tail bytes,
-//              no loads in the loop (tilemaps: most entries);
-//      steps   everything else runs in stream order: a long entry (> 32 bytes) is one warp-cooperative copy; short
-//              entries go up to FOUR PER STEP, eight lanes and four bytes per lane each, all loads of the step in flight
-//              before its stores.  The entries of a step must not read what the step writes: entry i + k joins only if
-//              its source ends below the destination of entry i (everything below that is final): one ballot.
-// (Measured first, profiles/r2_*: one match per lane in dependency rounds with per-class copy routines.  On tile sheets a
-//  round finds ~5 of 21 entries ready and an iteration of a tilemap holds ~8 entries, so the fixed cost per round
-//  dominated: ~200 instructions per round.)
+// Match resolution (resolver warp).  The queue of a batch holds {pos, len | d << 17} in stream order; every literal of the
+// batch is already in the ring.
+//   run merging: encoders split a long run (or a 32-byte tile) into maximum-length matches with the same distance that
+//   follow each other without a gap; such a chain is exactly one longer copy out[o] = out[o - d].  A lane-parallel pass
+//   compacts every chain into one entry in place (chains are cut at 32-entry blocks);
+//   replay: the merged entries run in stream order, a byte per lane and pass, two entries per step when the second one
+//   does not read what the first one writes (both loads before both stores), next entries prefetched from the queue.
+// Measured and rejected in round 2 (profiles/r2_resolver_experiments.md): one match per lane in dependency rounds with
+// per-class copy routines (fill / word / byte), pointer-jumping of tile chains, in-order steps of up to four hazard-free
+// matches on 8 lanes each, and lane-parallel copies by the PARSER of the matches whose source is already final.  All of
+// them issue fewer instructions per match on paper, none beat this loop: the resolver is ONE warp bound by the latency
+// of its dependent chain (entry -> addresses -> load -> store), not by its instruction count, dependency depth (tile
+// sheets: ~5 of 21 entries ready per round) starves the wide variants, and work moved to the parser competes for the
+// same issue slots.
 // ---------------------------------------------------------------------------------------------
-#ifndef AURORA_FILL_MAX
-#define AURORA_FILL_MAX 128
-#endif
-
 __device__ __forceinline__ void resolve_matches(uint32_t rb, uint32_t qaddr, uint32_t nq) {
     const uint32_t lane = lane_id();
+    if (nq == 0) return;
     const uint32_t lt = (1u << lane) - 1u;
-    // ---- A. merge + compact
     uint32_t nout = 0;
     for (uint32_t base = 0; base < nq; base += 32) {
         const uint32_t q = base + lane;
@@ -499,146 +492,48 @@ __device__ __forceinline__ void resolve_matches(uint32_t rb, uint32_t qaddr, uin
         const bool cont = have && lane > 0 && e.x == px + (py & 0x1FFFFu) && (e.y >> 17) == (py >> 17);
         const uint32_t heads = __ballot_sync(kFull, have && !cont);
         const uint32_t valid = __ballot_sync(kFull, have);
-        if (heads != valid) {
-            // last entry of my chain: the lane before the next head (or the last valid lane of the block)
-            const uint32_t after = heads & ~lt & ~(1u << lane);
-            const uint32_t last = after ? uint32_t(__ffs(after) - 2) : uint32_t(31 - __clz(valid));
-            const uint32_t tx = __shfl_sync(kFull, e.x, last & 31), ty = __shfl_sync(kFull, e.y, last & 31);
-            __syncwarp();
-            if (have && !cont) sts_u64(qaddr + 8 * (nout + __popc(heads & lt)), e.x, (tx + (ty & 0x1FFFFu) - e.x) | (e.y & 0xFFFE0000u));
-        } else if (nout != base) {
-            __syncwarp();
-            if (have) sts_u64(qaddr + 8 * (nout + lane), e.x, e.y);
-        }
+        // last entry of my chain: the lane before the next head (or the last valid lane of the block)
+        const uint32_t after = heads & ~lt & ~(1u << lane);
+        const uint32_t last = after ? uint32_t(__ffs(after) - 2) : uint32_t(31 - __clz(valid));
+        const uint32_t tx = __shfl_sync(kFull, e.x, last & 31), ty = __shfl_sync(kFull, e.y, last & 31);
+        __syncwarp();
+        if (have && !cont) sts_u64(qaddr + 8 * (nout + __popc(heads & lt)), e.x, (tx + (ty & 0x1FFFFu) - e.x) | (e.y & 0xFFFE0000u));
         nout += __popc(heads);
     }
     __syncwarp();
-    // ---- B.
-    const uint32_t sub = lane >> 3, o0 = 4 * (lane & 7);   // steps: my entry of a step, my four bytes of it
-    for (uint32_t base = 0; base < nout; base += 32) {
-        const uint32_t q = base + lane;
-        const bool have = q < nout;
-        uint2 e = make_uint2(0u, 0u);
-        if (have) e = lds_u64(qaddr + 8 * q);
-        // ---- fills that depend on nothing unresolved: all at once
-        {
-            const uint32_t len = e.y & 0x1FFFFu, d = e.y >> 17;
-            const uint32_t pend = __shfl_up_sync(kFull, e.x + len, 1);   // end of the entry before mine
-            const bool act = have && len <= uint32_t(AURORA_FILL_MAX) && (d == 1 || d == 2 || d == 4) &&
-                             (lane == 0 || int32_t(e.x - d - pend) >= 0);
-            const uint32_t fmask = __ballot_sync(kFull, act);
-            if (__popc(fmask) >= 3) {   // (one or two: the steps below are cheaper)
-                const uint32_t t0 = e.x & kRingMask, s0 = (e.x - d) & kRingMask;
-                const uint32_t n = act ? min(len, uint32_t(kRing) - t0) : 0u;   // up to the end of the ring
-                uint32_t w0 = 0;   // the four bytes a destination word at pos would get
-                if (act) {
-                    const uint32_t q0 = lds_u8(s0 | rb);
-                    w0 = q0 * 0x01010101u;
-                    if (d >= 2) {
-                        const uint32_t q1 = lds_u8(((s0 + 1) & kRingMask) | rb);
-                        w0 = (q0 | (q1 << 8)) * 0x00010001u;
-                        if (d == 4) {
-                            const uint32_t q2 = lds_u8(((s0 + 2) & kRingMask) | rb), q3 = lds_u8(((s0 + 3) & kRingMask) | rb);
-                            w0 = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
-                        }
-                    }
-                }
-                const uint32_t h = min((0u - e.x) & 3u, n);             // head bytes up to the first aligned word
-                const uint32_t w = __funnelshift_r(w0, w0, 8 * h);      // the pattern as every aligned word sees it
-                const uint32_t tp = t0 | rb;
-                if (h > 0) sts_u8(tp, w0);
-                if (h > 1) sts_u8(tp + 1, w0 >> 8);
-                if (h > 2) sts_u8(tp + 2, w0 >> 16);
-                const uint32_t nw = (n - h) >> 2, wp = tp + h;
-                const uint32_t wmax = __reduce_max_sync(kFull, nw);
-                for (uint32_t i = 0; i < wmax; i += 4) {
-                    if (i < nw) sts_u32(wp + 4 * i, w);
-                    if (i + 1 < nw) sts_u32(wp + 4 * i + 4, w);
-                    if (i + 2 < nw) sts_u32(wp + 4 * i + 8, w);
-                    if (i + 3 < nw) sts_u32(wp + 4 * i + 12, w);
-                }
-                const uint32_t tl = (n - h) & 3u, ep = wp + 4 * nw;
-                if (tl > 0) sts_u8(ep, w);
-                if (tl > 1) sts_u8(ep + 1, w >> 8);
-                if (tl > 2) sts_u8(ep + 2, w >> 16);
-                // done: a zero-length entry for the steps below (a fill cut at the end of the ring leaves them its rest)
-                e.x += n;
-                e.y -= n;
-                __syncwarp();
-            }
-        }
-        // ---- steps, in stream order.  How many entries a step that starts at entry i takes is known per lane up front:
-        //      entries i + 1 .. i + 3 join while they are short and their source ends below the destination of entry i
-        const uint32_t len = e.y & 0x1FFFFu, d = e.y >> 17;
-        const uint32_t ne = min(nout - base, 32u);
-        const uint32_t smask = __ballot_sync(kFull, have && len <= 32);
-        const uint32_t slast = e.x - d + min(len, d) - 1;   // my last source byte
-        uint32_t tk = 1;
-        {
-            const uint32_t s1 = __shfl_down_sync(kFull, slast, 1), s2 = __shfl_down_sync(kFull, slast, 2), s3 = __shfl_down_sync(kFull, slast, 3);
-            const uint32_t sm = smask >> lane;   // bit k: entry lane + k is short (0 beyond the block)
-            const bool ok1 = (sm & 2u) && int32_t(s1 - e.x) < 0;
-            const bool ok2 = ok1 && (sm & 4u) && int32_t(s2 - e.x) < 0;
-            const bool ok3 = ok2 && (sm & 8u) && int32_t(s3 - e.x) < 0;
-            tk = 1u + (ok1 ? 1u : 0u) + (ok2 ? 1u : 0u) + (ok3 ? 1u : 0u);
-        }
-        uint32_t i = 0;
-        while (i < ne) {
-            const uint32_t take = __shfl_sync(kFull, tk, i);
-            const uint32_t mx = __shfl_sync(kFull, e.x, (i + sub) & 31), my = __shfl_sync(kFull, e.y, (i + sub) & 31);
-            if (!((smask >> i) & 1u)) {   // long: the whole warp
-                const uint32_t px = __shfl_sync(kFull, mx, 0), py = __shfl_sync(kFull, my, 0);
-                ring_copy_any(rb, px, py >> 17, py & 0x1FFFFu);
-                __syncwarp();
-                i++;
-                continue;
-            }
-            const uint32_t mlen = my & 0x1FFFFu, md = my >> 17;
-            uint32_t nb = 0;   // my bytes: [o0, o0 + nb) of the entry
-            if (sub < take && o0 < mlen) nb = min(4u, mlen - o0);
-            const uint32_t t0 = (mx + o0) & kRingMask, s0 = (mx - md + o0) & kRingMask;
-            const uint32_t ta = t0 | rb, sa = s0 | rb;
-            const bool plain = md >= mlen && max(t0, s0) <= uint32_t(kRing - 4);   // no o mod d, not across the end of the ring
-            const uint32_t al = (t0 | s0 | nb) & 3u;                                  // 0: one word, 2: two halves
-            const uint32_t not_plain = __ballot_sync(kFull, nb && !plain), not_w = __ballot_sync(kFull, nb && al), not_h = __ballot_sync(kFull, nb && (al & 1u));
-            if (not_plain == 0 && not_w == 0) {
-                uint32_t v = 0;
-                if (nb) v = lds_u32(sa);
-                if (nb) sts_u32(ta, v);
-            } else if (not_plain == 0 && not_h == 0) {
+    // Two entries per step: when the second match's source ends at or before the first match's destination the two
+    // copies are independent, so both loads are issued before both stores (one barrier, twice the ILP); the slots
+    // past the end of the queue are readable (slack behind the queue).
+    uint2 e0 = lds_u64(qaddr), e1 = lds_u64(qaddr + 8);
+    uint32_t q = 0;
+    while (q + 1 < nout) {
+        const uint2 n0 = lds_u64(qaddr + 8 * (q + 2)), n1 = lds_u64(qaddr + 8 * (q + 3));
+        const uint32_t len0 = e0.y & 0x1FFFFu, d0 = e0.y >> 17, len1 = e1.y & 0x1FFFFu, d1 = e1.y >> 17;
+        if (max(len0, len1) < 512 && e1.x - d1 + min(len1, d1) <= e0.x) {
+            const uint32_t r0 = d0 < len0 ? c_rcp.v[d0] : 0u, r1 = d1 < len1 ? c_rcp.v[d1] : 0u;   // 0: no wrap, off = i
+            const uint32_t s0 = e0.x - d0, s1 = e1.x - d1, lmax = max(len0, len1);
+            for (uint32_t i = lane; i < lmax; i += 32) {
+                const uint32_t off0 = i - ((i * r0) >> 20) * d0, off1 = i - ((i * r1) >> 20) * d1;
                 uint32_t v0 = 0, v1 = 0;
-                if (nb > 0) v0 = lds_u16(sa);
-                if (nb > 2) v1 = lds_u16(sa + 2);
-                if (nb > 0) sts_u16(ta, v0);
-                if (nb > 2) sts_u16(ta + 2, v1);
-            } else if (not_plain == 0) {
-                uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-                if (nb > 0) v0 = lds_u8(sa);
-                if (nb > 1) v1 = lds_u8(sa + 1);
-                if (nb > 2) v2 = lds_u8(sa + 2);
-                if (nb > 3) v3 = lds_u8(sa + 3);
-                if (nb > 0) sts_u8(ta, v0);
-                if (nb > 1) sts_u8(ta + 1, v1);
-                if (nb > 2) sts_u8(ta + 2, v2);
-                if (nb > 3) sts_u8(ta + 3, v3);
-            } else {
-                // periodic (d < len: the source offset is o mod d) or across the end of the ring
-                const uint32_t r = md < 32 ? c_rcp.v[md] : 0u;   // 0: d >= 32 >= len, o mod d = o
-                uint32_t v[4];
-#pragma unroll
-                for (uint32_t j = 0; j < 4; j++) {
-                    const uint32_t o = o0 + j;
-                    const uint32_t so = o - ((o * r) >> 20) * md;
-                    v[j] = 0;
-                    if (j < nb) v[j] = lds_u8(((mx - md + so) & kRingMask) | rb);
-                }
-#pragma unroll
-                for (uint32_t j = 0; j < 4; j++)
-                    if (j < nb) sts_u8(((mx + o0 + j) & kRingMask) | rb, v[j]);
+                if (i < len0) v0 = lds_u8(((s0 + off0) & kRingMask) | rb);
+                if (i < len1) v1 = lds_u8(((s1 + off1) & kRingMask) | rb);
+                if (i < len0) sts_u8(((e0.x + i) & kRingMask) | rb, v0);
+                if (i < len1) sts_u8(((e1.x + i) & kRingMask) | rb, v1);
             }
             __syncwarp();
-            i += take;
+        } else {
+            ring_copy_any(rb, e0.x, d0, len0);
+            __syncwarp();
+            ring_copy_any(rb, e1.x, d1, len1);
+            __syncwarp();
         }
+        e0 = n0;
+        e1 = n1;
+        q += 2;
+    }
+    if (q < nout) {
+        ring_copy_any(rb, e0.x, e0.y >> 17, e0.y & 0x1FFFFu);
+        __syncwarp();
     }
 }
 
