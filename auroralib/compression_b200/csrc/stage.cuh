@@ -59,7 +59,7 @@ struct InStream {
         skew = uint32_t(reinterpret_cast<uintptr_t>(p) & 15);
         gbase = p - skew;
         const uint64_t lim = uint64_t((src_base + src_limit) - gbase);
-        glimit = lim > 0xFFFFFFF0ull ? 0xFFFFFFF0u : uint32_t(lim);
+        glimit = lim > 0xFFFF0000ull ? 0xFFFF0000u : uint32_t(lim);   // (the chunk count below must not wrap)
         nchunks = (glimit + kInChunk - 1) / kInChunk;
         rebase(0);
     }

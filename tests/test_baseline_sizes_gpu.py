@@ -1,0 +1,99 @@
+"""GPU parity at the sizes BASELINE.json names (configs C3 / C4), through the device-resident C ABI entry point.
+
+The oracle cannot decode gigabytes in seconds, so the full-size batches are checked through size-independent properties
+(encode -> decode round trip byte-exact against the raw input, all statuses OK) and a SAMPLE of the streams is decoded by
+the oracle and compared byte for byte (status, out_len, consumed, bytes)."""
+import numpy as np
+import pytest
+
+from auroralib.compression_b200 import _abi as A
+from tests.util import fmt_id
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_roundtrip(codec, oracle, fmt, raw, r_off, r_len, enc_opts, dec_opts, sample, src_pad=0, allow_unrepresentable=False):
+    """GPU encode -> tight pack -> GPU decode into adjacent, unaligned destination windows; oracle check on `sample`."""
+    import torch
+    import bench
+    dev = raw.device
+    ts = torch.cuda.Stream(device=dev)
+    packed, p_off, c_len, total, _ = bench.gpu_encode(codec, fmt, raw, r_off, r_len, enc_opts, dev, ts)
+    if src_pad:
+        # move the streams to the front of a much larger source allocation (the limit of the staged reads is then
+        # > 4 GiB behind every stream)
+        big = torch.zeros(total + src_pad + 16, dtype=torch.uint8, device=dev)
+        big[:total] = packed[:total]
+        packed = big
+    n = r_len.numel()
+    d_dst = torch.zeros(raw.numel(), dtype=torch.uint8, device=dev)
+    olen = torch.zeros(n, dtype=torch.int64, device=dev)
+    cons = torch.zeros(n, dtype=torch.int64, device=dev)
+    st = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    codec.decode_device(fmt, packed, p_off, c_len, d_dst, r_off, r_len, olen, cons, st, dec_opts, device=0, stream=ts.cuda_stream)
+    ts.synchronize()
+    bad = (st != 0).nonzero().flatten().tolist()
+    if allow_unrepresentable:
+        # The reference's LZO encoder (LZO.cs:170-176) shortens a match by up to 3 bytes to make room for a 4-byte literal
+        # run and then DROPS it when fewer than MinLength bytes are left: two literal runs follow each other, which LZO1X cannot
+        # express, and the reference's own decoder reads the second run as a match.  Such streams (a fraction of a percent of
+        # the tilemap class) do not round-trip through the reference either; for them the bar is parity with the oracle's
+        # decoder on the same compressed bytes.
+        assert len(bad) < n // 100, f"{fmt_id(fmt)}: {len(bad)} of {n} streams failed"
+        sample = list(sample) + bad[:6]
+    else:
+        assert not bad, f"{fmt_id(fmt)}: {len(bad)} of {n} streams failed, first {bad[:4]}"
+    good = st == 0
+    assert torch.equal(olen[good], r_len[good]) and torch.equal(cons[good], c_len[good]), fmt_id(fmt)
+    for i in bad:   # (their windows hold what the reference's decoder produces: checked below on a sample)
+        ro, rl = int(r_off[i]), int(r_len[i])
+        d_dst[ro:ro + rl] = raw[ro:ro + rl]
+    out_bytes = int(r_len.sum())
+    assert torch.equal(d_dst[:out_bytes], raw[:out_bytes]), f"{fmt_id(fmt)}: decoded bytes differ from the raw input"
+    # oracle on a sample of the streams: same compressed bytes -> same status / out_len / consumed / bytes
+    if bad:
+        d_dst.zero_()
+        codec.decode_device(fmt, packed, p_off, c_len, d_dst, r_off, r_len, olen, cons, st, dec_opts, device=0, stream=ts.cuda_stream)
+        ts.synchronize()
+    for i in sample:
+        po, cl, ro, rl = int(p_off[i]), int(c_len[i]), int(r_off[i]), int(r_len[i])
+        comp = packed[po:po + cl].cpu().numpy().tobytes()
+        ref, rlen, rcons, rst = oracle.decode_batch(fmt, [comp], [rl], dec_opts)
+        assert (int(st[i]), int(olen[i]), int(cons[i])) == (int(rst[0]), int(rlen[0]), int(rcons[0])), f"{fmt_id(fmt)} stream {i}"
+        assert ref[0] == d_dst[ro:ro + min(rl, int(rlen[0]))].cpu().numpy().tobytes(), f"{fmt_id(fmt)} stream {i}: GPU output differs from the oracle"
+
+
+@pytest.mark.parametrize("fmt", [A.FMT_YAZ0, A.FMT_YAY0, A.FMT_MIO0], ids=fmt_id)
+@pytest.mark.parametrize("order", [A.ENDIAN_BIG, A.ENDIAN_LITTLE], ids=["big", "little"])
+def test_c3_sizes(codec, oracle, fmt, order):
+    """Config C3: streams of 256 KiB - 4 MiB (classes T/M/X/B), both byte orders, largest-first hand-out (opts.balance)."""
+    import torch
+    import bench
+    dev = torch.device("cuda", 0)
+    raw, r_off, r_len = bench.ragged_corpus(96, 256 << 10, 4 << 20, "TMXB", 0xC3000 + fmt + 16 * order, dev, group=8)
+    _device_roundtrip(codec, oracle, fmt, raw, r_off, r_len, A.make_opts(quality=8, byte_order=order),
+                      A.make_opts(byte_order=order, balance=1), sample=[0, 50, 95])
+
+
+@pytest.mark.parametrize("fmt", [A.FMT_LZ4_BLOCK, A.FMT_SNAPPY_BLOCK, A.FMT_LZO], ids=fmt_id)
+def test_c4_sizes(codec, oracle, fmt):
+    """Config C4: 131 072 block streams of 4 - 64 KiB in ONE batch, destination windows adjacent and unaligned."""
+    import torch
+    import bench
+    dev = torch.device("cuda", 0)
+    n = 131072
+    raw, r_off, r_len = bench.ragged_corpus(n, 4 << 10, 64 << 10, "TMX", 0xC4000 + fmt, dev, group=4096)
+    _device_roundtrip(codec, oracle, fmt, raw, r_off, r_len, A.make_opts(quality=8), A.make_opts(), sample=[0, 1, 4095, 4096, n // 2, n - 1],
+                      allow_unrepresentable=fmt == A.FMT_LZO)
+
+
+@pytest.mark.parametrize("fmt", [A.FMT_LZ4_BLOCK, A.FMT_LZ10], ids=fmt_id)
+def test_source_allocation_over_4gib(codec, oracle, fmt):
+    """Streams at the front of a source allocation of more than 4 GiB (the full C4 batch is 8 GB of compressed data):
+    the staged input's byte limit is clamped to 32 bits per stream and must not wrap (round-2 regression)."""
+    import torch
+    import bench
+    dev = torch.device("cuda", 0)
+    raw, r_off, r_len = bench.ragged_corpus(2048, 4 << 10, 64 << 10, "TMX", 0x4614 + fmt, dev, group=512)
+    _device_roundtrip(codec, oracle, fmt, raw, r_off, r_len, A.make_opts(quality=8), A.make_opts(), sample=[0, 2047],
+                      src_pad=(4 << 30) + (64 << 20))

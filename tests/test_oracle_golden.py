@@ -155,3 +155,17 @@ def test_ragged_and_empty_inputs(oracle):
             else:   # the reference's own quirks: LZ4 block encoders reject < 5 bytes; empty LZ10/LZ11/LZ4Legacy/LZO do not
                 # decode; PRS's byte-order heuristic (PRS.cs:161-218) misfires on high-entropy data
                 assert len(r) < 5 or fmt == A.FMT_PRS
+
+
+def test_reference_lzo_encoder_back_to_back_literal_runs(oracle):
+    """A quirk of the reference's LZO encoder that the oracle (and the GPU encoder) reproduce: LZO.cs:168-176 shortens a match
+    that starts fewer than 4 bytes behind the cursor so that the literal run in front of it is 4 bytes long, and when
+    fewer than MinLength bytes of the match are left (:188) nothing is written for it — the next token is then a second
+    literal run, which LZO1X cannot express after a run (the decoder, :71-86, takes its flag for a 3-byte match at distance
+    > 2048).  Such a stream does not round-trip through the reference; the bar for it is decoder parity (tests/
+    test_baseline_sizes_gpu.py), and the bench's LZO line leaves these streams out and says how many."""
+    raw = bytes([247, 7] * 3 + [252, 13] * 40 + list(range(50)))
+    enc, st = oracle.encode(A.FMT_LZO, raw, A.make_opts(quality=8))
+    assert st == 0 and enc[:6] == bytes([0x01, 247, 7, 247, 7, 0x01])   # 4 literals, then ANOTHER literal-run flag
+    out, out_len, consumed, status = oracle.decode(A.FMT_LZO, enc, len(raw) + 64)
+    assert status == 0 and out_len != len(raw) and out[:len(raw)] != raw
