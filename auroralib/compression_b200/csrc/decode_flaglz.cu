@@ -46,7 +46,7 @@ constexpr int kIterCap = kRing - kWindow;   // output bytes of one iteration: wi
                                             // slots an iteration overwrites (positions 8192 lower) are below the window
                                             // and below everything not yet drained (< 512 bytes behind the iteration)
 #ifndef AURORA_REG_DELTA
-#define AURORA_REG_DELTA 24
+#define AURORA_REG_DELTA 16
 #endif
 
 
@@ -469,14 +469,19 @@ __device__ __forceinline__ void ring_copy_any(uint32_t rb, uint32_t pos, uint32_
 //   follow each other without a gap; such a chain is exactly one longer copy out[o] = out[o - d].  A lane-parallel pass
 //   compacts every chain into one entry in place (chains are cut at 32-entry blocks);
 //   replay: the merged entries run in stream order, a byte per lane and pass, two entries per step when the second one
-//   does not read what the first one writes (both loads before both stores), next entries prefetched from the queue.
-// Measured and rejected in round 2 (profiles/r2_resolver_experiments.md): one match per lane in dependency rounds with
-// per-class copy routines (fill / word / byte), pointer-jumping of tile chains, in-order steps of up to four hazard-free
-// matches on 8 lanes each, and lane-parallel copies by the PARSER of the matches whose source is already final.  All of
-// them issue fewer instructions per match on paper, none beat this loop: the resolver is ONE warp bound by the latency
-// of its dependent chain (entry -> addresses -> load -> store), not by its instruction count, dependency depth (tile
-// sheets: ~5 of 21 entries ready per round) starves the wide variants, and work moved to the parser competes for the
-// same issue slots.
+//   does not read what the first one writes (both loads before both stores), the next pair prefetched with one 16-byte
+//   load.  The merge pass already turns the common entry (<= 64 bytes, no ring wrap, not self-overlapping or a run of
+//   period 1 / 2 / 4) into ready-made shared addresses, so a pair of them costs ~25 instructions instead of ~55.
+// Measured and rejected in round 2 (profiles/r2_resolver_experiments.md): one entry per lane in dependency rounds — with a
+// watermark readiness test and per-class copy routines (9-22 rounds per 32 entries), and with EXACT dependencies from two
+// lane-parallel binary searches plus lane-local byte / word / 16-byte copies (tile sheets still need 8.4 rounds per 32
+// entries: chains of picks of the same tile; 569 M instead of 627 M instructions but 373 instead of 456 GB/s) —,
+// pointer-jumping of tile chains, in-order steps of up to four hazard-free matches on 8 lanes each, lane-parallel copies by
+// the PARSER of the matches whose source is already final, a pattern-word path for long runs of period 1 / 2 / 4, and three
+// queue buffers on polled shared-memory counters instead of the two named barriers (T +4 %, X -20 %).  The wide variants
+// issue fewer instructions per match on paper; none beat this loop: the resolver is ONE warp bound by the latency of its
+// dependent chain (entry -> addresses -> load -> store), dependency depth starves the rounds, and work moved to the
+// parser competes for the same issue slots.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void resolve_matches(uint32_t rb, uint32_t qaddr, uint32_t nq) {
     const uint32_t lane = lane_id();
@@ -497,43 +502,70 @@ __device__ __forceinline__ void resolve_matches(uint32_t rb, uint32_t qaddr, uin
         const uint32_t last = after ? uint32_t(__ffs(after) - 2) : uint32_t(31 - __clz(valid));
         const uint32_t tx = __shfl_sync(kFull, e.x, last & 31), ty = __shfl_sync(kFull, e.y, last & 31);
         __syncwarp();
-        if (have && !cont) sts_u64(qaddr + 8 * (nout + __popc(heads & lt)), e.x, (tx + (ty & 0x1FFFFu) - e.x) | (e.y & 0xFFFE0000u));
+        if (have && !cont) {
+            const uint32_t ml = tx + (ty & 0x1FFFFu) - e.x, d = e.y >> 17;
+            uint32_t ox = e.x, oy = ml | (e.y & 0xFFFE0000u);
+            // SIMPLE entry (the common case): at most 64 bytes, not self-overlapping or a run with period 1 / 2 / 4, neither
+            // range wraps the ring -> the replay loop gets ready-made shared addresses:
+            //   x = destination address | len << 18 | source index mask << 25,  y = source address | 1 << 31
+            const uint32_t da = e.x & kRingMask, sa = (e.x - d) & kRingMask;
+            const bool periodic = d < ml;
+            if (ml <= 64 && (!periodic || d == 1 || d == 2 || d == 4) && da + ml <= uint32_t(kRing) && sa + min(ml, d) <= uint32_t(kRing)) {
+                ox = (da | rb) | (ml << 18) | ((periodic ? d - 1 : 127u) << 25);
+                oy = (sa | rb) | 0x80000000u;
+            }
+            sts_u64(qaddr + 8 * (nout + __popc(heads & lt)), ox, oy);
+        }
         nout += __popc(heads);
     }
     __syncwarp();
-    // Two entries per step: when the second match's source ends at or before the first match's destination the two
-    // copies are independent, so both loads are issued before both stores (one barrier, twice the ILP); the slots
-    // past the end of the queue are readable (slack behind the queue).
-    uint2 e0 = lds_u64(qaddr), e1 = lds_u64(qaddr + 8);
-    uint32_t q = 0;
-    while (q + 1 < nout) {
-        const uint2 n0 = lds_u64(qaddr + 8 * (q + 2)), n1 = lds_u64(qaddr + 8 * (q + 3));
-        const uint32_t len0 = e0.y & 0x1FFFFu, d0 = e0.y >> 17, len1 = e1.y & 0x1FFFFu, d1 = e1.y >> 17;
-        if (max(len0, len1) < 512 && e1.x - d1 + min(len1, d1) <= e0.x) {
-            const uint32_t r0 = d0 < len0 ? c_rcp.v[d0] : 0u, r1 = d1 < len1 ? c_rcp.v[d1] : 0u;   // 0: no wrap, off = i
-            const uint32_t s0 = e0.x - d0, s1 = e1.x - d1, lmax = max(len0, len1);
-            for (uint32_t i = lane; i < lmax; i += 32) {
-                const uint32_t off0 = i - ((i * r0) >> 20) * d0, off1 = i - ((i * r1) >> 20) * d1;
-                uint32_t v0 = 0, v1 = 0;
-                if (i < len0) v0 = lds_u8(((s0 + off0) & kRingMask) | rb);
-                if (i < len1) v1 = lds_u8(((s1 + off1) & kRingMask) | rb);
-                if (i < len0) sts_u8(((e0.x + i) & kRingMask) | rb, v0);
-                if (i < len1) sts_u8(((e1.x + i) & kRingMask) | rb, v1);
+    // Two entries per step.  SIMPLE pairs (see the merge pass) take the short way: one byte per lane and half (lanes 0..31
+    // copy bytes 0..31, then 32..63), both loads before both stores when the second entry does not read what the first one
+    // writes; everything else goes through ring_copy_any.  The next pair is prefetched with one 16-byte load (the slots
+    // past the end of the queue are readable: slack behind the queue); an odd count is padded with an empty SIMPLE entry.
+    if (nout & 1u) {
+        if (lane == 0) sts_u64(qaddr + 8 * nout, 0u, 0x80000000u);
+        nout++;
+        __syncwarp();
+    }
+    uint4 cur = lds_u128(qaddr);
+#pragma unroll 1
+    for (uint32_t q = 0; q < nout; q += 2) {
+        const uint4 nx = lds_u128(qaddr + 8 * (q + 2));
+        const uint32_t dst0 = cur.x & 0x3FFFFu, len0 = (cur.x >> 18) & 0x7Fu, pm0 = cur.x >> 25, src0 = cur.y & 0x3FFFFu;
+        const uint32_t dst1 = cur.z & 0x3FFFFu, len1 = (cur.z >> 18) & 0x7Fu, pm1 = cur.z >> 25, src1 = cur.w & 0x3FFFFu;
+        if (((cur.y & cur.w) >> 31) && (src1 + min(len1, pm1 + 1) <= dst0 || src1 >= dst0 + len0)) {
+            uint32_t v0 = 0, v1 = 0;
+            if (lane < len0) v0 = lds_u8(src0 + (lane & pm0));
+            if (lane < len1) v1 = lds_u8(src1 + (lane & pm1));
+            if (lane < len0) sts_u8(dst0 + lane, v0);
+            if (lane < len1) sts_u8(dst1 + lane, v1);
+            if ((len0 | len1) > 32) {
+                const uint32_t l2 = lane + 32;
+                if (l2 < len0) v0 = lds_u8(src0 + (l2 & pm0));
+                if (l2 < len1) v1 = lds_u8(src1 + (l2 & pm1));
+                if (l2 < len0) sts_u8(dst0 + l2, v0);
+                if (l2 < len1) sts_u8(dst1 + l2, v1);
             }
             __syncwarp();
         } else {
-            ring_copy_any(rb, e0.x, d0, len0);
-            __syncwarp();
-            ring_copy_any(rb, e1.x, d1, len1);
-            __syncwarp();
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                const uint32_t x = h ? cur.z : cur.x, y = h ? cur.w : cur.y;
+                if (y >> 31) {
+                    const uint32_t dst = x & 0x3FFFFu, len = (x >> 18) & 0x7Fu, pm = x >> 25, src = y & 0x3FFFFu;
+                    uint32_t v = 0, w = 0;
+                    if (lane < len) v = lds_u8(src + (lane & pm));
+                    if (lane + 32 < len) w = lds_u8(src + ((lane + 32) & pm));
+                    if (lane < len) sts_u8(dst + lane, v);
+                    if (lane + 32 < len) sts_u8(dst + lane + 32, w);
+                } else {
+                    ring_copy_any(rb, x, y >> 17, y & 0x1FFFFu);
+                }
+                __syncwarp();
+            }
         }
-        e0 = n0;
-        e1 = n1;
-        q += 2;
-    }
-    if (q < nout) {
-        ring_copy_any(rb, e0.x, e0.y >> 17, e0.y & 0x1FFFFu);
-        __syncwarp();
+        cur = nx;
     }
 }
 
@@ -1090,7 +1122,7 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
         bool eos_here = false;
         // fast path: every token of every valid group executes (not the end of the output, all input bytes present)
         const uint32_t all_incl = __shfl_sync(kFull, incl, 31);
-        if (!((all_incl & 0xFFFFFu) <= min(remaining, cap) && (all_incl >> 20) <= uint32_t(kQueue) && cur + (ca - wa) <= slen)) {
+        if (!((all_incl & 0xFFFFFu) <= min(remaining, cap) && (all_incl >> 20) <= uint32_t(kIterMatches) && cur + (ca - wa) <= slen)) {
             jexec = 0;
             const uint32_t gabs = cur + myrel;
             uint32_t a = gabs + 1;

@@ -283,6 +283,29 @@ def ragged_corpus(n, lo, hi, classes, seed, dev, group):
     return raw, r_off, r_len
 
 
+def stream_mismatch(a, b, off, ln, chunk_bytes=1 << 30):
+    """Per-stream comparison of the windows [off, off + ln) of two flat uint8 tensors (windows ascending and disjoint)
+    -> bool tensor, True where a window differs."""
+    import torch
+    n = ln.numel()
+    out = torch.zeros(n, dtype=torch.bool, device=a.device)
+    ends = (off + ln).tolist()
+    offs = off.tolist()
+    s = 0
+    while s < n:
+        e = s + 1
+        while e < n and ends[e] - offs[s] <= chunk_bytes:
+            e += 1
+        lo, hi = offs[s], ends[e - 1]
+        c = torch.cumsum((a[lo:hi] != b[lo:hi]).to(torch.int32), 0)
+        c = torch.cat([torch.zeros(1, dtype=c.dtype, device=c.device), c])
+        o, l = off[s:e] - lo, ln[s:e]
+        out[s:e] = (c[o + l] - c[o]) != 0
+        del c
+        s = e
+    return out
+
+
 def bench_decode_config(codec, name, fmt, raw, r_off, r_len, dev, ts, peak, steps, warmup, orders, drop_unrepresentable=False):
     """Encode `raw` on the GPU, decode device-resident, verify.  `orders`: one entry per sub-batch of the streams — the byte
     order it is written in AND decoded with (the reference's FormatByteOrder is a property of the codec instance, so files
@@ -307,7 +330,7 @@ def bench_decode_config(codec, name, fmt, raw, r_off, r_len, dev, ts, peak, step
         dopts = A.make_opts(byte_order=order, balance=1)
         if drop_unrepresentable:
             _, _, d_st = time_decode(codec, fmt, packed, p_off, c_len, d_dst, ro, rl, dopts, 1, 0, ts)
-            keep = d_st == 0
+            keep = (d_st == 0) & ~stream_mismatch(d_dst, raw, ro, rl)
             dropped += int((~keep).sum())
             d_dst[int(ro[0]):int(ro[-1]) + int(rl[-1])].zero_()       # the timed passes rewrite every kept window
             for i in (~keep).nonzero().flatten().tolist():            # the dropped ones are not part of the comparison below
