@@ -12,12 +12,30 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "api_internal.hpp"
 #include "common.cuh"
 
 using namespace aurora;
 
 namespace {
+
+// NVTX ranges of the host scheduler (SURVEY.md §5 "tracing"): one range per device shard and, inside it, one per pipeline
+// piece (the enqueue of its H2D copy, kernel and D2H copies) and one for the final wait.  Header-only NVTX v3: no link
+// dependency, a no-op unless a profiler injects itself.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    NvtxRange(const char* what, int a, size_t b) {
+        char buf[96];
+        std::snprintf(buf, sizeof buf, "%s dev %d n %zu", what, a, b);
+        nvtxRangePushA(buf);
+    }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 
 struct DevBuf {
     void* p = nullptr;
@@ -247,6 +265,7 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
                  const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
                  const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t* out_len, uint64_t* consumed, int32_t* status,
                  int size_only, const uint64_t* raw_size = nullptr, const uint32_t* xor_key = nullptr, bool exact = false) {
+    NvtxRange nvtx_shard("aurora decode shard", d->dev, e - b);
     const size_t n = e - b;
     if (n == 0) return AURORA_OK;
     // exact (the sub-batches of the wrapper formats): only the bytes a stream produced are written to the host.  Otherwise the
@@ -353,6 +372,7 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
         for (size_t k = 0; k < pieces; k++) {
             const size_t i0 = cut[k], i1 = cut[k + 1];
             if (i1 <= i0) continue;
+            NvtxRange nvtx_piece("decode piece: H2D + kernel + D2H enqueue", int(k), i1 - i0);
             uint64_t lo = ~0ull, hi = 0;
             for (size_t i = i0; i < i1; i++) {
                 lo = std::min(lo, src_off[b + i]);
@@ -392,6 +412,7 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
             }
         }
         CU_TRY(ctx, cudaMemcpyAsync(h + 4 * n, dv + 4 * n, 2 * n * sizeof(uint64_t) + n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        NvtxRange nvtx_wait("decode shard: wait for the pipeline");
         CU_TRY(ctx, cudaStreamSynchronize(st));
         CU_TRY(ctx, cudaStreamSynchronize(d->s_out));
     } else {
@@ -544,6 +565,7 @@ int encode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
                  const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst_base,
                  const uint64_t* dst_off, const uint64_t* dst_cap, uint64_t* out_len, int32_t* status,
                  const uint32_t* xor_key = nullptr, uint32_t xor_skip = 0) {
+    NvtxRange nvtx_shard("aurora encode shard", d->dev, e - b);
     const size_t n = e - b;
     if (n == 0) return AURORA_OK;
     std::lock_guard<std::mutex> guard(d->mu);

@@ -72,6 +72,7 @@ struct GOut {
         for (uint32_t p = flushed + lane; p < written; p += 32)
             if (uint64_t(p) < cap) dst[p] = uint8_t(lds_u8((p & kORingMask) | rb));
         flushed = written;
+        __syncwarp();   // the next stream (or PRS's second attempt) rewrites these ring slots (racecheck: write-after-read)
     }
     // make everything decoded so far visible in global memory without disturbing the 512-byte drain cadence
     __device__ __forceinline__ void sync_tail() {
@@ -1205,6 +1206,7 @@ __device__ Res prs_decode(InStream& in, GOut& out, uint32_t slen, const uint8_t*
 #pragma unroll 1   // one inlined copy of the walk: the retry with the other order (PRS.cs:49-56) is the second trip
     for (int attempt = 0; attempt < 2; attempt++) {
         if (attempt) {
+            __syncwarp();   // the first attempt's ring reads are done before the second one rewrites the ring
             in.begin(P.src_base, P.src_limit, src);
             out.written = 0;
             out.flushed = 0;
