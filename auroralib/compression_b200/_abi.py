@@ -49,6 +49,12 @@ class CodecOpts(C.Structure):
                 ("lz00_key", C.c_uint32), ("ecd_plain_size", C.c_uint32)]
 
 
+# opts.strategy, library-specific bits (include/aurora_cuda.h): which byte-identical GPU match finder encodes
+STRATEGY_COMPATIBILITY = 1
+STRATEGY_PARALLEL_FINDER = 0x10000
+STRATEGY_SERIAL_FINDER = 0x20000
+
+
 def make_opts(byte_order=ENDIAN_DEFAULT, quality=-1, max_window_bits=0, strategy=0, vram_mode=-1,
               lzss=None, lzss_initial_fill=0, lz4_block_size=0, lz4_verify=0, yaz0_alignment=0, balance=0,
               lz77_type=0, lz77_chunk_size=0, level5_type=0, lz00_key=0, ecd_plain_size=0):

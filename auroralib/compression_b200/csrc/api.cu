@@ -151,6 +151,16 @@ int fill_decode_params(DecodeParams& p, int format, const aurora_codec_opts* o) 
 }
 
 cudaError_t launch_encode(const EncodeParams& p, int warps, cudaStream_t st) {
+    // LZ10 / BLZ / Yaz0 / LZSS at qualities below 10: the window search with one lane per position and shared-memory tables
+    // (encode_lz_par.cu).  Both encoders write the reference's bytes; which one runs is a speed decision: the parallel
+    // search wins while the chains are short (measured on C5: quality 0 14.3 vs 8.4 GB/s raw in, quality 8 7.8 vs 8.1),
+    // so it is the default up to maxChain 4 and can be forced either way (opts.strategy bits 16 / 17, AURORA_ENCODER).
+    static const int forced = [] {
+        const char* e = std::getenv("AURORA_ENCODER");
+        return !e ? 0 : std::strcmp(e, "serial") == 0 ? 2 : std::strcmp(e, "parallel") == 0 ? 1 : 0;
+    }();
+    const int want = p.finder_choice ? p.finder_choice : forced;
+    if (encode_lz_par_supported(p) && (want == 1 || (want == 0 && p.max_chain <= 4))) return launch_encode_lz_par(p, warps / 48, st);
     if (is_flaglz(p.format) || p.format == AURORA_FMT_BLZ) return launch_encode_lz(p, warps, st);   // BLZ: LZ10's layout
     return launch_encode_bytelz(p, warps, st);
 }
@@ -555,6 +565,7 @@ int fill_encode_params(EncodeParams& p, int format, const aurora_codec_opts* o) 
     p.max_length = lz.max_length;
     p.min_distance = lz.min_distance;
     p.no_self_overlap = o ? (o->strategy & 1) : 0;
+    p.finder_choice = !o ? 0 : (o->strategy & AURORA_STRATEGY_PARALLEL_FINDER) ? 1 : (o->strategy & AURORA_STRATEGY_SERIAL_FINDER) ? 2 : 0;
     p.use_min_table = q >= 10;
     p.yaz0_alignment = o ? o->yaz0_alignment : 0;
     p.lzss = LzssParams{lz.windows_bits, lz.length_bits, lz.min_length, lz.max_distance, lz.windows_start, 0};

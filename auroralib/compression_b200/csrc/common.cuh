@@ -56,6 +56,7 @@ struct EncodeParams {
     // CompressionSettings -> LzChainMatchFinder parameters (LzChainMatchFinder.cs:108-119)
     int max_chain, lazy_threshold, hash_bits, chain_bits, min_length, max_length, min_distance, max_distance, no_self_overlap,
         use_min_table;
+    int finder_choice;   // 0 automatic, 1 one lane per window position (encode_lz_par.cu), 2 sequential replay (finder.cuh)
     uint32_t yaz0_alignment;
     uint32_t lz4_block_size;
     LzssParams lzss;
@@ -72,6 +73,8 @@ cudaError_t launch_reverse_bytes(uint8_t* base, const uint64_t* d_off, const uin
                                  cudaStream_t st);
 cudaError_t launch_encode_lz(const EncodeParams& p, int warps, cudaStream_t st);
 cudaError_t launch_encode_bytelz(const EncodeParams& p, int warps, cudaStream_t st);
+bool encode_lz_par_supported(const EncodeParams& p);   // encode_lz_par.cu: one lane per window position
+cudaError_t launch_encode_lz_par(const EncodeParams& p, int sm_count, cudaStream_t st);
 size_t encode_scratch_per_warp(int format, int hash_bits, int chain_bits, uint64_t max_src_len);
 int encode_resident_warps(int sm_count);
 cudaError_t launch_size_order(const uint64_t* d_size, uint32_t n, uint32_t* d_hist64, uint32_t* d_order, cudaStream_t st);

@@ -1,0 +1,534 @@
+// encode_lz_par.cu — the window match search of the flag-byte encoders with ONE LANE PER WINDOW POSITION and shared-memory
+// hash tables (LZ10 / BLZ, Yaz0 / Yaz1, LZSS at qualities below 10).  One raw buffer per warp, 32 positions per step.
+//
+// The output is byte-identical to the reference encoder (and to the sequential replay in encode_lz.cu / finder.cuh, which
+// stays for the other formats and qualities): what LzChainMatchFinder computes at a position depends only on the bytes
+// before it, not on the parse —
+//   * every position up to length - 4 is inserted into the head / chain tables, in order, whether it is searched
+//     (MatchSearch, LzChainMatchFinder.cs:214-246) or lies inside a match (the insert loop of FindNextBestMatch, :196-205);
+//   * so the candidates of position p are exactly the earlier positions with the same hash value, nearest first, at most
+//     maxChain of them, until the distance exceeds MaxDistance (ChainMatches, :248-282) — a function of the data alone.
+// The search can therefore run at ALL positions in parallel, and the reference's greedy parse with its one-step lazy
+// lookahead (:157-212) becomes a cheap walk over the per-position results.
+//
+// Tables (28 KiB of shared memory per warp instead of the reference's 2 MiB head table per stream):
+//   data[8192]  u8   ring of the raw bytes (window + step + lookahead), refilled 512 bytes at a time with 16-byte loads;
+//   head[2048]  u16  latest position (mod 2^16) whose hash falls into the bucket = low 11 bits of the reference's hash;
+//   node[4096]  u32  ring over the last 4096 positions: distance to the previous position of the same BUCKET (0: none) in
+//                    the low half, the remaining high bits of the reference's hash (the tag) above — a chain node counts
+//                    as a candidate (and as one of the maxChain attempts) only when its tag equals the searching position's
+//                    tag, which reproduces the reference's per-hash-value chains exactly.
+// Positions of the step that is being searched are not in the ring yet (they would overwrite the far end of the window):
+// the candidates among them are the lanes with the same hash value (match.any), walked as a bit mask.
+// Per step: hashes, bucket groups (match.any), chain walk with a word-wise common-prefix comparison per candidate, ring
+// update; the parse of the PREVIOUS step (its lazy test needs the first result of this one) walks only the matches —
+// literal runs are mask operations — and all tokens of a step are written at once: one warp scan gives byte offsets, flag
+// bytes are assembled with match.any / redux.or per group of eight tokens.
+#include "common.cuh"
+#include "stage.cuh"
+
+namespace aurora {
+
+namespace {
+
+constexpr int kParWarps = 8;             // 8 x 28 KiB per block, one block per SM
+constexpr int kBuckets = 2048, kBucketMask = kBuckets - 1, kBucketBits = 11;
+constexpr int kWin = 4096, kWinMask = kWin - 1;
+constexpr int kData = 8192, kDataMask = kData - 1;   // ring of the raw bytes: the window, the step and the longest lookahead
+constexpr int kChunk = 512;              // raw bytes staged per refill (16 bytes per lane)
+constexpr int kTablesPerWarp = kBuckets * 2 + kWin * 4 + kData;   // head + node ring + data
+
+enum ParKind { P_LZ10 = 0, P_YAZ0 = 1, P_LZSS = 2 };
+
+struct ParState {
+    // tables (shared addresses)
+    uint32_t head, node, data;
+    uint32_t skew;           // ring index of position 0 (the source's offset inside its 16-byte line)
+    int staged;              // positions below this are in the data ring
+    // source
+    const uint8_t* src;
+    const uint8_t* src_lim;        // 16-byte lines starting below this may be read
+    int n, limit;
+    // finder parameters
+    int hash_shift, max_chain, lazy, min_len, max_len, min_dist, max_dist;
+    uint32_t hash_mask;
+    bool no_self_overlap, blz;
+    // output
+    uint8_t* out;
+    uint64_t cap, pos;
+    uint32_t ntok;         // tokens written so far
+    uint32_t carry_flag;   // bits of the open flag group
+    uint64_t carry_pos;    // ... and where its byte lives
+    bool overflow;
+    // parse state: offset of the next token start relative to the step that is parsed next, and whether that token is the
+    // match the lazy test already chose
+    int cur_off;
+    bool forced, pending;
+    // LZSS token fields
+    int lz_n, lz_f, lz_start, lz_lbits;
+};
+
+__device__ __forceinline__ uint32_t ring_u8(const ParState& S, int pos) { return lds_u8(S.data + ((uint32_t(pos) + S.skew) & kDataMask)); }
+
+// four bytes at an arbitrary position (little-endian) from the data ring
+__device__ __forceinline__ uint32_t ring_u32(const ParState& S, int pos) {
+    const uint32_t a = uint32_t(pos) + S.skew;
+    const uint32_t lo = lds_u32(S.data + (a & kDataMask & ~3u)), hi = lds_u32(S.data + ((a + 4) & kDataMask & ~3u));
+    return __funnelshift_r(lo, hi, (a & 3u) * 8);
+}
+
+// stage raw bytes until position `upto` (exclusive, clamped to the stream) is in the ring: whole 16-byte lines, 512 bytes per pass
+__device__ __forceinline__ void stage(ParState& S, int upto) {
+    upto = min(upto, S.n);
+    while (S.staged < upto) {
+        // line index l covers positions [16 l - skew, 16 l - skew + 16)
+        const uint32_t first_line = (uint32_t(S.staged) + S.skew) >> 4;
+        const uint32_t line = first_line + lane_id();
+        const uint8_t* g = S.src - S.skew + size_t(line) * 16;
+        if (g < S.src_lim) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(g));
+            sts_u128(S.data + ((line * 16) & kDataMask), v.x, v.y, v.z, v.w);
+        }
+        S.staged = int((first_line + 32) * 16 - S.skew);
+    }
+    __syncwarp();
+}
+
+// common prefix of the bytes at positions a and b, at most cap bytes, the first `known` of them known to be equal
+// (GetMatchLength, LzChainMatchFinder.cs:338-357)
+__device__ __forceinline__ int prefix_len(const ParState& S, int a, int b, int cap, int known) {
+    int len = known & ~3;
+    if (((a ^ b) & 3) == 0) {
+        // distance a multiple of 4 (tile data): the two byte strings have the same alignment, aligned words compare directly
+        uint32_t ia = uint32_t(a + len) + S.skew, ib = uint32_t(b + len) + S.skew;
+        const uint32_t r = ia & 3u;
+        uint32_t mask = 0xFFFFFFFFu << (8 * r);
+        ia &= ~3u;
+        ib &= ~3u;
+        int l = len - int(r);
+        while (l < cap) {
+            const uint32_t x = (lds_u32(S.data + (ia & kDataMask)) ^ lds_u32(S.data + (ib & kDataMask))) & mask;
+            if (x) return min(l + ((__ffs(int(x)) - 1) >> 3), cap);
+            mask = 0xFFFFFFFFu;
+            l += 4;
+            ia += 4;
+            ib += 4;
+        }
+        return cap;
+    }
+    while (len + 4 <= cap) {
+        const uint32_t x = ring_u32(S, a + len) ^ ring_u32(S, b + len);
+        if (x) return len + ((__ffs(int(x)) - 1) >> 3);
+        len += 4;
+    }
+    while (len < cap && ring_u8(S, a + len) == ring_u8(S, b + len)) len++;
+    return len;
+}
+
+template <int K>
+__device__ __forceinline__ uint32_t token_size(int len) {
+    if (K == P_YAZ0) return len < 18 ? 2u : 3u;
+    return 2u;
+}
+
+// ---- the parse of one step (FindNextBestMatch, :157-212).  `len`: the search results of the step's 32 positions (0 where
+// nothing was found, the position lies behind `limit`, or it was not searched because an earlier match covers it).
+// Returns the literal and match token masks.  A token that starts at lane 31 with a short match needs the result of the next
+// step's first position for the lazy test: it is left pending (S.pending) and resolved by the caller after the next search.
+__device__ __forceinline__ void parse_step(ParState& S, int base, int len, uint32_t& lit_out, uint32_t& mat_out) {
+    const uint32_t mmask = __ballot_sync(kFull, len >= S.min_len);
+    uint32_t lit = 0, mat = 0;
+    int c = S.cur_off;
+    bool forced = S.forced;
+    while (c < 32) {
+        int k;
+        if (forced) {
+            k = c;
+        } else {
+            const uint32_t rest = mmask >> c;
+            if (rest == 0) {
+                lit |= ~0u << c;
+                c = 32;
+                break;
+            }
+            k = c + __ffs(int(rest)) - 1;
+            lit |= ((1u << k) - 1u) & (~0u << c);
+        }
+        const int lk = __shfl_sync(kFull, len, k);
+        if (!forced && lk <= S.lazy && base + k + 1 <= S.limit) {
+            if (k == 31) {   // the lazy test needs the next step
+                S.pending = true;
+                c = 32;
+                break;
+            }
+            const int ln = __shfl_sync(kFull, len, k + 1);
+            if (ln > lk) {   // the next position has the longer match: literal here
+                lit |= 1u << k;
+                forced = true;
+                c = k + 1;
+                continue;
+            }
+        }
+        mat |= 1u << k;
+        forced = false;
+        c = k + lk;
+    }
+    S.cur_off = c - 32;
+    S.forced = forced;
+    lit_out = lit;
+    mat_out = mat;
+}
+
+// ---- the tokens of one step: `lit` / `mat` = the lanes that start a literal / a match token (len, dist: their results)
+template <int K>
+__device__ __forceinline__ void write_step(ParState& S, int base, int len, int dist, uint32_t lit, uint32_t mat) {
+    const int lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    // positions at or behind the end of the data are no tokens
+    const uint32_t inb = base + 32 <= S.n ? ~0u : (S.n > base ? (1u << (S.n - base)) - 1u : 0u);
+    lit &= inb;
+    mat &= inb;
+    const uint32_t tok = lit | mat;
+    if (tok == 0) return;
+    const bool is_tok = (tok >> lane) & 1u, is_mat = (mat >> lane) & 1u;
+    // ---- byte offsets: token bytes + one flag byte in front of every eighth token
+    const uint32_t T = S.ntok + __popc(tok & lt);
+    const bool opens = is_tok && (T & 7u) == 0;
+    const uint32_t sz = !is_tok ? 0u : (is_mat ? token_size<K>(len) : 1u) + (opens ? 1u : 0u);
+    const uint32_t incl = warp_incl_scan(sz);
+    const uint64_t at = S.pos + (incl - sz);          // first byte of my token (its flag byte, when it opens a group)
+    const uint64_t tb = at + (opens ? 1u : 0u);       // token bytes
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    // ---- flag bytes.  LZ10: 1 = match, MSB first; Yaz0: 1 = literal, MSB first; LZSS: 1 = literal, LSB first
+    {
+        const bool bitv = (K == P_LZ10) ? is_mat : !is_mat;
+        const uint32_t sh = (K == P_LZSS) ? (T & 7u) : 7u - (T & 7u);
+        const uint32_t contrib = (is_tok && bitv) ? 1u << sh : 0u;
+        const uint32_t g = T >> 3;
+        const uint32_t gm = __match_any_sync(kFull, is_tok ? g : 0xFFFFFFFFu);
+        uint32_t fv = __reduce_or_sync(gm, contrib);
+        const bool leader = is_tok && (gm & lt) == 0;   // first token of the group within this step
+        uint64_t fpos = at;                             // a group opened in this step: the byte in front of its first token
+        if (leader && !opens) {                         // the group was opened by an earlier step
+            fv |= S.carry_flag;
+            fpos = S.carry_pos;
+        }
+        if (leader) {
+            if (fpos < S.cap) S.out[fpos] = uint8_t(fv);
+            else S.overflow = true;
+        }
+        // carry the last group when it is still open
+        const uint32_t ntok = __popc(tok);
+        const int last = 31 - __clz(int(tok));
+        const uint32_t lead_lane = __ffs(int(__shfl_sync(kFull, gm, last))) - 1;
+        const uint32_t cf = __shfl_sync(kFull, fv, lead_lane);
+        const uint32_t cplo = __shfl_sync(kFull, uint32_t(fpos), lead_lane), cphi = __shfl_sync(kFull, uint32_t(fpos >> 32), lead_lane);
+        S.ntok += ntok;
+        S.carry_flag = (S.ntok & 7u) ? cf : 0u;
+        S.carry_pos = uint64_t(cplo) | (uint64_t(cphi) << 32);
+    }
+    // ---- token bytes
+    if (is_tok) {
+        uint32_t b0, b1, b2 = 0, nb;
+        if (!is_mat) {
+            b0 = ring_u8(S, base + lane);
+            b1 = 0;
+            nb = 1;
+        } else if (K == P_LZ10) {
+            const uint32_t v = uint32_t(len - 3) << 12 | (uint32_t(dist - (S.blz ? 3 : 1)) & 0xFFFu);   // BLZ.cs: distance - 3
+            b0 = (v >> 8) & 0xFF;
+            b1 = v & 0xFF;
+            nb = 2;
+        } else if (K == P_YAZ0) {
+            const uint32_t d1 = uint32_t(dist - 1) & 0xFFFu;
+            if (len < 18) {
+                const uint32_t v = (uint32_t(dist - 1) | uint32_t(len - 2) << 12) & 0xFFFFu;
+                b0 = v >> 8;
+                b1 = v & 0xFF;
+                nb = 2;
+            } else {
+                b0 = d1 >> 8;
+                b1 = d1 & 0xFF;
+                b2 = uint32_t(len - 0x12) & 0xFF;
+                nb = 3;
+            }
+        } else {
+            // LZSS.cs:132-160: the token holds the ring offset of the source, sp = position behind... of the match start
+            const int offset = (S.lz_start + (base + lane) - dist) & S.lz_n;
+            const uint32_t v = (uint32_t(offset & 0xFF) | uint32_t(offset & 0xFF00) << S.lz_lbits | uint32_t((len - S.min_len) & S.lz_f) << 8) & 0xFFFFu;
+            b0 = v & 0xFF;
+            b1 = v >> 8;
+            nb = 2;
+        }
+        if (tb + nb <= S.cap) {
+            S.out[tb] = uint8_t(b0);
+            if (nb > 1) S.out[tb + 1] = uint8_t(b1);
+            if (nb > 2) S.out[tb + 2] = uint8_t(b2);
+        } else {
+            S.overflow = true;
+        }
+    }
+    S.pos += total;
+}
+
+__device__ __forceinline__ void put_byte(ParState& S, uint32_t b) {
+    if (S.pos < S.cap) {
+        if (lane_id() == 0) S.out[S.pos] = uint8_t(b);
+    } else {
+        S.overflow = true;
+    }
+    S.pos++;
+}
+__device__ __forceinline__ void put_u32p(ParState& S, uint32_t v, bool big) {
+    for (int i = 0; i < 4; i++) put_byte(S, big ? (v >> (24 - 8 * i)) & 0xFF : (v >> (8 * i)) & 0xFF);
+}
+
+template <int K>
+__device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState& S) {
+    const int lane = lane_id();
+    const uint64_t n64 = P.src_len[idx];
+    int status = AURORA_OK;
+    uint64_t out_len = 0;
+    if (n64 > 0x7FFFFFF0ull) {
+        status = AURORA_INVALID_ARGUMENT;
+    } else {
+        const int n = int(n64);
+        S.src = P.src_base + P.src_off[idx];
+        S.skew = uint32_t(reinterpret_cast<uintptr_t>(S.src) & 15);
+        S.src_lim = P.src_base + P.src_limit;   // (a 16-byte line that starts inside the batch's source bytes is readable)
+        S.staged = 0;
+        S.n = n;
+        S.limit = n - 4;
+        S.out = P.dst_base + P.dst_off[idx];
+        S.cap = P.dst_cap[idx];
+        S.pos = 0;
+        S.ntok = 0;
+        S.carry_flag = 0;
+        S.carry_pos = 0;
+        S.overflow = false;
+        S.cur_off = 0;
+        S.forced = false;
+        S.pending = false;
+        const bool big = P.byte_order != AURORA_ENDIAN_LITTLE;
+        // ---- headers (as encode_lz.cu: LZ10.cs:67-80, Yaz0.cs:82-98, LZSS.cs:72-89; BLZ has none)
+        if (K == P_LZ10) {
+            if (P.format != AURORA_FMT_BLZ) {
+                if (n <= 0xFFFFFF) {
+                    put_u32p(S, 0x10u | (uint32_t(n) << 8), false);
+                } else {
+                    put_u32p(S, 0x10u, false);
+                    put_u32p(S, uint32_t(n), false);
+                }
+            }
+        } else if (K == P_YAZ0) {
+            const char* magic = P.format == AURORA_FMT_YAZ1 ? "Yaz1" : "Yaz0";
+            for (int i = 0; i < 4; i++) put_byte(S, uint8_t(magic[i]));
+            put_u32p(S, uint32_t(n), big);
+            put_u32p(S, P.yaz0_alignment, big);
+            put_u32p(S, 0, false);
+        } else {
+            put_byte(S, 'L'); put_byte(S, 'Z'); put_byte(S, 'S'); put_byte(S, 'S');
+            put_u32p(S, uint32_t(n), true);
+            put_u32p(S, 0, false);   // compressed size, patched below
+            put_u32p(S, 0, false);
+        }
+        const uint64_t body_start = S.pos;
+        // ---- tables: every head is 8192 positions back (behind the window)
+        {
+            const uint32_t far = uint32_t(0 - 8192) & 0xFFFFu;
+            const uint32_t w = far | (far << 16);
+            for (int i = lane; i < kBuckets / 2; i += 32) sts_u32(S.head + 4 * i, w);
+        }
+        __syncwarp();
+
+        int plen = 0, pdist = 0;   // results of the previous step
+        for (int base = 0; base < n; base += 32) {
+            stage(S, base + 32 + S.max_len + 8);
+            if (base && (base & 0x3FFF) == 0) {
+                // heads that fell out of the window are parked 8192 positions back, so that their 16-bit age never wraps
+                const uint32_t b16 = uint32_t(base) & 0xFFFFu;
+                for (int i = lane; i < kBuckets; i += 32) {
+                    const uint32_t e = lds_u16(S.head + 2 * i);
+                    if (((b16 - e) & 0xFFFFu) > uint32_t(kWin)) sts_u16(S.head + 2 * i, (b16 - 8192u) & 0xFFFFu);
+                }
+                __syncwarp();
+            }
+            const int p = base + lane;
+            const bool valid = p <= S.limit;
+            // lanes inside a match that is already written are inserted but not searched (their results are never looked at)
+            const bool searched = valid && (S.pending || lane >= S.cur_off);
+            int best_len = 0, best_dist = 0;
+            uint32_t h = 0xFFFFFFFFu, bucket = 0xFFFFFFFFu;
+            if (valid) {
+                h = ((ring_u32(S, p) * 2654435761u) >> S.hash_shift) & S.hash_mask;   // ComputeHash, :288-299
+                bucket = h & kBucketMask;
+            }
+            const uint32_t tag = h >> kBucketBits;
+            const uint32_t lt = (1u << lane) - 1u;
+            const uint32_t gmb = __match_any_sync(kFull, bucket);   // lanes of my bucket
+            const uint32_t gmh = __match_any_sync(kFull, h);        // lanes with my hash value: the candidates inside this step
+            uint32_t blink = 0;
+            if (valid) {
+                // ---- the bucket's chain before this step starts at its head
+                const uint32_t e = lds_u16(S.head + 2 * bucket);
+                const uint32_t dd = (uint32_t(p) - e) & 0xFFFFu;
+                const bool head_ok = dd >= 1 && dd <= uint32_t(kWin) && int(dd) <= p;
+                const uint32_t belowb = gmb & lt;
+                blink = belowb ? uint32_t(lane - (31 - __clz(int(belowb)))) : (head_ok ? dd : 0u);
+                // ---- chain walk (ChainMatches, :248-282): the candidates are the earlier positions with my hash value, nearest first
+                const int best_possible = min(n - p, S.max_len);
+                int attempts = S.max_chain;
+                bool done = false;
+                auto candidate = [&](int distance) {
+                    attempts--;
+                    if (distance >= S.min_dist) {
+                        // the same distance as 32 positions earlier: that match's bytes behind the first 32 are equal here too
+                        const int known = (distance == pdist && plen > 32) ? min(plen - 32, best_possible) : 0;
+                        int l = prefix_len(S, p, p - distance, best_possible, known);
+                        if (S.no_self_overlap && l > distance) l = distance;
+                        if (l >= S.min_len && l > best_len) {
+                            best_len = l;
+                            best_dist = distance;
+                            if (best_len == best_possible) done = true;
+                        }
+                    }
+                    if (attempts <= 0) done = true;
+                };
+                uint32_t inl = searched ? gmh & lt : 0u;   // (a) inside the step
+                done = !searched;
+                while (inl && !done) {
+                    const int k = 31 - __clz(int(inl));
+                    inl &= ~(1u << k);
+                    candidate(lane - k);
+                }
+                if (!done && head_ok && int(dd) <= S.max_dist) {   // (b) the ring: skip the nodes of my bucket with another tag
+                    int distance = int(dd);
+                    for (;;) {
+                        const uint32_t nd = lds_u32(S.node + 4 * (uint32_t(p - distance) & kWinMask));
+                        if ((nd >> 16) == tag) {
+                            candidate(distance);
+                            if (done) break;
+                        }
+                        const int bl = int(nd & 0xFFFFu);
+                        if (bl == 0 || distance + bl > S.max_dist) break;
+                        distance += bl;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- the step's positions enter the ring and the heads
+            if (valid) {
+                sts_u32(S.node + 4 * (uint32_t(p) & kWinMask), blink | (tag << 16));
+                if ((gmb >> lane) <= 1u) sts_u16(S.head + 2 * bucket, uint32_t(p) & 0xFFFFu);   // the last lane of the bucket's group
+            }
+            __syncwarp();
+            // ---- the token left pending at the end of the previous step: lazy test against this step's first result
+            if (S.pending) {
+                const int ln = __shfl_sync(kFull, best_len, 0), lk = __shfl_sync(kFull, plen, 31);
+                S.pending = false;
+                if (ln > lk) {
+                    write_step<K>(S, base - 32, plen, pdist, 0x80000000u, 0u);
+                    S.forced = true;
+                    S.cur_off = 0;
+                } else {
+                    write_step<K>(S, base - 32, plen, pdist, 0u, 0x80000000u);
+                    S.forced = false;
+                    S.cur_off = lk - 1;
+                }
+            }
+            // ---- parse + write this step
+            uint32_t lit, mat;
+            parse_step(S, base, best_len, lit, mat);
+            write_step<K>(S, base, best_len, best_dist, lit, mat);
+            plen = best_len;
+            pdist = best_dist;
+        }
+        if (K == P_LZSS) {
+            const uint64_t save = S.pos;
+            S.pos = 8;
+            put_u32p(S, uint32_t(save - body_start), true);
+            S.pos = save;
+        }
+        out_len = S.pos;
+        if (S.overflow) status = AURORA_DST_TOO_SMALL;
+    }
+    const uint32_t ov = __ballot_sync(kFull, status != AURORA_OK);
+    if (lane == 0) {
+        P.out_len[idx] = out_len;
+        P.status[idx] = ov ? (n64 > 0x7FFFFFF0ull ? AURORA_INVALID_ARGUMENT : AURORA_DST_TOO_SMALL) : AURORA_OK;
+    }
+    __syncwarp();
+}
+
+template <int K>
+__global__ void __launch_bounds__(kParWarps * 32, 1) encode_lz_par_kernel(const EncodeParams P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    ParState S;
+    const uint32_t t0 = smem_u32(smem) + uint32_t(warp) * kTablesPerWarp;
+    S.head = t0;
+    S.node = t0 + kBuckets * 2;
+    S.data = S.node + kWin * 4;
+    S.hash_shift = 32 - P.hash_bits;
+    S.hash_mask = (1u << P.hash_bits) - 1u;
+    S.max_chain = P.max_chain;
+    S.lazy = P.lazy_threshold;
+    S.min_len = P.min_length;
+    S.max_len = P.max_length;
+    S.min_dist = P.min_distance;
+    S.max_dist = P.max_distance;
+    S.no_self_overlap = P.no_self_overlap != 0;
+    S.blz = P.format == AURORA_FMT_BLZ;
+    S.lz_n = P.lzss.max_distance - 1;
+    S.lz_f = (1 << P.lzss.length_bits) - 1;
+    S.lz_start = P.lzss.windows_start;
+    S.lz_lbits = P.lzss.length_bits;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane_id() == 0) t = atomicAdd(P.ticket, 1u);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= P.n) break;
+        encode_stream_par<K>(P, t, S);
+    }
+}
+
+template <int K>
+cudaError_t launch_par(const EncodeParams& p, int sm_count, cudaStream_t st) {
+    const size_t smem = size_t(kParWarps) * kTablesPerWarp;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(encode_lz_par_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = true;
+    }
+    int blocks = sm_count;
+    const int needed = int((p.n + kParWarps - 1) / kParWarps);
+    if (needed < blocks) blocks = needed > 0 ? needed : 1;
+    encode_lz_par_kernel<K><<<blocks, kParWarps * 32, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// the formats / settings the parallel search reproduces exactly (everything else: encode_lz.cu)
+bool encode_lz_par_supported(const EncodeParams& p) {
+    const bool fmt = p.format == AURORA_FMT_LZ10 || p.format == AURORA_FMT_BLZ || p.format == AURORA_FMT_YAZ0 || p.format == AURORA_FMT_YAZ1 ||
+                     p.format == AURORA_FMT_LZSS;
+    return fmt && !p.use_min_table && p.hash_bits >= kBucketBits && p.hash_bits <= kBucketBits + 8 && p.max_distance <= kWin && p.chain_bits >= 12 &&
+           p.max_length <= 1024 && p.min_length >= 1 && p.min_distance >= 1;
+}
+
+cudaError_t launch_encode_lz_par(const EncodeParams& p, int sm_count, cudaStream_t st) {
+    switch (p.format) {
+        case AURORA_FMT_LZ10:
+        case AURORA_FMT_BLZ: return launch_par<P_LZ10>(p, sm_count, st);
+        case AURORA_FMT_YAZ0:
+        case AURORA_FMT_YAZ1: return launch_par<P_YAZ0>(p, sm_count, st);
+        case AURORA_FMT_LZSS: return launch_par<P_LZSS>(p, sm_count, st);
+        default: return cudaErrorNotSupported;
+    }
+}
+
+}  // namespace aurora

@@ -372,8 +372,12 @@ def other_configs(codec, dev, ts, peak, raw_c2, args):
     #      against the oracle: tests/) and compared in size with the oracle's encoder on a sample
     r_off = torch.arange(n2, **_i64(dev)) * size
     r_len = torch.full((n2,), size, **_i64(dev))
-    for name, fmt in (("C5_lz10_encode", A.FMT_LZ10), ("C5_yaz0_encode", A.FMT_YAZ0)):
-        opts = A.make_opts(quality=QUALITY)
+    # (the two match finders write the same bytes: the sequential replay is the default at quality 8, the search with one lane
+    #  per window position — the kernel family BASELINE.json's north star names — is timed next to it)
+    for name, fmt, strategy in (("C5_lz10_encode", A.FMT_LZ10, 0), ("C5_yaz0_encode", A.FMT_YAZ0, 0),
+                                ("C5_lz10_encode_lane_per_position", A.FMT_LZ10, A.STRATEGY_PARALLEL_FINDER),
+                                ("C5_yaz0_encode_lane_per_position", A.FMT_YAZ0, A.STRATEGY_PARALLEL_FINDER)):
+        opts = A.make_opts(quality=QUALITY, strategy=strategy)
         best, packed = 1e30, None
         for _ in range(2):
             if packed is not None:
@@ -436,15 +440,25 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200: the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev0 = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev0)
+        # one NCCL collective up front (every rank joins the communicator); the barriers around the timed regions then run
+        # on a gloo group: rank 0 drives EVERY device through one library context, and the NCCL barrier kernel of a waiting
+        # rank would sit on that rank's GPU and time-slice with the decode kernels rank 0 launches there (measured: every
+        # step took twice the kernel time at N = 2 and 4)
+        t = torch.ones(1, device=dev0)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+        assert int(t.item()) == world
+        cpu_group = dist.new_group(backend="gloo")
 
     def barrier():
         torch.cuda.set_device(dev0)
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=cpu_group)
         torch.cuda.synchronize()
 
     if rank != 0:

@@ -110,13 +110,19 @@ typedef struct aurora_lz_props {
 } aurora_lz_props;
 
 /* Blittable option block shared by decode and encode.  Zero-initialise, set struct_size. */
+/* opts.strategy, library-specific bits: which of the two byte-identical match finders encodes LZ10 / BLZ / Yaz0 / Yaz1 /
+ * LZSS at quality < 10 (default: the parallel one up to maxChain 4, i.e. quality <= 3) */
+#define AURORA_STRATEGY_PARALLEL_FINDER 0x10000   /* one lane per window position, shared-memory tables (encode_lz_par.cu) */
+#define AURORA_STRATEGY_SERIAL_FINDER   0x20000   /* sequential replay of LzChainMatchFinder (finder.cuh)                  */
+
 typedef struct aurora_codec_opts {
     uint32_t struct_size;      /* sizeof(aurora_codec_opts)                                            */
     int32_t  byte_order;       /* aurora_endian: FormatByteOrder (Yaz0/Yay0/MIO0/PRS)                  */
     /* CompressionSettings (encode only).  quality < 0 means default(CompressionSettings) == 8.        */
     int32_t  quality;          /* 0..15                                                                */
     int32_t  max_window_bits;  /* 0 or 7..28                                                           */
-    int32_t  strategy;         /* bit0 = CompresionStrategy.CompatibilityMode                          */
+    int32_t  strategy;         /* bit0 = CompresionStrategy.CompatibilityMode; bits 16 / 17 pick the GPU match finder
+                                  (AURORA_STRATEGY_*_FINDER below) — the encoded bytes are the same either way      */
     int32_t  vram_mode;        /* LZ10/LZ11 GbaVramCompatibilityMode: -1 class default, 0 off, 1 on    */
     /* LZSS */
     aurora_lz_props lzss;      /* windows_bits == 0 -> LZSS.DefaultProperties ((byte)12, 4, 2)         */

@@ -101,3 +101,20 @@ def test_container_options(codec, oracle, bmp):
     _check(codec, oracle, A.FMT_SNAPPY, raws, A.make_opts(quality=0))                       # stored chunks + CRC32C
     for order in (A.ENDIAN_BIG, A.ENDIAN_LITTLE):
         _check(codec, oracle, A.FMT_PRS, [bmp[:40000], bytes(3000), bmp[1000:1100]], A.make_opts(quality=8, byte_order=order))
+
+
+PAR_FORMATS = [A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS]
+
+
+@pytest.mark.parametrize("fmt", PAR_FORMATS, ids=fmt_id)
+@pytest.mark.parametrize("finder", [A.STRATEGY_PARALLEL_FINDER, A.STRATEGY_SERIAL_FINDER], ids=["parallel", "serial"])
+@pytest.mark.parametrize("quality", [0, 3, 5, 8, 9])
+def test_both_finders_write_the_reference_bytes(codec, oracle, bmp, fmt, finder, quality):
+    """The window search with one lane per position (encode_lz_par.cu) and the sequential replay (finder.cuh) are two
+    schedules of the same function: the reference's bytes, whichever is forced (opts.strategy bits 16 / 17), at every
+    quality below 10 — including streams longer than 64 KiB (16-bit table positions wrap), the lazy test across a 32-position
+    step, CompatibilityMode and ragged lengths."""
+    rng = np.random.default_rng(4242 + fmt + quality)
+    raws = [bmp[:n] for n in (5, 33, 4097, 200000)] + [synth(rng, int(n), i % 5) for i, n in enumerate([0, 1, 4, 31, 32, 33, 64, 65, 1000, 4096, 70000, 140000])]
+    _check(codec, oracle, fmt, raws, A.make_opts(quality=quality, strategy=finder))
+    _check(codec, oracle, fmt, raws[:8], A.make_opts(quality=quality, strategy=finder | A.STRATEGY_COMPATIBILITY))
