@@ -30,6 +30,7 @@ def _device_roundtrip(codec, oracle, fmt, raw, r_off, r_len, enc_opts, dec_opts,
     olen = torch.zeros(n, dtype=torch.int64, device=dev)
     cons = torch.zeros(n, dtype=torch.int64, device=dev)
     st = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(dev)   # the buffers above were filled on torch's current stream, the decode runs on `ts`
     codec.decode_device(fmt, packed, p_off, c_len, d_dst, r_off, r_len, olen, cons, st, dec_opts, device=0, stream=ts.cuda_stream)
     ts.synchronize()
     bad = ((st != 0) | (olen != r_len) | (cons != c_len) | bench.stream_mismatch(d_dst, raw, r_off, r_len)).nonzero().flatten().tolist()
