@@ -171,7 +171,8 @@ class _SizedCodec(_Codec):
     # IProvidesDecompressedSize.GetDecompressedSize(Stream source): a peek
     def GetDecompressedSize(self, source):
         _, data = _remaining(source)
-        size, st = default_codec().decoded_size_batch(self.FORMAT, [data[:16]], self._opts())
+        # the whole remaining stream, as the reference does: MIO0 / Yay0 detect their byte order on the real stream length
+        size, st = default_codec().decoded_size_batch(self.FORMAT, [data], self._opts())
         _raise_for(int(st[0]))
         return int(size[0])
 

@@ -58,7 +58,7 @@ namespace AuroraLib.Compression.Cuda
             {
                 Native.aurora_decoded_size_batch(Context.Value, (int)Format, &o, (UIntPtr)1, ps, &off, &len, 1, &size, &st);
                 ulong cap = st == 0 ? size : 0;
-                byte[] dst = new byte[Math.Max(cap, 1)];
+                byte[] dst = new byte[checked((int)Math.Max(cap, 1UL))];   // (ulong, ulong) overload; a managed array is int-indexed
                 fixed (byte* pd = dst)
                 {
                     int rc = Native.aurora_decode_batch(Context.Value, (int)Format, &o, (UIntPtr)1, ps, &off, &len, pd, &dOff, &cap, &outLen, &consumed, &st);

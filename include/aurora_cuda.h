@@ -215,6 +215,9 @@ int aurora_encode_batch(aurora_ctx* ctx, int format, const aurora_codec_opts* op
  * descriptor arrays are device arrays too.  src_off/dst_off must be multiples of 16.
  * `stream` is a cudaStream_t passed as void* (NULL = the context's own stream for that device);
  * the call is asynchronous with respect to the host: synchronise the stream before reading results.
+ * Calls on ONE device must be stream-ordered with each other and with the host-buffer entry points: a device's work
+ * counter, size-order array and encoder scratch are per device, not per call, so two batches of the same device may not
+ * run concurrently (use one stream per device, or order the streams with events); different devices are independent.
  */
 int aurora_decode_batch_device(aurora_ctx* ctx, int device, int format, const aurora_codec_opts* opts,
                                size_t n, const uint8_t* d_src_base, uint64_t src_total,
