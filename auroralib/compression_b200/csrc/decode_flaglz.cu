@@ -35,7 +35,7 @@ constexpr int kWindow = 4096;        // largest back-reference distance of the f
 constexpr int kSubMax = 2048;        // token-per-lane core: output bytes resolved per sub-batch
 constexpr int kFlush = 512;          // bytes per ring->HBM drain step (16 B per lane)
 #ifndef AURORA_HANDOFF_AT
-#define AURORA_HANDOFF_AT 32
+#define AURORA_HANDOFF_AT 48
 #endif
 constexpr int kIterMatches = 144 - AURORA_HANDOFF_AT;    // match descriptors one iteration may queue (an iteration is cut at the group that would exceed it)
 constexpr int kHandoffAt = AURORA_HANDOFF_AT;       // queued matches at which a batch is handed to the resolver warp
@@ -883,8 +883,13 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
                     continue;
                 }
             } else {
-                const uint32_t k = __ffs(nok) - 1;   // >= 1: groups 0..k start where the guess says; walk from group k
+                uint32_t k = __ffs(nok) - 1;   // >= 1: groups 0..k start where the guess says; go on from group k
                 uint32_t ca = wa + k * s;
+                chain_end = 0;
+                // (Measured and rejected, round 2: guessing that the groups behind group k are all-literal — 80 % of the C2
+                //  corpus's groups are — and finding the first lane that is not with one ballot per round.  ~12 instructions and
+                //  two dependent shared-memory loads per round against 4 instructions per group here: 508 vs 545 GB/s.)
+                if (chain_end == 0) {
 #define AURORA_CHAIN_STEP(g)                                   \
     case g:                                                    \
         sts_u32(gaddr + 4 * g, ca);                            \
@@ -904,6 +909,7 @@ __device__ BodyResult decode_body_g32(InStream* in, Sink& sink, const uint32_t g
                 __syncwarp();
                 if (lane > k) mya = lds_u32(gaddr + 4 * lane);
                 __syncwarp();   // the table is rewritten by the next iteration's walk
+                }
             }
         }
         const uint32_t myrel = mya - wa;
