@@ -1,6 +1,7 @@
 // matchfinder.cpp — CPU ORACLE (test infrastructure, NOT product code).
 // Restatement of MatchFinder/LzChainMatchFinder.cs (single-LzProperties use only; the multi-property
 // scoring path :301-321 is used by FastLZ/aPLib/RefPack/ALLZ, none of which is on the hot path).
+#include <cstdlib>
 #include <cmath>
 
 #include "oracle_core.hpp"
@@ -30,6 +31,11 @@ MatchFinder::MatchFinder(const LzProps& p, const Settings& s) {
     int maxChainSizeBits = 17 + isqrt2q(q);
     int maxWindowBits = s.MaxWindowBits;
     bool useMinTable = q >= 10;
+    // (investigation knob, tests/test_oracle_golden.py: Benchmarks.md's Q15 columns of the 4 KiB-window formats)
+    if (std::getenv("ORACLE_NO_MINTABLE")) useMinTable = false;
+    if (const char* e = std::getenv("ORACLE_LAZY")) lazyThreshold = std::atoi(e);
+    if (const char* e = std::getenv("ORACLE_MAXCHAIN")) maxChain = std::atoi(e);
+    if (const char* e = std::getenv("ORACLE_HASHBITS")) hashBits = std::atoi(e);
 
     minMatchLength_ = p.MinLength;
     maxMatchLength_ = p.MaxLength;
