@@ -145,6 +145,13 @@ def run_reference(args):
     comp = np.zeros(ctotal + 16, dtype=np.uint8)
     clen, st = O.encode_packed(A.FMT_LZ10, raw_h, roff, rlen, comp, coff, caps, A.make_opts(quality=QUALITY), threads)
     assert (st == 0).all()
+    if args.dump_batch:
+        # the same sample for baseline/dotnet (the reference's C# decoder under Parallel.ForEach): packed.bin + index.bin
+        os.makedirs(args.dump_batch, exist_ok=True)
+        comp.tofile(os.path.join(args.dump_batch, "packed.bin"))
+        np.stack([coff.astype(np.uint64), clen.astype(np.uint64), rlen], axis=1).astype("<u8").tofile(os.path.join(args.dump_batch, "index.bin"))
+        print(json.dumps({"dumped": args.dump_batch, "streams": int(sample), "format": "LZ10"}), flush=True)
+        return 0
     dst = np.zeros(sample * STREAM_BYTES + 16, dtype=np.uint8)
     times = []
     for it in range(args.warmup + args.steps):
@@ -678,8 +685,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="headline only (skip C3 / C4 / C5)")
     ap.add_argument("--quick", action="store_true", help="C5 only among the other configs")
+    ap.add_argument("--dump-batch", default=None, help="write the reference arm's C2 sample (packed.bin, index.bin) for baseline/dotnet and exit")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "reference" or args.dump_batch:
         return run_reference(args)
     return run_ours(args)
 
