@@ -540,7 +540,7 @@ __device__ __forceinline__ void resolve_matches(uint32_t rb, uint32_t qaddr, uin
             if (lane < len1) v1 = lds_u8(src1 + (lane & pm1));
             if (lane < len0) sts_u8(dst0 + lane, v0);
             if (lane < len1) sts_u8(dst1 + lane, v1);
-            if ((len0 | len1) > 32) {
+            if (max(len0, len1) > 32) {
                 const uint32_t l2 = lane + 32;
                 if (l2 < len0) v0 = lds_u8(src0 + (l2 & pm0));
                 if (l2 < len1) v1 = lds_u8(src1 + (l2 & pm1));
@@ -1036,6 +1036,29 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
         in[0].ensure(cur, kInMirror - 16);
         const uint32_t wa = smem_u32(in[0].window(cur));
         const uint32_t wlimit = kInMirror - 48;   // a group may start in the first 592 bytes of the window (it is <= 33 bytes)
+        // ---- 32 all-literal groups (random / incompressible stretches): 256 bytes, lane g copies in[9 g + 1 .. 9 g + 8] to
+        //      out[8 g .. 8 g + 7] — the same fast path as the fixed-token core (round 2: Yaz0 on mixed-entropy data 342 -> see
+        //      profiles/r2_probe_all_formats.log)
+        if (nkeep == 0 && chain_rel == 0 && size - written >= 256 && cur + 288 <= slen) {
+            const uint32_t ga = wa + 9 * lane;
+            if (__all_sync(kFull, mbits(lds_u8(ga)) == 0)) {
+                sink.acquire_deferred(256);
+                const uint32_t t = written + 8 * lane;
+                if ((written & kRingMask) <= uint32_t(kRing - 256)) {
+                    const uint32_t ta = (t & kRingMask) | rb;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) sts_u8(ta + j, lds_u8(ga + 1 + j));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) sts_u8(((t + j) & kRingMask) | rb, lds_u8(ga + 1 + j));
+                }
+                written += 256;
+                cur += 288;
+                consumed = cur;
+                sink.submit_deferred(0, written);
+                continue;
+            }
+        }
         // ---- exact chain of group starts (offsets relative to the window)
         uint32_t nvalid;
         {
