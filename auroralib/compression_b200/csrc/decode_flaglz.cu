@@ -1322,6 +1322,24 @@ __device__ BodyResult decode_body_g32_split(InStream* in, Sink& sink, const uint
         const uint32_t fa = smem_u32(in[0].window(cur)), ca = smem_u32(in[1].window(ccur)), la = smem_u32(in[2].window(lcur));
         const uint32_t f = lds_u8(fa + lane);
         const uint32_t m = f ^ 0xFFu;   // match bits, MSB first
+        // ---- 256 literals in a row (random / incompressible stretches): one contiguous copy out of the literal stream
+        if (__all_sync(kFull, m == 0) && size - written >= 256 && 0x10 + cur + 32 <= slen && lit_off + lcur + 256 <= slen) {
+            sink.acquire_deferred(256);
+            const uint32_t t = written + 8 * lane, sa = la + 8 * lane;
+            if ((written & kRingMask) <= uint32_t(kRing - 256)) {
+                const uint32_t ta = (t & kRingMask) | rb;
+#pragma unroll
+                for (int j = 0; j < 8; j++) sts_u8(ta + j, lds_u8(sa + j));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) sts_u8(((t + j) & kRingMask) | rb, lds_u8(sa + j));
+            }
+            written += 256;
+            cur += 32;
+            lcur += 256;
+            sink.submit_deferred(0, written);
+            continue;
+        }
         const uint32_t nm = __popc(m);
         const uint32_t mincl = warp_incl_scan(nm);
         const uint32_t mb = mincl - nm;   // matches before my group
