@@ -76,12 +76,14 @@ def test_options(codec, oracle, bmp):
         _check(codec, oracle, A.FMT_LZSS, raws, A.make_opts(quality=8, lzss=props))
 
 
-def test_capacity_too_small(codec, bmp):
+@pytest.mark.parametrize("finder", [A.STRATEGY_PARALLEL_FINDER, A.STRATEGY_SERIAL_FINDER], ids=["parallel", "serial"])
+@pytest.mark.parametrize("fmt", [A.FMT_LZ10, A.FMT_YAZ0, A.FMT_LZSS], ids=fmt_id)
+def test_capacity_too_small(codec, bmp, fmt, finder):
     from auroralib.compression_b200.batch import layout, pack
     base, off, ln = pack([bmp[:20000]])
     caps, doff, total = layout([100])
     dst = np.zeros(256, dtype=np.uint8)
-    out_len, status = codec.encode_packed(A.FMT_LZ10, base, off, ln, dst, doff, caps)
+    out_len, status = codec.encode_packed(fmt, base, off, ln, dst, doff, caps, A.make_opts(quality=3, strategy=finder))
     assert status[0] == A.DST_TOO_SMALL and out_len[0] > 100
     assert dst[100:].sum() == 0   # nothing written past the capacity
 
