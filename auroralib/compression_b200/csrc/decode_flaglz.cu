@@ -1070,10 +1070,26 @@ __device__ BodyResult decode_body_g32_var(InStream* in, Sink& sink, const uint32
 #pragma unroll 1
         for (uint32_t g = nvalid; g < 32; g++) {
             if (ca - wa > wlimit) break;
-            sts_u32(gaddr + 4 * g, ca - wa);
             const uint32_t fb = lds_u8(ca);
-            const uint32_t hi4 = sel(lds_u8(ca + 1 + lane));
             uint32_t mm = mbits(fb), x = 0, cnt = 0;                                       // match bits, MSB first
+#ifndef AURORA_NO_LITRUN
+            if (mm == 0) {
+                // All-literal groups (9 bytes, ~80 % of the groups of asset data) come in runs: lane i looks at the flag byte
+                // group g + i has if the run reaches it, one ballot measures the run and all of its starts are stored at once
+                // (a step of this walk costs ~14 instructions per group).
+                const uint32_t sa = ca + 9 * lane;
+                const bool lit = sa - wa <= wlimit && lane < 32 - g && mbits(lds_u8(sa)) == 0;
+                const uint32_t lm = __ballot_sync(kFull, lit);
+                const uint32_t run = lm == 0xFFFFFFFFu ? 32u : uint32_t(__ffs(int(~lm))) - 1u;   // >= 1: lane 0 is this group
+                if (lane < run) sts_u32(gaddr + 4 * (g + lane), sa - wa);
+                ca += 9 * run;
+                g += run - 1;
+                nvalid = g + 1;
+                continue;
+            }
+#endif
+            sts_u32(gaddr + 4 * g, ca - wa);
+            const uint32_t hi4 = sel(lds_u8(ca + 1 + lane));
             if (mm) {   // an all-literal group is 9 bytes: no extension masks, no walk
                 const uint32_t E = __ballot_sync(kFull, hi4 == 0);                         // +1 byte
                 const uint32_t E2 = kFour ? __ballot_sync(kFull, hi4 == 1) : 0u;           // +2 bytes (LZ11 / LZ40 4-byte tokens)
