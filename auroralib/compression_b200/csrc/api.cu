@@ -153,14 +153,15 @@ int fill_decode_params(DecodeParams& p, int format, const aurora_codec_opts* o) 
 cudaError_t launch_encode(const EncodeParams& p, int warps, cudaStream_t st) {
     // LZ10 / BLZ / Yaz0 / LZSS at qualities below 10: the window search with one lane per position and shared-memory tables
     // (encode_lz_par.cu).  Both encoders write the reference's bytes; which one runs is a speed decision: the parallel
-    // search wins while the chains are short (measured on C5: quality 0 14.3 vs 8.4 GB/s raw in, quality 8 7.8 vs 8.1),
-    // so it is the default up to maxChain 4 and can be forced either way (opts.strategy bits 16 / 17, AURORA_ENCODER).
+    // search is the default wherever it applies (measured on C5, 65 536 x 64 KiB, GB/s raw in: quality 0 14.1 / 14.9 for
+    // LZ10 / Yaz0 against 8.4 / 8.9 of the sequential replay, quality 8 10.4 / 11.4 against 8.1 / 10.4) and either can be
+    // forced (opts.strategy bits 16 / 17, AURORA_ENCODER).
     static const int forced = [] {
         const char* e = std::getenv("AURORA_ENCODER");
         return !e ? 0 : std::strcmp(e, "serial") == 0 ? 2 : std::strcmp(e, "parallel") == 0 ? 1 : 0;
     }();
     const int want = p.finder_choice ? p.finder_choice : forced;
-    if (encode_lz_par_supported(p) && (want == 1 || (want == 0 && p.max_chain <= 4))) return launch_encode_lz_par(p, warps / 48, st);
+    if (encode_lz_par_supported(p) && want != 2) return launch_encode_lz_par(p, warps / 48, st);
     if (is_flaglz(p.format) || p.format == AURORA_FMT_BLZ) return launch_encode_lz(p, warps, st);   // BLZ: LZ10's layout
     return launch_encode_bytelz(p, warps, st);
 }

@@ -11,13 +11,14 @@
 // The search can therefore run at ALL positions in parallel, and the reference's greedy parse with its one-step lazy
 // lookahead (:157-212) becomes a cheap walk over the per-position results.
 //
-// Tables (28 KiB of shared memory per warp instead of the reference's 2 MiB head table per stream):
+// Tables (20 KiB of shared memory per warp instead of the reference's 2 MiB head table per stream):
 //   data[8192]  u8   ring of the raw bytes (window + step + lookahead), refilled 512 bytes at a time with 16-byte loads;
 //   head[2048]  u16  latest position (mod 2^16) whose hash falls into the bucket = low 11 bits of the reference's hash;
-//   node[4096]  u32  ring over the last 4096 positions: distance to the previous position of the same BUCKET (0: none) in
-//                    the low half, the remaining high bits of the reference's hash (the tag) above — a chain node counts
-//                    as a candidate (and as one of the maxChain attempts) only when its tag equals the searching position's
-//                    tag, which reproduces the reference's per-hash-value chains exactly.
+//   node[4096]  u16  ring over the last 4096 positions: distance to the previous position of the same BUCKET (0: none) in
+//                    13 bits and three of the reference's remaining hash bits above — a chain node counts as a candidate
+//                    (and as one of the maxChain attempts) only when its whole hash value equals the searching position's
+//                    (the three bits reject most foreign nodes, the rest are confirmed by hashing the node's four bytes
+//                    again), which reproduces the reference's per-hash-value chains exactly.
 // Positions of the step that is being searched are not in the ring yet (they would overwrite the far end of the window):
 // the candidates among them are the lanes with the same hash value (match.any), walked as a bit mask.
 // Per step: hashes, bucket groups (match.any), chain walk with a word-wise common-prefix comparison per candidate, ring
@@ -31,12 +32,23 @@ namespace aurora {
 
 namespace {
 
-constexpr int kParWarps = 8;             // 8 x 28 KiB per block, one block per SM
-constexpr int kBuckets = 2048, kBucketMask = kBuckets - 1, kBucketBits = 11;
+#ifndef AURORA_ENC_BUCKET_BITS
+#define AURORA_ENC_BUCKET_BITS 11
+#endif
+#ifndef AURORA_ENC_DATA
+#define AURORA_ENC_DATA 5120
+#endif
+constexpr int kBucketBits = AURORA_ENC_BUCKET_BITS, kBuckets = 1 << kBucketBits, kBucketMask = kBuckets - 1;
 constexpr int kWin = 4096, kWinMask = kWin - 1;
-constexpr int kData = 8192, kDataMask = kData - 1;   // ring of the raw bytes: the window, the step and the longest lookahead
+// ring of the raw bytes: the 4 KiB window, the step, the longest lookahead (max_length <= 288) and the refill granularity
+// (512 + 16 bytes) need 4936 bytes; the index is a modulo by a constant (a multiply-high), not a mask: 5 KiB instead of 8 KiB
+// per warp is two more resident warps per SM, and the kernel is latency bound (measured at quality 8, LZ10 / Yaz0 GB/s raw in: 8 KiB ring
+// + 2048 buckets = 11 warps 12.5 / 13.5; 5 KiB + 2048 = 13 warps 13.3 / 14.0; 5 KiB + 1024 buckets = 15 warps 12.4 / 12.7)
+constexpr uint32_t kData = AURORA_ENC_DATA;
+__device__ __forceinline__ uint32_t didx(uint32_t x) { return x % kData; }
 constexpr int kChunk = 512;              // raw bytes staged per refill (16 bytes per lane)
-constexpr int kTablesPerWarp = kBuckets * 2 + kWin * 4 + kData;   // head + node ring + data
+constexpr int kTablesPerWarp = kBuckets * 2 + kWin * 2 + int(kData);   // head + node ring + data
+constexpr int kParWarps = (227 * 1024) / kTablesPerWarp > 16 ? 16 : (227 * 1024) / kTablesPerWarp;   // one block per SM
 
 enum ParKind { P_LZ10 = 0, P_YAZ0 = 1, P_LZSS = 2 };
 
@@ -68,12 +80,12 @@ struct ParState {
     int lz_n, lz_f, lz_start, lz_lbits;
 };
 
-__device__ __forceinline__ uint32_t ring_u8(const ParState& S, int pos) { return lds_u8(S.data + ((uint32_t(pos) + S.skew) & kDataMask)); }
+__device__ __forceinline__ uint32_t ring_u8(const ParState& S, int pos) { return lds_u8(S.data + didx(uint32_t(pos) + S.skew)); }
 
 // four bytes at an arbitrary position (little-endian) from the data ring
 __device__ __forceinline__ uint32_t ring_u32(const ParState& S, int pos) {
     const uint32_t a = uint32_t(pos) + S.skew;
-    const uint32_t lo = lds_u32(S.data + (a & kDataMask & ~3u)), hi = lds_u32(S.data + ((a + 4) & kDataMask & ~3u));
+    const uint32_t lo = lds_u32(S.data + didx(a & ~3u)), hi = lds_u32(S.data + didx((a + 4) & ~3u));
     return __funnelshift_r(lo, hi, (a & 3u) * 8);
 }
 
@@ -87,7 +99,7 @@ __device__ __forceinline__ void stage(ParState& S, int upto) {
         const uint8_t* g = S.src - S.skew + size_t(line) * 16;
         if (g < S.src_lim) {
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(g));
-            sts_u128(S.data + ((line * 16) & kDataMask), v.x, v.y, v.z, v.w);
+            sts_u128(S.data + didx(line * 16), v.x, v.y, v.z, v.w);
         }
         S.staged = int((first_line + 32) * 16 - S.skew);
     }
@@ -107,7 +119,7 @@ __device__ __forceinline__ int prefix_len(const ParState& S, int a, int b, int c
         ib &= ~3u;
         int l = len - int(r);
         while (l < cap) {
-            const uint32_t x = (lds_u32(S.data + (ia & kDataMask)) ^ lds_u32(S.data + (ib & kDataMask))) & mask;
+            const uint32_t x = (lds_u32(S.data + didx(ia)) ^ lds_u32(S.data + didx(ib))) & mask;
             if (x) return min(l + ((__ffs(int(x)) - 1) >> 3), cap);
             mask = 0xFFFFFFFFu;
             l += 4;
@@ -381,7 +393,9 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                 bool done = false;
                 auto candidate = [&](int distance) {
                     attempts--;
-                    if (distance >= S.min_dist) {
+                    // a candidate can only beat the best match so far if it also matches at offset best_len: one byte decides
+                    // most of the later candidates of a chain (the result is the same: a longer match agrees on that byte)
+                    if (distance >= S.min_dist && (best_len == 0 || ring_u8(S, p + best_len) == ring_u8(S, p - distance + best_len))) {
                         // the same distance as 32 positions earlier: that match's bytes behind the first 32 are equal here too
                         const int known = (distance == pdist && plen > 32) ? min(plen - 32, best_possible) : 0;
                         int l = prefix_len(S, p, p - distance, best_possible, known);
@@ -404,12 +418,13 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                 if (!done && head_ok && int(dd) <= S.max_dist) {   // (b) the ring: skip the nodes of my bucket with another tag
                     int distance = int(dd);
                     for (;;) {
-                        const uint32_t nd = lds_u32(S.node + 4 * (uint32_t(p - distance) & kWinMask));
-                        if ((nd >> 16) == tag) {
+                        const uint32_t nd = lds_u16(S.node + 2 * (uint32_t(p - distance) & kWinMask));
+                        // three tag bits live in the node; a node that passes them is confirmed by hashing its four bytes again
+                        if ((nd >> 13) == (tag & 7u) && (((ring_u32(S, p - distance) * 2654435761u) >> S.hash_shift) & S.hash_mask) == h) {
                             candidate(distance);
                             if (done) break;
                         }
-                        const int bl = int(nd & 0xFFFFu);
+                        const int bl = int(nd & 0x1FFFu);
                         if (bl == 0 || distance + bl > S.max_dist) break;
                         distance += bl;
                     }
@@ -418,7 +433,7 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
             __syncwarp();
             // ---- the step's positions enter the ring and the heads
             if (valid) {
-                sts_u32(S.node + 4 * (uint32_t(p) & kWinMask), blink | (tag << 16));
+                sts_u16(S.node + 2 * (uint32_t(p) & kWinMask), blink | ((tag & 7u) << 13));
                 if ((gmb >> lane) <= 1u) sts_u16(S.head + 2 * bucket, uint32_t(p) & 0xFFFFu);   // the last lane of the bucket's group
             }
             __syncwarp();
@@ -468,7 +483,7 @@ __global__ void __launch_bounds__(kParWarps * 32, 1) encode_lz_par_kernel(const 
     const uint32_t t0 = smem_u32(smem) + uint32_t(warp) * kTablesPerWarp;
     S.head = t0;
     S.node = t0 + kBuckets * 2;
-    S.data = S.node + kWin * 4;
+    S.data = S.node + kWin * 2;
     S.hash_shift = 32 - P.hash_bits;
     S.hash_mask = (1u << P.hash_bits) - 1u;
     S.max_chain = P.max_chain;
@@ -516,8 +531,8 @@ cudaError_t launch_par(const EncodeParams& p, int sm_count, cudaStream_t st) {
 bool encode_lz_par_supported(const EncodeParams& p) {
     const bool fmt = p.format == AURORA_FMT_LZ10 || p.format == AURORA_FMT_BLZ || p.format == AURORA_FMT_YAZ0 || p.format == AURORA_FMT_YAZ1 ||
                      p.format == AURORA_FMT_LZSS;
-    return fmt && !p.use_min_table && p.hash_bits >= kBucketBits && p.hash_bits <= kBucketBits + 8 && p.max_distance <= kWin && p.chain_bits >= 12 &&
-           p.max_length <= 1024 && p.min_length >= 1 && p.min_distance >= 1;
+    return fmt && !p.use_min_table && p.hash_bits >= kBucketBits && p.hash_bits <= 24 && p.max_distance <= kWin && p.chain_bits >= 12 &&
+           p.max_length <= 288 && p.min_length >= 1 && p.min_distance >= 1;
 }
 
 cudaError_t launch_encode_lz_par(const EncodeParams& p, int sm_count, cudaStream_t st) {

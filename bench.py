@@ -379,11 +379,11 @@ def other_configs(codec, dev, ts, peak, raw_c2, args):
     #      against the oracle: tests/) and compared in size with the oracle's encoder on a sample
     r_off = torch.arange(n2, **_i64(dev)) * size
     r_len = torch.full((n2,), size, **_i64(dev))
-    # (the two match finders write the same bytes: the sequential replay is the default at quality 8, the search with one lane
-    #  per window position — the kernel family BASELINE.json's north star names — is timed next to it)
+    # (the two match finders write the same bytes: the search with one lane per window position — the kernel family BASELINE.json's
+    #  north star names — is the default; the sequential replay of the reference's loop is timed next to it)
     for name, fmt, strategy in (("C5_lz10_encode", A.FMT_LZ10, 0), ("C5_yaz0_encode", A.FMT_YAZ0, 0),
-                                ("C5_lz10_encode_lane_per_position", A.FMT_LZ10, A.STRATEGY_PARALLEL_FINDER),
-                                ("C5_yaz0_encode_lane_per_position", A.FMT_YAZ0, A.STRATEGY_PARALLEL_FINDER)):
+                                ("C5_lz10_encode_sequential_replay", A.FMT_LZ10, A.STRATEGY_SERIAL_FINDER),
+                                ("C5_yaz0_encode_sequential_replay", A.FMT_YAZ0, A.STRATEGY_SERIAL_FINDER)):
         opts = A.make_opts(quality=QUALITY, strategy=strategy)
         best, packed = 1e30, None
         for _ in range(2):

@@ -111,7 +111,7 @@ typedef struct aurora_lz_props {
 
 /* Blittable option block shared by decode and encode.  Zero-initialise, set struct_size. */
 /* opts.strategy, library-specific bits: which of the two byte-identical match finders encodes LZ10 / BLZ / Yaz0 / Yaz1 /
- * LZSS at quality < 10 (default: the parallel one up to maxChain 4, i.e. quality <= 3) */
+ * LZSS at quality < 10 (default: the parallel one) */
 #define AURORA_STRATEGY_PARALLEL_FINDER 0x10000   /* one lane per window position, shared-memory tables (encode_lz_par.cu) */
 #define AURORA_STRATEGY_SERIAL_FINDER   0x20000   /* sequential replay of LzChainMatchFinder (finder.cuh)                  */
 

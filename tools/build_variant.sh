@@ -12,7 +12,7 @@ B=$SRC/build/variant_$NAME
 mkdir -p "$OUT" "$B"
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 for f in api wrappers decode_flaglz decode_bytelz decode_blz encode_lz encode_lz_par encode_bytelz ismatch keystream; do
-  if [ "$f" = decode_flaglz ] || [ "$f" = decode_bytelz ] || [ "$f" = decode_blz ] || [ ! -f "$SRC/build/$f.o" ]; then
+  if [ "$f" = decode_flaglz ] || [ "$f" = decode_bytelz ] || [ "$f" = decode_blz ] || [ "$f" = encode_lz_par ] || [ ! -f "$SRC/build/$f.o" ]; then
     nvcc $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -cudart static $FLAGS -c "$SRC/$f.cu" -o "$B/$f.o" &
   else
     cp "$SRC/build/$f.o" "$B/$f.o"
