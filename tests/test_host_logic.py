@@ -85,3 +85,39 @@ def test_reference_arm_ranks_other_than_zero_do_nothing():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          env=env, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_stream_mismatch_flags_exactly_the_windows_that_differ():
+    """bench.stream_mismatch (the per-stream verifier of the C3 / C4 bench lines and of tests/test_baseline_sizes_gpu.py):
+    ragged adjacent windows, an empty one, chunked over several passes."""
+    import torch
+    import bench
+    g = torch.Generator().manual_seed(5)
+    a = torch.randint(0, 256, (50000,), dtype=torch.uint8, generator=g)
+    b = a.clone()
+    ln = torch.tensor([100, 200, 0, 300, 50, 4096, 1, 7000], dtype=torch.int64)
+    off = torch.cumsum(ln, 0) - ln + 7
+    for i, at in ((1, 5), (4, 49), (7, 6999)):          # first, last and a middle byte of three windows
+        b[int(off[i]) + at] ^= 0x5A
+    b[int(off[3]) - 0 + 300 + 0] = b[int(off[3]) + 300]   # (untouched: the byte behind window 3 belongs to window 4)
+    want = [False, True, False, False, True, False, False, True]
+    for chunk in (1 << 30, 350, 64):
+        assert bench.stream_mismatch(a, b, off, ln, chunk_bytes=chunk).tolist() == want
+
+
+def test_bench_dump_batch_writes_the_reference_arm_sample(tmp_path, oracle):
+    """`bench.py --dump-batch DIR` (the input of baseline/dotnet): packed.bin holds the LZ10 streams of the reference arm's
+    sample at the offsets index.bin lists, and the oracle decodes them to 64 KiB each."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--dump-batch", str(tmp_path), "--streams", "8"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-400:]
+    idx = np.fromfile(tmp_path / "index.bin", dtype="<u8").reshape(-1, 3)
+    packed = np.fromfile(tmp_path / "packed.bin", dtype=np.uint8)
+    assert idx.shape == (8, 3) and (idx[:, 2] == 65536).all()
+    for o, l, size in idx.tolist():
+        blob = packed[o:o + l].tobytes()
+        assert blob[0] == 0x10   # LZ10
+        dec, out_len, consumed, st = oracle.decode(A.FMT_LZ10, blob, size)
+        assert st == 0 and out_len == size and consumed == l
