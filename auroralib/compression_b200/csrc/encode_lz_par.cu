@@ -82,10 +82,17 @@ struct ParState {
 
 __device__ __forceinline__ uint32_t ring_u8(const ParState& S, int pos) { return lds_u8(S.data + didx(uint32_t(pos) + S.skew)); }
 
+// the ring index 4 bytes further (indices are multiples of 4 here, the ring size is too: no straddling)
+__device__ __forceinline__ uint32_t dnext(uint32_t i) {
+    i += 4;
+    return i >= kData ? i - kData : i;
+}
+
 // four bytes at an arbitrary position (little-endian) from the data ring
 __device__ __forceinline__ uint32_t ring_u32(const ParState& S, int pos) {
     const uint32_t a = uint32_t(pos) + S.skew;
-    const uint32_t lo = lds_u32(S.data + didx(a & ~3u)), hi = lds_u32(S.data + didx((a + 4) & ~3u));
+    const uint32_t i0 = didx(a & ~3u);
+    const uint32_t lo = lds_u32(S.data + i0), hi = lds_u32(S.data + dnext(i0));
     return __funnelshift_r(lo, hi, (a & 3u) * 8);
 }
 
@@ -110,27 +117,34 @@ __device__ __forceinline__ void stage(ParState& S, int upto) {
 // (GetMatchLength, LzChainMatchFinder.cs:338-357)
 __device__ __forceinline__ int prefix_len(const ParState& S, int a, int b, int cap, int known) {
     int len = known & ~3;
+    const uint32_t pa = uint32_t(a + len) + S.skew, pb = uint32_t(b + len) + S.skew;
+    // (one modulo per string: the ring indices then advance by 4 with a compare-and-subtract)
+    uint32_t ia = didx(pa & ~3u), ib = didx(pb & ~3u);
     if (((a ^ b) & 3) == 0) {
         // distance a multiple of 4 (tile data): the two byte strings have the same alignment, aligned words compare directly
-        uint32_t ia = uint32_t(a + len) + S.skew, ib = uint32_t(b + len) + S.skew;
-        const uint32_t r = ia & 3u;
+        const uint32_t r = pa & 3u;
         uint32_t mask = 0xFFFFFFFFu << (8 * r);
-        ia &= ~3u;
-        ib &= ~3u;
         int l = len - int(r);
         while (l < cap) {
-            const uint32_t x = (lds_u32(S.data + didx(ia)) ^ lds_u32(S.data + didx(ib))) & mask;
+            const uint32_t x = (lds_u32(S.data + ia) ^ lds_u32(S.data + ib)) & mask;
             if (x) return min(l + ((__ffs(int(x)) - 1) >> 3), cap);
             mask = 0xFFFFFFFFu;
             l += 4;
-            ia += 4;
-            ib += 4;
+            ia = dnext(ia);
+            ib = dnext(ib);
         }
         return cap;
     }
+    const uint32_t sha = (pa & 3u) * 8, shb = (pb & 3u) * 8;
+    uint32_t wa = lds_u32(S.data + ia), wb = lds_u32(S.data + ib);
     while (len + 4 <= cap) {
-        const uint32_t x = ring_u32(S, a + len) ^ ring_u32(S, b + len);
+        ia = dnext(ia);
+        ib = dnext(ib);
+        const uint32_t na = lds_u32(S.data + ia), nb = lds_u32(S.data + ib);
+        const uint32_t x = __funnelshift_r(wa, na, sha) ^ __funnelshift_r(wb, nb, shb);
         if (x) return len + ((__ffs(int(x)) - 1) >> 3);
+        wa = na;
+        wb = nb;
         len += 4;
     }
     while (len < cap && ring_u8(S, a + len) == ring_u8(S, b + len)) len++;
