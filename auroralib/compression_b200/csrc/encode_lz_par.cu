@@ -88,13 +88,17 @@ __device__ __forceinline__ uint32_t dnext(uint32_t i) {
     return i >= kData ? i - kData : i;
 }
 
-// four bytes at an arbitrary position (little-endian) from the data ring
-__device__ __forceinline__ uint32_t ring_u32(const ParState& S, int pos) {
-    const uint32_t a = uint32_t(pos) + S.skew;
-    const uint32_t i0 = didx(a & ~3u);
+// i < 2 * kData folded back into the ring
+__device__ __forceinline__ uint32_t dwrap(uint32_t i) { return i >= kData ? i - kData : i; }
+
+// four bytes at ring index i (any alignment; (i & 3) is the byte position inside the aligned word)
+__device__ __forceinline__ uint32_t ring_u32_at(const ParState& S, uint32_t i) {
+    const uint32_t i0 = i & ~3u;
     const uint32_t lo = lds_u32(S.data + i0), hi = lds_u32(S.data + dnext(i0));
-    return __funnelshift_r(lo, hi, (a & 3u) * 8);
+    return __funnelshift_r(lo, hi, (i & 3u) * 8);
 }
+// four bytes at an arbitrary position (little-endian) from the data ring
+__device__ __forceinline__ uint32_t ring_u32(const ParState& S, int pos) { return ring_u32_at(S, didx(uint32_t(pos) + S.skew)); }
 
 // stage raw bytes until position `upto` (exclusive, clamped to the stream) is in the ring: whole 16-byte lines, 512 bytes per pass
 __device__ __forceinline__ void stage(ParState& S, int upto) {
@@ -115,12 +119,12 @@ __device__ __forceinline__ void stage(ParState& S, int upto) {
 
 // common prefix of the bytes at positions a and b, at most cap bytes, the first `known` of them known to be equal
 // (GetMatchLength, LzChainMatchFinder.cs:338-357)
-__device__ __forceinline__ int prefix_len(const ParState& S, int a, int b, int cap, int known) {
+// ia / ib: ring indices of the two strings' first bytes (one modulo per position and step; everything below is index arithmetic)
+__device__ __forceinline__ int prefix_len(const ParState& S, uint32_t ia0, uint32_t ib0, int cap, int known) {
     int len = known & ~3;
-    const uint32_t pa = uint32_t(a + len) + S.skew, pb = uint32_t(b + len) + S.skew;
-    // (one modulo per string: the ring indices then advance by 4 with a compare-and-subtract)
-    uint32_t ia = didx(pa & ~3u), ib = didx(pb & ~3u);
-    if (((a ^ b) & 3) == 0) {
+    const uint32_t pa = dwrap(ia0 + uint32_t(len)), pb = dwrap(ib0 + uint32_t(len));   // (len <= max_length <= 288 < kData)
+    uint32_t ia = pa & ~3u, ib = pb & ~3u;
+    if (((pa ^ pb) & 3u) == 0) {
         // distance a multiple of 4 (tile data): the two byte strings have the same alignment, aligned words compare directly
         const uint32_t r = pa & 3u;
         uint32_t mask = 0xFFFFFFFFu << (8 * r);
@@ -147,7 +151,7 @@ __device__ __forceinline__ int prefix_len(const ParState& S, int a, int b, int c
         wb = nb;
         len += 4;
     }
-    while (len < cap && ring_u8(S, a + len) == ring_u8(S, b + len)) len++;
+    while (len < cap && lds_u8(S.data + dwrap(ia0 + uint32_t(len))) == lds_u8(S.data + dwrap(ib0 + uint32_t(len)))) len++;
     return len;
 }
 
@@ -384,9 +388,10 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
             // lanes inside a match that is already written are inserted but not searched (their results are never looked at)
             const bool searched = valid && (S.pending || lane >= S.cur_off);
             int best_len = 0, best_dist = 0;
-            uint32_t h = 0xFFFFFFFFu, bucket = 0xFFFFFFFFu;
+            uint32_t h = 0xFFFFFFFFu, bucket = 0xFFFFFFFFu, ip = 0;   // ip: ring index of my position
             if (valid) {
-                h = ((ring_u32(S, p) * 2654435761u) >> S.hash_shift) & S.hash_mask;   // ComputeHash, :288-299
+                ip = didx(uint32_t(p) + S.skew);
+                h = ((ring_u32_at(S, ip) * 2654435761u) >> S.hash_shift) & S.hash_mask;   // ComputeHash, :288-299
                 bucket = h & kBucketMask;
             }
             const uint32_t tag = h >> kBucketBits;
@@ -409,10 +414,11 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                     attempts--;
                     // a candidate can only beat the best match so far if it also matches at offset best_len: one byte decides
                     // most of the later candidates of a chain (the result is the same: a longer match agrees on that byte)
-                    if (distance >= S.min_dist && (best_len == 0 || ring_u8(S, p + best_len) == ring_u8(S, p - distance + best_len))) {
+                    const uint32_t ic = dwrap(ip + kData - uint32_t(distance));   // ring index of the candidate (distance <= 4096 < kData)
+                    if (distance >= S.min_dist && (best_len == 0 || lds_u8(S.data + dwrap(ip + uint32_t(best_len))) == lds_u8(S.data + dwrap(ic + uint32_t(best_len))))) {
                         // the same distance as 32 positions earlier: that match's bytes behind the first 32 are equal here too
                         const int known = (distance == pdist && plen > 32) ? min(plen - 32, best_possible) : 0;
-                        int l = prefix_len(S, p, p - distance, best_possible, known);
+                        int l = prefix_len(S, ip, ic, best_possible, known);
                         if (S.no_self_overlap && l > distance) l = distance;
                         if (l >= S.min_len && l > best_len) {
                             best_len = l;
@@ -434,7 +440,7 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                     for (;;) {
                         const uint32_t nd = lds_u16(S.node + 2 * (uint32_t(p - distance) & kWinMask));
                         // three tag bits live in the node; a node that passes them is confirmed by hashing its four bytes again
-                        if ((nd >> 13) == (tag & 7u) && (((ring_u32(S, p - distance) * 2654435761u) >> S.hash_shift) & S.hash_mask) == h) {
+                        if ((nd >> 13) == (tag & 7u) && (((ring_u32_at(S, dwrap(ip + kData - uint32_t(distance))) * 2654435761u) >> S.hash_shift) & S.hash_mask) == h) {
                             candidate(distance);
                             if (done) break;
                         }
