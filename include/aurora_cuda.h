@@ -172,6 +172,11 @@ void aurora_codec_opts_init(aurora_codec_opts* opts);
  * dst_base[dst_off[i] .. dst_off[i]+dst_cap[i]).  All per-stream arrays have n entries.
  * Streams are sharded over the context's devices by size; no stream aborts the batch: errors
  * are reported in status[i].  Returns AURORA_OK, AURORA_INVALID_ARGUMENT or AURORA_CUDA_ERROR.
+ * What the library writes into dst_base: the destination windows and nothing else, with ONE exception — windows that follow
+ * each other in ascending order at most 15 bytes apart (the alignment padding of a packed batch) are copied back as one
+ * piece, padding included, so those padding bytes are overwritten with unspecified values.  Offsets may have any alignment;
+ * bytes in front of the first window, behind the last one and in gaps of 16 bytes or more are never touched.  (The wrapper
+ * formats, which run several sub-batches over one destination, write only the bytes every stream produced.)
  */
 
 /* IProvidesDecompressedSize.GetDecompressedSize for n streams.  Formats without a size header

@@ -335,3 +335,33 @@ def test_multi_device_sharding(oracle, bmp):
         assert (st == 0).all() and enc == ref
     finally:
         c.close()
+
+
+def test_host_path_writes_only_the_destination_windows(codec, oracle, bmp):
+    """include/aurora_cuda.h: the host path writes the destination windows and nothing else (alignment padding of at most 15
+    bytes between consecutive windows excepted).  Unaligned offsets, gaps of 16..300 bytes and a margin on both sides are
+    filled with a sentinel that must survive; some windows are larger than the decoded size."""
+    rng = np.random.default_rng(515)
+    raws = [bmp[int(o):int(o) + int(n)] for o, n in zip(rng.integers(0, 900000, size=400), rng.integers(1, 9000, size=400))]
+    for fmt in (A.FMT_LZ10, A.FMT_YAZ0, A.FMT_LZ4_BLOCK):
+        comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=0))
+        keep = [i for i in range(len(raws)) if st[i] == 0]
+        comps, rr = [comps[i] for i in keep], [raws[i] for i in keep]
+        from auroralib.compression_b200.batch import pack
+        base, off, ln = pack(comps, align=1)
+        caps = np.array([len(r) + int(rng.choice([0, 0, 7, 100])) for r in rr], dtype=np.uint64)
+        gaps = rng.integers(16, 300, size=len(rr)).astype(np.uint64)
+        doff = np.zeros(len(rr), dtype=np.uint64)
+        pos = 37   # margin in front, odd alignment
+        for i in range(len(rr)):
+            doff[i] = pos
+            pos += int(caps[i]) + int(gaps[i])
+        dst = np.full(pos + 64, 0xA5, dtype=np.uint8)
+        out_len, consumed, status = codec.decode_packed(fmt, base, off, ln, dst, doff, caps)
+        assert (status == 0).all(), fmt_id(fmt)
+        covered = np.zeros(len(dst), dtype=bool)
+        for i, r in enumerate(rr):
+            a = int(doff[i])
+            assert dst[a:a + len(r)].tobytes() == r, (fmt_id(fmt), i)
+            covered[a:a + int(caps[i])] = True
+        assert (dst[~covered] == 0xA5).all(), f"{fmt_id(fmt)}: {int((dst[~covered] != 0xA5).sum())} bytes outside the windows were written"

@@ -245,3 +245,28 @@ def test_gpu_wrapper_mirror_classes(bmp):
     chunked.Type, chunked.ChunkSize = LZ77.CHUNK_LZ10_TYPE, 0x800
     blob = chunked.Compress(raw, settings=CompressionSettings(8)).getvalue()
     assert blob[4] == 0xF7 and LZ77().Decompress(io.BytesIO(blob)).getvalue() == raw
+
+
+@pytest.mark.gpu
+def test_lz77_mixed_sub_types_in_one_batch(codec, oracle, bmp):
+    """a wrapped batch that needs more than one core batch (LZ77 resolves type 0x10 to LZ10, 0x11 to LZ11 and 0xF7
+    to ChunkLZ10) runs several core batches over ONE destination; every stream must keep the bytes its own core batch decoded,
+    also when two chunked files fail and are decoded once more."""
+    rng = np.random.default_rng(77)
+    raws = [bmp[int(o):int(o) + int(n)] for o, n in zip(rng.integers(0, 900000, size=90), rng.integers(200, 30000, size=90))]
+    types = [(0x10, 0), (0x11, 0), (0xF7, 0), (0xF7, 0x400)]
+    comps = []
+    for i, r in enumerate(raws):
+        t, cs = types[i % 4]
+        c, st = oracle.encode(A.FMT_LZ77, r, A.make_opts(quality=8, lz77_type=t, lz77_chunk_size=cs))
+        assert st == 0
+        comps.append(c)
+    # two chunked files that fail: cut inside their last chunk
+    for k in (2, 6):
+        comps[k] = comps[k][:len(comps[k]) - 40]
+    caps = [len(r) for r in raws]
+    outs, out_len, consumed, status = codec.decode_batch(A.FMT_LZ77, comps, caps)
+    ref, rlen, rcons, rst = oracle.decode_batch(A.FMT_LZ77, comps, caps)
+    assert (status == rst).all() and (out_len == rlen).all() and (consumed == rcons).all()
+    assert outs == ref
+    assert sum(1 for i in range(len(raws)) if status[i] == 0 and outs[i] == raws[i]) == len(raws) - 2
