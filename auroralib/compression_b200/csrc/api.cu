@@ -369,7 +369,20 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
         CU_TRY(ctx, cudaMemsetAsync(d->ticket.p, 0, 256, st));
         CU_TRY(ctx, cudaEventRecord(d->ev_k[0], st));   // descriptors + tickets are in place
         CU_TRY(ctx, cudaStreamWaitEvent(d->s_in, d->ev_k[0], 0));
-        // piece boundaries by cumulative bytes
+        // piece boundaries by cumulative bytes.  The first regular piece is cut in three (1/8, 3/8, 1/2 of it): the download
+        // engine is the bottleneck of the pipeline and idles until the first kernel has finished, so the first upload is short.
+        std::vector<uint64_t> bound;
+        bound.push_back(total_bytes / (8 * pieces));
+        bound.push_back(total_bytes / (2 * pieces));
+        for (size_t k = 1; k < pieces; k++) bound.push_back(total_bytes * k / pieces);
+        pieces = bound.size() + 1;
+        while (d->ev_in.size() < pieces) {
+            cudaEvent_t e1, e2;
+            CU_TRY(ctx, cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            d->ev_in.push_back(e1);
+            d->ev_k.push_back(e2);
+        }
         std::vector<size_t> cut(pieces + 1, n);
         cut[0] = 0;
         {
@@ -377,7 +390,7 @@ int decode_shard(aurora_ctx* ctx, DeviceCtx* d, int format, const aurora_codec_o
             size_t k = 1;
             for (size_t i = 0; i < n && k < pieces; i++) {
                 acc += src_len[b + i] + (size_only ? 0 : dst_cap[b + i]);
-                if (acc >= total_bytes * k / pieces) cut[k++] = i + 1;
+                while (k < pieces && acc >= bound[k - 1]) cut[k++] = i + 1;
             }
         }
         for (size_t k = 0; k < pieces; k++) {
