@@ -88,3 +88,13 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.replace("the oracle", "").replace("oracle encoder", "").replace("oracle decoder", "").replace("CPU oracle", "").replace("oracle's", "") \
                     or f in ("corpus.py",), f"{f} references oracle/"
+
+
+def test_strategy_bits_match_the_header():
+    """The library-specific bits of opts.strategy (which byte-identical match finder encodes) are the same in the C header and
+    in the Python mirror, and leave bit 0 (CompresionStrategy.CompatibilityMode, the only bit the oracle reads) alone."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "aurora_cuda.h")).read()
+    vals = {m.group(1): int(m.group(2), 16) for m in re.finditer(r"#define (AURORA_STRATEGY_\w+)\s+(0x[0-9A-Fa-f]+)", hdr)}
+    assert vals == {"AURORA_STRATEGY_PARALLEL_FINDER": A.STRATEGY_PARALLEL_FINDER, "AURORA_STRATEGY_SERIAL_FINDER": A.STRATEGY_SERIAL_FINDER}
+    assert A.STRATEGY_COMPATIBILITY == 1 and (A.STRATEGY_PARALLEL_FINDER | A.STRATEGY_SERIAL_FINDER) & 1 == 0
