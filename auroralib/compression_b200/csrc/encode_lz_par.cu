@@ -1,5 +1,5 @@
 // encode_lz_par.cu — the window match search of the flag-byte encoders with ONE LANE PER WINDOW POSITION and shared-memory
-// hash tables (LZ10 / BLZ, Yaz0 / Yaz1, LZSS at qualities below 10).  One raw buffer per warp, 32 positions per step.
+// hash tables (LZ10 / BLZ, Yaz0 / Yaz1, LZSS, MIO0, Yay0 at qualities below 10).  One raw buffer per warp, 32 positions per step.
 //
 // The output is byte-identical to the reference encoder (and to the sequential replay in encode_lz.cu / finder.cuh, which
 // stays for the other formats and qualities): what LzChainMatchFinder computes at a position depends only on the bytes
@@ -50,7 +50,10 @@ constexpr int kChunk = 512;              // raw bytes staged per refill (16 byte
 constexpr int kTablesPerWarp = kBuckets * 2 + kWin * 2 + int(kData);   // head + node ring + data
 constexpr int kParWarps = (227 * 1024) / kTablesPerWarp > 16 ? 16 : (227 * 1024) / kTablesPerWarp;   // one block per SM
 
-enum ParKind { P_LZ10 = 0, P_YAZ0 = 1, P_LZSS = 2 };
+enum ParKind { P_LZ10 = 0, P_YAZ0 = 1, P_LZSS = 2, P_MIO0 = 3, P_YAY0 = 4 };
+// MIO0 / Yay0 write three sections (flag bytes, match codes, literal bytes: MIO0.cs:159-184, Yay0.cs:152-184)
+template <int K>
+constexpr bool kSplit = K == P_MIO0 || K == P_YAY0;
 
 struct ParState {
     // tables (shared addresses)
@@ -78,6 +81,13 @@ struct ParState {
     bool forced, pending;
     // LZSS token fields
     int lz_n, lz_f, lz_start, lz_lbits;
+    // MIO0 / Yay0: the code and literal sections are staged in this warp's slice of the global scratch buffer until the
+    // length of the flag section in front of them is known
+    uint8_t* scratch;
+    uint8_t* codes;
+    uint8_t* lits;
+    uint32_t ncodes, nlits;
+    uint64_t flag_base;    // first byte of the flag section (one byte per eight tokens)
 };
 
 __device__ __forceinline__ uint32_t ring_u8(const ParState& S, int pos) { return lds_u8(S.data + didx(uint32_t(pos) + S.skew)); }
@@ -301,6 +311,70 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
     S.pos += total;
 }
 
+// ---- the same for the split formats: one flag bit per token into the flag section (1 = literal, MSB first), two code
+// bytes per match into the code section; literal bytes and (Yay0, length >= 18) the extended length byte into the
+// literal section, all in token order
+template <int K>
+__device__ __forceinline__ void write_step_split(ParState& S, int base, int len, int dist, uint32_t lit, uint32_t mat) {
+    const int lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t inb = base + 32 <= S.n ? ~0u : (S.n > base ? (1u << (S.n - base)) - 1u : 0u);
+    lit &= inb;
+    mat &= inb;
+    const uint32_t tok = lit | mat;
+    if (tok == 0) return;
+    const bool is_tok = (tok >> lane) & 1u, is_mat = (mat >> lane) & 1u;
+    const uint32_t T = S.ntok + __popc(tok & lt);
+    // ---- section offsets: literal bytes in the low half, code bytes in the high half of one scan (<= 32 / <= 64 per step)
+    const bool ext = K == P_YAY0 && is_mat && len >= 18;
+    const uint32_t sz = !is_tok ? 0u : is_mat ? (0x20000u | (ext ? 1u : 0u)) : 1u;
+    const uint32_t incl = warp_incl_scan(sz);
+    const uint32_t excl = incl - sz;
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    const uint32_t lit_at = S.nlits + (excl & 0xFFFFu), code_at = S.ncodes + (excl >> 16);
+    // ---- flag bytes
+    {
+        const uint32_t contrib = (is_tok && !is_mat) ? 0x80u >> (T & 7u) : 0u;
+        const uint32_t g = T >> 3;
+        const uint32_t gm = __match_any_sync(kFull, is_tok ? g : 0xFFFFFFFFu);
+        uint32_t fv = __reduce_or_sync(gm, contrib);
+        const bool leader = is_tok && (gm & lt) == 0;
+        if (leader && (T & 7u) != 0) fv |= S.carry_flag;   // the group was opened by an earlier step
+        if (leader) {
+            const uint64_t fpos = S.flag_base + g;
+            if (fpos < S.cap) S.out[fpos] = uint8_t(fv);
+            else S.overflow = true;
+        }
+        const int last = 31 - __clz(int(tok));
+        const uint32_t lead_lane = __ffs(int(__shfl_sync(kFull, gm, last))) - 1;
+        const uint32_t cf = __shfl_sync(kFull, fv, lead_lane);
+        S.ntok += __popc(tok);
+        S.carry_flag = (S.ntok & 7u) ? cf : 0u;
+    }
+    // ---- section bytes
+    if (is_tok) {
+        if (!is_mat) {
+            S.lits[lit_at] = uint8_t(ring_u8(S, base + lane));
+        } else {
+            uint32_t v;
+            if (K == P_MIO0) v = (uint32_t(dist - 1) | uint32_t(len - 3) << 12) & 0xFFFFu;
+            else if (len < 18) v = (uint32_t(dist - 1) | uint32_t(len - 2) << 12) & 0xFFFFu;
+            else v = uint32_t(dist - 1) & 0xFFFu;
+            S.codes[code_at] = uint8_t(v >> 8);
+            S.codes[code_at + 1] = uint8_t(v & 0xFF);
+            if (ext) S.lits[lit_at] = uint8_t(len - 0x12);
+        }
+    }
+    S.nlits += total & 0xFFFFu;
+    S.ncodes += total >> 16;
+}
+
+template <int K>
+__device__ __forceinline__ void emit_step(ParState& S, int base, int len, int dist, uint32_t lit, uint32_t mat) {
+    if constexpr (kSplit<K>) write_step_split<K>(S, base, len, dist, lit, mat);
+    else write_step<K>(S, base, len, dist, lit, mat);
+}
+
 __device__ __forceinline__ void put_byte(ParState& S, uint32_t b) {
     if (S.pos < S.cap) {
         if (lane_id() == 0) S.out[S.pos] = uint8_t(b);
@@ -356,6 +430,18 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
             put_u32p(S, uint32_t(n), big);
             put_u32p(S, P.yaz0_alignment, big);
             put_u32p(S, 0, false);
+        } else if (kSplit<K>) {
+            // MIO0.cs:64-81, Yay0.cs:63-78: magic, size, offsets of the code and the literal section (patched below)
+            const char* magic = K == P_MIO0 ? "MIO0" : "Yay0";
+            for (int i = 0; i < 4; i++) put_byte(S, uint8_t(magic[i]));
+            put_u32p(S, uint32_t(n), big);
+            put_u32p(S, 0, false);
+            put_u32p(S, 0, false);
+            // worst case n literal bytes / n code bytes: the layout of encode_lz.cu behind the (unused) finder tables
+            S.codes = S.scratch + P.scratch_per_warp - 2 * (size_t(n) + 64);
+            S.lits = S.codes + size_t(n) + 32;
+            S.ncodes = S.nlits = 0;
+            S.flag_base = S.pos;
         } else {
             put_byte(S, 'L'); put_byte(S, 'Z'); put_byte(S, 'S'); put_byte(S, 'S');
             put_u32p(S, uint32_t(n), true);
@@ -462,11 +548,11 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                 const int ln = __shfl_sync(kFull, best_len, 0), lk = __shfl_sync(kFull, plen, 31);
                 S.pending = false;
                 if (ln > lk) {
-                    write_step<K>(S, base - 32, plen, pdist, 0x80000000u, 0u);
+                    emit_step<K>(S, base - 32, plen, pdist, 0x80000000u, 0u);
                     S.forced = true;
                     S.cur_off = 0;
                 } else {
-                    write_step<K>(S, base - 32, plen, pdist, 0u, 0x80000000u);
+                    emit_step<K>(S, base - 32, plen, pdist, 0u, 0x80000000u);
                     S.forced = false;
                     S.cur_off = lk - 1;
                 }
@@ -474,7 +560,7 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
             // ---- parse + write this step
             uint32_t lit, mat;
             parse_step(S, base, best_len, lit, mat);
-            write_step<K>(S, base, best_len, best_dist, lit, mat);
+            emit_step<K>(S, base, best_len, best_dist, lit, mat);
             plen = best_len;
             pdist = best_dist;
         }
@@ -483,6 +569,21 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
             S.pos = 8;
             put_u32p(S, uint32_t(save - body_start), true);
             S.pos = save;
+        }
+        if (kSplit<K>) {
+            // the flag section is complete (every step wrote its groups, open ones included): codes and literals follow it
+            __syncwarp();
+            const uint64_t comp_off = body_start + ((S.ntok + 7u) >> 3), lit_off = comp_off + S.ncodes;
+            for (uint32_t i = lane; i < S.ncodes; i += 32)
+                if (comp_off + i < S.cap) S.out[comp_off + i] = S.codes[i];
+            for (uint32_t i = lane; i < S.nlits; i += 32)
+                if (lit_off + i < S.cap) S.out[lit_off + i] = S.lits[i];
+            if (lit_off + S.nlits > S.cap) S.overflow = true;
+            S.pos = 8;
+            put_u32p(S, uint32_t(comp_off), big);
+            put_u32p(S, uint32_t(lit_off), big);
+            S.pos = lit_off + S.nlits;
+            __syncwarp();
         }
         out_len = S.pos;
         if (S.overflow) status = AURORA_DST_TOO_SMALL;
@@ -518,6 +619,7 @@ __global__ void __launch_bounds__(kParWarps * 32, 1) encode_lz_par_kernel(const 
     S.lz_f = (1 << P.lzss.length_bits) - 1;
     S.lz_start = P.lzss.windows_start;
     S.lz_lbits = P.lzss.length_bits;
+    S.scratch = P.scratch + size_t(blockIdx.x * kParWarps + warp) * P.scratch_per_warp;
     for (;;) {
         uint32_t t = 0;
         if (lane_id() == 0) t = atomicAdd(P.ticket, 1u);
@@ -550,7 +652,7 @@ cudaError_t launch_par(const EncodeParams& p, int sm_count, cudaStream_t st) {
 // the formats / settings the parallel search reproduces exactly (everything else: encode_lz.cu)
 bool encode_lz_par_supported(const EncodeParams& p) {
     const bool fmt = p.format == AURORA_FMT_LZ10 || p.format == AURORA_FMT_BLZ || p.format == AURORA_FMT_YAZ0 || p.format == AURORA_FMT_YAZ1 ||
-                     p.format == AURORA_FMT_LZSS;
+                     p.format == AURORA_FMT_LZSS || p.format == AURORA_FMT_MIO0 || p.format == AURORA_FMT_YAY0;
     return fmt && !p.use_min_table && p.hash_bits >= kBucketBits && p.hash_bits <= 24 && p.max_distance <= kWin && p.chain_bits >= 12 &&
            p.max_length <= 288 && p.min_length >= 1 && p.min_distance >= 1;
 }
@@ -562,6 +664,8 @@ cudaError_t launch_encode_lz_par(const EncodeParams& p, int sm_count, cudaStream
         case AURORA_FMT_YAZ0:
         case AURORA_FMT_YAZ1: return launch_par<P_YAZ0>(p, sm_count, st);
         case AURORA_FMT_LZSS: return launch_par<P_LZSS>(p, sm_count, st);
+        case AURORA_FMT_MIO0: return launch_par<P_MIO0>(p, sm_count, st);
+        case AURORA_FMT_YAY0: return launch_par<P_YAY0>(p, sm_count, st);
         default: return cudaErrorNotSupported;
     }
 }

@@ -77,7 +77,7 @@ def test_options(codec, oracle, bmp):
 
 
 @pytest.mark.parametrize("finder", [A.STRATEGY_PARALLEL_FINDER, A.STRATEGY_SERIAL_FINDER], ids=["parallel", "serial"])
-@pytest.mark.parametrize("fmt", [A.FMT_LZ10, A.FMT_YAZ0, A.FMT_LZSS], ids=fmt_id)
+@pytest.mark.parametrize("fmt", [A.FMT_LZ10, A.FMT_YAZ0, A.FMT_LZSS, A.FMT_MIO0, A.FMT_YAY0], ids=fmt_id)
 def test_capacity_too_small(codec, bmp, fmt, finder):
     from auroralib.compression_b200.batch import layout, pack
     base, off, ln = pack([bmp[:20000]])
@@ -105,7 +105,7 @@ def test_container_options(codec, oracle, bmp):
         _check(codec, oracle, A.FMT_PRS, [bmp[:40000], bytes(3000), bmp[1000:1100]], A.make_opts(quality=8, byte_order=order))
 
 
-PAR_FORMATS = [A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS]
+PAR_FORMATS = [A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS, A.FMT_MIO0, A.FMT_YAY0]
 
 
 @pytest.mark.parametrize("fmt", PAR_FORMATS, ids=fmt_id)
