@@ -151,17 +151,21 @@ int fill_decode_params(DecodeParams& p, int format, const aurora_codec_opts* o) 
 }
 
 cudaError_t launch_encode(const EncodeParams& p, int warps, cudaStream_t st) {
-    // LZ10 / BLZ / Yaz0 / LZSS at qualities below 10: the window search with one lane per position and shared-memory tables
-    // (encode_lz_par.cu).  Both encoders write the reference's bytes; which one runs is a speed decision: the parallel
-    // search is the default wherever it applies (measured on C5, 65 536 x 64 KiB, GB/s raw in: quality 0 14.1 / 14.9 for
-    // LZ10 / Yaz0 against 8.4 / 8.9 of the sequential replay, quality 8 10.4 / 11.4 against 8.1 / 10.4) and either can be
-    // forced (opts.strategy bits 16 / 17, AURORA_ENCODER).
+    // Flag-byte formats (LZ10 / BLZ, LZ11 / LZ40 / LZ60, Yaz0 / Yaz1, LZSS, MIO0, Yay0): the window search with one lane per
+    // position and shared-memory tables (encode_lz_par.cu).  Both encoders write the reference's bytes; which one runs is a
+    // speed decision.  Measured on the C2 corpus (64 KiB streams, GB/s raw in, parallel / sequential replay): quality 8 LZ10
+    // 14.6 / 8.1, Yaz0 16.1 / 10.4, MIO0 12.6 / 6.5, Yay0 13.3 / 6.4, LZ11 10.8 / 5.9; quality 10-12 LZ10 5.3 / 4.3, LZ11
+    // 5.1 / 4.3; quality 15 LZ10 5.1 / 4.2 but LZ11 1.7 / 2.4 — with matches longer than a few words and chains of 256+
+    // candidates every lane walks its whole chain, and the warp-cooperative comparison of the sequential replay wins.
+    // Default: parallel, except long-match formats from quality 13 on; either can be forced (opts.strategy bits 16 / 17,
+    // AURORA_ENCODER).
     static const int forced = [] {
         const char* e = std::getenv("AURORA_ENCODER");
         return !e ? 0 : std::strcmp(e, "serial") == 0 ? 2 : std::strcmp(e, "parallel") == 0 ? 1 : 0;
     }();
     const int want = p.finder_choice ? p.finder_choice : forced;
-    if (encode_lz_par_supported(p) && want != 2) return launch_encode_lz_par(p, warps / 48, st);
+    const bool par_default = p.max_chain <= 128 || p.max_length <= 32;
+    if (encode_lz_par_supported(p) && (want == 1 || (want == 0 && par_default))) return launch_encode_lz_par(p, warps / 48, st);
     if (is_flaglz(p.format) || p.format == AURORA_FMT_BLZ) return launch_encode_lz(p, warps, st);   // BLZ: LZ10's layout
     return launch_encode_bytelz(p, warps, st);
 }

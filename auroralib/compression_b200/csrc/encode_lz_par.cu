@@ -46,11 +46,16 @@ constexpr int kWin = 4096, kWinMask = kWin - 1;
 // + 2048 buckets = 11 warps 12.5 / 13.5; 5 KiB + 2048 = 13 warps 13.3 / 14.0; 5 KiB + 1024 buckets = 15 warps 12.4 / 12.7)
 constexpr uint32_t kData = AURORA_ENC_DATA;
 __device__ __forceinline__ uint32_t didx(uint32_t x) { return x % kData; }
+constexpr int kLook = 288;                // bytes behind a position the ring guarantees (the longest match of every format but the LZ11 family)
 constexpr int kChunk = 512;              // raw bytes staged per refill (16 bytes per lane)
-constexpr int kTablesPerWarp = kBuckets * 2 + kWin * 2 + int(kData);   // head + node ring + data
-constexpr int kParWarps = (227 * 1024) / kTablesPerWarp > 16 ? 16 : (227 * 1024) / kTablesPerWarp;   // one block per SM
+// head + node ring + data; qualities >= 10 add a second head / node ring pair for the reference's small-match table
+// (`M`: LzChainMatchFinder.cs:85-91, :236-244 — the latest position whose first min_length bytes hash to the same 16-bit value)
+template <bool M>
+constexpr int kTablesPerWarp = (kBuckets * 2 + kWin * 2) * (M ? 2 : 1) + int(kData);
+template <bool M>
+constexpr int kParWarps = (227 * 1024) / kTablesPerWarp<M> > 16 ? 16 : (227 * 1024) / kTablesPerWarp<M>;   // one block per SM
 
-enum ParKind { P_LZ10 = 0, P_YAZ0 = 1, P_LZSS = 2, P_MIO0 = 3, P_YAY0 = 4 };
+enum ParKind { P_LZ10 = 0, P_YAZ0 = 1, P_LZSS = 2, P_MIO0 = 3, P_YAY0 = 4, P_LZ11 = 5 };   // P_LZ11: LZ11 / LZ40 / LZ60
 // MIO0 / Yay0 write three sections (flag bytes, match codes, literal bytes: MIO0.cs:159-184, Yay0.cs:152-184)
 template <int K>
 constexpr bool kSplit = K == P_MIO0 || K == P_YAY0;
@@ -58,6 +63,8 @@ constexpr bool kSplit = K == P_MIO0 || K == P_YAY0;
 struct ParState {
     // tables (shared addresses)
     uint32_t head, node, data;
+    uint32_t head2, node2;   // small-match table (qualities >= 10): buckets and chains over the 16-bit hash of the first min_length bytes
+    uint32_t min_mask;
     uint32_t skew;           // ring index of position 0 (the source's offset inside its 16-byte line)
     int staged;              // positions below this are in the data ring
     // source
@@ -67,7 +74,8 @@ struct ParState {
     // finder parameters
     int hash_shift, max_chain, lazy, min_len, max_len, min_dist, max_dist;
     uint32_t hash_mask;
-    bool no_self_overlap, blz;
+    int look;                // min(max_len, kLook): prefix comparisons inside the data ring; longer ones continue in global memory
+    bool no_self_overlap, blz, lz40;
     // output
     uint8_t* out;
     uint64_t cap, pos;
@@ -166,9 +174,26 @@ __device__ __forceinline__ int prefix_len(const ParState& S, uint32_t ia0, uint3
 }
 
 template <int K>
-__device__ __forceinline__ uint32_t token_size(int len) {
+__device__ __forceinline__ uint32_t token_size(const ParState& S, int len) {
     if (K == P_YAZ0) return len < 18 ? 2u : 3u;
+    if (K == P_LZ11) return S.lz40 ? (len < 16 ? 2u : len < 272 ? 3u : 4u) : (len <= 16 ? 2u : len <= 272 ? 3u : 4u);   // LZ40.cs:126-168, LZ11.cs:135-171
     return 2u;
+}
+
+// the common prefix beyond the ring's lookahead (LZ11 family: matches of up to 0x4000 bytes), byte by byte from the source
+__device__ __noinline__ int extend_global(const uint8_t* a, int distance, int l, int cap) {
+    const uint8_t* b = a - distance;
+    while (l + 4 <= cap) {
+        const uint32_t a0 = __ldg(a + l), a1 = __ldg(a + l + 1), a2 = __ldg(a + l + 2), a3 = __ldg(a + l + 3);
+        const uint32_t b0 = __ldg(b + l), b1 = __ldg(b + l + 1), b2 = __ldg(b + l + 2), b3 = __ldg(b + l + 3);
+        if (a0 != b0) return l;
+        if (a1 != b1) return l + 1;
+        if (a2 != b2) return l + 2;
+        if (a3 != b3) return l + 3;
+        l += 4;
+    }
+    while (l < cap && __ldg(a + l) == __ldg(b + l)) l++;
+    return l;
 }
 
 // ---- the parse of one step (FindNextBestMatch, :157-212).  `len`: the search results of the step's 32 positions (0 where
@@ -234,14 +259,14 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
     // ---- byte offsets: token bytes + one flag byte in front of every eighth token
     const uint32_t T = S.ntok + __popc(tok & lt);
     const bool opens = is_tok && (T & 7u) == 0;
-    const uint32_t sz = !is_tok ? 0u : (is_mat ? token_size<K>(len) : 1u) + (opens ? 1u : 0u);
+    const uint32_t sz = !is_tok ? 0u : (is_mat ? token_size<K>(S, len) : 1u) + (opens ? 1u : 0u);
     const uint32_t incl = warp_incl_scan(sz);
     const uint64_t at = S.pos + (incl - sz);          // first byte of my token (its flag byte, when it opens a group)
     const uint64_t tb = at + (opens ? 1u : 0u);       // token bytes
     const uint32_t total = __shfl_sync(kFull, incl, 31);
     // ---- flag bytes.  LZ10: 1 = match, MSB first; Yaz0: 1 = literal, MSB first; LZSS: 1 = literal, LSB first
     {
-        const bool bitv = (K == P_LZ10) ? is_mat : !is_mat;
+        const bool bitv = (K == P_LZ10 || K == P_LZ11) ? is_mat : !is_mat;
         const uint32_t sh = (K == P_LZSS) ? (T & 7u) : 7u - (T & 7u);
         const uint32_t contrib = (is_tok && bitv) ? 1u << sh : 0u;
         const uint32_t g = T >> 3;
@@ -254,7 +279,7 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
             fpos = S.carry_pos;
         }
         if (leader) {
-            if (fpos < S.cap) S.out[fpos] = uint8_t(fv);
+            if (fpos < S.cap) S.out[fpos] = uint8_t((K == P_LZ11 && S.lz40) ? 0u - fv : fv);   // LZ40.cs:137: (byte)-flag
             else S.overflow = true;
         }
         // carry the last group when it is still open
@@ -269,7 +294,7 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
     }
     // ---- token bytes
     if (is_tok) {
-        uint32_t b0, b1, b2 = 0, nb;
+        uint32_t b0, b1, b2 = 0, b3 = 0, nb;
         if (!is_mat) {
             b0 = ring_u8(S, base + lane);
             b1 = 0;
@@ -279,6 +304,44 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
             b0 = (v >> 8) & 0xFF;
             b1 = v & 0xFF;
             nb = 2;
+        } else if (K == P_LZ11 && S.lz40) {
+            // (ushort)(Distance << 4 | ...), little-endian: a distance of 0x1000 truncates to 0
+            const uint32_t dd = (uint32_t(dist) << 4) & 0xFFFFu;
+            b1 = dd >> 8;
+            if (len < 16) {
+                b0 = (dd | uint32_t(len)) & 0xFF;
+                nb = 2;
+            } else if (len < 272) {
+                b0 = dd & 0xFF;
+                b2 = uint32_t(len - 16) & 0xFF;
+                nb = 3;
+            } else {
+                b0 = (dd | 1u) & 0xFF;
+                b2 = uint32_t(len - 272) & 0xFF;
+                b3 = (uint32_t(len - 272) >> 8) & 0xFF;
+                nb = 4;
+            }
+        } else if (K == P_LZ11) {
+            const uint32_t d1 = uint32_t(dist - 1) & 0xFFFu;
+            if (len <= 16) {
+                const uint32_t v = (uint32_t(len - 1) << 12 | d1) & 0xFFFFu;
+                b0 = v >> 8;
+                b1 = v & 0xFF;
+                nb = 2;
+            } else if (len <= 272) {
+                const uint32_t v = (uint32_t(len - 17) << 12 | d1) & 0xFFFFu;
+                b0 = (uint32_t(len - 17) & 0xFF) >> 4;
+                b1 = v >> 8;
+                b2 = v & 0xFF;
+                nb = 3;
+            } else {
+                const uint32_t v = 0x10000000u | (uint32_t(len - 273) & 0xFFFFu) << 12 | d1;
+                b0 = v >> 24;
+                b1 = (v >> 16) & 0xFF;
+                b2 = (v >> 8) & 0xFF;
+                b3 = v & 0xFF;
+                nb = 4;
+            }
         } else if (K == P_YAZ0) {
             const uint32_t d1 = uint32_t(dist - 1) & 0xFFFu;
             if (len < 18) {
@@ -304,6 +367,7 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
             S.out[tb] = uint8_t(b0);
             if (nb > 1) S.out[tb + 1] = uint8_t(b1);
             if (nb > 2) S.out[tb + 2] = uint8_t(b2);
+            if (nb > 3) S.out[tb + 3] = uint8_t(b3);
         } else {
             S.overflow = true;
         }
@@ -387,7 +451,7 @@ __device__ __forceinline__ void put_u32p(ParState& S, uint32_t v, bool big) {
     for (int i = 0; i < 4; i++) put_byte(S, big ? (v >> (24 - 8 * i)) & 0xFF : (v >> (8 * i)) & 0xFF);
 }
 
-template <int K>
+template <int K, bool M>
 __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState& S) {
     const int lane = lane_id();
     const uint64_t n64 = P.src_len[idx];
@@ -415,12 +479,13 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
         S.pending = false;
         const bool big = P.byte_order != AURORA_ENDIAN_LITTLE;
         // ---- headers (as encode_lz.cu: LZ10.cs:67-80, Yaz0.cs:82-98, LZSS.cs:72-89; BLZ has none)
-        if (K == P_LZ10) {
+        if (K == P_LZ10 || K == P_LZ11) {
             if (P.format != AURORA_FMT_BLZ) {
+                const uint32_t id = K == P_LZ10 ? 0x10u : P.format == AURORA_FMT_LZ40 ? 0x40u : P.format == AURORA_FMT_LZ60 ? 0x60u : 0x11u;
                 if (n <= 0xFFFFFF) {
-                    put_u32p(S, 0x10u | (uint32_t(n) << 8), false);
+                    put_u32p(S, id | (uint32_t(n) << 8), false);
                 } else {
-                    put_u32p(S, 0x10u, false);
+                    put_u32p(S, id, false);
                     put_u32p(S, uint32_t(n), false);
                 }
             }
@@ -454,18 +519,24 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
             const uint32_t far = uint32_t(0 - 8192) & 0xFFFFu;
             const uint32_t w = far | (far << 16);
             for (int i = lane; i < kBuckets / 2; i += 32) sts_u32(S.head + 4 * i, w);
+            if (M)
+                for (int i = lane; i < kBuckets / 2; i += 32) sts_u32(S.head2 + 4 * i, w);
         }
         __syncwarp();
 
         int plen = 0, pdist = 0;   // results of the previous step
         for (int base = 0; base < n; base += 32) {
-            stage(S, base + 32 + S.max_len + 8);
+            stage(S, base + 32 + S.look + 8);
             if (base && (base & 0x3FFF) == 0) {
                 // heads that fell out of the window are parked 8192 positions back, so that their 16-bit age never wraps
                 const uint32_t b16 = uint32_t(base) & 0xFFFFu;
                 for (int i = lane; i < kBuckets; i += 32) {
                     const uint32_t e = lds_u16(S.head + 2 * i);
                     if (((b16 - e) & 0xFFFFu) > uint32_t(kWin)) sts_u16(S.head + 2 * i, (b16 - 8192u) & 0xFFFFu);
+                    if (M) {
+                        const uint32_t e2 = lds_u16(S.head2 + 2 * i);
+                        if (((b16 - e2) & 0xFFFFu) > uint32_t(kWin)) sts_u16(S.head2 + 2 * i, (b16 - 8192u) & 0xFFFFu);
+                    }
                 }
                 __syncwarp();
             }
@@ -475,10 +546,21 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
             const bool searched = valid && (S.pending || lane >= S.cur_off);
             int best_len = 0, best_dist = 0;
             uint32_t h = 0xFFFFFFFFu, bucket = 0xFFFFFFFFu, ip = 0;   // ip: ring index of my position
+            uint32_t hm = 0xFFFFFFFFu, bucket2 = 0xFFFFFFFFu;
             if (valid) {
                 ip = didx(uint32_t(p) + S.skew);
-                h = ((ring_u32_at(S, ip) * 2654435761u) >> S.hash_shift) & S.hash_mask;   // ComputeHash, :288-299
+                const uint32_t v4 = ring_u32_at(S, ip);
+                h = ((v4 * 2654435761u) >> S.hash_shift) & S.hash_mask;   // ComputeHash, :288-299
                 bucket = h & kBucketMask;
+                if (M) {
+                    hm = (((v4 & S.min_mask) * 2654435761u) >> 16) & 0xFFFFu;
+                    bucket2 = hm & kBucketMask;
+                }
+            }
+            uint32_t gm2b = 0, gm2h = 0, blink2 = 0;
+            if (M) {
+                gm2b = __match_any_sync(kFull, bucket2);
+                gm2h = __match_any_sync(kFull, hm);
             }
             const uint32_t tag = h >> kBucketBits;
             const uint32_t lt = (1u << lane) - 1u;
@@ -496,15 +578,22 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                 const int best_possible = min(n - p, S.max_len);
                 int attempts = S.max_chain;
                 bool done = false;
+                const int ring_cap = min(best_possible, S.look);   // what the ring can compare
                 auto candidate = [&](int distance) {
                     attempts--;
                     // a candidate can only beat the best match so far if it also matches at offset best_len: one byte decides
                     // most of the later candidates of a chain (the result is the same: a longer match agrees on that byte)
                     const uint32_t ic = dwrap(ip + kData - uint32_t(distance));   // ring index of the candidate (distance <= 4096 < kData)
-                    if (distance >= S.min_dist && (best_len == 0 || lds_u8(S.data + dwrap(ip + uint32_t(best_len))) == lds_u8(S.data + dwrap(ic + uint32_t(best_len))))) {
+                    bool may_win = distance >= S.min_dist;
+                    if (may_win && best_len != 0) {
+                        if (K != P_LZ11 || best_len < ring_cap) may_win = lds_u8(S.data + dwrap(ip + uint32_t(best_len))) == lds_u8(S.data + dwrap(ic + uint32_t(best_len)));
+                        else may_win = __ldg(S.src + p + best_len) == __ldg(S.src + p - distance + best_len);   // (best_len < best_possible <= n - p)
+                    }
+                    if (may_win) {
                         // the same distance as 32 positions earlier: that match's bytes behind the first 32 are equal here too
                         const int known = (distance == pdist && plen > 32) ? min(plen - 32, best_possible) : 0;
-                        int l = prefix_len(S, ip, ic, best_possible, known);
+                        int l = prefix_len(S, ip, ic, ring_cap, min(known, ring_cap));
+                        if (K == P_LZ11 && l == ring_cap && ring_cap < best_possible) l = extend_global(S.src + p, distance, max(known, ring_cap), best_possible);
                         if (S.no_self_overlap && l > distance) l = distance;
                         if (l >= S.min_len && l > best_len) {
                             best_len = l;
@@ -535,12 +624,57 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                         distance += bl;
                     }
                 }
+                if (M) {
+                    // ---- the small-match table (MatchSearch, :236-244): only when the chain gave nothing; ONE candidate, the latest
+                    // earlier position with my 16-bit hash of the first min_length bytes — whatever its distance
+                    const uint32_t e2 = lds_u16(S.head2 + 2 * bucket2);
+                    const uint32_t dd2 = (uint32_t(p) - e2) & 0xFFFFu;
+                    const bool head2_ok = dd2 >= 1 && dd2 <= uint32_t(kWin) && int(dd2) <= p;
+                    const uint32_t below2b = gm2b & lt;
+                    blink2 = below2b ? uint32_t(lane - (31 - __clz(int(below2b)))) : (head2_ok ? dd2 : 0u);
+                    if (searched && best_len == 0) {
+                        int qd = 0;
+                        const uint32_t below2h = gm2h & lt;
+                        if (below2h) {
+                            qd = lane - (31 - __clz(int(below2h)));
+                        } else if (head2_ok && int(dd2) <= S.max_dist) {
+                            int distance = int(dd2);
+                            for (;;) {
+                                const uint32_t nd = lds_u16(S.node2 + 2 * (uint32_t(p - distance) & kWinMask));
+                                if ((nd >> 13) == ((hm >> kBucketBits) & 7u) &&
+                                    ((((ring_u32_at(S, dwrap(ip + kData - uint32_t(distance))) & S.min_mask) * 2654435761u) >> 16) & 0xFFFFu) == hm) {
+                                    qd = distance;
+                                    break;
+                                }
+                                const int bl = int(nd & 0x1FFFu);
+                                if (bl == 0 || distance + bl > S.max_dist) break;
+                                distance += bl;
+                            }
+                        }
+                        if (qd) {
+                            const int distance = qd < S.min_dist ? S.min_dist : qd;
+                            // (a raised distance that points in front of the buffer is no match: finder.cuh, DESIGN.md section 2, deviation 6)
+                            if (distance <= S.max_dist && p - distance >= 0) {
+                                const uint32_t ic = dwrap(ip + kData - uint32_t(distance));
+                                int l = prefix_len(S, ip, ic, ring_cap, 0);
+                                if (K == P_LZ11 && l == ring_cap && ring_cap < best_possible) l = extend_global(S.src + p, distance, ring_cap, best_possible);
+                                if (S.no_self_overlap && l > distance) l = distance;
+                                best_len = l;
+                                best_dist = distance;
+                            }
+                        }
+                    }
+                }
             }
             __syncwarp();
             // ---- the step's positions enter the ring and the heads
             if (valid) {
                 sts_u16(S.node + 2 * (uint32_t(p) & kWinMask), blink | ((tag & 7u) << 13));
                 if ((gmb >> lane) <= 1u) sts_u16(S.head + 2 * bucket, uint32_t(p) & 0xFFFFu);   // the last lane of the bucket's group
+                if (M) {
+                    sts_u16(S.node2 + 2 * (uint32_t(p) & kWinMask), blink2 | (((hm >> kBucketBits) & 7u) << 13));
+                    if ((gm2b >> lane) <= 1u) sts_u16(S.head2 + 2 * bucket2, uint32_t(p) & 0xFFFFu);
+                }
             }
             __syncwarp();
             // ---- the token left pending at the end of the previous step: lazy test against this step's first result
@@ -596,21 +730,26 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
     __syncwarp();
 }
 
-template <int K>
-__global__ void __launch_bounds__(kParWarps * 32, 1) encode_lz_par_kernel(const EncodeParams P) {
+template <int K, bool M>
+__global__ void __launch_bounds__(kParWarps<M> * 32, 1) encode_lz_par_kernel(const EncodeParams P) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     ParState S;
-    const uint32_t t0 = smem_u32(smem) + uint32_t(warp) * kTablesPerWarp;
+    const uint32_t t0 = smem_u32(smem) + uint32_t(warp) * kTablesPerWarp<M>;
     S.head = t0;
     S.node = t0 + kBuckets * 2;
     S.data = S.node + kWin * 2;
+    S.head2 = S.data + kData;
+    S.node2 = S.head2 + kBuckets * 2;
+    S.min_mask = 0xFFFFFFFFu >> ((4 - (P.min_length < 4 ? P.min_length : 4)) * 8);
     S.hash_shift = 32 - P.hash_bits;
     S.hash_mask = (1u << P.hash_bits) - 1u;
     S.max_chain = P.max_chain;
     S.lazy = P.lazy_threshold;
     S.min_len = P.min_length;
     S.max_len = P.max_length;
+    S.look = P.max_length < kLook ? P.max_length : kLook;
+    S.lz40 = P.format == AURORA_FMT_LZ40 || P.format == AURORA_FMT_LZ60;
     S.min_dist = P.min_distance;
     S.max_dist = P.max_distance;
     S.no_self_overlap = P.no_self_overlap != 0;
@@ -619,32 +758,38 @@ __global__ void __launch_bounds__(kParWarps * 32, 1) encode_lz_par_kernel(const 
     S.lz_f = (1 << P.lzss.length_bits) - 1;
     S.lz_start = P.lzss.windows_start;
     S.lz_lbits = P.lzss.length_bits;
-    S.scratch = P.scratch + size_t(blockIdx.x * kParWarps + warp) * P.scratch_per_warp;
+    S.scratch = P.scratch + size_t(blockIdx.x * kParWarps<M> + warp) * P.scratch_per_warp;
     for (;;) {
         uint32_t t = 0;
         if (lane_id() == 0) t = atomicAdd(P.ticket, 1u);
         t = __shfl_sync(kFull, t, 0);
         if (t >= P.n) break;
-        encode_stream_par<K>(P, t, S);
+        encode_stream_par<K, M>(P, t, S);
     }
 }
 
-template <int K>
-cudaError_t launch_par(const EncodeParams& p, int sm_count, cudaStream_t st) {
-    const size_t smem = size_t(kParWarps) * kTablesPerWarp;
+template <int K, bool M>
+cudaError_t launch_par_m(const EncodeParams& p, int sm_count, cudaStream_t st) {
+    const size_t smem = size_t(kParWarps<M>) * kTablesPerWarp<M>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(encode_lz_par_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaError_t e = cudaFuncSetAttribute(encode_lz_par_kernel<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
     int blocks = sm_count;
-    const int needed = int((p.n + kParWarps - 1) / kParWarps);
+    const int needed = int((p.n + kParWarps<M> - 1) / kParWarps<M>);
     if (needed < blocks) blocks = needed > 0 ? needed : 1;
-    encode_lz_par_kernel<K><<<blocks, kParWarps * 32, smem, st>>>(p);
+    encode_lz_par_kernel<K, M><<<blocks, kParWarps<M> * 32, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+// the small-match table only exists at qualities >= 10 for formats whose shortest match is below 4 bytes (finder.cuh has_min)
+template <int K>
+cudaError_t launch_par(const EncodeParams& p, int sm_count, cudaStream_t st) {
+    return (p.use_min_table && p.min_length < 4) ? launch_par_m<K, true>(p, sm_count, st) : launch_par_m<K, false>(p, sm_count, st);
 }
 
 }  // namespace
@@ -653,8 +798,9 @@ cudaError_t launch_par(const EncodeParams& p, int sm_count, cudaStream_t st) {
 bool encode_lz_par_supported(const EncodeParams& p) {
     const bool fmt = p.format == AURORA_FMT_LZ10 || p.format == AURORA_FMT_BLZ || p.format == AURORA_FMT_YAZ0 || p.format == AURORA_FMT_YAZ1 ||
                      p.format == AURORA_FMT_LZSS || p.format == AURORA_FMT_MIO0 || p.format == AURORA_FMT_YAY0;
-    return fmt && !p.use_min_table && p.hash_bits >= kBucketBits && p.hash_bits <= 24 && p.max_distance <= kWin && p.chain_bits >= 12 &&
-           p.max_length <= 288 && p.min_length >= 1 && p.min_distance >= 1;
+    const bool lz11 = p.format == AURORA_FMT_LZ11 || p.format == AURORA_FMT_LZ40 || p.format == AURORA_FMT_LZ60;   // any max_length
+    return (lz11 || (fmt && p.max_length <= kLook)) && p.hash_bits >= kBucketBits && p.hash_bits <= 24 && p.max_distance <= kWin && p.chain_bits >= 12 &&
+           p.min_length >= 1 && p.min_distance >= 1;
 }
 
 cudaError_t launch_encode_lz_par(const EncodeParams& p, int sm_count, cudaStream_t st) {
@@ -666,6 +812,9 @@ cudaError_t launch_encode_lz_par(const EncodeParams& p, int sm_count, cudaStream
         case AURORA_FMT_LZSS: return launch_par<P_LZSS>(p, sm_count, st);
         case AURORA_FMT_MIO0: return launch_par<P_MIO0>(p, sm_count, st);
         case AURORA_FMT_YAY0: return launch_par<P_YAY0>(p, sm_count, st);
+        case AURORA_FMT_LZ11:
+        case AURORA_FMT_LZ40:
+        case AURORA_FMT_LZ60: return launch_par<P_LZ11>(p, sm_count, st);
         default: return cudaErrorNotSupported;
     }
 }

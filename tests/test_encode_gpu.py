@@ -105,18 +105,53 @@ def test_container_options(codec, oracle, bmp):
         _check(codec, oracle, A.FMT_PRS, [bmp[:40000], bytes(3000), bmp[1000:1100]], A.make_opts(quality=8, byte_order=order))
 
 
-PAR_FORMATS = [A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS, A.FMT_MIO0, A.FMT_YAY0]
+PAR_FORMATS = [A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS]
+PAR_FORMATS_WIDE = PAR_FORMATS + [A.FMT_MIO0, A.FMT_YAY0, A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60]
+FINDERS = pytest.mark.parametrize("finder", [A.STRATEGY_PARALLEL_FINDER, A.STRATEGY_SERIAL_FINDER], ids=["parallel", "serial"])
+
+
+def _finder_raws(bmp, rng, big):
+    sizes = [0, 1, 4, 31, 32, 33, 64, 65, 1000, 4096, 70000, 140000] if big else [0, 1, 4, 31, 32, 33, 64, 65, 1000, 4096, 20000]
+    return [bmp[:n] for n in ((5, 33, 4097, 200000) if big else (5, 33, 4097, 70000))] + [synth(rng, int(n), i % 5) for i, n in enumerate(sizes)]
 
 
 @pytest.mark.parametrize("fmt", PAR_FORMATS, ids=fmt_id)
-@pytest.mark.parametrize("finder", [A.STRATEGY_PARALLEL_FINDER, A.STRATEGY_SERIAL_FINDER], ids=["parallel", "serial"])
+@FINDERS
 @pytest.mark.parametrize("quality", [0, 3, 5, 8, 9])
 def test_both_finders_write_the_reference_bytes(codec, oracle, bmp, fmt, finder, quality):
     """The window search with one lane per position (encode_lz_par.cu) and the sequential replay (finder.cuh) are two
-    schedules of the same function: the reference's bytes, whichever is forced (opts.strategy bits 16 / 17), at every
-    quality below 10 — including streams longer than 64 KiB (16-bit table positions wrap), the lazy test across a 32-position
-    step, CompatibilityMode and ragged lengths."""
+    schedules of the same function: the reference's bytes, whichever is forced (opts.strategy bits 16 / 17) — including
+    streams longer than 64 KiB (16-bit table positions wrap), the lazy test across a 32-position step, CompatibilityMode
+    and ragged lengths."""
     rng = np.random.default_rng(4242 + fmt + quality)
-    raws = [bmp[:n] for n in (5, 33, 4097, 200000)] + [synth(rng, int(n), i % 5) for i, n in enumerate([0, 1, 4, 31, 32, 33, 64, 65, 1000, 4096, 70000, 140000])]
+    raws = _finder_raws(bmp, rng, big=True)
     _check(codec, oracle, fmt, raws, A.make_opts(quality=quality, strategy=finder))
     _check(codec, oracle, fmt, raws[:8], A.make_opts(quality=quality, strategy=finder | A.STRATEGY_COMPATIBILITY))
+
+
+@pytest.mark.parametrize("fmt", PAR_FORMATS_WIDE, ids=fmt_id)
+@FINDERS
+@pytest.mark.parametrize("quality", [2, 10, 15])
+def test_both_finders_every_format_and_quality(codec, oracle, bmp, fmt, finder, quality):
+    """The same for the formats and qualities added later: MIO0 / Yay0 (three output sections), the LZ11 family, and the
+    qualities from 10 on, where the reference consults its small-match table (smaller inputs: a quality-15 chain walk of
+    one 200 000-byte stream on ONE warp takes seconds)."""
+    rng = np.random.default_rng(977 + fmt + quality)
+    raws = _finder_raws(bmp, rng, big=False)
+    _check(codec, oracle, fmt, raws, A.make_opts(quality=quality, strategy=finder))
+    _check(codec, oracle, fmt, raws[4:10], A.make_opts(quality=quality, strategy=finder | A.STRATEGY_COMPATIBILITY))
+
+
+@pytest.mark.parametrize("fmt", [A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60], ids=fmt_id)
+@FINDERS
+@pytest.mark.parametrize("quality", [2, 11])
+def test_long_matches_of_the_lz11_family(codec, oracle, bmp, fmt, finder, quality):
+    """LZ11 / LZ40 / LZ60 matches reach 0x4000 bytes: the lane-per-position search compares the first 288 bytes in its
+    shared-memory ring and the rest from the source (4-byte tokens, runs, long periods, matches that end the stream)."""
+    rng = np.random.default_rng(77 + fmt + quality)
+    noise = rng.integers(0, 256, size=3000, dtype=np.uint8).tobytes()
+    raws = [bytes(100000), b"abcdefg" * 9000, bmp[:5000] + bytes(20000) + bmp[:5000] + bytes(40000), noise[:300] * 200,
+            noise + noise + noise[:1500] + noise, bytes(289), bytes(320), b"\x01" * 16384 + b"\x02" * 16390 + b"\x01" * 17000,
+            noise[:1000] + bytes(273 + 4) + noise[:999] + bytes(272 + 4) + noise[:17] + bytes(0x4000 + 5)]
+    _check(codec, oracle, fmt, raws, A.make_opts(quality=quality, strategy=finder))
+    _check(codec, oracle, fmt, raws[:5], A.make_opts(quality=quality, strategy=finder | A.STRATEGY_COMPATIBILITY))
