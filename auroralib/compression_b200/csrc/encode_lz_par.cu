@@ -730,14 +730,11 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
     __syncwarp();
 }
 
-template <int K, bool M>
-__global__ void __launch_bounds__(kParWarps<M> * 32, 1) encode_lz_par_kernel(const EncodeParams P) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int warp = threadIdx.x >> 5;
-    ParState S;
-    const uint32_t t0 = smem_u32(smem) + uint32_t(warp) * kTablesPerWarp<M>;
-    S.head = t0;
-    S.node = t0 + kBuckets * 2;
+// the per-warp state from the batch parameters; `tables`: shared address of this warp's tables, `scratch`: its slice of the
+// global scratch buffer (MIO0 / Yay0 sections).  (Also called by the CPU lane emulation of tests/simt.)
+__device__ __forceinline__ void par_setup(ParState& S, const EncodeParams& P, uint32_t tables, uint8_t* scratch) {
+    S.head = tables;
+    S.node = tables + kBuckets * 2;
     S.data = S.node + kWin * 2;
     S.head2 = S.data + kData;
     S.node2 = S.head2 + kBuckets * 2;
@@ -758,7 +755,16 @@ __global__ void __launch_bounds__(kParWarps<M> * 32, 1) encode_lz_par_kernel(con
     S.lz_f = (1 << P.lzss.length_bits) - 1;
     S.lz_start = P.lzss.windows_start;
     S.lz_lbits = P.lzss.length_bits;
-    S.scratch = P.scratch + size_t(blockIdx.x * kParWarps<M> + warp) * P.scratch_per_warp;
+    S.scratch = scratch;
+}
+
+// ---- kernel
+template <int K, bool M>
+__global__ void __launch_bounds__(kParWarps<M> * 32, 1) encode_lz_par_kernel(const EncodeParams P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    ParState S;
+    par_setup(S, P, smem_u32(smem) + uint32_t(warp) * kTablesPerWarp<M>, P.scratch + size_t(blockIdx.x * kParWarps<M> + warp) * P.scratch_per_warp);
     for (;;) {
         uint32_t t = 0;
         if (lane_id() == 0) t = atomicAdd(P.ticket, 1u);

@@ -1,0 +1,18 @@
+// tests/simt/cuda_runtime.h — stand-in for the CUDA runtime header when a kernel source file is compiled for the CPU lane
+// emulation (tests/simt/simt.hpp).  Only what csrc/common.cuh's host part and csrc/encode_lz_par.cu's device part mention.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+struct uint4 {
+    uint32_t x, y, z, w;
+};
+struct uint2 {
+    uint32_t x, y;
+};
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))

@@ -1,0 +1,186 @@
+// tests/simt/simt.hpp — a 32-lane warp on the CPU: every lane is a fiber (ucontext), warp collectives are rendezvous points.
+// TEST INFRASTRUCTURE.  It lets the `-m "not gpu"` suite execute the DEVICE SOURCE of a kernel (compiled by g++ with the
+// stand-in headers of this directory) and compare its output with the oracle, so the lane-level logic of the shipped
+// kernel — not a second restatement of it — is checked where there is no GPU.  What it models: lanes run one after the
+// other between collectives; __shfl / __shfl_up / __ballot / __match_any / __reduce_or / __syncwarp need ALL 32 lanes
+// (the emulated sources only use them convergently) and fail loudly on a divergent call; shared memory is a bounds-checked
+// byte array addressed by offsets; __ldg checks the registered source range.  What it does not model: timing, memory
+// ordering between lanes inside a collective-free region (a missing __syncwarp is only caught when the lane order exposes it).
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <functional>
+
+namespace simt {
+
+enum Op { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_BALLOT, OP_MATCH_ANY, OP_REDUCE_OR, OP_SYNC };
+
+struct Warp {
+    static constexpr int kLanes = 32;
+    static constexpr size_t kStack = 256 * 1024;
+    ucontext_t sched, ctx[kLanes];
+    char* stack[kLanes];
+    bool finished[kLanes], waiting[kLanes];
+    int cur = 0;
+    int op[kLanes];
+    uint64_t val[kLanes], res[kLanes];
+    uint32_t aux[kLanes];
+    std::function<void(int)> body;
+    // memory
+    uint8_t* smem = nullptr;
+    size_t smem_size = 0;
+    const uint8_t* g_lo = nullptr;   // readable global range for __ldg
+    const uint8_t* g_hi = nullptr;
+    const char* error = nullptr;
+    uint64_t collectives = 0;
+};
+
+inline Warp*& current() {
+    static thread_local Warp* w = nullptr;
+    return w;
+}
+
+[[noreturn]] inline void fail(const char* what) {
+    fprintf(stderr, "simt: %s (lane %d)\n", what, current() ? current()->cur : -1);
+    abort();
+}
+
+inline void trampoline(int lane) {
+    Warp* w = current();
+    w->body(lane);
+    w->finished[lane] = true;
+    swapcontext(&w->ctx[lane], &w->sched);
+}
+
+// deposit an operand and yield until every lane has arrived
+inline uint64_t collective(int op, uint64_t v, uint32_t aux) {
+    Warp* w = current();
+    const int l = w->cur;
+    w->op[l] = op;
+    w->val[l] = v;
+    w->aux[l] = aux;
+    w->waiting[l] = true;
+    swapcontext(&w->ctx[l], &w->sched);
+    return w->res[l];
+}
+
+inline void resolve(Warp* w) {
+    const int op = w->op[0];
+    for (int l = 0; l < Warp::kLanes; l++)
+        if (w->op[l] != op) fail("divergent collective: lanes wait in different warp primitives");
+    w->collectives++;
+    for (int l = 0; l < Warp::kLanes; l++) {
+        uint64_t r = 0;
+        switch (op) {
+            case OP_SHFL: r = w->val[w->aux[l] & 31]; break;
+            case OP_SHFL_UP: r = l >= int(w->aux[l]) ? w->val[l - int(w->aux[l])] : w->val[l]; break;
+            case OP_BALLOT:
+                for (int j = 0; j < 32; j++) r |= uint64_t(w->val[j] != 0) << j;
+                break;
+            case OP_MATCH_ANY:
+                for (int j = 0; j < 32; j++) r |= uint64_t(w->val[j] == w->val[l]) << j;
+                break;
+            case OP_REDUCE_OR:
+                if (!((w->aux[l] >> l) & 1u)) fail("__reduce_or_sync: the calling lane is not in its own mask");
+                for (int j = 0; j < 32; j++)
+                    if ((w->aux[l] >> j) & 1u) {
+                        if (w->aux[j] != w->aux[l]) fail("__reduce_or_sync: lanes of one group passed different masks");
+                        r |= w->val[j];
+                    }
+                break;
+            default: break;
+        }
+        w->res[l] = r;
+    }
+    for (int l = 0; l < Warp::kLanes; l++) w->waiting[l] = false;
+}
+
+// run `body(lane)` on 32 lanes to completion
+inline void run_warp(Warp& w, std::function<void(int)> body) {
+    current() = &w;
+    w.body = std::move(body);
+    for (int l = 0; l < Warp::kLanes; l++) {
+        w.finished[l] = w.waiting[l] = false;
+        w.stack[l] = static_cast<char*>(malloc(Warp::kStack));
+        getcontext(&w.ctx[l]);
+        w.ctx[l].uc_stack.ss_sp = w.stack[l];
+        w.ctx[l].uc_stack.ss_size = Warp::kStack;
+        w.ctx[l].uc_link = &w.sched;
+        makecontext(&w.ctx[l], reinterpret_cast<void (*)()>(trampoline), 1, l);
+    }
+    for (;;) {
+        int done = 0, waiting = 0;
+        for (int l = 0; l < Warp::kLanes; l++) {
+            if (w.finished[l]) {
+                done++;
+                continue;
+            }
+            if (!w.waiting[l]) {
+                w.cur = l;
+                swapcontext(&w.sched, &w.ctx[l]);
+            }
+            if (w.finished[l]) done++;
+            else if (w.waiting[l]) waiting++;
+        }
+        if (done == Warp::kLanes) break;
+        if (waiting + done == Warp::kLanes) {
+            if (done != 0) fail("a lane left the kernel while others wait in a warp primitive");
+            resolve(&w);
+        }
+    }
+    for (int l = 0; l < Warp::kLanes; l++) free(w.stack[l]);
+    current() = nullptr;
+}
+
+}  // namespace simt
+
+// ---- the CUDA names the emulated sources use -------------------------------------------------------------------------------
+inline int simt_lane() { return simt::current()->cur; }
+template <class T>
+inline T __shfl_sync(unsigned mask, T v, int src) {
+    if (mask != 0xFFFFFFFFu) simt::fail("__shfl_sync with a partial mask is not modelled");
+    return T(simt::collective(simt::OP_SHFL, uint64_t(v), uint32_t(src)));
+}
+template <class T>
+inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
+    if (mask != 0xFFFFFFFFu) simt::fail("__shfl_up_sync with a partial mask is not modelled");
+    return T(simt::collective(simt::OP_SHFL_UP, uint64_t(v), delta));
+}
+inline unsigned __ballot_sync(unsigned mask, int pred) {
+    if (mask != 0xFFFFFFFFu) simt::fail("__ballot_sync with a partial mask is not modelled");
+    return unsigned(simt::collective(simt::OP_BALLOT, uint64_t(pred != 0), 0));
+}
+inline unsigned __match_any_sync(unsigned mask, uint32_t v) {
+    if (mask != 0xFFFFFFFFu) simt::fail("__match_any_sync with a partial mask is not modelled");
+    return unsigned(simt::collective(simt::OP_MATCH_ANY, uint64_t(v), 0));
+}
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v) { return unsigned(simt::collective(simt::OP_REDUCE_OR, uint64_t(v), mask)); }
+inline void __syncwarp() { simt::collective(simt::OP_SYNC, 0, 0); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(unsigned(v)); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) { return uint32_t(((uint64_t(hi) << 32) | lo) >> (shift & 31)); }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+template <class T>
+inline T __ldg(const T* p) {
+    const simt::Warp* w = simt::current();
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(p);
+    if (b < w->g_lo || b + sizeof(T) > w->g_hi) simt::fail("__ldg outside the batch's source bytes");
+    T v;
+    memcpy(&v, p, sizeof(T));
+    return v;
+}
+// shared memory: addresses are byte offsets into the warp's array
+inline uint8_t* simt_smem(uint32_t addr, uint32_t bytes) {
+    simt::Warp* w = simt::current();
+    if (size_t(addr) + bytes > w->smem_size) simt::fail("shared-memory access outside the warp's tables");
+    if (addr % bytes) simt::fail("misaligned shared-memory access");
+    return w->smem + addr;
+}

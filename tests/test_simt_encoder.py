@@ -1,0 +1,167 @@
+"""The lane-per-position encoder kernel's DEVICE SOURCE (csrc/encode_lz_par.cu, everything above its kernel entry) compiled by
+g++ and run on a 32-lane CPU emulation (tests/simt/: one fiber per lane, warp primitives as rendezvous points, bounds-checked
+shared memory), compared byte for byte with the oracle.  No GPU: this is the check of the kernel's lane-level logic that runs in
+the CPU suite — every format and quality of the search, the small-match table, matches beyond the data ring's lookahead, the
+three-section writer, CompatibilityMode, unaligned sources, too-small destinations — on more inputs than GPU time allows."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from auroralib.compression_b200 import _abi as A
+from tests.util import fmt_id, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIMT = os.path.join(ROOT, "tests", "simt")
+CSRC = os.path.join(ROOT, "auroralib", "compression_b200", "csrc")
+PAR_FORMATS = [A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS, A.FMT_MIO0, A.FMT_YAY0, A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60]
+
+
+@pytest.fixture(scope="session")
+def simt_lib():
+    build = os.path.join(SIMT, "build")
+    os.makedirs(build, exist_ok=True)
+    src = open(os.path.join(CSRC, "encode_lz_par.cu")).read()
+    inc = os.path.join(build, "encode_lz_par_device.inc")
+    with open(inc, "w") as f:
+        f.write(src[:src.index("// ---- kernel\n")])   # the device functions; the kernel entry and the launcher stay out
+    so = os.path.join(build, "libsimt_par.so")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-I", SIMT,
+                           f'-DAURORA_REAL_COMMON="{os.path.join(CSRC, "common.cuh")}"', f'-DPAR_DEVICE_INC="{inc}"',
+                           os.path.join(SIMT, "par_harness.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    lib.simt_encode_lz_par.restype = C.c_int
+    return lib
+
+
+def _isqrt2q(q):
+    r = 0
+    while (r + 1) * (r + 1) <= 2 * q:
+        r += 1
+    return r
+
+
+def finder_params(fmt, quality, strategy=0, vram_mode=-1, lzss=None):
+    """CompressionSettings + LzProperties -> LzChainMatchFinder parameters (LzChainMatchFinder.cs:42-119), as api.cu
+    fill_encode_params derives them."""
+    if fmt == A.FMT_LZ10:
+        lz = A.lz_props_window(0x1000, 18, 3, 0, 2 if vram_mode != 0 else 1)
+    elif fmt == A.FMT_BLZ:
+        lz = A.lz_props_window(0x1000, 18, 3, 0, 3)
+    elif fmt in (A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60):
+        lz = A.lz_props_window(0x1000, 0x4000, 3, 0, 2 if vram_mode > 0 else 1)
+    elif fmt in (A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_YAY0):
+        lz = A.lz_props_window(0x1000, 0xFF + 0x12, 3, 0, 1)
+    elif fmt == A.FMT_MIO0:
+        lz = A.lz_props_window(0x1000, 18, 3, 0, 1)
+    else:
+        lz = lzss if lzss is not None else A.lz_props_bits(12, 4, 2)
+    q = quality
+    max_chain = q + 1 if q < 6 else 1 << (q - 5) if q >= 11 else (1 << (q >> 1)) | ((1 << (q >> 1)) >> (q & 1))
+    finder = [max_chain, 3 + q // 3, 15 + _isqrt2q(q), min(17 + _isqrt2q(q), max(1, lz.windows_bits)), lz.min_length, lz.max_length,
+              lz.min_distance, lz.max_distance, strategy & 1, 1 if q >= 10 else 0]
+    return finder, [lz.windows_bits, lz.length_bits, lz.min_length, lz.max_distance, lz.windows_start]
+
+
+def simt_encode(lib, fmt, raws, quality, strategy=0, byte_order=A.ENDIAN_DEFAULT, vram_mode=-1, lzss=None, yaz0_alignment=0,
+                caps=None, skew=0):
+    n = len(raws)
+    finder, lzp = finder_params(fmt, quality, strategy, vram_mode, lzss)
+    # sources back to back from an odd offset (any alignment is allowed), readable up to the next multiple of 16
+    off, pos = [], skew
+    for r in raws:
+        off.append(pos)
+        pos += len(r) + (pos % 3)
+    limit = (pos + 15) & ~15
+    backing = np.zeros(limit + 64, dtype=np.uint8)
+    a0 = (-backing.ctypes.data) % 16
+    src = backing[a0:a0 + limit]
+    for o, r in zip(off, raws):
+        src[o:o + len(r)] = np.frombuffer(r, dtype=np.uint8)
+    if caps is None:
+        caps = [len(r) + len(r) // 8 + 64 for r in raws]
+    doff, dpos = [], 0
+    for c in caps:
+        doff.append(dpos)
+        dpos += c + 8
+    dst = np.full(dpos + 8, 0xEE, dtype=np.uint8)
+    longest = max([len(r) for r in raws] + [0])
+    spw = 2 * (longest + 64) + 256
+    scratch = np.full(spw + 64, 0xEE, dtype=np.uint8)
+    out_len = np.zeros(n, dtype=np.uint64)
+    status = np.full(n, 77, dtype=np.int32)
+    u64 = lambda v: np.asarray(v, dtype=np.uint64)
+    src_off, src_len, dst_off, dst_cap = u64(off), u64([len(r) for r in raws]), u64(doff), u64(caps)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.simt_encode_lz_par(C.c_int(fmt), C.c_int(byte_order), (C.c_int * 10)(*finder), C.c_uint32(yaz0_alignment), (C.c_int * 5)(*lzp),
+                                p(src), C.c_uint64(limit), p(src_off), p(src_len), p(dst), p(dst_off), p(dst_cap), p(out_len), p(status),
+                                C.c_uint32(n), p(scratch), C.c_uint64(spw))
+    assert rc == 0
+    assert (scratch[spw:] == 0xEE).all(), "the section staging ran over its slice of the scratch buffer"
+    outs = []
+    for i in range(n):
+        assert (dst[doff[i] + caps[i]:doff[i] + caps[i] + 8] == 0xEE).all(), f"stream {i}: bytes written past the capacity"
+        outs.append(dst[doff[i]:doff[i] + min(int(out_len[i]), caps[i])].tobytes())
+    return outs, status, out_len
+
+
+def _check(lib, oracle, fmt, raws, quality, **kw):
+    okw = {k: v for k, v in kw.items() if k not in ("skew",)}
+    ref, rst = oracle.encode_batch(fmt, raws, A.make_opts(quality=quality, **okw))
+    if fmt == A.FMT_BLZ:
+        # BLZ.cs:143-215: the kernel writes the token body of the REVERSED source (LZ10's layout, distance - 3); the host side
+        # reverses that body and appends padding + footer (api.cu), so the reference's stream starts with the reversed body
+        got, st, _ = simt_encode(lib, fmt, [r[::-1] for r in raws], quality, **kw)
+        assert (st == 0).all()
+        bad = [i for i in range(len(raws)) if rst[i] == 0 and not (ref[i].startswith(got[i][::-1]) and len(ref[i]) - len(got[i]) <= 24)]
+    else:
+        got, st, _ = simt_encode(lib, fmt, raws, quality, **kw)
+        assert (st == rst).all(), (fmt_id(fmt), quality, st, rst)
+        bad = [i for i in range(len(raws)) if got[i] != ref[i]]
+    assert not bad, f"{fmt_id(fmt)} q{quality}: stream #{bad[0]} (len {len(raws[bad[0]])}) differs from the oracle encoder: {len(got[bad[0]])} vs {len(ref[bad[0]])} bytes"
+
+
+@pytest.mark.parametrize("fmt", PAR_FORMATS, ids=fmt_id)
+@pytest.mark.parametrize("quality", [0, 3, 8, 10, 15])
+def test_kernel_source_on_emulated_lanes(simt_lib, oracle, bmp, fmt, quality):
+    rng = np.random.default_rng(31 * fmt + quality)
+    raws = [bmp[:n] for n in (5, 33, 4097, 9000)] + [synth(rng, int(n), i % 5) for i, n in enumerate([0, 1, 4, 31, 32, 33, 64, 65, 1000, 4096, 6000, 12000])]
+    _check(simt_lib, oracle, fmt, raws, quality, skew=int(rng.integers(0, 16)))
+    _check(simt_lib, oracle, fmt, raws[3:12], quality, strategy=A.STRATEGY_COMPATIBILITY, skew=int(rng.integers(0, 16)))
+
+
+@pytest.mark.parametrize("fmt", [A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60], ids=fmt_id)
+@pytest.mark.parametrize("quality", [2, 11])
+def test_matches_beyond_the_ring_lookahead(simt_lib, oracle, bmp, fmt, quality):
+    rng = np.random.default_rng(5 + fmt + quality)
+    noise = rng.integers(0, 256, size=3000, dtype=np.uint8).tobytes()
+    raws = [bytes(40000), b"abcdefg" * 3000, noise[:300] * 60, noise + noise + noise[:1500] + noise, bytes(289), bytes(320),
+            b"\x01" * 16384 + b"\x02" * 16390 + b"\x01" * 400, noise[:1000] + bytes(273 + 4) + noise[:999] + bytes(272 + 4) + noise[:17] + bytes(0x4000 + 5)]
+    _check(simt_lib, oracle, fmt, raws, quality, skew=3)
+    _check(simt_lib, oracle, fmt, [raws[3], raws[4], raws[5]], quality, strategy=A.STRATEGY_COMPATIBILITY)
+
+
+def test_streams_over_64k_wrap_the_table_positions(simt_lib, oracle, bmp):
+    rng = np.random.default_rng(8)
+    raws = [bmp[:70000], synth(rng, 140000, 0), synth(rng, 70000, 2)]
+    for fmt, q in ((A.FMT_LZ10, 8), (A.FMT_YAZ0, 5), (A.FMT_MIO0, 10), (A.FMT_LZ11, 12)):
+        _check(simt_lib, oracle, fmt, raws, q)
+
+
+def test_options_and_small_destinations(simt_lib, oracle, bmp):
+    raws = [bmp[1000:9000], bytes(5000), bmp[:7]]
+    for vram in (0, 1):
+        _check(simt_lib, oracle, A.FMT_LZ10, raws, 8, vram_mode=vram)
+        _check(simt_lib, oracle, A.FMT_LZ11, raws, 10, vram_mode=vram)
+    for order in (A.ENDIAN_BIG, A.ENDIAN_LITTLE):
+        for fmt in (A.FMT_YAZ0, A.FMT_YAY0, A.FMT_MIO0):
+            _check(simt_lib, oracle, fmt, raws, 4, byte_order=order)
+    _check(simt_lib, oracle, A.FMT_YAZ0, raws, 4, yaz0_alignment=0x20)
+    for props in (A.lz_props_bits(10, 6, 2), A.lz_props_bits(12, 4, 2), A.lz_props_window(0x1000, 18, 3, 0xFEE)):
+        _check(simt_lib, oracle, A.FMT_LZSS, raws, 8, lzss=props)
+        _check(simt_lib, oracle, A.FMT_LZSS, raws, 12, lzss=props)
+    for fmt in PAR_FORMATS:   # a destination of 100 bytes: DST_TOO_SMALL, the needed length reported, nothing written past the capacity
+        got, st, out_len = simt_encode(simt_lib, fmt, [bmp[:20000]], 3, caps=[100])
+        assert st[0] == A.DST_TOO_SMALL and out_len[0] > 100, fmt_id(fmt)
