@@ -304,6 +304,7 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
                     status = lz4_block_encode(f, src + sp, block_len, o);
                     const uint64_t csize = o.pos - hdr - 4;
                     if (csize >= bs) {   // stored block
+                        __syncwarp();   // the attempt's bytes (all lanes copy literals) are overwritten: order the two
                         o.pos = hdr;
                         o.u32le(uint32_t(block_len) | 0x80000000u);
                         o.copy(src + sp, uint32_t(block_len));
@@ -334,6 +335,7 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
                     snappy_block_encode(f, src + p, chunk, o);
                     const uint64_t csize = o.pos - hdr - 8;
                     if (csize >= uint64_t(chunk)) {   // stored chunk
+                        __syncwarp();   // (as for LZ4's stored blocks; found by the lane emulation of tests/simt)
                         o.pos = hdr;
                         o.byte(1);
                         o.u24le(uint32_t(chunk + 4));
@@ -373,6 +375,7 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
     __syncwarp();
 }
 
+// ---- kernel
 __global__ void __launch_bounds__(kEncWarpsPerBlock * 32) encode_bytelz_kernel(const EncodeParams P) {
     const int warp_global = blockIdx.x * kEncWarpsPerBlock + (threadIdx.x >> 5);
     uint8_t* scratch = P.scratch + size_t(warp_global) * P.scratch_per_warp;

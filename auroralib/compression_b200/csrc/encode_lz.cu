@@ -261,6 +261,7 @@ __device__ void encode_stream(const EncodeParams& P, uint32_t idx, Finder& f) {
     __syncwarp();
 }
 
+// ---- kernel
 template <int K>
 __global__ void __launch_bounds__(kEncWarpsPerBlock * 32) encode_lz_kernel(const EncodeParams P) {
     const int warp_global = blockIdx.x * kEncWarpsPerBlock + (threadIdx.x >> 5);

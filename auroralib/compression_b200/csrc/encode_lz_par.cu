@@ -591,10 +591,13 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                     }
                     if (may_win) {
                         // the same distance as 32 positions earlier: that match's bytes behind the first 32 are equal here too
-                        const int known = (distance == pdist && plen > 32) ? min(plen - 32, best_possible) : 0;
-                        int l = prefix_len(S, ip, ic, ring_cap, min(known, ring_cap));
-                        if (K == P_LZ11 && l == ring_cap && ring_cap < best_possible) l = extend_global(S.src + p, distance, max(known, ring_cap), best_possible);
-                        if (S.no_self_overlap && l > distance) l = distance;
+                        // CompatibilityMode cuts a match to its distance (LzChainMatchFinder.cs:304): comparing further cannot change the result (the
+                        // reference compares best_possible bytes first, which makes long runs quadratic there)
+                        const int cap = S.no_self_overlap ? min(best_possible, distance) : best_possible;
+                        const int rcap = min(cap, ring_cap);
+                        const int known = (distance == pdist && plen > 32) ? min(plen - 32, cap) : 0;
+                        int l = prefix_len(S, ip, ic, rcap, min(known, rcap));
+                        if (K == P_LZ11 && l == rcap && rcap < cap) l = extend_global(S.src + p, distance, max(known, rcap), cap);
                         if (l >= S.min_len && l > best_len) {
                             best_len = l;
                             best_dist = distance;
@@ -656,9 +659,10 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                             // (a raised distance that points in front of the buffer is no match: finder.cuh, DESIGN.md section 2, deviation 6)
                             if (distance <= S.max_dist && p - distance >= 0) {
                                 const uint32_t ic = dwrap(ip + kData - uint32_t(distance));
-                                int l = prefix_len(S, ip, ic, ring_cap, 0);
-                                if (K == P_LZ11 && l == ring_cap && ring_cap < best_possible) l = extend_global(S.src + p, distance, ring_cap, best_possible);
-                                if (S.no_self_overlap && l > distance) l = distance;
+                                const int cap = S.no_self_overlap ? min(best_possible, distance) : best_possible;
+                                const int rcap = min(cap, ring_cap);
+                                int l = prefix_len(S, ip, ic, rcap, 0);
+                                if (K == P_LZ11 && l == rcap && rcap < cap) l = extend_global(S.src + p, distance, rcap, cap);
                                 best_len = l;
                                 best_dist = distance;
                             }

@@ -71,8 +71,8 @@ static __device__ __forceinline__ void match_search(Finder& f, const uint8_t* da
             cur = next;
             continue;
         }
-        int len = match_length(data, pos, cur, best_possible);
-        if (f.no_self_overlap && len > distance) len = distance;
+        // CompatibilityMode cuts a match to its distance (:304): comparing further cannot change the result
+        const int len = match_length(data, pos, cur, f.no_self_overlap ? min(best_possible, distance) : best_possible);
         const int score = len - f.min_len;
         if (score > best_score) {
             best_score = score;
@@ -90,8 +90,7 @@ static __device__ __forceinline__ void match_search(Finder& f, const uint8_t* da
             // (a raised distance that points in front of the buffer is no match: the reference compares through an unsafe
             //  pointer against whatever memory precedes the source there — undefined; DESIGN.md section 2, deviation 6)
             if (distance <= f.max_dist && pos - distance >= 0) {
-                best_len = match_length(data, pos, pos - distance, best_possible);
-                if (f.no_self_overlap && best_len > distance) best_len = distance;
+                best_len = match_length(data, pos, pos - distance, f.no_self_overlap ? min(best_possible, distance) : best_possible);
                 best_dist = distance;
             }
         }

@@ -16,3 +16,9 @@ struct uint2 {
 #define __global__
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
+struct int4 {
+    int x, y, z, w;
+};
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+#define __constant__
+static inline void __threadfence_block() {}

@@ -1,4 +1,5 @@
-"""The lane-per-position encoder kernel's DEVICE SOURCE (csrc/encode_lz_par.cu, everything above its kernel entry) compiled by
+"""The encoder kernels' DEVICE SOURCE (csrc/encode_lz_par.cu: one lane per window position; csrc/encode_lz.cu, encode_bytelz.cu
+with finder.cuh: the sequential replay — everything above each file's kernel entry) compiled by
 g++ and run on a 32-lane CPU emulation (tests/simt/: one fiber per lane, warp primitives as rendezvous points, bounds-checked
 shared memory), compared byte for byte with the oracle.  No GPU: this is the check of the kernel's lane-level logic that runs in
 the CPU suite — every format and quality of the search, the small-match table, matches beyond the data ring's lookahead, the
@@ -19,21 +20,36 @@ CSRC = os.path.join(ROOT, "auroralib", "compression_b200", "csrc")
 PAR_FORMATS = [A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS, A.FMT_MIO0, A.FMT_YAY0, A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60]
 
 
-@pytest.fixture(scope="session")
-def simt_lib():
+def _build(name, harness, macro, extra=()):
     build = os.path.join(SIMT, "build")
     os.makedirs(build, exist_ok=True)
-    src = open(os.path.join(CSRC, "encode_lz_par.cu")).read()
-    inc = os.path.join(build, "encode_lz_par_device.inc")
+    src = open(os.path.join(CSRC, name + ".cu")).read()
+    inc = os.path.join(build, name + "_device.inc")
     with open(inc, "w") as f:
         f.write(src[:src.index("// ---- kernel\n")])   # the device functions; the kernel entry and the launcher stay out
-    so = os.path.join(build, "libsimt_par.so")
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-I", SIMT,
-                           f'-DAURORA_REAL_COMMON="{os.path.join(CSRC, "common.cuh")}"', f'-DPAR_DEVICE_INC="{inc}"',
-                           os.path.join(SIMT, "par_harness.cpp"), "-o", so])
-    lib = C.CDLL(so)
-    lib.simt_encode_lz_par.restype = C.c_int
-    return lib
+    so = os.path.join(build, f"libsimt_{name}.so")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-I", SIMT, "-I", CSRC,
+                           f'-DAURORA_REAL_COMMON="{os.path.join(CSRC, "common.cuh")}"', f'-D{macro}="{inc}"', *extra,
+                           os.path.join(SIMT, harness), "-o", so])
+    return C.CDLL(so)
+
+
+class SimtLibs:
+    def __init__(self):
+        self.par = _build("encode_lz_par", "par_harness.cpp", "PAR_DEVICE_INC").simt_encode_lz_par
+        self.seq_flag = _build("encode_lz", "seq_harness.cpp", "SEQ_DEVICE_INC").simt_encode_seq
+        self.seq_byte = _build("encode_bytelz", "seq_harness.cpp", "SEQ_DEVICE_INC", ["-DSEQ_BYTELZ"]).simt_encode_seq
+        for f in (self.par, self.seq_flag, self.seq_byte):
+            f.restype = C.c_int
+
+
+@pytest.fixture(scope="session")
+def simt_lib():
+    return SimtLibs()
+
+
+BYTE_FORMATS = [A.FMT_LZ4, A.FMT_LZ4_LEGACY, A.FMT_LZ4_BLOCK, A.FMT_LZO, A.FMT_SNAPPY, A.FMT_SNAPPY_BLOCK, A.FMT_PRS]
+SEQ_FLAG_FORMATS = PAR_FORMATS + [A.FMT_LZHUDSON, A.FMT_SMSR00]
 
 
 def _isqrt2q(q):
@@ -52,10 +68,18 @@ def finder_params(fmt, quality, strategy=0, vram_mode=-1, lzss=None):
         lz = A.lz_props_window(0x1000, 18, 3, 0, 3)
     elif fmt in (A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60):
         lz = A.lz_props_window(0x1000, 0x4000, 3, 0, 2 if vram_mode > 0 else 1)
-    elif fmt in (A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_YAY0):
+    elif fmt in (A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_YAY0, A.FMT_LZHUDSON):
         lz = A.lz_props_window(0x1000, 0xFF + 0x12, 3, 0, 1)
-    elif fmt == A.FMT_MIO0:
+    elif fmt in (A.FMT_MIO0, A.FMT_SMSR00):
         lz = A.lz_props_window(0x1000, 18, 3, 0, 1)
+    elif fmt in (A.FMT_LZ4, A.FMT_LZ4_LEGACY, A.FMT_LZ4_BLOCK):
+        lz = A.lz_props_window(0xFFFF, 0x7FFFFFFF, 4, 0, 1)
+    elif fmt == A.FMT_LZO:
+        lz = A.lz_props_window(0xBFFF, 0x7FFFFFFF, 3, 0, 1)
+    elif fmt in (A.FMT_SNAPPY, A.FMT_SNAPPY_BLOCK):
+        lz = A.lz_props_window(0x8000, 64, 4, 0, 1)
+    elif fmt == A.FMT_PRS:
+        lz = A.lz_props_window(0x1FFF, 0x100, 2, 0, 1)
     else:
         lz = lzss if lzss is not None else A.lz_props_bits(12, 4, 2)
     q = quality
@@ -66,7 +90,8 @@ def finder_params(fmt, quality, strategy=0, vram_mode=-1, lzss=None):
 
 
 def simt_encode(lib, fmt, raws, quality, strategy=0, byte_order=A.ENDIAN_DEFAULT, vram_mode=-1, lzss=None, yaz0_alignment=0,
-                caps=None, skew=0):
+                caps=None, skew=0, seq=False, lz4_block_size=0):
+    """One emulated warp encodes `raws`: the lane-per-position search, or (seq) the sequential replay of finder.cuh."""
     n = len(raws)
     finder, lzp = finder_params(fmt, quality, strategy, vram_mode, lzss)
     # sources back to back from an odd offset (any alignment is allowed), readable up to the next multiple of 16
@@ -81,7 +106,7 @@ def simt_encode(lib, fmt, raws, quality, strategy=0, byte_order=A.ENDIAN_DEFAULT
     for o, r in zip(off, raws):
         src[o:o + len(r)] = np.frombuffer(r, dtype=np.uint8)
     if caps is None:
-        caps = [len(r) + len(r) // 8 + 64 for r in raws]
+        caps = [len(r) + len(r) // 6 + 256 for r in raws]
     doff, dpos = [], 0
     for c in caps:
         doff.append(dpos)
@@ -89,15 +114,24 @@ def simt_encode(lib, fmt, raws, quality, strategy=0, byte_order=A.ENDIAN_DEFAULT
     dst = np.full(dpos + 8, 0xEE, dtype=np.uint8)
     longest = max([len(r) for r in raws] + [0])
     spw = 2 * (longest + 64) + 256
-    scratch = np.full(spw + 64, 0xEE, dtype=np.uint8)
+    if seq:   # csrc/encode_lz.cu encode_scratch_per_warp: head + chain + small-match tables in front of the section staging
+        spw = ((4 << finder[2]) + (4 << finder[3]) + 65536 * 4 + 2 * (longest + 64) + 255) & ~255
+    backing_s = np.full(spw + 128, 0xEE, dtype=np.uint8)
+    s0 = (-backing_s.ctypes.data) % 16
+    scratch = backing_s[s0:s0 + spw + 64]
     out_len = np.zeros(n, dtype=np.uint64)
     status = np.full(n, 77, dtype=np.int32)
     u64 = lambda v: np.asarray(v, dtype=np.uint64)
     src_off, src_len, dst_off, dst_cap = u64(off), u64([len(r) for r in raws]), u64(doff), u64(caps)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.simt_encode_lz_par(C.c_int(fmt), C.c_int(byte_order), (C.c_int * 10)(*finder), C.c_uint32(yaz0_alignment), (C.c_int * 5)(*lzp),
-                                p(src), C.c_uint64(limit), p(src_off), p(src_len), p(dst), p(dst_off), p(dst_cap), p(out_len), p(status),
-                                C.c_uint32(n), p(scratch), C.c_uint64(spw))
+    tail = (p(src), C.c_uint64(limit), p(src_off), p(src_len), p(dst), p(dst_off), p(dst_cap), p(out_len), p(status), C.c_uint32(n),
+            p(scratch), C.c_uint64(spw))
+    head = (C.c_int(fmt), C.c_int(byte_order), (C.c_int * 10)(*finder), C.c_uint32(yaz0_alignment))
+    if seq:
+        entry = lib.seq_byte if fmt in BYTE_FORMATS else lib.seq_flag
+        rc = entry(*head, C.c_uint32(lz4_block_size or 0x400000), (C.c_int * 5)(*lzp), *tail)
+    else:
+        rc = lib.par(*head, (C.c_int * 5)(*lzp), *tail)
     assert rc == 0
     assert (scratch[spw:] == 0xEE).all(), "the section staging ran over its slice of the scratch buffer"
     outs = []
@@ -108,18 +142,19 @@ def simt_encode(lib, fmt, raws, quality, strategy=0, byte_order=A.ENDIAN_DEFAULT
 
 
 def _check(lib, oracle, fmt, raws, quality, **kw):
-    okw = {k: v for k, v in kw.items() if k not in ("skew",)}
+    okw = {k: v for k, v in kw.items() if k not in ("skew", "seq")}
     ref, rst = oracle.encode_batch(fmt, raws, A.make_opts(quality=quality, **okw))
     if fmt == A.FMT_BLZ:
         # BLZ.cs:143-215: the kernel writes the token body of the REVERSED source (LZ10's layout, distance - 3); the host side
         # reverses that body and appends padding + footer (api.cu), so the reference's stream starts with the reversed body
         got, st, _ = simt_encode(lib, fmt, [r[::-1] for r in raws], quality, **kw)
         assert (st == 0).all()
+        ref = [x if len(r) else b"" for x, r in zip(ref, raws)]
         bad = [i for i in range(len(raws)) if rst[i] == 0 and not (ref[i].startswith(got[i][::-1]) and len(ref[i]) - len(got[i]) <= 24)]
     else:
         got, st, _ = simt_encode(lib, fmt, raws, quality, **kw)
         assert (st == rst).all(), (fmt_id(fmt), quality, st, rst)
-        bad = [i for i in range(len(raws)) if got[i] != ref[i]]
+        bad = [i for i in range(len(raws)) if rst[i] == 0 and got[i] != ref[i]]   # (a failed stream's bytes are unspecified)
     assert not bad, f"{fmt_id(fmt)} q{quality}: stream #{bad[0]} (len {len(raws[bad[0]])}) differs from the oracle encoder: {len(got[bad[0]])} vs {len(ref[bad[0]])} bytes"
 
 
@@ -165,3 +200,13 @@ def test_options_and_small_destinations(simt_lib, oracle, bmp):
     for fmt in PAR_FORMATS:   # a destination of 100 bytes: DST_TOO_SMALL, the needed length reported, nothing written past the capacity
         got, st, out_len = simt_encode(simt_lib, fmt, [bmp[:20000]], 3, caps=[100])
         assert st[0] == A.DST_TOO_SMALL and out_len[0] > 100, fmt_id(fmt)
+
+
+@pytest.mark.parametrize("fmt", SEQ_FLAG_FORMATS + BYTE_FORMATS, ids=fmt_id)
+@pytest.mark.parametrize("quality", [0, 8, 12])
+def test_sequential_replay_on_emulated_lanes(simt_lib, oracle, bmp, fmt, quality):
+    """finder.cuh with the token writers of encode_lz.cu / encode_bytelz.cu: the finder every format falls back to."""
+    rng = np.random.default_rng(17 * fmt + quality)
+    raws = [bmp[:n] for n in (5, 33, 4097, 6000)] + [synth(rng, int(n), i % 5) for i, n in enumerate([0, 1, 4, 31, 32, 33, 64, 65, 1000, 4096, 5000, 7000])]
+    _check(simt_lib, oracle, fmt, raws, quality, seq=True, skew=int(rng.integers(0, 16)))
+    _check(simt_lib, oracle, fmt, raws[3:12], quality, seq=True, strategy=A.STRATEGY_COMPATIBILITY)
