@@ -13,7 +13,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 O.build()
 codec = BatchCodec(1)
 bad_total = cases = 0
-for fmt in (A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS, A.FMT_MIO0, A.FMT_LZ11, A.FMT_LZ4_BLOCK, A.FMT_LZO, A.FMT_PRS):
+for fmt in (A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS, A.FMT_MIO0, A.FMT_YAY0, A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60, A.FMT_LZ4_BLOCK, A.FMT_LZO, A.FMT_PRS):
     for q in (0, 1, 2, 4, 6, 7, 9, 10, 15):
         rng = np.random.default_rng(seed * 100000 + fmt * 100 + q)
         raws = [synth(rng, int(rng.choice([rng.integers(0, 70), rng.integers(70, 5000), rng.integers(5000, 150000)], p=[0.2, 0.5, 0.3])), int(rng.integers(0, 5))) for _ in range(n)]
