@@ -151,7 +151,7 @@ int fill_decode_params(DecodeParams& p, int format, const aurora_codec_opts* o) 
 }
 
 cudaError_t launch_encode(const EncodeParams& p, int warps, cudaStream_t st) {
-    // Flag-byte formats (LZ10 / BLZ, LZ11 / LZ40 / LZ60, Yaz0 / Yaz1, LZSS, MIO0, Yay0): the window search with one lane per
+    // Flag-byte formats (LZ10 / BLZ, LZ11 / LZ40 / LZ60, Yaz0 / Yaz1, LZSS, MIO0, Yay0, LZHudson, SMSR00): the window search with one lane per
     // position and shared-memory tables (encode_lz_par.cu).  Both encoders write the reference's bytes; which one runs is a
     // speed decision.  Measured on the C2 corpus (64 KiB streams, GB/s raw in, parallel / sequential replay): quality 8 LZ10
     // 14.6 / 8.1, Yaz0 16.1 / 10.4, MIO0 12.6 / 6.5, Yay0 13.3 / 6.4, LZ11 10.8 / 5.9; quality 10-12 LZ10 5.3 / 4.3, LZ11

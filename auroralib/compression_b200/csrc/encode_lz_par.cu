@@ -1,5 +1,5 @@
 // encode_lz_par.cu — the window match search of the flag-byte encoders with ONE LANE PER WINDOW POSITION and shared-memory
-// hash tables (LZ10 / BLZ, Yaz0 / Yaz1, LZSS, MIO0, Yay0 at qualities below 10).  One raw buffer per warp, 32 positions per step.
+// hash tables (LZ10 / BLZ, LZ11 / LZ40 / LZ60, Yaz0 / Yaz1, LZSS, MIO0, Yay0, LZHudson, SMSR00; every quality).  One raw buffer per warp, 32 positions per step.
 //
 // The output is byte-identical to the reference encoder (and to the sequential replay in encode_lz.cu / finder.cuh, which
 // stays for the other formats and qualities): what LzChainMatchFinder computes at a position depends only on the bytes
@@ -55,7 +55,11 @@ constexpr int kTablesPerWarp = (kBuckets * 2 + kWin * 2) * (M ? 2 : 1) + int(kDa
 template <bool M>
 constexpr int kParWarps = (227 * 1024) / kTablesPerWarp<M> > 16 ? 16 : (227 * 1024) / kTablesPerWarp<M>;   // one block per SM
 
-enum ParKind { P_LZ10 = 0, P_YAZ0 = 1, P_LZSS = 2, P_MIO0 = 3, P_YAY0 = 4, P_LZ11 = 5 };   // P_LZ11: LZ11 / LZ40 / LZ60
+enum ParKind { P_LZ10 = 0, P_YAZ0 = 1, P_LZSS = 2, P_MIO0 = 3, P_YAY0 = 4, P_LZ11 = 5, P_HUDSON = 6, P_SMSR = 7 };   // P_LZ11: LZ11 / LZ40 / LZ60
+// tokens per flag word: LZHudson writes Yaz0's tokens under 32-bit big-endian flag words (LZHudson.cs:48-59), SMSR00 MIO0's
+// codes under 16-bit ones with the literals in a section of their own (SMSR00.cs:60-75); everything else has flag bytes
+template <int K>
+constexpr uint32_t kGroup = K == P_HUDSON ? 32u : K == P_SMSR ? 16u : 8u;
 // MIO0 / Yay0 write three sections (flag bytes, match codes, literal bytes: MIO0.cs:159-184, Yay0.cs:152-184)
 template <int K>
 constexpr bool kSplit = K == P_MIO0 || K == P_YAY0;
@@ -175,7 +179,7 @@ __device__ __forceinline__ int prefix_len(const ParState& S, uint32_t ia0, uint3
 
 template <int K>
 __device__ __forceinline__ uint32_t token_size(const ParState& S, int len) {
-    if (K == P_YAZ0) return len < 18 ? 2u : 3u;
+    if (K == P_YAZ0 || K == P_HUDSON) return len < 18 ? 2u : 3u;
     if (K == P_LZ11) return S.lz40 ? (len < 16 ? 2u : len < 272 ? 3u : 4u) : (len <= 16 ? 2u : len <= 272 ? 3u : 4u);   // LZ40.cs:126-168, LZ11.cs:135-171
     return 2u;
 }
@@ -256,31 +260,41 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
     const uint32_t tok = lit | mat;
     if (tok == 0) return;
     const bool is_tok = (tok >> lane) & 1u, is_mat = (mat >> lane) & 1u;
-    // ---- byte offsets: token bytes + one flag byte in front of every eighth token
+    // ---- byte offsets: token bytes + one flag word (G / 8 bytes) in front of every G-th token
+    constexpr uint32_t G = kGroup<K>, FB = G / 8;
     const uint32_t T = S.ntok + __popc(tok & lt);
-    const bool opens = is_tok && (T & 7u) == 0;
-    const uint32_t sz = !is_tok ? 0u : (is_mat ? token_size<K>(S, len) : 1u) + (opens ? 1u : 0u);
+    const bool opens = is_tok && (T & (G - 1u)) == 0;
+    const uint32_t sz = !is_tok ? 0u : (is_mat ? token_size<K>(S, len) : (K == P_SMSR ? 0u : 1u)) + (opens ? FB : 0u);
     const uint32_t incl = warp_incl_scan(sz);
-    const uint64_t at = S.pos + (incl - sz);          // first byte of my token (its flag byte, when it opens a group)
-    const uint64_t tb = at + (opens ? 1u : 0u);       // token bytes
+    const uint64_t at = S.pos + (incl - sz);          // first byte of my token (its flag word, when it opens a group)
+    const uint64_t tb = at + (opens ? FB : 0u);       // token bytes
     const uint32_t total = __shfl_sync(kFull, incl, 31);
-    // ---- flag bytes.  LZ10: 1 = match, MSB first; Yaz0: 1 = literal, MSB first; LZSS: 1 = literal, LSB first
+    // ---- flag words.  LZ10 / LZ11: 1 = match, MSB first; Yaz0 / LZHudson / SMSR00: 1 = literal, MSB first; LZSS: 1 = literal, LSB first
     {
         const bool bitv = (K == P_LZ10 || K == P_LZ11) ? is_mat : !is_mat;
-        const uint32_t sh = (K == P_LZSS) ? (T & 7u) : 7u - (T & 7u);
+        const uint32_t sh = (K == P_LZSS) ? (T & 7u) : G - 1u - (T & (G - 1u));
         const uint32_t contrib = (is_tok && bitv) ? 1u << sh : 0u;
-        const uint32_t g = T >> 3;
+        const uint32_t g = T / G;
         const uint32_t gm = __match_any_sync(kFull, is_tok ? g : 0xFFFFFFFFu);
         uint32_t fv = __reduce_or_sync(gm, contrib);
         const bool leader = is_tok && (gm & lt) == 0;   // first token of the group within this step
-        uint64_t fpos = at;                             // a group opened in this step: the byte in front of its first token
+        uint64_t fpos = at;                             // a group opened in this step: the word in front of its first token
         if (leader && !opens) {                         // the group was opened by an earlier step
             fv |= S.carry_flag;
             fpos = S.carry_pos;
         }
         if (leader) {
-            if (fpos < S.cap) S.out[fpos] = uint8_t((K == P_LZ11 && S.lz40) ? 0u - fv : fv);   // LZ40.cs:137: (byte)-flag
-            else S.overflow = true;
+            if (fpos + FB <= S.cap) {
+                if (FB == 1) {
+                    S.out[fpos] = uint8_t((K == P_LZ11 && S.lz40) ? 0u - fv : fv);   // LZ40.cs:137: (byte)-flag
+                } else {
+                    for (uint32_t i = 0; i < FB; i++) S.out[fpos + i] = uint8_t(fv >> (8 * (FB - 1 - i)));   // big-endian word
+                }
+            } else {
+                for (uint32_t i = 0; i < FB; i++)
+                    if (fpos + i < S.cap) S.out[fpos + i] = uint8_t(fv >> (8 * (FB - 1 - i)));
+                S.overflow = true;
+            }
         }
         // carry the last group when it is still open
         const uint32_t ntok = __popc(tok);
@@ -289,7 +303,7 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
         const uint32_t cf = __shfl_sync(kFull, fv, lead_lane);
         const uint32_t cplo = __shfl_sync(kFull, uint32_t(fpos), lead_lane), cphi = __shfl_sync(kFull, uint32_t(fpos >> 32), lead_lane);
         S.ntok += ntok;
-        S.carry_flag = (S.ntok & 7u) ? cf : 0u;
+        S.carry_flag = (S.ntok & (G - 1u)) ? cf : 0u;
         S.carry_pos = uint64_t(cplo) | (uint64_t(cphi) << 32);
     }
     // ---- token bytes
@@ -299,6 +313,15 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
             b0 = ring_u8(S, base + lane);
             b1 = 0;
             nb = 1;
+            if (K == P_SMSR) {   // the literal section, in token order
+                S.lits[S.nlits + __popc(lit & lt)] = uint8_t(b0);
+                nb = 0;
+            }
+        } else if (K == P_SMSR) {
+            const uint32_t v = (uint32_t(dist - 1) | uint32_t(len - 3) << 12) & 0xFFFFu;   // MIO0's code
+            b0 = v >> 8;
+            b1 = v & 0xFF;
+            nb = 2;
         } else if (K == P_LZ10) {
             const uint32_t v = uint32_t(len - 3) << 12 | (uint32_t(dist - (S.blz ? 3 : 1)) & 0xFFFu);   // BLZ.cs: distance - 3
             b0 = (v >> 8) & 0xFF;
@@ -342,7 +365,7 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
                 b3 = v & 0xFF;
                 nb = 4;
             }
-        } else if (K == P_YAZ0) {
+        } else if (K == P_YAZ0 || K == P_HUDSON) {
             const uint32_t d1 = uint32_t(dist - 1) & 0xFFFu;
             if (len < 18) {
                 const uint32_t v = (uint32_t(dist - 1) | uint32_t(len - 2) << 12) & 0xFFFFu;
@@ -364,7 +387,7 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
             nb = 2;
         }
         if (tb + nb <= S.cap) {
-            S.out[tb] = uint8_t(b0);
+            if (nb > 0) S.out[tb] = uint8_t(b0);
             if (nb > 1) S.out[tb + 1] = uint8_t(b1);
             if (nb > 2) S.out[tb + 2] = uint8_t(b2);
             if (nb > 3) S.out[tb + 3] = uint8_t(b3);
@@ -372,6 +395,7 @@ __device__ __forceinline__ void write_step(ParState& S, int base, int len, int d
             S.overflow = true;
         }
     }
+    if (K == P_SMSR) S.nlits += __popc(lit);
     S.pos += total;
 }
 
@@ -489,6 +513,19 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
                     put_u32p(S, uint32_t(n), false);
                 }
             }
+        } else if (K == P_HUDSON) {
+            put_u32p(S, uint32_t(n), true);   // LZHudson.cs:48-59: the size, then Yay0.CompressHeaderless under 4-byte flag words
+        } else if (K == P_SMSR) {
+            // SMSR00.cs:60-75: "SMSR00", u16 0, BE size, BE pointer to the literal section (patched below)
+            const char* magic = "SMSR00";
+            for (int i = 0; i < 6; i++) put_byte(S, uint8_t(magic[i]));
+            put_byte(S, 0);
+            put_byte(S, 0);
+            put_u32p(S, uint32_t(n), true);
+            put_u32p(S, 0, true);
+            S.codes = S.scratch + P.scratch_per_warp - 2 * (size_t(n) + 64);   // (the layout of encode_lz.cu; only the literal half is used)
+            S.lits = S.codes + size_t(n) + 32;
+            S.ncodes = S.nlits = 0;
         } else if (K == P_YAZ0) {
             const char* magic = P.format == AURORA_FMT_YAZ1 ? "Yaz1" : "Yaz0";
             for (int i = 0; i < 4; i++) put_byte(S, uint8_t(magic[i]));
@@ -708,6 +745,18 @@ __device__ void encode_stream_par(const EncodeParams& P, uint32_t idx, ParState&
             put_u32p(S, uint32_t(save - body_start), true);
             S.pos = save;
         }
+        if (K == P_SMSR) {
+            // the literal section follows the mask / code section
+            __syncwarp();
+            const uint64_t lit_off = S.pos;
+            for (uint32_t i = lane; i < S.nlits; i += 32)
+                if (lit_off + i < S.cap) S.out[lit_off + i] = S.lits[i];
+            if (lit_off + S.nlits > S.cap) S.overflow = true;
+            S.pos = 12;
+            put_u32p(S, uint32_t(lit_off), true);
+            S.pos = lit_off + S.nlits;
+            __syncwarp();
+        }
         if (kSplit<K>) {
             // the flag section is complete (every step wrote its groups, open ones included): codes and literals follow it
             __syncwarp();
@@ -807,7 +856,8 @@ cudaError_t launch_par(const EncodeParams& p, int sm_count, cudaStream_t st) {
 // the formats / settings the parallel search reproduces exactly (everything else: encode_lz.cu)
 bool encode_lz_par_supported(const EncodeParams& p) {
     const bool fmt = p.format == AURORA_FMT_LZ10 || p.format == AURORA_FMT_BLZ || p.format == AURORA_FMT_YAZ0 || p.format == AURORA_FMT_YAZ1 ||
-                     p.format == AURORA_FMT_LZSS || p.format == AURORA_FMT_MIO0 || p.format == AURORA_FMT_YAY0;
+                     p.format == AURORA_FMT_LZSS || p.format == AURORA_FMT_MIO0 || p.format == AURORA_FMT_YAY0 ||
+                     p.format == AURORA_FMT_LZHUDSON || p.format == AURORA_FMT_SMSR00;
     const bool lz11 = p.format == AURORA_FMT_LZ11 || p.format == AURORA_FMT_LZ40 || p.format == AURORA_FMT_LZ60;   // any max_length
     return (lz11 || (fmt && p.max_length <= kLook)) && p.hash_bits >= kBucketBits && p.hash_bits <= 24 && p.max_distance <= kWin && p.chain_bits >= 12 &&
            p.min_length >= 1 && p.min_distance >= 1;
@@ -825,6 +875,8 @@ cudaError_t launch_encode_lz_par(const EncodeParams& p, int sm_count, cudaStream
         case AURORA_FMT_LZ11:
         case AURORA_FMT_LZ40:
         case AURORA_FMT_LZ60: return launch_par<P_LZ11>(p, sm_count, st);
+        case AURORA_FMT_LZHUDSON: return launch_par<P_HUDSON>(p, sm_count, st);
+        case AURORA_FMT_SMSR00: return launch_par<P_SMSR>(p, sm_count, st);
         default: return cudaErrorNotSupported;
     }
 }

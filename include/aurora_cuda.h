@@ -111,7 +111,7 @@ typedef struct aurora_lz_props {
 
 /* Blittable option block shared by decode and encode.  Zero-initialise, set struct_size. */
 /* opts.strategy, library-specific bits: which of the two byte-identical match finders encodes the flag-byte formats
- * (LZ10 / BLZ, LZ11 / LZ40 / LZ60, Yaz0 / Yaz1, LZSS, MIO0, Yay0; every quality).  Default: the parallel one, except the
+ * (LZ10 / BLZ, LZ11 / LZ40 / LZ60, Yaz0 / Yaz1, LZSS, MIO0, Yay0, LZHudson, SMSR00; every quality).  Default: the parallel one, except the
  * formats with matches longer than 32 bytes from quality 13 on, where the sequential replay is faster */
 #define AURORA_STRATEGY_PARALLEL_FINDER 0x10000   /* one lane per window position, shared-memory tables (encode_lz_par.cu) */
 #define AURORA_STRATEGY_SERIAL_FINDER   0x20000   /* sequential replay of LzChainMatchFinder (finder.cuh)                  */

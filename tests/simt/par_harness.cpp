@@ -77,6 +77,8 @@ extern "C" int simt_encode_lz_par(int format, int byte_order, const int* finder 
         case AURORA_FMT_LZ11:
         case AURORA_FMT_LZ40:
         case AURORA_FMT_LZ60: return run_kind<P_LZ11>(P);
+        case AURORA_FMT_LZHUDSON: return run_kind<P_HUDSON>(P);
+        case AURORA_FMT_SMSR00: return run_kind<P_SMSR>(P);
         default: return -1;
     }
 }

@@ -106,7 +106,7 @@ def test_container_options(codec, oracle, bmp):
 
 
 PAR_FORMATS = [A.FMT_LZ10, A.FMT_BLZ, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS]
-PAR_FORMATS_WIDE = PAR_FORMATS + [A.FMT_MIO0, A.FMT_YAY0, A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60]
+PAR_FORMATS_WIDE = PAR_FORMATS + [A.FMT_MIO0, A.FMT_YAY0, A.FMT_LZ11, A.FMT_LZ40, A.FMT_LZ60, A.FMT_LZHUDSON, A.FMT_SMSR00]
 FINDERS = pytest.mark.parametrize("finder", [A.STRATEGY_PARALLEL_FINDER, A.STRATEGY_SERIAL_FINDER], ids=["parallel", "serial"])
 
 
@@ -133,7 +133,8 @@ def test_both_finders_write_the_reference_bytes(codec, oracle, bmp, fmt, finder,
 @FINDERS
 @pytest.mark.parametrize("quality", [2, 10, 15])
 def test_both_finders_every_format_and_quality(codec, oracle, bmp, fmt, finder, quality):
-    """The same for the formats and qualities added later: MIO0 / Yay0 (three output sections), the LZ11 family, and the
+    """The same for the formats and qualities added later: MIO0 / Yay0 (three output sections), the LZ11 family, LZHudson /
+    SMSR00 (32- and 16-token flag words), and the
     qualities from 10 on, where the reference consults its small-match table (smaller inputs: a quality-15 chain walk of
     one 200 000-byte stream on ONE warp takes seconds)."""
     rng = np.random.default_rng(977 + fmt + quality)
