@@ -405,9 +405,7 @@ def other_configs(codec, dev, ts, peak, raw_c2, args):
     r_len = torch.full((n2,), size, **_i64(dev))
     # (the two match finders write the same bytes: the search with one lane per window position — the kernel family BASELINE.json's
     #  north star names — is the default; the sequential replay of the reference's loop is timed next to it)
-    for name, fmt, strategy in (("C5_lz10_encode", A.FMT_LZ10, 0), ("C5_yaz0_encode", A.FMT_YAZ0, 0),
-                                ("C5_lz10_encode_sequential_replay", A.FMT_LZ10, A.STRATEGY_SERIAL_FINDER),
-                                ("C5_yaz0_encode_sequential_replay", A.FMT_YAZ0, A.STRATEGY_SERIAL_FINDER)):
+    def c5(name, fmt, strategy):
         opts = A.make_opts(quality=QUALITY, strategy=strategy)
         best, packed = 1e30, None
         for _ in range(2):
@@ -427,6 +425,20 @@ def other_configs(codec, dev, ts, peak, raw_c2, args):
                                                   "algorithmic_bytes": n2 * size + comp_bytes, "kernel_ms": round(best, 3)}}
         del packed, d_dst
         torch.cuda.empty_cache()
+
+    for name, fmt, strategy in (("C5_lz10_encode", A.FMT_LZ10, 0), ("C5_yaz0_encode", A.FMT_YAZ0, 0),
+                                ("C5_lz10_encode_sequential_replay", A.FMT_LZ10, A.STRATEGY_SERIAL_FINDER),
+                                ("C5_yaz0_encode_sequential_replay", A.FMT_YAZ0, A.STRATEGY_SERIAL_FINDER)):
+        c5(name, fmt, strategy)
+    # the other formats of the lane-per-position search (added at the end of round 2): reported, never allowed to break the line
+    for name, fmt in (("C5_mio0_encode", A.FMT_MIO0), ("C5_yay0_encode", A.FMT_YAY0), ("C5_lz11_encode", A.FMT_LZ11)):
+        try:
+            c5(name, fmt, 0)
+        except Exception as e:   # noqa: BLE001
+            out[name] = {"format": A.FORMAT_NAMES[fmt], "error": f"{type(e).__name__}: {e}"[:200], "verified": False}
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
     if args.quick:
         return out
     # (the library's device buffers only grow — encoder scratch is sized by the largest stream of a batch — so every group of
