@@ -1,5 +1,5 @@
 """Developer tool (no GPU): differential fuzz of the lane-per-position encoder's device source on the CPU lane emulation
-(tests/simt) against the oracle.  Usage: python tools/fuzz_simt.py [cases] [seed]
+(tests/simt) against the oracle.  Usage: python tools/fuzz_simt.py [cases] [seed] [big]
 Every case runs the lane-per-position search and, for a third of the cases, the sequential replay (any encoder format)."""
 import os
 import sys
@@ -18,6 +18,7 @@ from tests.util import synth  # noqa: E402
 def main():
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    big = len(sys.argv) > 3 and sys.argv[3] == "big"   # a third of the buffers over 64 KiB (16-bit table positions wrap)
     lib = T.SimtLibs()   # builds the three emulation libraries from the current kernel sources
     O.build()
     rng = np.random.default_rng(seed)
@@ -40,6 +41,8 @@ def main():
         raws = []
         for i in range(int(rng.integers(1, 10))):
             n = int(rng.choice([0, 1, 3, 4, 5, 31, 32, 33, 63, 64, 65, 100, 1000, 4095, 4096, 4097, 5000, 9000, 20000]))
+            if big and rng.integers(0, 3) == 0:
+                n = int(rng.integers(65536, 150000))
             kind = int(rng.integers(0, 6))
             if kind == 5:
                 o = int(rng.integers(0, len(bmp) - n - 1))
