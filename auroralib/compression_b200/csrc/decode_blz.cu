@@ -112,6 +112,7 @@ __device__ void blz_decode_stream(const DecodeParams& P, uint32_t idx) {
     __syncwarp();
 }
 
+// ---- kernel
 __global__ void __launch_bounds__(kBlzWarpsPerBlock * 32) decode_blz_kernel(const DecodeParams P) {
     for (;;) {
         uint32_t t = 0;

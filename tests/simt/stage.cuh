@@ -24,6 +24,15 @@ inline void sts_u128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
     const uint32_t v[4] = {x, y, z, w};
     memcpy(simt_smem(a, 16), v, 16);
 }
+// ceil(2^20 / d) (csrc/stage.cuh: the constant-memory reciprocal table of the self-overlapping copies)
+struct RcpTable {
+    uint32_t v[512];
+    constexpr RcpTable() : v() {
+        for (uint32_t d = 1; d < 512; ++d) v[d] = ((1u << 20) + d - 1) / d;
+    }
+};
+static const RcpTable c_rcp = RcpTable();
+
 // the same code as csrc/stage.cuh
 inline uint32_t warp_incl_scan(uint32_t v) {
     const int lane = lane_id();

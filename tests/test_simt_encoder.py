@@ -211,3 +211,62 @@ def test_sequential_replay_on_emulated_lanes(simt_lib, oracle, bmp, fmt, quality
     raws = [bmp[:n] for n in (5, 33, 4097, 6000)] + [synth(rng, int(n), i % 5) for i, n in enumerate([0, 1, 4, 31, 32, 33, 64, 65, 1000, 4096, 5000, 7000])]
     _check(simt_lib, oracle, fmt, raws, quality, seq=True, skew=int(rng.integers(0, 16)))
     _check(simt_lib, oracle, fmt, raws[3:12], quality, seq=True, strategy=A.STRATEGY_COMPATIBILITY)
+
+
+# ---- a decoder on the same emulation: Nintendo BLZ (csrc/decode_blz.cu, the one kernel that keeps everything in global memory)
+@pytest.fixture(scope="session")
+def simt_blz():
+    f = _build("decode_blz", "blz_harness.cpp", "BLZ_DEVICE_INC").simt_decode_blz
+    f.restype = C.c_int
+    return f
+
+
+def simt_decode_blz(entry, comps, caps):
+    n = len(comps)
+    off, pos = [], 5
+    for c in comps:
+        off.append(pos)
+        pos += len(c) + 3
+    src = np.zeros(pos + 32, dtype=np.uint8)
+    for o, c in zip(off, comps):
+        src[o:o + len(c)] = np.frombuffer(c, dtype=np.uint8)
+    doff, dpos = [], 0
+    for c in caps:
+        doff.append(dpos)
+        dpos += c + 8
+    dst = np.full(dpos + 8, 0xEE, dtype=np.uint8)
+    out_len, consumed = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+    status = np.full(n, 77, dtype=np.int32)
+    u64 = lambda v: np.asarray(v, dtype=np.uint64)
+    src_off, src_len, dst_off, dst_cap = u64(off), u64([len(c) for c in comps]), u64(doff), u64(caps)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    entry(p(src), C.c_uint64(len(src)), p(src_off), p(src_len), p(dst), p(dst_off), p(dst_cap), p(out_len), p(consumed), p(status),
+          C.c_uint32(n), C.c_int(0))
+    outs = []
+    for i in range(n):
+        assert (dst[doff[i] + caps[i]:doff[i] + caps[i] + 8] == 0xEE).all(), f"stream {i}: bytes written past the capacity"
+        outs.append(dst[doff[i]:doff[i] + int(out_len[i])].tobytes() if status[i] == 0 else b"")
+    return outs, out_len, consumed, status
+
+
+def test_blz_decoder_on_emulated_lanes(simt_blz, oracle, bmp):
+    from tests.util import corrupt
+    rng = np.random.default_rng(2026)
+    raws = [bmp[:n] for n in (33, 4097, 9000)] + [synth(rng, int(n), i % 5) for i, n in enumerate([1, 4, 31, 32, 33, 64, 65, 1000, 4096, 6000, 12000])]
+    comps, st = oracle.encode_batch(A.FMT_BLZ, raws, A.make_opts(quality=8))
+    assert (st == 0).all()
+    streams, caps = [], []
+    for i, (c, r) in enumerate(zip(comps, raws)):
+        streams.append(c)
+        caps.append(len(r))
+        for mode in range(5):   # truncated, one byte flipped, garbage appended, empty, cut inside the header
+            streams.append(corrupt(rng, c, mode))
+            caps.append(len(r) if i % 2 else len(r) + 100)
+        streams.append(c)       # destination one byte short
+        caps.append(max(len(r) - 1, 0))
+    ref, rlen, rcons, rst = oracle.decode_batch(A.FMT_BLZ, streams, caps, A.make_opts())
+    got, out_len, consumed, status = simt_decode_blz(simt_blz, streams, caps)
+    assert (status == rst).all(), [(i, int(status[i]), int(rst[i])) for i in range(len(streams)) if status[i] != rst[i]][:5]
+    assert (out_len == rlen).all() and (consumed == rcons).all()
+    assert all(g == r for g, r, s in zip(got, ref, rst) if s == 0)
+    assert (rst == 0).sum() >= len(raws)
