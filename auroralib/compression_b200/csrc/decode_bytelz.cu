@@ -55,9 +55,7 @@ struct GOut {
         while (written - flushed >= uint32_t(kOPiece)) {
             const uint64_t end = uint64_t(flushed) + kOPiece;
             if (end <= cap && aligned) {
-                uint4 v;
-                const uint32_t a = ((flushed + lane * 16) & kORingMask) | rb;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+                const uint4 v = lds_u128(((flushed + lane * 16) & kORingMask) | rb);
                 *reinterpret_cast<uint4*>(dst + flushed + lane * 16) = v;
             } else {
                 for (uint32_t i = lane; i < uint32_t(kOPiece); i += 32)
@@ -1269,6 +1267,7 @@ struct BlockShape {
     static constexpr int kWarps = (K == B_LZ4_BLOCK || K == B_SNAPPY_BLOCK) ? AURORA_LZ4_WARPS : K == B_LZO ? AURORA_LZO_WARPS : (K == B_LZ4 || K == B_SNAPPY) ? 16 : K == B_PRS ? AURORA_PRS_WARPS : kWarpsPerBlock;
 };
 
+// ---- kernel
 template <int K>
 __global__ void __launch_bounds__(BlockShape<K>::kWarps * 32, 2) decode_bytelz_kernel(const DecodeParams P) {
     constexpr int kWarpsPerBlock = BlockShape<K>::kWarps;

@@ -11,6 +11,44 @@ constexpr int kLookahead = 192;      // input bytes one parse step may touch pas
 constexpr int kInMirror = 640;       // copy of slot 0's head behind the ring: any window of <= 640 bytes is contiguous
 constexpr int kInStage = kInRing + kInMirror;   // shared-memory bytes of one staged sub-stream
 
+#ifndef AURORA_SIMT   // (tests/simt supplies these on its CPU lane emulation)
+// ---- shared-memory accessors on 32-bit shared addresses (explicit program order for the ring traffic)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // TMA-staged input sub-stream: a 2 x 1 KiB shared-memory ring filled by cp.async.bulk (1-D TMA) with one
 // mbarrier per slot.  All members are warp-uniform registers.  Loads are numbered by a counter that runs
@@ -108,50 +146,11 @@ struct InStream {
         issue_trig = nend >= nchunks ? 0xFFFFFFFFu : (nend - 1) * kInChunk;
     }
     __device__ __forceinline__ uint32_t at(uint32_t pos) const {
-        uint32_t v;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(smem_u32(ring) + ((pos + rbias) & kInMask)) : "memory");
-        return v;
+        return lds_u8(smem_u32(ring) + ((pos + rbias) & kInMask));
     }
     // pointer to relative byte `pos`, contiguous for kInMirror bytes (after ensure(pos, <= kInMirror))
     __device__ __forceinline__ const uint8_t* window(uint32_t pos) const { return ring + ((pos + rbias) & kInMask); }
 };
-
-// ---- shared-memory accessors on 32-bit shared addresses (explicit program order for the ring traffic)
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_u128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
-}
-
 
 // ceil(2^20 / d): i mod d for the self-overlapping copy without an integer division (exact for i, d < 512)
 struct RcpTable {
@@ -160,7 +159,11 @@ struct RcpTable {
         for (uint32_t d = 1; d < 512; ++d) v[d] = ((1u << 20) + d - 1) / d;
     }
 };
+#ifndef AURORA_SIMT
 static __constant__ RcpTable c_rcp = RcpTable();
+#else
+static const RcpTable c_rcp = RcpTable();
+#endif
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     const int lane = lane_id();

@@ -2,7 +2,7 @@
 // TEST INFRASTRUCTURE.  It lets the `-m "not gpu"` suite execute the DEVICE SOURCE of a kernel (compiled by g++ with the
 // stand-in headers of this directory) and compare its output with the oracle, so the lane-level logic of the shipped
 // kernel — not a second restatement of it — is checked where there is no GPU.  What it models: lanes run one after the
-// other between collectives; __shfl / __shfl_up / __ballot / __match_any / __reduce_or / __syncwarp need ALL 32 lanes
+// other between collectives; __shfl / __shfl_up / __ballot / __match_any / __reduce_or / __reduce_max / __syncwarp need ALL 32 lanes
 // (the emulated sources only use them convergently) and fail loudly on a divergent call; shared memory is a bounds-checked
 // byte array addressed by offsets; __ldg checks the registered source range.  What it does not model: timing, memory
 // ordering between lanes inside a collective-free region (a missing __syncwarp is only caught when the lane order exposes it).
@@ -17,7 +17,7 @@
 
 namespace simt {
 
-enum Op { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_BALLOT, OP_MATCH_ANY, OP_REDUCE_OR, OP_SYNC };
+enum Op { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_BALLOT, OP_MATCH_ANY, OP_REDUCE_OR, OP_REDUCE_MAX, OP_SYNC };
 
 struct Warp {
     static constexpr int kLanes = 32;
@@ -92,6 +92,10 @@ inline void resolve(Warp* w) {
                         r |= w->val[j];
                     }
                 break;
+            case OP_REDUCE_MAX:
+                for (int j = 0; j < 32; j++)
+                    if (w->val[j] > r) r = w->val[j];
+                break;
             default: break;
         }
         w->res[l] = r;
@@ -159,7 +163,16 @@ inline unsigned __match_any_sync(unsigned mask, uint32_t v) {
     return unsigned(simt::collective(simt::OP_MATCH_ANY, uint64_t(v), 0));
 }
 inline unsigned __reduce_or_sync(unsigned mask, unsigned v) { return unsigned(simt::collective(simt::OP_REDUCE_OR, uint64_t(v), mask)); }
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    if (mask != 0xFFFFFFFFu) simt::fail("__reduce_max_sync with a partial mask is not modelled");
+    return unsigned(simt::collective(simt::OP_REDUCE_MAX, uint64_t(v), 0));
+}
 inline void __syncwarp() { simt::collective(simt::OP_SYNC, 0, 0); }
+inline unsigned __brev(unsigned v) {
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
+    return r;
+}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(unsigned(v)); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
@@ -168,6 +181,15 @@ inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+inline uint64_t min(uint64_t a, uint64_t b) { return a < b ? a : b; }
+inline uint64_t max(uint64_t a, uint64_t b) { return a > b ? a : b; }
+inline int64_t min(int64_t a, int64_t b) { return a < b ? a : b; }
+inline int64_t max(int64_t a, int64_t b) { return a > b ? a : b; }
+// CUDA's mixed overloads: (unsigned, int) compares as unsigned
+inline uint32_t min(uint32_t a, int b) { return min(a, uint32_t(b)); }
+inline uint32_t min(int a, uint32_t b) { return min(uint32_t(a), b); }
+inline uint32_t max(uint32_t a, int b) { return max(a, uint32_t(b)); }
+inline uint32_t max(int a, uint32_t b) { return max(uint32_t(a), b); }
 template <class T>
 inline T __ldg(const T* p) {
     const simt::Warp* w = simt::current();

@@ -30,7 +30,8 @@ def _build(name, harness, macro, extra=()):
         f.write(src[:src.index("// ---- kernel\n")])   # the device functions; the kernel entry and the launcher stay out
     so = os.path.join(build, f"libsimt_{name}.so")
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-I", SIMT, "-I", CSRC,
-                           f'-DAURORA_REAL_COMMON="{os.path.join(CSRC, "common.cuh")}"', f'-D{macro}="{inc}"', *extra,
+                           f'-DAURORA_REAL_COMMON="{os.path.join(CSRC, "common.cuh")}"', f'-DAURORA_REAL_STAGE="{os.path.join(CSRC, "stage.cuh")}"',
+                           f'-D{macro}="{inc}"', *extra,
                            os.path.join(SIMT, harness), "-o", so])
     return C.CDLL(so)
 
@@ -268,5 +269,74 @@ def test_blz_decoder_on_emulated_lanes(simt_blz, oracle, bmp):
     got, out_len, consumed, status = simt_decode_blz(simt_blz, streams, caps)
     assert (status == rst).all(), [(i, int(status[i]), int(rst[i])) for i in range(len(streams)) if status[i] != rst[i]][:5]
     assert (out_len == rlen).all() and (consumed == rcons).all()
+    assert all(g == r for g, r, s in zip(got, ref, rst) if s == 0)
+    assert (rst == 0).sum() >= len(raws)
+
+
+# ---- the byte-LZ decode kernel (csrc/decode_bytelz.cu: LZ4 block / legacy / frame, Snappy block / framed, LZO, PRS) with the real
+#      staged input stream of csrc/stage.cuh over an emulated TMA (a checked memcpy that completes at once)
+@pytest.fixture(scope="session")
+def simt_bytelz_dec():
+    f = _build("decode_bytelz", "bytelz_dec_harness.cpp", "DEC_DEVICE_INC").simt_decode_bytelz
+    f.restype = C.c_int
+    return f
+
+
+def simt_decode_bytelz(entry, fmt, comps, caps, byte_order=A.ENDIAN_DEFAULT, lz4_verify=0):
+    n = len(comps)
+    off, pos = [], 7
+    for c in comps:
+        off.append(pos)
+        pos += len(c) + (pos % 5)
+    limit = (pos + 15) & ~15
+    backing = np.zeros(limit + 64, dtype=np.uint8)
+    a0 = (-backing.ctypes.data) % 16
+    src = backing[a0:a0 + limit]
+    for o, c in zip(off, comps):
+        src[o:o + len(c)] = np.frombuffer(c, dtype=np.uint8)
+    doff, dpos = [], 0
+    for i, c in enumerate(caps):
+        doff.append(dpos)
+        dpos += ((c + 8 + 15) & ~15) + (16 if i % 2 else 3)   # aligned and unaligned destinations
+    dst = np.full(dpos + 8, 0xEE, dtype=np.uint8)
+    out_len, consumed = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+    status = np.full(n, 77, dtype=np.int32)
+    u64 = lambda v: np.asarray(v, dtype=np.uint64)
+    src_off, src_len, dst_off, dst_cap = u64(off), u64([len(c) for c in comps]), u64(doff), u64(caps)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = entry(C.c_int(fmt), C.c_int(byte_order), C.c_int(lz4_verify), C.c_int(0), p(src), C.c_uint64(limit), p(src_off), p(src_len), p(dst),
+               p(dst_off), p(dst_cap), p(out_len), p(consumed), p(status), C.c_uint32(n))
+    assert rc == 0
+    outs = []
+    for i in range(n):
+        assert (dst[doff[i] + caps[i]:doff[i] + caps[i] + 8] == 0xEE).all(), f"stream {i}: bytes written past the capacity"
+        outs.append(dst[doff[i]:doff[i] + min(int(out_len[i]), caps[i])].tobytes())
+    return outs, out_len, consumed, status
+
+
+@pytest.mark.parametrize("fmt", BYTE_FORMATS, ids=fmt_id)
+def test_bytelz_decoder_on_emulated_lanes(simt_bytelz_dec, oracle, bmp, fmt):
+    from tests.util import corrupt
+    rng = np.random.default_rng(404 + fmt)
+    raws = [bmp[:n] for n in (33, 4097, 9000, 70000)] + [synth(rng, int(n), i % 5) for i, n in enumerate([5, 6, 31, 32, 33, 64, 65, 1000, 4096, 6000, 12000, 70000])]
+    streams, caps = [], []
+    for q in (0, 8):
+        comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=q))
+        for i, (c, r) in enumerate(zip(comps, raws)):
+            if st[i] != 0:
+                continue
+            streams.append(c)
+            caps.append(len(r))
+            if len(r) <= 12000:
+                for mode in range(5):   # truncated, one byte flipped, garbage appended, empty, cut inside the header
+                    streams.append(corrupt(rng, c, mode))
+                    caps.append(len(r) if i % 2 else len(r) + 100)
+                streams.append(c)       # destination one byte short
+                caps.append(max(len(r) - 1, 0))
+    ref, rlen, rcons, rst = oracle.decode_batch(fmt, streams, caps, A.make_opts())
+    got, out_len, consumed, status = simt_decode_bytelz(simt_bytelz_dec, fmt, streams, caps)
+    bad = [(i, int(status[i]), int(rst[i]), int(out_len[i]), int(rlen[i]), int(consumed[i]), int(rcons[i])) for i in range(len(streams))
+           if status[i] != rst[i] or out_len[i] != rlen[i] or consumed[i] != rcons[i]]
+    assert not bad, f"{fmt_id(fmt)}: (stream, status, ref, out_len, ref, consumed, ref) {bad[:5]} of {len(bad)}"
     assert all(g == r for g, r, s in zip(got, ref, rst) if s == 0)
     assert (rst == 0).sum() >= len(raws)
