@@ -598,8 +598,10 @@ __device__ __forceinline__ void long_match_copy(OutState& out, uint32_t pos, uin
 // ---------------------------------------------------------------------------------------------
 enum : uint32_t { kMsgBegin = 1u, kMsgFinish = 2u, kMsgLong = 4u, kMsgExit = 8u };
 
+#ifndef AURORA_SIMT   // (tests/simt models the two named barriers of a slot on its CPU lane emulation)
 __device__ __forceinline__ void bar_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+#endif
 
 struct SlotSink {
     uint32_t rbase;        // shared address of the slot's ring
@@ -1652,6 +1654,7 @@ __device__ void decode_stream(const DecodeParams& P, uint32_t idx, InStream* in,
     }
 }
 
+// ---- kernel
 template <int K>
 __global__ void __launch_bounds__(Traits<K>::kSlots * 64, Traits<K>::kBlocksPerSM) decode_flaglz_kernel(const DecodeParams P) {
     using T = Traits<K>;

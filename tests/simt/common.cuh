@@ -31,4 +31,7 @@ inline void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, u
     memcpy(d, g, bytes);
 }
 inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
+// the named barriers of the flag-LZ decode kernel's warp pairs (PTX bar.sync / bar.arrive id, 64)
+inline void bar_sync(uint32_t id) { simt::named_barrier(id, true); }
+inline void bar_arrive(uint32_t id) { simt::named_barrier(id, false); }
 }  // namespace aurora

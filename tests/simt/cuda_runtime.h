@@ -22,3 +22,10 @@ struct int4 {
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 #define __constant__
 static inline void __threadfence_block() {}
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) {   // one emulated block at a time: no concurrency
+    const unsigned old = *p;
+    *p += v;
+    return old;
+}
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }

@@ -17,11 +17,17 @@
 
 namespace simt {
 
-enum Op { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_BALLOT, OP_MATCH_ANY, OP_REDUCE_OR, OP_REDUCE_MAX, OP_SYNC };
+enum Op { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_BALLOT, OP_MATCH_ANY, OP_REDUCE_OR, OP_REDUCE_MAX, OP_SYNC };
 
-struct Warp {
-    static constexpr int kLanes = 32;
+struct Warp {   // (a block of up to two warps: the parser / resolver pairs of the flag-LZ decode kernel)
+    static constexpr int kLanes = 64;
     static constexpr size_t kStack = 256 * 1024;
+    int nlanes = 32;
+    // named barriers (PTX bar.sync / bar.arrive with a thread count): arrivals so far and the generation waiters sleep on
+    static constexpr int kBars = 16;
+    uint32_t bar_count[kBars] = {}, bar_gen[kBars] = {};
+    int bar_wait_id[kLanes];       // -1: not waiting on a named barrier
+    uint32_t bar_wait_gen[kLanes];
     ucontext_t sched, ctx[kLanes];
     char* stack[kLanes];
     bool finished[kLanes], waiting[kLanes];
@@ -45,7 +51,7 @@ inline Warp*& current() {
 }
 
 [[noreturn]] inline void fail(const char* what) {
-    fprintf(stderr, "simt: %s (lane %d)\n", what, current() ? current()->cur : -1);
+    fprintf(stderr, "simt: %s (thread %d)\n", what, current() ? current()->cur : -1);
     abort();
 }
 
@@ -68,47 +74,75 @@ inline uint64_t collective(int op, uint64_t v, uint32_t aux) {
     return w->res[l];
 }
 
-inline void resolve(Warp* w) {
-    const int op = w->op[0];
-    for (int l = 0; l < Warp::kLanes; l++)
-        if (w->op[l] != op) fail("divergent collective: lanes wait in different warp primitives");
+inline void resolve(Warp* w, int base) {   // the 32 lanes from `base` all wait in a warp primitive
+    const int op = w->op[base];
+    for (int l = 0; l < 32; l++)
+        if (w->op[base + l] != op) fail("divergent collective: lanes wait in different warp primitives");
     w->collectives++;
-    for (int l = 0; l < Warp::kLanes; l++) {
+    const uint64_t* val = w->val + base;
+    const uint32_t* aux = w->aux + base;
+    for (int l = 0; l < 32; l++) {
         uint64_t r = 0;
         switch (op) {
-            case OP_SHFL: r = w->val[w->aux[l] & 31]; break;
-            case OP_SHFL_UP: r = l >= int(w->aux[l]) ? w->val[l - int(w->aux[l])] : w->val[l]; break;
+            case OP_SHFL: r = val[aux[l] & 31]; break;
+            case OP_SHFL_UP: r = l >= int(aux[l]) ? val[l - int(aux[l])] : val[l]; break;
+            case OP_SHFL_DOWN: r = l + int(aux[l]) < 32 ? val[l + int(aux[l])] : val[l]; break;
             case OP_BALLOT:
-                for (int j = 0; j < 32; j++) r |= uint64_t(w->val[j] != 0) << j;
+                for (int j = 0; j < 32; j++) r |= uint64_t(val[j] != 0) << j;
                 break;
             case OP_MATCH_ANY:
-                for (int j = 0; j < 32; j++) r |= uint64_t(w->val[j] == w->val[l]) << j;
+                for (int j = 0; j < 32; j++) r |= uint64_t(val[j] == val[l]) << j;
                 break;
             case OP_REDUCE_OR:
-                if (!((w->aux[l] >> l) & 1u)) fail("__reduce_or_sync: the calling lane is not in its own mask");
+                if (!((aux[l] >> l) & 1u)) fail("__reduce_or_sync: the calling lane is not in its own mask");
                 for (int j = 0; j < 32; j++)
-                    if ((w->aux[l] >> j) & 1u) {
-                        if (w->aux[j] != w->aux[l]) fail("__reduce_or_sync: lanes of one group passed different masks");
-                        r |= w->val[j];
+                    if ((aux[l] >> j) & 1u) {
+                        if (aux[j] != aux[l]) fail("__reduce_or_sync: lanes of one group passed different masks");
+                        r |= val[j];
                     }
                 break;
             case OP_REDUCE_MAX:
                 for (int j = 0; j < 32; j++)
-                    if (w->val[j] > r) r = w->val[j];
+                    if (val[j] > r) r = val[j];
                 break;
             default: break;
         }
-        w->res[l] = r;
+        w->res[base + l] = r;
     }
-    for (int l = 0; l < Warp::kLanes; l++) w->waiting[l] = false;
+    for (int l = 0; l < 32; l++) w->waiting[base + l] = false;
 }
 
-// run `body(lane)` on 32 lanes to completion
-inline void run_warp(Warp& w, std::function<void(int)> body) {
+// PTX bar.arrive / bar.sync a, 64: every calling THREAD counts; the 64th arrival releases the sleepers and resets the barrier
+inline void bar_arrive_impl(Warp* w, uint32_t id) {
+    if (id >= uint32_t(Warp::kBars)) fail("named barrier id out of range");
+    if (++w->bar_count[id] == 64) {
+        w->bar_count[id] = 0;
+        w->bar_gen[id]++;
+    } else if (w->bar_count[id] > 64) {
+        fail("named barrier over-subscribed");
+    }
+}
+inline void named_barrier(uint32_t id, bool wait) {
+    Warp* w = current();
+    const int l = w->cur;
+    const uint32_t gen = w->bar_gen[id < uint32_t(Warp::kBars) ? id : 0];
+    bar_arrive_impl(w, id);
+    if (!wait) return;
+    if (w->bar_gen[id] != gen) return;   // this arrival completed it
+    w->bar_wait_id[l] = int(id);
+    w->bar_wait_gen[l] = gen;
+    swapcontext(&w->ctx[l], &w->sched);
+}
+
+// run `body(thread)` on `nwarps` x 32 lanes to completion (thread = warp * 32 + lane)
+inline void run_block(Warp& w, int nwarps, std::function<void(int)> body) {
     current() = &w;
     w.body = std::move(body);
-    for (int l = 0; l < Warp::kLanes; l++) {
+    w.nlanes = 32 * nwarps;
+    if (w.nlanes > Warp::kLanes) fail("too many warps for the emulated block");
+    for (int l = 0; l < w.nlanes; l++) {
         w.finished[l] = w.waiting[l] = false;
+        w.bar_wait_id[l] = -1;
         w.stack[l] = static_cast<char*>(malloc(Warp::kStack));
         getcontext(&w.ctx[l]);
         w.ctx[l].uc_stack.ss_sp = w.stack[l];
@@ -117,33 +151,50 @@ inline void run_warp(Warp& w, std::function<void(int)> body) {
         makecontext(&w.ctx[l], reinterpret_cast<void (*)()>(trampoline), 1, l);
     }
     for (;;) {
-        int done = 0, waiting = 0;
-        for (int l = 0; l < Warp::kLanes; l++) {
+        bool progress = false;
+        int done = 0;
+        for (int l = 0; l < w.nlanes; l++) {
             if (w.finished[l]) {
                 done++;
                 continue;
             }
+            if (w.bar_wait_id[l] >= 0) {
+                if (w.bar_gen[w.bar_wait_id[l]] == w.bar_wait_gen[l]) continue;   // still asleep in the named barrier
+                w.bar_wait_id[l] = -1;
+            }
             if (!w.waiting[l]) {
                 w.cur = l;
                 swapcontext(&w.sched, &w.ctx[l]);
+                progress = true;
+                if (w.finished[l]) done++;
             }
-            if (w.finished[l]) done++;
-            else if (w.waiting[l]) waiting++;
         }
-        if (done == Warp::kLanes) break;
-        if (waiting + done == Warp::kLanes) {
-            if (done != 0) fail("a lane left the kernel while others wait in a warp primitive");
-            resolve(&w);
+        if (done == w.nlanes) break;
+        for (int base = 0; base < w.nlanes; base += 32) {
+            int waiting = 0, fin = 0;
+            for (int l = base; l < base + 32; l++) {
+                waiting += w.waiting[l] ? 1 : 0;
+                fin += w.finished[l] ? 1 : 0;
+            }
+            if (waiting == 0) continue;
+            if (waiting + fin == 32) {
+                if (fin != 0) fail("a lane left the kernel while others of its warp wait in a warp primitive");
+                resolve(&w, base);
+                progress = true;
+            }
         }
+        if (!progress) fail("deadlock: every lane waits (a named barrier that never completes, or a divergent warp primitive)");
     }
-    for (int l = 0; l < Warp::kLanes; l++) free(w.stack[l]);
+    for (int l = 0; l < w.nlanes; l++) free(w.stack[l]);
     current() = nullptr;
 }
+inline void run_warp(Warp& w, std::function<void(int)> body) { run_block(w, 1, std::move(body)); }
 
 }  // namespace simt
 
 // ---- the CUDA names the emulated sources use -------------------------------------------------------------------------------
-inline int simt_lane() { return simt::current()->cur; }
+inline int simt_lane() { return simt::current()->cur & 31; }
+inline int simt_warp() { return simt::current()->cur >> 5; }
 template <class T>
 inline T __shfl_sync(unsigned mask, T v, int src) {
     if (mask != 0xFFFFFFFFu) simt::fail("__shfl_sync with a partial mask is not modelled");
@@ -154,6 +205,14 @@ inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
     if (mask != 0xFFFFFFFFu) simt::fail("__shfl_up_sync with a partial mask is not modelled");
     return T(simt::collective(simt::OP_SHFL_UP, uint64_t(v), delta));
 }
+template <class T>
+inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
+    if (mask != 0xFFFFFFFFu) simt::fail("__shfl_down_sync with a partial mask is not modelled");
+    return T(simt::collective(simt::OP_SHFL_DOWN, uint64_t(v), delta));
+}
+inline unsigned __ballot_sync(unsigned mask, int pred);
+inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xFFFFFFFFu; }
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 inline unsigned __ballot_sync(unsigned mask, int pred) {
     if (mask != 0xFFFFFFFFu) simt::fail("__ballot_sync with a partial mask is not modelled");
     return unsigned(simt::collective(simt::OP_BALLOT, uint64_t(pred != 0), 0));

@@ -282,7 +282,8 @@ def simt_bytelz_dec():
     return f
 
 
-def simt_decode_bytelz(entry, fmt, comps, caps, byte_order=A.ENDIAN_DEFAULT, lz4_verify=0):
+def simt_decode_bytelz(entry, fmt, comps, caps, byte_order=A.ENDIAN_DEFAULT, lz4_verify=0, flag_lz=False, lzss=None):
+    """One emulated warp (byte-LZ kernel) or parser / resolver warp pair (flag_lz: the flag-LZ kernel) decodes `comps`."""
     n = len(comps)
     off, pos = [], 7
     for c in comps:
@@ -304,8 +305,13 @@ def simt_decode_bytelz(entry, fmt, comps, caps, byte_order=A.ENDIAN_DEFAULT, lz4
     u64 = lambda v: np.asarray(v, dtype=np.uint64)
     src_off, src_len, dst_off, dst_cap = u64(off), u64([len(c) for c in comps]), u64(doff), u64(caps)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = entry(C.c_int(fmt), C.c_int(byte_order), C.c_int(lz4_verify), C.c_int(0), p(src), C.c_uint64(limit), p(src_off), p(src_len), p(dst),
-               p(dst_off), p(dst_cap), p(out_len), p(consumed), p(status), C.c_uint32(n))
+    if flag_lz:
+        lz = lzss if lzss is not None else A.lz_props_bits(12, 4, 2)   # LZSS.DefaultProperties (api.cu fill_decode_params)
+        head = (C.c_int(fmt), C.c_int(byte_order), C.c_int(0), (C.c_int * 6)(lz.windows_bits, lz.length_bits, lz.min_length, lz.max_distance, lz.windows_start, 0))
+    else:
+        head = (C.c_int(fmt), C.c_int(byte_order), C.c_int(lz4_verify), C.c_int(0))
+    rc = entry(*head, p(src), C.c_uint64(limit), p(src_off), p(src_len), p(dst), p(dst_off), p(dst_cap), p(out_len), p(consumed), p(status),
+               C.c_uint32(n))
     assert rc == 0
     outs = []
     for i in range(n):
@@ -335,6 +341,47 @@ def test_bytelz_decoder_on_emulated_lanes(simt_bytelz_dec, oracle, bmp, fmt):
                 caps.append(max(len(r) - 1, 0))
     ref, rlen, rcons, rst = oracle.decode_batch(fmt, streams, caps, A.make_opts())
     got, out_len, consumed, status = simt_decode_bytelz(simt_bytelz_dec, fmt, streams, caps)
+    bad = [(i, int(status[i]), int(rst[i]), int(out_len[i]), int(rlen[i]), int(consumed[i]), int(rcons[i])) for i in range(len(streams))
+           if status[i] != rst[i] or out_len[i] != rlen[i] or consumed[i] != rcons[i]]
+    assert not bad, f"{fmt_id(fmt)}: (stream, status, ref, out_len, ref, consumed, ref) {bad[:5]} of {len(bad)}"
+    assert all(g == r for g, r, s in zip(got, ref, rst) if s == 0)
+    assert (rst == 0).sum() >= len(raws)
+
+
+# ---- the flag-LZ decode kernel (csrc/decode_flaglz.cu, the headline kernel): one stream slot = a parser warp and a resolver warp
+#      (64 fibers) handing batches over through two emulated named barriers
+@pytest.fixture(scope="session")
+def simt_flaglz_dec():
+    f = _build("decode_flaglz", "flaglz_dec_harness.cpp", "DEC_DEVICE_INC").simt_decode_flaglz
+    f.restype = C.c_int
+    return f
+
+
+FLAG_DEC_FORMATS = [A.FMT_LZ10, A.FMT_LZ11, A.FMT_YAZ0, A.FMT_YAZ1, A.FMT_LZSS, A.FMT_MIO0, A.FMT_YAY0, A.FMT_LZHUDSON, A.FMT_LZ40, A.FMT_LZ60,
+                    A.FMT_SMSR00]
+
+
+@pytest.mark.parametrize("fmt", FLAG_DEC_FORMATS, ids=fmt_id)
+def test_flaglz_decoder_on_emulated_lanes(simt_flaglz_dec, oracle, bmp, fmt):
+    from tests.util import corrupt
+    rng = np.random.default_rng(808 + fmt)
+    raws = [bmp[:n] for n in (33, 4097, 9000, 70000)] + [synth(rng, int(n), i % 5) for i, n in enumerate([1, 6, 31, 32, 33, 64, 65, 1000, 4096, 6000, 12000, 70000])]
+    streams, caps = [], []
+    for q in (0, 8):
+        comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=q))
+        for i, (c, r) in enumerate(zip(comps, raws)):
+            if st[i] != 0:
+                continue
+            streams.append(c)
+            caps.append(len(r))
+            if len(r) <= 12000:
+                for mode in range(5):   # truncated, one byte flipped, garbage appended, empty, cut inside the header
+                    streams.append(corrupt(rng, c, mode))
+                    caps.append(len(r) if i % 2 else len(r) + 100)
+                streams.append(c)       # destination one byte short
+                caps.append(max(len(r) - 1, 0))
+    ref, rlen, rcons, rst = oracle.decode_batch(fmt, streams, caps, A.make_opts())
+    got, out_len, consumed, status = simt_decode_bytelz(simt_flaglz_dec, fmt, streams, caps, flag_lz=True)
     bad = [(i, int(status[i]), int(rst[i]), int(out_len[i]), int(rlen[i]), int(consumed[i]), int(rcons[i])) for i in range(len(streams))
            if status[i] != rst[i] or out_len[i] != rlen[i] or consumed[i] != rcons[i]]
     assert not bad, f"{fmt_id(fmt)}: (stream, status, ref, out_len, ref, consumed, ref) {bad[:5]} of {len(bad)}"
