@@ -52,6 +52,7 @@ struct GOut {
 
     __device__ __forceinline__ void drain() {
         const uint32_t lane = lane_id();
+        if (written - flushed < uint32_t(kOPiece)) return;
         while (written - flushed >= uint32_t(kOPiece)) {
             const uint64_t end = uint64_t(flushed) + kOPiece;
             if (end <= cap && aligned) {
@@ -63,6 +64,9 @@ struct GOut {
             }
             flushed += kOPiece;
         }
+        // a far back-reference of the NEXT copy may read these bytes back from global memory on another lane: order the
+        // stores before it (lock-step execution hid the missing order on the GPU; the lane emulation of tests/simt did not)
+        __syncwarp();
     }
     __device__ __forceinline__ void finish() {
         const uint32_t lane = lane_id();
