@@ -1,5 +1,5 @@
 // tests/simt/blz_harness.cpp — runs the DEVICE part of csrc/decode_blz.cu (everything above its "// ---- kernel" line, cut out
-// of the real file by tests/test_simt_encoder.py) on the CPU lane emulation of simt.hpp.  TEST INFRASTRUCTURE.
+// of the real file by tests/test_simt_kernels.py) on the CPU lane emulation of simt.hpp.  TEST INFRASTRUCTURE.
 #include "common.cuh"
 #include "stage.cuh"
 #include BLZ_DEVICE_INC   // opens `namespace aurora { namespace {` and leaves both open

@@ -1,5 +1,5 @@
 // tests/simt/bytelz_dec_harness.cpp — runs the DEVICE part of csrc/decode_bytelz.cu (LZ4 block / legacy / frame, Snappy block /
-// framed, LZO, PRS; everything above the file's "// ---- kernel" line, cut out of the real file by tests/test_simt_encoder.py)
+// framed, LZO, PRS; everything above the file's "// ---- kernel" line, cut out of the real file by tests/test_simt_kernels.py)
 // on the CPU lane emulation of simt.hpp, with the REAL staged input stream of csrc/stage.cuh over an emulated TMA.
 // TEST INFRASTRUCTURE: the product never loads this.
 #include <vector>

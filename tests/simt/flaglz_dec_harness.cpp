@@ -1,6 +1,6 @@
 // tests/simt/flaglz_dec_harness.cpp — runs the DEVICE part of csrc/decode_flaglz.cu (the headline kernel: LZ10, LZ11 / LZ40 / LZ60,
 // Yaz0 / Yaz1, LZSS, MIO0, Yay0, LZHudson, SMSR00; everything above the file's "// ---- kernel" line, cut out of the real file by
-// tests/test_simt_encoder.py) on the CPU lane emulation of simt.hpp: ONE stream slot = a parser warp and a resolver warp (64
+// tests/test_simt_kernels.py) on the CPU lane emulation of simt.hpp: ONE stream slot = a parser warp and a resolver warp (64
 // fibers) that hand batches over through two emulated named barriers, the real staged input streams over an emulated TMA.
 // The slot is carved and the two roles are started exactly as decode_flaglz_kernel does (csrc/decode_flaglz.cu, "// ---- kernel").
 // TEST INFRASTRUCTURE: the product never loads this.

@@ -1,5 +1,5 @@
 // tests/simt/par_harness.cpp — runs the DEVICE part of csrc/encode_lz_par.cu (everything above its "// ---- kernel" line, cut
-// out of the real file by tests/test_simt_encoder.py and included below) on the CPU lane emulation of simt.hpp.
+// out of the real file by tests/test_simt_kernels.py and included below) on the CPU lane emulation of simt.hpp.
 // TEST INFRASTRUCTURE: the product never loads this.  One emulated warp encodes the streams of a batch one after the other
 // with the same tables, as a resident warp of the kernel does.
 #include <vector>

@@ -1,6 +1,6 @@
 // tests/simt/seq_harness.cpp — runs the DEVICE part of csrc/encode_lz.cu or csrc/encode_bytelz.cu (with csrc/finder.cuh: the
 // sequential replay of the reference's match finder; everything above the file's "// ---- kernel" line, cut out of the real
-// file by tests/test_simt_encoder.py) on the CPU lane emulation of simt.hpp.  TEST INFRASTRUCTURE: the product never loads this.
+// file by tests/test_simt_kernels.py) on the CPU lane emulation of simt.hpp.  TEST INFRASTRUCTURE: the product never loads this.
 #include <vector>
 
 #include "common.cuh"

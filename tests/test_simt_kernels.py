@@ -1,9 +1,12 @@
-"""The encoder kernels' DEVICE SOURCE (csrc/encode_lz_par.cu: one lane per window position; csrc/encode_lz.cu, encode_bytelz.cu
-with finder.cuh: the sequential replay — everything above each file's kernel entry) compiled by
-g++ and run on a 32-lane CPU emulation (tests/simt/: one fiber per lane, warp primitives as rendezvous points, bounds-checked
-shared memory), compared byte for byte with the oracle.  No GPU: this is the check of the kernel's lane-level logic that runs in
-the CPU suite — every format and quality of the search, the small-match table, matches beyond the data ring's lookahead, the
-three-section writer, CompatibilityMode, unaligned sources, too-small destinations — on more inputs than GPU time allows."""
+"""The kernels' DEVICE SOURCE on a CPU lane emulation (tests/simt/: one fiber per lane, warp primitives and named barriers as
+rendezvous points, bounds-checked shared memory, a synchronous checked TMA), compared with the oracle.  The device part of each
+real kernel file (everything above its "// ---- kernel" line) is compiled by g++ against stand-in headers:
+  * encoders — csrc/encode_lz_par.cu (one lane per window position) and csrc/encode_lz.cu / encode_bytelz.cu with finder.cuh (the
+    sequential replay): every format and quality, the small-match table, matches beyond the data ring's lookahead, the
+    three-section writers, CompatibilityMode, unaligned sources, too-small destinations;
+  * decoders — csrc/decode_flaglz.cu (the headline kernel: a parser warp and a resolver warp per stream slot), decode_bytelz.cu,
+    decode_blz.cu: valid and corrupt streams, exact / short / larger destinations; status, out_len, consumed and bytes.
+No GPU: this is the check of the kernels' lane-level logic that runs in the CPU suite, on more inputs than GPU time allows."""
 import ctypes as C
 import os
 import subprocess

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from auroralib.compression_b200 import _abi as A  # noqa: E402
 from oracle import oracle as O  # noqa: E402
-from tests import test_simt_encoder as T  # noqa: E402
+from tests import test_simt_kernels as T  # noqa: E402
 from tests.util import synth  # noqa: E402
 
 
