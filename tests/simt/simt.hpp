@@ -14,6 +14,7 @@
 #include <ucontext.h>
 
 #include <functional>
+#include <map>
 
 namespace simt {
 
@@ -28,6 +29,15 @@ struct Warp {   // (a block of up to two warps: the parser / resolver pairs of t
     uint32_t bar_count[kBars] = {}, bar_gen[kBars] = {};
     int bar_wait_id[kLanes];       // -1: not waiting on a named barrier
     uint32_t bar_wait_gen[kLanes];
+    // mbarriers (keyed by their shared-memory address): arrivals still expected in the current phase, transaction bytes still
+    // in flight, completed phases; a lane sleeps in mbar_wait until the phase of the parity it names has completed
+    struct MBar {
+        uint32_t count = 1, pending = 1, phase = 0;
+        int64_t tx = 0;
+    };
+    std::map<const void*, MBar> mbar;
+    const void* mbar_wait_ptr[kLanes];   // nullptr: not waiting on an mbarrier
+    uint32_t mbar_wait_parity[kLanes];
     ucontext_t sched, ctx[kLanes];
     char* stack[kLanes];
     bool finished[kLanes], waiting[kLanes];
@@ -43,6 +53,10 @@ struct Warp {   // (a block of up to two warps: the parser / resolver pairs of t
     const uint8_t* g_hi = nullptr;
     const char* error = nullptr;
     uint64_t collectives = 0;
+    // SIMT_SHUFFLE=<seed>: the lanes run in a new random order on every scheduler pass instead of 0, 1, 2, ... — a lane that
+    // reads what another lane wrote earlier in program order WITHOUT a warp primitive in between then sees stale data some of the
+    // time, so the comparison with the oracle doubles as a detector of missing __syncwarp / barrier orderings
+    uint64_t shuffle = 0;
 };
 
 inline Warp*& current() {
@@ -122,6 +136,40 @@ inline void bar_arrive_impl(Warp* w, uint32_t id) {
         fail("named barrier over-subscribed");
     }
 }
+inline void mbar_settle(Warp::MBar& b) {
+    if (b.pending == 0 && b.tx == 0) {
+        b.phase++;
+        b.pending = b.count;
+    }
+}
+inline void mbar_init_impl(const void* bar, uint32_t count) {
+    Warp::MBar& b = current()->mbar[bar];
+    b.count = b.pending = count;
+    b.phase = 0;
+    b.tx = 0;
+}
+inline void mbar_arrive_impl(const void* bar, int64_t expect_tx) {
+    Warp::MBar& b = current()->mbar[bar];
+    if (b.pending == 0) fail("mbarrier: more arrivals than its count");
+    b.tx += expect_tx;
+    b.pending--;
+    mbar_settle(b);
+}
+inline void mbar_complete_tx(const void* bar, int64_t bytes) {
+    Warp::MBar& b = current()->mbar[bar];
+    b.tx -= bytes;
+    mbar_settle(b);
+}
+inline bool mbar_test(const void* bar, uint32_t parity) { return (current()->mbar[bar].phase & 1u) != (parity & 1u); }
+inline void mbar_wait_impl(const void* bar, uint32_t parity) {
+    Warp* w = current();
+    if (mbar_test(bar, parity)) return;
+    const int l = w->cur;
+    w->mbar_wait_ptr[l] = bar;
+    w->mbar_wait_parity[l] = parity;
+    swapcontext(&w->ctx[l], &w->sched);
+}
+
 inline void named_barrier(uint32_t id, bool wait) {
     Warp* w = current();
     const int l = w->cur;
@@ -143,6 +191,7 @@ inline void run_block(Warp& w, int nwarps, std::function<void(int)> body) {
     for (int l = 0; l < w.nlanes; l++) {
         w.finished[l] = w.waiting[l] = false;
         w.bar_wait_id[l] = -1;
+        w.mbar_wait_ptr[l] = nullptr;
         w.stack[l] = static_cast<char*>(malloc(Warp::kStack));
         getcontext(&w.ctx[l]);
         w.ctx[l].uc_stack.ss_sp = w.stack[l];
@@ -150,10 +199,25 @@ inline void run_block(Warp& w, int nwarps, std::function<void(int)> body) {
         w.ctx[l].uc_link = &w.sched;
         makecontext(&w.ctx[l], reinterpret_cast<void (*)()>(trampoline), 1, l);
     }
+    if (const char* e = getenv("SIMT_SHUFFLE")) w.shuffle = strtoull(e, nullptr, 10) * 0x9E3779B97F4A7C15ull + 1;
+    int order[Warp::kLanes];
+    for (int l = 0; l < w.nlanes; l++) order[l] = l;
     for (;;) {
         bool progress = false;
         int done = 0;
-        for (int l = 0; l < w.nlanes; l++) {
+        if (w.shuffle) {
+            for (int i = w.nlanes - 1; i > 0; i--) {
+                w.shuffle ^= w.shuffle << 13;
+                w.shuffle ^= w.shuffle >> 7;
+                w.shuffle ^= w.shuffle << 17;
+                const int j = int(w.shuffle % uint64_t(i + 1));
+                const int t = order[i];
+                order[i] = order[j];
+                order[j] = t;
+            }
+        }
+        for (int k = 0; k < w.nlanes; k++) {
+            const int l = order[k];
             if (w.finished[l]) {
                 done++;
                 continue;
@@ -161,6 +225,10 @@ inline void run_block(Warp& w, int nwarps, std::function<void(int)> body) {
             if (w.bar_wait_id[l] >= 0) {
                 if (w.bar_gen[w.bar_wait_id[l]] == w.bar_wait_gen[l]) continue;   // still asleep in the named barrier
                 w.bar_wait_id[l] = -1;
+            }
+            if (w.mbar_wait_ptr[l]) {
+                if (!mbar_test(w.mbar_wait_ptr[l], w.mbar_wait_parity[l])) continue;   // still asleep in the mbarrier
+                w.mbar_wait_ptr[l] = nullptr;
             }
             if (!w.waiting[l]) {
                 w.cur = l;
