@@ -390,3 +390,36 @@ def test_flaglz_decoder_on_emulated_lanes(simt_flaglz_dec, oracle, bmp, fmt):
     assert not bad, f"{fmt_id(fmt)}: (stream, status, ref, out_len, ref, consumed, ref) {bad[:5]} of {len(bad)}"
     assert all(g == r for g, r, s in zip(got, ref, rst) if s == 0)
     assert (rst == 0).sum() >= len(raws)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_lane_order(simt_lib, simt_flaglz_dec, simt_bytelz_dec, oracle, bmp, seed, monkeypatch):
+    """SIMT_SHUFFLE: the emulated lanes run in a new random order on every scheduler pass.  A lane that reads what another lane
+    wrote earlier in program order without a warp primitive / barrier in between then sees stale data some of the time, so
+    equality with the oracle under random orders is evidence that the kernels' intra-warp and parser / resolver orderings are
+    all explicit."""
+    monkeypatch.setenv("SIMT_SHUFFLE", str(seed))
+    rng = np.random.default_rng(seed)
+    raws = [bmp[:9000], synth(rng, 6000, 0), synth(rng, 6000, 1), synth(rng, 12000, 2), synth(rng, 5000, 3), synth(rng, 3000, 4), bmp[5000:5033]]
+    for fmt, q in ((A.FMT_LZ10, 8), (A.FMT_YAY0, 10), (A.FMT_LZ11, 3)):
+        _check(simt_lib, oracle, fmt, raws, q)
+    for fmt in (A.FMT_LZ4, A.FMT_SNAPPY, A.FMT_LZO):
+        _check(simt_lib, oracle, fmt, raws, 8, seq=True)
+    for fmt, entry, flag in ((A.FMT_LZ10, simt_flaglz_dec, True), (A.FMT_YAZ0, simt_flaglz_dec, True), (A.FMT_MIO0, simt_flaglz_dec, True),
+                             (A.FMT_LZ4_BLOCK, simt_bytelz_dec, False), (A.FMT_LZO, simt_bytelz_dec, False), (A.FMT_PRS, simt_bytelz_dec, False)):
+        comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=8))
+        caps = [len(r) for r in raws]
+        ref, rlen, rcons, rst = oracle.decode_batch(fmt, comps, caps, A.make_opts())
+        got, out_len, consumed, status = simt_decode_bytelz(entry, fmt, comps, caps, flag_lz=flag)
+        assert (status == rst).all() and (out_len == rlen).all() and (consumed == rcons).all(), fmt_id(fmt)
+        assert all(g == r for g, r, s in zip(got, ref, rst) if s == 0), fmt_id(fmt)
+
+
+def test_far_reference_right_after_a_drain_step(simt_bytelz_dec, oracle):
+    """The stream on which tools/fuzz_simt_decode.py caught the byte-LZ decoder reading drained bytes back from global memory
+    without a warp barrier after the drain step (422 of 4096 bytes stale on the emulation; lock-step execution hid it on the GPU)."""
+    s = open(os.path.join(ROOT, "tests", "golden", "lzo_far_reference_after_drain.lzo"), "rb").read()
+    ref, rlen, rcons, rst = oracle.decode_batch(A.FMT_LZO, [s], [4096], A.make_opts())
+    got, out_len, consumed, status = simt_decode_bytelz(simt_bytelz_dec, A.FMT_LZO, [s], [4096])
+    assert rst[0] == 0 and status[0] == 0 and out_len[0] == rlen[0] == 4096 and consumed[0] == rcons[0]
+    assert got[0] == ref[0]
