@@ -208,7 +208,7 @@ def test_options_and_small_destinations(simt_lib, oracle, bmp):
 
 
 @pytest.mark.parametrize("fmt", SEQ_FLAG_FORMATS + BYTE_FORMATS, ids=fmt_id)
-@pytest.mark.parametrize("quality", [0, 8, 12])
+@pytest.mark.parametrize("quality", [0, 12])
 def test_sequential_replay_on_emulated_lanes(simt_lib, oracle, bmp, fmt, quality):
     """finder.cuh with the token writers of encode_lz.cu / encode_bytelz.cu: the finder every format falls back to."""
     rng = np.random.default_rng(17 * fmt + quality)
