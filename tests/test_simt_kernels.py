@@ -285,7 +285,7 @@ def simt_bytelz_dec():
     return f
 
 
-def simt_decode_bytelz(entry, fmt, comps, caps, byte_order=A.ENDIAN_DEFAULT, lz4_verify=0, flag_lz=False, lzss=None):
+def simt_decode_bytelz(entry, fmt, comps, caps, byte_order=A.ENDIAN_DEFAULT, lz4_verify=0, flag_lz=False, lzss=None, size_only=0):
     """One emulated warp (byte-LZ kernel) or parser / resolver warp pair (flag_lz: the flag-LZ kernel) decodes `comps`."""
     n = len(comps)
     off, pos = [], 7
@@ -312,7 +312,7 @@ def simt_decode_bytelz(entry, fmt, comps, caps, byte_order=A.ENDIAN_DEFAULT, lz4
         lz = lzss if lzss is not None else A.lz_props_bits(12, 4, 2)   # LZSS.DefaultProperties (api.cu fill_decode_params)
         head = (C.c_int(fmt), C.c_int(byte_order), C.c_int(0), (C.c_int * 6)(lz.windows_bits, lz.length_bits, lz.min_length, lz.max_distance, lz.windows_start, 0))
     else:
-        head = (C.c_int(fmt), C.c_int(byte_order), C.c_int(lz4_verify), C.c_int(0))
+        head = (C.c_int(fmt), C.c_int(byte_order), C.c_int(lz4_verify), C.c_int(size_only))
     rc = entry(*head, p(src), C.c_uint64(limit), p(src_off), p(src_len), p(dst), p(dst_off), p(dst_cap), p(out_len), p(consumed), p(status),
                C.c_uint32(n))
     assert rc == 0
@@ -423,3 +423,18 @@ def test_far_reference_right_after_a_drain_step(simt_bytelz_dec, oracle):
     got, out_len, consumed, status = simt_decode_bytelz(simt_bytelz_dec, A.FMT_LZO, [s], [4096])
     assert rst[0] == 0 and status[0] == 0 and out_len[0] == rlen[0] == 4096 and consumed[0] == rcons[0]
     assert got[0] == ref[0]
+
+
+@pytest.mark.parametrize("fmt", BYTE_FORMATS, ids=fmt_id)
+def test_bytelz_size_scan_on_emulated_lanes(simt_bytelz_dec, oracle, bmp, fmt):
+    """size_only (aurora_decoded_size_batch's scan for the formats whose header does not carry the size): the same walk with the
+    stores dropped — the decoded length of every valid stream, nothing written."""
+    rng = np.random.default_rng(55 + fmt)
+    raws = [bmp[:9000]] + [synth(rng, int(n), i % 5) for i, n in enumerate([5, 33, 1000, 4096, 6000, 12000, 70000])]
+    comps, st = oracle.encode_batch(fmt, raws, A.make_opts(quality=8))
+    keep = [i for i in range(len(raws)) if st[i] == 0]
+    comps, raws = [comps[i] for i in keep], [raws[i] for i in keep]
+    got, out_len, consumed, status = simt_decode_bytelz(simt_bytelz_dec, fmt, comps, [0] * len(comps), size_only=1)
+    # (the kernel reports the length with DST_TOO_SMALL against the zero capacity; api.cu's size path reads out_len)
+    assert (status == A.DST_TOO_SMALL).all() and [int(x) for x in out_len] == [len(r) for r in raws]
+    assert [int(x) for x in consumed] == [len(c) for c in comps]
