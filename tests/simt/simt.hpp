@@ -11,12 +11,51 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#if !defined(__x86_64__)
 #include <ucontext.h>
+#endif
 
 #include <functional>
 #include <map>
 
 namespace simt {
+
+// ---- fibers: a minimal stack switch on x86-64 (callee-saved registers and the stack pointer; glibc's swapcontext costs a
+// signal-mask system call per switch, and a warp primitive is 64 switches), ucontext elsewhere
+#if defined(__x86_64__)
+struct Ctx {
+    void* sp;
+};
+extern "C" void simt_switch(Ctx* from, Ctx* to) __attribute__((visibility("hidden")));
+asm(R"(
+    .text
+    .hidden simt_switch
+    .globl simt_switch
+    .type simt_switch,@function
+simt_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq (%rsi), %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size simt_switch,.-simt_switch
+)");
+#else
+struct Ctx {
+    ucontext_t uc;
+};
+inline void simt_switch(Ctx* from, Ctx* to) { swapcontext(&from->uc, &to->uc); }
+#endif
 
 enum Op { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_BALLOT, OP_MATCH_ANY, OP_REDUCE_OR, OP_REDUCE_MAX, OP_SYNC };
 
@@ -38,7 +77,7 @@ struct Warp {   // (a block of up to two warps: the parser / resolver pairs of t
     std::map<const void*, MBar> mbar;
     const void* mbar_wait_ptr[kLanes];   // nullptr: not waiting on an mbarrier
     uint32_t mbar_wait_parity[kLanes];
-    ucontext_t sched, ctx[kLanes];
+    Ctx sched, ctx[kLanes];
     char* stack[kLanes];
     bool finished[kLanes], waiting[kLanes];
     int cur = 0;
@@ -69,11 +108,28 @@ inline Warp*& current() {
     abort();
 }
 
-inline void trampoline(int lane) {
+inline void trampoline() {   // first activation of a fiber: the scheduler has set `cur`
     Warp* w = current();
+    const int lane = w->cur;
     w->body(lane);
     w->finished[lane] = true;
-    swapcontext(&w->ctx[lane], &w->sched);
+    simt_switch(&w->ctx[lane], &w->sched);
+    abort();   // a finished fiber is never resumed
+}
+inline void make_fiber(Warp& w, int l) {
+#if defined(__x86_64__)
+    void** sp = reinterpret_cast<void**>(reinterpret_cast<uintptr_t>(w.stack[l] + Warp::kStack) & ~uintptr_t(15));
+    *--sp = nullptr;                                     // the "return address" of trampoline (never used): rsp % 16 == 8 at its entry
+    *--sp = reinterpret_cast<void*>(&trampoline);        // simt_switch's `ret` lands here
+    for (int i = 0; i < 6; i++) *--sp = nullptr;         // rbp, rbx, r12 - r15
+    w.ctx[l].sp = sp;
+#else
+    getcontext(&w.ctx[l].uc);
+    w.ctx[l].uc.uc_stack.ss_sp = w.stack[l];
+    w.ctx[l].uc.uc_stack.ss_size = Warp::kStack;
+    w.ctx[l].uc.uc_link = &w.sched.uc;
+    makecontext(&w.ctx[l].uc, reinterpret_cast<void (*)()>(trampoline), 0);
+#endif
 }
 
 // deposit an operand and yield until every lane has arrived
@@ -84,7 +140,7 @@ inline uint64_t collective(int op, uint64_t v, uint32_t aux) {
     w->val[l] = v;
     w->aux[l] = aux;
     w->waiting[l] = true;
-    swapcontext(&w->ctx[l], &w->sched);
+    simt_switch(&w->ctx[l], &w->sched);
     return w->res[l];
 }
 
@@ -167,7 +223,7 @@ inline void mbar_wait_impl(const void* bar, uint32_t parity) {
     const int l = w->cur;
     w->mbar_wait_ptr[l] = bar;
     w->mbar_wait_parity[l] = parity;
-    swapcontext(&w->ctx[l], &w->sched);
+    simt_switch(&w->ctx[l], &w->sched);
 }
 
 inline void named_barrier(uint32_t id, bool wait) {
@@ -179,7 +235,7 @@ inline void named_barrier(uint32_t id, bool wait) {
     if (w->bar_gen[id] != gen) return;   // this arrival completed it
     w->bar_wait_id[l] = int(id);
     w->bar_wait_gen[l] = gen;
-    swapcontext(&w->ctx[l], &w->sched);
+    simt_switch(&w->ctx[l], &w->sched);
 }
 
 // run `body(thread)` on `nwarps` x 32 lanes to completion (thread = warp * 32 + lane)
@@ -193,11 +249,7 @@ inline void run_block(Warp& w, int nwarps, std::function<void(int)> body) {
         w.bar_wait_id[l] = -1;
         w.mbar_wait_ptr[l] = nullptr;
         w.stack[l] = static_cast<char*>(malloc(Warp::kStack));
-        getcontext(&w.ctx[l]);
-        w.ctx[l].uc_stack.ss_sp = w.stack[l];
-        w.ctx[l].uc_stack.ss_size = Warp::kStack;
-        w.ctx[l].uc_link = &w.sched;
-        makecontext(&w.ctx[l], reinterpret_cast<void (*)()>(trampoline), 1, l);
+        make_fiber(w, l);
     }
     if (const char* e = getenv("SIMT_SHUFFLE")) w.shuffle = strtoull(e, nullptr, 10) * 0x9E3779B97F4A7C15ull + 1;
     int order[Warp::kLanes];
@@ -232,7 +284,7 @@ inline void run_block(Warp& w, int nwarps, std::function<void(int)> body) {
             }
             if (!w.waiting[l]) {
                 w.cur = l;
-                swapcontext(&w.sched, &w.ctx[l]);
+                simt_switch(&w.sched, &w.ctx[l]);
                 progress = true;
                 if (w.finished[l]) done++;
             }

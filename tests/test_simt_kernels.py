@@ -32,7 +32,7 @@ def _build(name, harness, macro, extra=()):
     with open(inc, "w") as f:
         f.write(src[:src.index("// ---- kernel\n")])   # the device functions; the kernel entry and the launcher stay out
     so = os.path.join(build, f"libsimt_{name}.so")
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-I", SIMT, "-I", CSRC,
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", SIMT, "-I", CSRC,
                            f'-DAURORA_REAL_COMMON="{os.path.join(CSRC, "common.cuh")}"', f'-DAURORA_REAL_STAGE="{os.path.join(CSRC, "stage.cuh")}"',
                            f'-D{macro}="{inc}"', *extra,
                            os.path.join(SIMT, harness), "-o", so])
@@ -164,7 +164,7 @@ def _check(lib, oracle, fmt, raws, quality, **kw):
 
 
 @pytest.mark.parametrize("fmt", PAR_FORMATS, ids=fmt_id)
-@pytest.mark.parametrize("quality", [0, 8, 10, 15])
+@pytest.mark.parametrize("quality", [0, 3, 8, 10, 15])
 def test_kernel_source_on_emulated_lanes(simt_lib, oracle, bmp, fmt, quality):
     rng = np.random.default_rng(31 * fmt + quality)
     raws = [bmp[:n] for n in (5, 33, 4097, 9000)] + [synth(rng, int(n), i % 5) for i, n in enumerate([0, 1, 4, 31, 32, 33, 64, 65, 1000, 4096, 6000, 12000])]
@@ -208,7 +208,7 @@ def test_options_and_small_destinations(simt_lib, oracle, bmp):
 
 
 @pytest.mark.parametrize("fmt", SEQ_FLAG_FORMATS + BYTE_FORMATS, ids=fmt_id)
-@pytest.mark.parametrize("quality", [0, 12])
+@pytest.mark.parametrize("quality", [0, 8, 12])
 def test_sequential_replay_on_emulated_lanes(simt_lib, oracle, bmp, fmt, quality):
     """finder.cuh with the token writers of encode_lz.cu / encode_bytelz.cu: the finder every format falls back to."""
     rng = np.random.default_rng(17 * fmt + quality)
